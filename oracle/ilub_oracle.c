@@ -1,0 +1,381 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's ILU(0)/IChol(0) hot path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library, and there only as the checker.  The product path (ilupp_b200/, libilub.so)
+ * never links, imports or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle.py checks every function below against
+ *   (1) the reference's own golden / known-answer tests for this path (test/tests.py:26-31,
+ *       197-207,229-259,286-306,324-338 restated in tests/test_reference_cases.py),
+ *   (2) the unmodified reference compiled from /root/reference/src (oracle/_ref, bit-for-bit on
+ *       factors and apply outputs), and
+ *   (3) fixtures generated from that compiled reference (tests/golden/, scripts/make_golden.py).
+ * Exception: level sets -- the reference computes none (its solves are sequential), so
+ * oracle_levels_* is a restatement of the definition in SURVEY.md section 8(c) and is pinned only
+ * by closed-form known answers (tridiagonal: lev[i]=i; N^d lexicographic stencil: sum of coords).
+ *
+ * All index arrays are int32 (reference default: declarations.h:49-53), values fp64
+ * (declarations.h:55).  Compile with -ffp-contract=off: every a-b*c below is a rounded multiply
+ * followed by a rounded subtract, exactly like the reference built with plain -O2 on x86-64.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------
+ * ILU(0) numeric factorisation, storage treated as CSR (CSC input => this factors A^T).
+ * Follows compute_ilu0 + sparse_vec_update, ILU0.hpp:8-66.  lu has A's pattern.
+ * returns 0, or -(i+1) if row i has no stored diagonal (the reference has undefined behaviour
+ * there, ILU0.hpp:31,39-40,64; the restatement refuses instead).
+ * ------------------------------------------------------------------------------------------ */
+API int oracle_ilu0_values(int32_t n, const int32_t* ptr, const int32_t* idx, const double* a, double* lu) {
+    double* diag = (double*)malloc(sizeof(double) * (size_t)n);
+    if (!diag) return -1000000000;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t dpos = -1;
+        for (int32_t p = ptr[i]; p < ptr[i + 1]; ++p) { /* ILU0.hpp:36-45 */
+            lu[p] = a[p];
+            if (idx[p] == i) dpos = p;
+        }
+        if (dpos < 0) {
+            free(diag);
+            return -(i + 1);
+        }
+        for (int32_t kk = ptr[i]; kk < ptr[i + 1]; ++kk) { /* ILU0.hpp:47-62 */
+            const int32_t k = idx[kk];
+            if (k >= i) continue;
+            const double lik = lu[kk] / diag[k]; /* true division, ILU0.hpp:52 */
+            int32_t l1 = ptr[i], u1 = ptr[i + 1], l2 = ptr[k], u2 = ptr[k + 1];
+            while (l1 < u1 && l2 < u2) { /* two-pointer merge, ILU0.hpp:11-22 */
+                if (idx[l1] == idx[l2]) {
+                    if (idx[l1] > k) lu[l1] -= lik * lu[l2];
+                    ++l1;
+                    ++l2;
+                } else if (idx[l1] < idx[l2])
+                    ++l1;
+                else
+                    ++l2;
+            }
+            lu[kk] = lik; /* ILU0.hpp:61 */
+        }
+        diag[i] = lu[dpos]; /* ILU0.hpp:64 */
+    }
+    free(diag);
+    return 0;
+}
+
+/* L/U split, ILU0.hpp:69-98: L = strict lower + explicit 1.0 diagonal LAST, U = diagonal FIRST +
+ * strict upper, both with the major-axis layout of the input.  Caller sizes the outputs with
+ * oracle_ilu0_split_sizes.  The CSC relabelling (ILU0.hpp:100-105: swap L and U, flip both
+ * orientation flags) is a pure renaming of these arrays and is done by the caller. */
+API void oracle_ilu0_split_sizes(int32_t n, const int32_t* ptr, const int32_t* idx, int64_t* nnzL, int64_t* nnzU) {
+    int64_t l = 0, u = 0;
+    for (int32_t i = 0; i < n; ++i)
+        for (int32_t p = ptr[i]; p < ptr[i + 1]; ++p) { /* ILU0.hpp:42-44 */
+            if (idx[p] <= i) ++l;
+            if (idx[p] >= i) ++u;
+        }
+    *nnzL = l;
+    *nnzU = u;
+}
+
+API void oracle_ilu0_split(int32_t n, const int32_t* ptr, const int32_t* idx, const double* lu, int32_t* Lp,
+                           int32_t* Li, double* Lx, int32_t* Up, int32_t* Ui, double* Ux) {
+    int32_t l = 0, u = 0;
+    Lp[0] = Up[0] = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        for (int32_t p = ptr[i]; p < ptr[i + 1]; ++p) {
+            const int32_t j = idx[p];
+            if (j < i) {
+                Li[l] = j;
+                Lx[l++] = lu[p];
+            } else {
+                Ui[u] = j;
+                Ux[u++] = lu[p];
+            }
+        }
+        Li[l] = i; /* ILU0.hpp:93 */
+        Lx[l++] = 1.0;
+        Lp[i + 1] = l;
+        Up[i + 1] = u;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * IChol(0).  natural_triangular_part(true) (sparse_implementation.h:2568-2592) keeps j <= i along
+ * the major axis; IChol0 (IChol.hpp:62-73) relabels a CSC result as ROW, so in both cases the
+ * factor pattern is tril(arrays-read-as-CSR) and the result is CSR lower with the diagonal last.
+ * ------------------------------------------------------------------------------------------ */
+API int64_t oracle_tril_nnz(int32_t n, const int32_t* ptr, const int32_t* idx) {
+    int64_t c = 0;
+    for (int32_t i = 0; i < n; ++i)
+        for (int32_t p = ptr[i]; p < ptr[i + 1]; ++p)
+            if (idx[p] <= i) ++c;
+    return c;
+}
+
+API void oracle_tril(int32_t n, const int32_t* ptr, const int32_t* idx, const double* a, int32_t* Lp, int32_t* Li,
+                     double* Lx) {
+    int32_t l = 0;
+    Lp[0] = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        for (int32_t p = ptr[i]; p < ptr[i + 1]; ++p)
+            if (idx[p] <= i) {
+                Li[l] = idx[p];
+                Lx[l++] = a[p];
+            }
+        Lp[i + 1] = l;
+    }
+}
+
+/* compute_ichol0 + sparse_dot_product, IChol.hpp:15-59.  T = (Lp, Li, Tx) lower triangular CSR,
+ * diagonal last in every row; out = new values on the same pattern.
+ * returns 0, or -(i+1) if row i has an entry above the diagonal (reference throws logic_error). */
+API int oracle_ichol0_values(int32_t n, const int32_t* Lp, const int32_t* Li, const double* Tx, double* out) {
+    for (int32_t i = 0; i < n; ++i) {
+        for (int32_t k = Lp[i]; k < Lp[i + 1]; ++k) {
+            const int32_t j = Li[k];
+            if (j > i) return -(i + 1);
+            double dp = 0.0; /* IChol.hpp:18-27 */
+            int32_t l1 = Lp[i], u1 = Lp[i + 1] - 1, l2 = Lp[j], u2 = Lp[j + 1] - 1;
+            while (l1 < u1 && l2 < u2) {
+                if (Li[l1] == Li[l2])
+                    dp += out[l1++] * out[l2++];
+                else if (Li[l1] < Li[l2])
+                    ++l1;
+                else
+                    ++l2;
+            }
+            if (j < i)
+                out[k] = (Tx[k] - dp) / out[Lp[j + 1] - 1]; /* IChol.hpp:49-51 */
+            else
+                out[k] = sqrt(Tx[k] - dp); /* IChol.hpp:52-53 */
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * The four triangular-solve loops, matrix_sparse::triangular_solve,
+ * sparse_implementation.h:4040-4087.  In place on x.  (ptr, idx, v) are the stored arrays of the
+ * factor, whatever its orientation label.
+ * ------------------------------------------------------------------------------------------ */
+API void oracle_fwd_gather(int32_t n, const int32_t* ptr, const int32_t* idx, const double* v, double* x) {
+    for (int32_t k = 0; k < n; ++k) { /* :4045-4054, diagonal LAST */
+        for (int32_t j = ptr[k]; j < ptr[k + 1] - 1; ++j) x[k] -= v[j] * x[idx[j]];
+        x[k] /= v[ptr[k + 1] - 1];
+    }
+}
+API void oracle_fwd_scatter(int32_t n, const int32_t* ptr, const int32_t* idx, const double* v, double* x) {
+    for (int32_t k = 0; k < n; ++k) { /* :4055-4065, diagonal FIRST */
+        x[k] /= v[ptr[k]];
+        for (int32_t j = ptr[k] + 1; j < ptr[k + 1]; ++j) x[idx[j]] -= v[j] * x[k];
+    }
+}
+API void oracle_bwd_gather(int32_t n, const int32_t* ptr, const int32_t* idx, const double* v, double* x) {
+    for (int32_t k = n - 1; k >= 0; --k) { /* :4066-4074, diagonal FIRST */
+        for (int32_t j = ptr[k] + 1; j < ptr[k + 1]; ++j) x[k] -= v[j] * x[idx[j]];
+        x[k] /= v[ptr[k]];
+    }
+}
+API void oracle_bwd_scatter(int32_t n, const int32_t* ptr, const int32_t* idx, const double* v, double* x) {
+    for (int32_t k = n - 1; k >= 0; --k) { /* :4075-4084, diagonal LAST */
+        x[k] /= v[ptr[k + 1] - 1];
+        for (int32_t j = ptr[k]; j < ptr[k + 1] - 1; ++j) x[idx[j]] -= v[j] * x[k];
+    }
+}
+
+/* apply / apply_trans of the two preconditioner classes.
+ * LU class (preconditioner_implementation.h:102-111,321-334): ID => left(L) then right(U);
+ * TRANSPOSE => right then left.  Which loop each solve takes follows the dispatch table at
+ * sparse_implementation.h:4043-4084 for (form, orientation, use).
+ *   factors_csr != 0 (CSR input): L is ROW unit-lower diag-last, U is ROW upper diag-first
+ *   factors_csr == 0 (CSC input): L is COLUMN lower diag-first (non-unit), U is COLUMN upper diag-last (unit)
+ */
+API void oracle_apply_lu(int32_t n, int factors_csr, int transpose, const int32_t* Lp, const int32_t* Li,
+                         const double* Lx, const int32_t* Up, const int32_t* Ui, const double* Ux, double* x) {
+    if (!transpose) {
+        if (factors_csr) {
+            oracle_fwd_gather(n, Lp, Li, Lx, x);  /* (LOWER,ROW,ID) */
+            oracle_bwd_gather(n, Up, Ui, Ux, x);  /* (UPPER,ROW,ID) */
+        } else {
+            oracle_fwd_scatter(n, Lp, Li, Lx, x); /* (LOWER,COLUMN,ID) */
+            oracle_bwd_scatter(n, Up, Ui, Ux, x); /* (UPPER,COLUMN,ID) */
+        }
+    } else {
+        if (factors_csr) {
+            oracle_fwd_scatter(n, Up, Ui, Ux, x); /* (UPPER,ROW,TRANSPOSE) */
+            oracle_bwd_scatter(n, Lp, Li, Lx, x); /* (LOWER,ROW,TRANSPOSE) */
+        } else {
+            oracle_fwd_gather(n, Up, Ui, Ux, x);  /* (UPPER,COLUMN,TRANSPOSE) */
+            oracle_bwd_gather(n, Lp, Li, Lx, x);  /* (LOWER,COLUMN,TRANSPOSE) */
+        }
+    }
+}
+
+/* LL^T class (preconditioner_implementation.h:381-394): left = L with `use`, right = L with
+ * other_usage(use); ID => left,right; TRANSPOSE => right,left -- both orders come out as
+ * (LOWER,ROW,ID) then (LOWER,ROW,TRANSPOSE).  L is always CSR (IChol.hpp:67-68). */
+API void oracle_apply_llt(int32_t n, const int32_t* Lp, const int32_t* Li, const double* Lx, double* x) {
+    oracle_fwd_gather(n, Lp, Li, Lx, x);
+    oracle_bwd_scatter(n, Lp, Li, Lx, x);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Level sets (no reference code -- definition from SURVEY.md 8(c) / Appendix B).
+ * lower != 0: lev[i] = 0 if row i has no column < i, else 1 + max lev[j] over columns j < i.
+ * lower == 0: mirrored (rows descending, columns j > i).  Rows are those of the CSR-read arrays.
+ * returns the number of levels.
+ * ------------------------------------------------------------------------------------------ */
+API int32_t oracle_levels(int32_t n, const int32_t* ptr, const int32_t* idx, int lower, int32_t* lev) {
+    int32_t nlev = 0;
+    if (lower) {
+        for (int32_t i = 0; i < n; ++i) {
+            int32_t l = 0;
+            for (int32_t p = ptr[i]; p < ptr[i + 1]; ++p)
+                if (idx[p] < i && lev[idx[p]] + 1 > l) l = lev[idx[p]] + 1;
+            lev[i] = l;
+            if (l + 1 > nlev) nlev = l + 1;
+        }
+    } else {
+        for (int32_t i = n - 1; i >= 0; --i) {
+            int32_t l = 0;
+            for (int32_t p = ptr[i]; p < ptr[i + 1]; ++p)
+                if (idx[p] > i && lev[idx[p]] + 1 > l) l = lev[idx[p]] + 1;
+            lev[i] = l;
+            if (l + 1 > nlev) nlev = l + 1;
+        }
+    }
+    return nlev;
+}
+
+/* Level sets of the TRANSPOSED triangle (the DAG of a scatter-form solve): row i of
+ * (strict-upper)^T depends on every k < i with a stored (k, i), and mirrored. */
+API int32_t oracle_levels_transposed(int32_t n, const int32_t* ptr, const int32_t* idx, int lower, int32_t* lev) {
+    int32_t nlev = 0;
+    memset(lev, 0, sizeof(int32_t) * (size_t)n);
+    if (lower) { /* DAG of fwd-scatter: entry (k, i) with i > k pushes lev[k]+1 into lev[i] */
+        for (int32_t k = 0; k < n; ++k) {
+            for (int32_t p = ptr[k]; p < ptr[k + 1]; ++p)
+                if (idx[p] > k && lev[k] + 1 > lev[idx[p]]) lev[idx[p]] = lev[k] + 1;
+            if (lev[k] + 1 > nlev) nlev = lev[k] + 1;
+        }
+    } else { /* DAG of bwd-scatter: entry (k, i) with i < k */
+        for (int32_t k = n - 1; k >= 0; --k) {
+            for (int32_t p = ptr[k]; p < ptr[k + 1]; ++p)
+                if (idx[p] < k && lev[k] + 1 > lev[idx[p]]) lev[idx[p]] = lev[k] + 1;
+            if (lev[k] + 1 > nlev) nlev = lev[k] + 1;
+        }
+    }
+    return nlev;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SpMV, generic_matrix_vector_multiplication_addition, sparse_implementation.h:2733-2760:
+ * gather form for (ROW, ID); scatter form for (COLUMN, ID).  y is zeroed first
+ * (matrix_vector_multiplication, :3151-3158).
+ * ------------------------------------------------------------------------------------------ */
+API void oracle_spmv(int32_t n, int is_csr, const int32_t* ptr, const int32_t* idx, const double* v, const double* x,
+                     double* y) {
+    for (int32_t i = 0; i < n; ++i) y[i] = 0.0;
+    if (is_csr) {
+        for (int32_t i = 0; i < n; ++i)
+            for (int32_t j = ptr[i]; j < ptr[i + 1]; ++j) y[i] += v[j] * x[idx[j]];
+    } else {
+        for (int32_t i = 0; i < n; ++i)
+            for (int32_t j = ptr[i]; j < ptr[i + 1]; ++j) y[idx[j]] += v[j] * x[i];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * BiCGStab with SPLIT preconditioning, zero start, min_iter = 1:
+ * bicgstab, iterative_solvers_implementation.h:384-529 as driven by solve_linear_system
+ * (solving_routines_implementation.h:56,66,81) and the SPLIT composition
+ * (preconditioner_implementation.h:143-147,225-227,250-252).  The preconditioner is given by its
+ * reference-layout factors; kind 0 = LU class, kind 1 = LL^T class.
+ * Tolerances round-trip through -log10 / exp exactly like binding.cpp:211-212 and
+ * iterative_solvers_implementation.h:422-423.
+ * returns 1 on success (criterion :498).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int kind, factors_csr;
+    int32_t n;
+    const int32_t *Lp, *Li, *Up, *Ui;
+    const double *Lx, *Ux;
+} pre_t;
+
+static void pre_left(const pre_t* P, double* w) { /* apply_preconditioner_left(ID, w) */
+    if (P->kind == 1 || P->factors_csr)
+        oracle_fwd_gather(P->n, P->Lp, P->Li, P->Lx, w);
+    else
+        oracle_fwd_scatter(P->n, P->Lp, P->Li, P->Lx, w);
+}
+static void pre_right(const pre_t* P, double* w) { /* apply_preconditioner_right(ID, w) */
+    if (P->kind == 1)
+        oracle_bwd_scatter(P->n, P->Lp, P->Li, P->Lx, w);
+    else if (P->factors_csr)
+        oracle_bwd_gather(P->n, P->Up, P->Ui, P->Ux, w);
+    else
+        oracle_bwd_scatter(P->n, P->Up, P->Ui, P->Ux, w);
+}
+static double dot(int32_t n, const double* a, const double* b) { /* sparse_implementation.h:414-425 */
+    double h = 0.0;
+    for (int32_t i = 0; i < n; ++i) h += a[i] * b[i];
+    return h;
+}
+
+API int oracle_bicgstab(int kind, int factors_csr, int32_t n, const int32_t* Lp, const int32_t* Li, const double* Lx,
+                        const int32_t* Up, const int32_t* Ui, const double* Ux, int a_is_csr, const int32_t* Ap,
+                        const int32_t* Ai, const double* Ax, const double* b, double* x, double rtol, double atol,
+                        int32_t max_iter, int32_t* iters, double* rel_achieved, double* abs_achieved) {
+    pre_t P = {kind, factors_csr, n, Lp, Li, Up, Ui, Lx, Ux};
+    double rel_tol = -log10(rtol), abs_tol = -log10(atol); /* binding.cpp:211-212 */
+    rel_tol = exp(-rel_tol * log(10.0));                   /* :422-423 */
+    abs_tol = exp(-abs_tol * log(10.0));
+    const size_t nb = sizeof(double) * (size_t)n;
+    double *r = malloc(nb), *y = calloc((size_t)n, sizeof(double)), *p = malloc(nb), *s = malloc(nb),
+           *Apv = malloc(nb), *As = malloc(nb), *r0 = malloc(nb), *t = malloc(nb);
+    memcpy(r, b, nb); /* r0star = b; r = L^-1 r0star  (:438,444) */
+    pre_left(&P, r);
+    memcpy(r0, r, nb); /* :446-447 */
+    memcpy(p, r, nb);
+    double initial_res = sqrt(dot(n, r, r)), res = initial_res; /* :448-449 */
+    int32_t iter = 0;
+    const int32_t min_iter = 1;
+    while ((((res / initial_res > rel_tol) || res > abs_tol) && (iter < max_iter)) || (iter < min_iter)) { /* :455 */
+        ++iter;
+        /* Ap = L^-1 A U^-1 p   (preconditioner_implementation.h:143-147) */
+        memcpy(t, p, nb);
+        pre_right(&P, t);
+        oracle_spmv(n, a_is_csr, Ap, Ai, Ax, t, Apv);
+        pre_left(&P, Apv);
+        const double rho = dot(n, r, r0);         /* :466 */
+        const double alpha = rho / dot(n, Apv, r0); /* :467 */
+        for (int32_t i = 0; i < n; ++i) s[i] = r[i] + (-alpha * Apv[i]); /* :468, sparse_implementation.h:278 */
+        memcpy(t, s, nb);
+        pre_right(&P, t);
+        oracle_spmv(n, a_is_csr, Ap, Ai, Ax, t, As);
+        pre_left(&P, As); /* :473 */
+        const double product = dot(n, As, As);   /* :478 */
+        const double omega = dot(n, As, s) / product; /* :482 */
+        for (int32_t i = 0; i < n; ++i) y[i] += alpha * p[i]; /* :484 */
+        for (int32_t i = 0; i < n; ++i) y[i] += omega * s[i]; /* :485 */
+        for (int32_t i = 0; i < n; ++i) r[i] = s[i] + (-omega * As[i]); /* :486 */
+        const double beta = (dot(n, r, r0) / rho) * (alpha / omega);    /* :487 */
+        for (int32_t i = 0; i < n; ++i) p[i] += -omega * Apv[i];        /* :488 */
+        for (int32_t i = 0; i < n; ++i) p[i] = beta * p[i] + r[i];      /* :489 */
+        res = sqrt(dot(n, r, r));                                       /* :490 */
+    }
+    memcpy(x, y, nb); /* x = U^-1 y (:496) */
+    pre_right(&P, x);
+    *iters = iter;
+    const int ok = (res / initial_res < rel_tol) && (res < abs_tol); /* :498 */
+    *rel_achieved = pow(10.0, log10(res / initial_res));              /* :499 + binding.cpp:226 */
+    *abs_achieved = pow(10.0, log10(res));
+    free(r); free(y); free(p); free(s); free(Apv); free(As); free(r0); free(t);
+    return ok;
+}
