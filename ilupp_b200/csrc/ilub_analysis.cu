@@ -1,0 +1,682 @@
+// Symbolic phase on the GPU: structure validation + diagonal pointers, transposed patterns for the
+// scatter-form solves, sync-free level-set analysis of each triangular DAG, row -> CTA partition,
+// (part, level, row) ordering and the packed solve layout (32-row chunks, SELL slabs).
+//
+// Replaces what the reference does inline and sequentially: the diagonal search / nnzL,nnzU count
+// of compute_ilu0 (ILU0.hpp:36-45), natural_triangular_part (sparse_implementation.h:2568-2592)
+// and the implicit "rows in index order" schedule of triangular_solve (:4040-4087).  The level
+// sets themselves have no reference counterpart.
+#include <algorithm>
+#include <cub/cub.cuh>
+
+#include "ilub_common.cuh"
+
+namespace ilub {
+
+Options& options() {
+    static Options o;
+    return o;
+}
+
+namespace {
+
+inline int blocks_for(int64_t work, int threads) { return (int)((work + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------
+// validation + diagonal pointer.  8 lanes per row stride over the row (coalesced), the lane that
+// sees column == row records the position; a ballot over the group detects a missing diagonal.
+// status[0] = 0 ok | 1 unsorted/duplicate | 2 out of range | 3 missing diagonal ; status[1] = row
+__global__ void k_validate(int n, const int* __restrict__ ptr, const int* __restrict__ idx, int* __restrict__ dpos,
+                           int* status) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+    const int64_t row64 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool valid = row64 < n;
+    const int row = valid ? (int)row64 : 0;
+    int err = 0;
+    bool found = false;
+    if (valid) {
+        const int b = ptr[row], e = ptr[row + 1];
+        if (e < b) err = 1;
+        for (int p = b + gl; p < e; p += 8) {
+            const int c = idx[p];
+            if (c < 0 || c >= n) err = 2;
+            if (p > b && idx[p - 1] >= c && !err) err = 1;
+            if (c == row) {
+                found = true;
+                dpos[row] = p;
+            }
+        }
+    }
+    const unsigned fm = __ballot_sync(0xffffffffu, found);
+    if (valid && !err && gl == 0 && ((fm >> (g * 8)) & 0xffu) == 0) err = 3;
+    if (err) {
+        if (atomicCAS(&status[0], 0, err) == 0) status[1] = row;
+    }
+}
+
+__global__ void k_count_tri(int n, const int* __restrict__ ptr, const int* __restrict__ dpos,
+                            unsigned long long* out /*[2] lower, upper*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long lo = 0, up = 0;
+    if (i < n) {
+        lo = (unsigned long long)(dpos[i] - ptr[i]);
+        up = (unsigned long long)(ptr[i + 1] - dpos[i] - 1);
+    }
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    lo = BR(tmp).Sum(lo);
+    __syncthreads();
+    up = BR(tmp).Sum(up);
+    if (threadIdx.x == 0) {
+        atomicAdd(&out[0], lo);
+        atomicAdd(&out[1], up);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// transposed pattern of the strict upper / strict lower triangle
+__global__ void k_tri_count_cols(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                 const int* __restrict__ dpos, int upper, int* __restrict__ colcnt,
+                                 int* __restrict__ rowcnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = upper ? dpos[i] + 1 : ptr[i];
+    const int e = upper ? ptr[i + 1] : dpos[i];
+    rowcnt[i] = e - b;
+    for (int p = b; p < e; ++p) atomicAdd(&colcnt[idx[p]], 1);
+}
+
+__global__ void k_tri_emit(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+                           const int* __restrict__ dpos, int upper, const int* __restrict__ rowoff,
+                           int* __restrict__ keys, unsigned long long* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = upper ? dpos[i] + 1 : ptr[i];
+    const int e = upper ? ptr[i + 1] : dpos[i];
+    int o = rowoff[i];
+    for (int p = b; p < e; ++p, ++o) {
+        keys[o] = idx[p];
+        vals[o] = ((unsigned long long)(unsigned)i << 32) | (unsigned)p;
+    }
+}
+
+__global__ void k_tri_unpack(int64_t nt, const unsigned long long* __restrict__ vals, int* __restrict__ tidx,
+                             int* __restrict__ tpos) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    tidx[t] = (int)(vals[t] >> 32);
+    tpos[t] = (int)(vals[t] & 0xffffffffu);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sync-free level analysis: one thread per row, rows handed out in dependency-safe order by a
+// ticket counter (a warp only ever waits for rows whose ticket was drawn before its own, and those
+// warps are running), levels published with volatile stores -- the value itself is the flag.
+__global__ void __launch_bounds__(256) k_levels(SrcDev S, int n, int* level, int* ticket, int* nlev,
+                                                long long spin_limit, int* status) {
+    const int lane = threadIdx.x & 31;
+    volatile int* vlevel = level;
+    while (true) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        const int64_t base = (int64_t)t * 32;
+        if (base >= n) break;
+        const int64_t r = base + lane;
+        const bool valid = r < n;
+        const int row = valid ? (S.backward ? n - 1 - (int)r : (int)r) : 0;
+        int p = valid ? src_beg(S, row) : 0;
+        const int e = valid ? src_end(S, row) : 0;
+        int lv = 0;
+        bool fin = !valid;
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (true) {
+            if (!fin) {
+                while (p < e) {
+                    const int l = vlevel[S.dep_idx[p]];
+                    if (l < 0) break;
+                    lv = max(lv, l + 1);
+                    ++p;
+                }
+                if (p >= e) {
+                    vlevel[row] = lv;
+                    fin = true;
+                }
+            }
+            if (__all_sync(0xffffffffu, fin)) break;
+            if ((++spins & 255u) == 0) {
+                if (clock64() - t0 > spin_limit || *(volatile int*)status != 0) {
+                    if (lane == 0) atomicCAS(status, 0, 100);
+                    return;
+                }
+            }
+        }
+        const int m = __reduce_max_sync(0xffffffffu, valid ? lv + 1 : 0);
+        if (lane == 0) atomicMax(nlev, m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// partition: contiguous row ranges balanced by work (entries + per-row overhead)
+struct WeightOp {
+    SrcDev S;
+    __host__ __device__ __forceinline__ long long operator()(int i) const {
+        return (long long)(src_end(S, i) - src_beg(S, i)) + 2;
+    }
+};
+
+__global__ void k_partition(int n, const long long* __restrict__ wsum /*inclusive*/, SrcDev S, int nparts,
+                            const int* __restrict__ level, unsigned long long* __restrict__ keys,
+                            int* __restrict__ rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long total = wsum[n - 1];
+    const long long w = (long long)(src_end(S, i) - src_beg(S, i)) + 2;
+    const long long start = wsum[i] - w;
+    int p = (int)((__int128)start * nparts / total);
+    if (p >= nparts) p = nparts - 1;
+    keys[i] = ((unsigned long long)(unsigned)p << 32) | (unsigned)level[i];
+    rows[i] = i;
+}
+
+// rows of part p occupy sorted positions [rstart[p], rstart[p+1]); chunks [pcp[p], pcp[p+1])
+__global__ void k_part_bounds(int n, int nparts, const unsigned long long* __restrict__ skeys, int* rstart,
+                              int* pcp) {
+    // single block
+    for (int p = threadIdx.x; p <= nparts; p += blockDim.x) {
+        int lo = 0, hi = n;  // first sorted position whose part >= p
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if ((int)(skeys[mid] >> 32) < p)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        rstart[p] = lo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int p = 0; p < nparts; ++p) {
+            pcp[p] = acc;
+            acc += (rstart[p + 1] - rstart[p] + 31) >> 5;
+        }
+        pcp[nparts] = acc;
+    }
+}
+
+__global__ void k_place_rows(int n, const unsigned long long* __restrict__ skeys, const int* __restrict__ order,
+                             const int* __restrict__ rstart, const int* __restrict__ pcp, int* __restrict__ rows,
+                             int* __restrict__ rowpos) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int p = (int)(skeys[s] >> 32);
+    const int rank = s - rstart[p];
+    const int pos = ((pcp[p] + (rank >> 5)) << 5) | (rank & 31);
+    const int row = order[s];
+    rows[pos] = row;
+    rowpos[row] = pos;
+}
+
+// one warp per chunk: lengths, width, kind, slab count
+__global__ void k_chunk_shape(int nchunks, SrcDev S, const int* __restrict__ rows, int wcap,
+                              int* __restrict__ rlen, int* __restrict__ cslabs, unsigned char* __restrict__ ckind,
+                              int* __restrict__ maxw_a, int* __restrict__ any_b) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= nchunks) return;
+    const int row = rows[c * 32 + lane];
+    const int len = row >= 0 ? src_end(S, row) - src_beg(S, row) : 0;
+    rlen[c * 32 + lane] = len;
+    const int w = __reduce_max_sync(0xffffffffu, len);
+    const int tot = __reduce_add_sync(0xffffffffu, len);
+    if (lane == 0) {
+        if (w <= wcap) {
+            ckind[c] = 0;
+            cslabs[c] = w;
+            atomicMax(maxw_a, w);
+        } else {
+            ckind[c] = 1;
+            cslabs[c] = (tot + 31) >> 5;
+            *any_b = 1;
+        }
+    }
+}
+
+__global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows, const int* __restrict__ rlen,
+                             const int* __restrict__ chunk_ptr, const int* __restrict__ rowpos,
+                             const int* __restrict__ pcp, int nparts, int near, unsigned char* __restrict__ ckind,
+                             int* __restrict__ idx, int* __restrict__ srcpos, int* __restrict__ diagpos) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= nchunks) return;
+    // owning part: last p with pcp[p] <= c
+    int lo = 0, hi = nparts;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pcp[mid] <= c)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const int cfirst = pcp[lo];
+    const int row = rows[c * 32 + lane];
+    const int len = rlen[c * 32 + lane];
+    const int kind = ckind[c] & 1;
+    const int64_t base = (int64_t)chunk_ptr[c] * 32;
+    const int w = chunk_ptr[c + 1] - chunk_ptr[c];
+    diagpos[c * 32 + lane] = (row >= 0 && S.diag_pos) ? S.diag_pos[row] : -1;
+    int off = 0;
+    if (kind) {  // exclusive scan of len over the warp
+        int v = len;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += t;
+        }
+        off = v - len;
+        const int tot = __shfl_sync(0xffffffffu, v, 31);
+        for (int64_t t = tot + lane; t < (int64_t)w * 32; t += 32) {  // tail padding
+            idx[base + t] = 0;
+            srcpos[base + t] = -1;
+        }
+    }
+    bool intra = false;
+    const int b = row >= 0 ? src_beg(S, row) : 0;
+    const int e = b + len;
+    for (int j = 0; j < (kind ? len : w); ++j) {
+        const int64_t at = kind ? base + off + j : base + (int64_t)j * 32 + lane;
+        if (j >= len) {
+            idx[at] = 0;
+            srcpos[at] = -1;
+            continue;
+        }
+        const int q = S.reverse ? e - 1 - j : b + j;
+        const int d = S.dep_idx[q];
+        const int pd = rowpos[d];
+        const int dc = pd >> 5;
+        unsigned enc;
+        if (dc == c) {
+            enc = kLocalBit | kIntraBit | (unsigned)(pd & 31);
+            intra = true;
+        } else if (dc >= cfirst && dc < c && c - dc <= near) {
+            enc = kLocalBit | (unsigned)(pd - (cfirst << 5));
+        } else {
+            enc = (unsigned)d;
+        }
+        idx[at] = (int)enc;
+        srcpos[at] = S.val_pos ? S.val_pos[q] : q;
+    }
+    if (__any_sync(0xffffffffu, intra) && lane == 0) ckind[c] |= 2;
+}
+
+__global__ void k_pack_values(int64_t nent, const int* __restrict__ srcpos, const double* __restrict__ lu,
+                              double* __restrict__ val) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nent) return;
+    const int s = srcpos[t];
+    val[t] = s >= 0 ? lu[s] : 0.0;
+}
+__global__ void k_pack_diag(int64_t nent, const int* __restrict__ diagpos, const double* __restrict__ lu,
+                            double* __restrict__ diag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nent) return;
+    const int s = diagpos[t];
+    diag[t] = s >= 0 ? lu[s] : 1.0;
+}
+
+__global__ void k_iota(int n, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+__global__ void k_level_ptr(int n, int nlevels, const int* __restrict__ slev, int* __restrict__ lptr) {
+    // lptr[l] = first sorted position with level >= l
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > nlevels) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (slev[mid] < l)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    lptr[l] = lo;
+}
+
+__global__ void k_expand_batched(int32_t n1, int64_t nnz1, int32_t nsys, const int* __restrict__ ptr1,
+                                 const int* __restrict__ idx1, int* __restrict__ ptr, int* __restrict__ idx) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nnz = nnz1 * nsys;
+    if (t < nnz) {
+        const int s = (int)(t / nnz1);
+        idx[t] = idx1[t - (int64_t)s * nnz1] + s * n1;
+    }
+    const int64_t n = (int64_t)n1 * nsys;
+    if (t <= n) {
+        const int s = (int)(t / n1);
+        ptr[t] = (int)(ptr1[t - (int64_t)s * n1] + (int64_t)s * nnz1);
+    }
+}
+
+int bits_for(unsigned v) {
+    int b = 1;
+    while (b < 32 && (v >> b)) ++b;
+    return b;
+}
+
+}  // namespace
+
+// ================================================================================================
+int read_status(ilub_handle* h, cudaStream_t s) {
+    int st[2] = {0, 0};
+    ILUB_CUDA(cudaMemcpyAsync(st, h->status.p, sizeof(st), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    if (st[0] == 0) return 0;
+    if (st[0] >= 100) {
+        ILUB_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(int) * 4, s));
+        throw Error{ILUB_ERR_WATCHDOG, "sync-free kernel exceeded its spin limit (code " + std::to_string(st[0]) + ")"};
+    }
+    const char* what = st[0] == 1   ? "column indices are not strictly ascending (unsorted or duplicate entries)"
+                       : st[0] == 2 ? "column index out of range"
+                                    : "structurally missing diagonal entry";
+    throw Error{ILUB_ERR_STRUCTURE, std::string(what) + " in row " + std::to_string(st[1])};
+}
+
+void validate_and_find_diag(ilub_handle* h, cudaStream_t s) {
+    const int n = h->n;
+    h->dpos.alloc(n);
+    h->status.alloc(8);
+    ILUB_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(int) * 8, s));
+    k_validate<<<blocks_for((int64_t)n * 8, 256), 256, 0, s>>>(n, h->ptr.p, h->idx.p, h->dpos.p, h->status.p);
+    h->launches++;
+    read_status(h, s);
+    DevBuf<unsigned long long> cnt;
+    cnt.alloc(2);
+    ILUB_CUDA(cudaMemsetAsync(cnt.p, 0, 16, s));
+    k_count_tri<<<blocks_for(n, 256), 256, 0, s>>>(n, h->ptr.p, h->dpos.p, cnt.p);
+    h->launches++;
+    unsigned long long hc[2];
+    ILUB_CUDA(cudaMemcpyAsync(hc, cnt.p, 16, cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    h->nnz_lower = (int64_t)hc[0];
+    h->nnz_upper = (int64_t)hc[1];
+}
+
+void build_transposed(ilub_handle* h, bool upper, cudaStream_t s) {
+    Transposed& T = upper ? h->t_upper : h->t_lower;
+    if (T.built) return;
+    const int n = h->n;
+    const int64_t nt = upper ? h->nnz_upper : h->nnz_lower;
+    T.nt = nt;
+    T.tptr.alloc(n + 1);
+    T.tidx.alloc(nt);
+    T.tpos.alloc(nt);
+    DevBuf<int> colcnt, rowcnt, rowoff, keys, keys2;
+    DevBuf<unsigned long long> vals, vals2;
+    colcnt.alloc(n + 1);
+    rowcnt.alloc(n);
+    rowoff.alloc(n);
+    keys.alloc(nt);
+    keys2.alloc(nt);
+    vals.alloc(nt);
+    vals2.alloc(nt);
+    ILUB_CUDA(cudaMemsetAsync(colcnt.p, 0, sizeof(int) * (n + 1), s));
+    k_tri_count_cols<<<blocks_for(n, 256), 256, 0, s>>>(n, h->ptr.p, h->idx.p, h->dpos.p, upper ? 1 : 0, colcnt.p,
+                                                        rowcnt.p);
+    size_t tb1 = 0, tb2 = 0, tb3 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb1, colcnt.p, T.tptr.p, n + 1, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, rowcnt.p, rowoff.p, n, s);
+    cub::DoubleBuffer<int> dk(keys.p, keys2.p);
+    cub::DoubleBuffer<unsigned long long> dv(vals.p, vals2.p);
+    const int kb = bits_for((unsigned)n);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb3, dk, dv, (int)nt, 0, kb, s);
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(std::max(tb1, std::max(tb2, tb3)));
+    size_t tb = tmp.n;
+    ILUB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, colcnt.p, T.tptr.p, n + 1, s));
+    tb = tmp.n;
+    ILUB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, rowcnt.p, rowoff.p, n, s));
+    k_tri_emit<<<blocks_for(n, 256), 256, 0, s>>>(n, h->ptr.p, h->idx.p, h->dpos.p, upper ? 1 : 0, rowoff.p, keys.p,
+                                                  vals.p);
+    if (nt > 0) {
+        tb = tmp.n;
+        ILUB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int)nt, 0, kb, s));
+        k_tri_unpack<<<blocks_for(nt, 256), 256, 0, s>>>(nt, dv.Current(), T.tidx.p, T.tpos.p);
+    }
+    h->launches += 6;
+    ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here
+    T.built = true;
+}
+
+SolveSource solve_source(ilub_handle* h, int slot) {
+    SolveSource S;
+    const bool ichol = h->kind == KIND_ICHOL0;
+    switch (slot) {
+        case 0:  // gather, forward, strict lower of the CSR-read arrays
+            S.beg_a = h->ptr.p;
+            S.end_a = h->dpos.p;
+            S.dep_idx = h->idx.p;
+            S.unit_diag = !ichol;
+            S.diag_pos = ichol ? h->dpos.p : nullptr;
+            break;
+        case 1:  // gather, backward, strict upper
+            S.beg_a = h->dpos.p;
+            S.beg_off = 1;
+            S.end_a = h->ptr.p + 1;
+            S.dep_idx = h->idx.p;
+            S.diag_pos = h->dpos.p;
+            S.backward = true;
+            break;
+        case 2:  // transposed strict upper, forward (scatter-form U^T solve)
+            S.beg_a = h->t_upper.tptr.p;
+            S.end_a = h->t_upper.tptr.p + 1;
+            S.dep_idx = h->t_upper.tidx.p;
+            S.val_pos = h->t_upper.tpos.p;
+            S.diag_pos = h->dpos.p;
+            break;
+        default:  // 3: transposed strict lower, backward, entries accumulated in descending order
+            S.beg_a = h->t_lower.tptr.p;
+            S.end_a = h->t_lower.tptr.p + 1;
+            S.dep_idx = h->t_lower.tidx.p;
+            S.val_pos = h->t_lower.tpos.p;
+            S.unit_diag = !ichol;
+            S.diag_pos = ichol ? h->dpos.p : nullptr;
+            S.backward = true;
+            S.reverse_entries = true;
+            break;
+    }
+    return S;
+}
+
+void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    if (T.built) return;
+    if (slot == 2) build_transposed(h, true, s);
+    if (slot == 3) build_transposed(h, false, s);
+    const Options& opt = options();
+    const int n = h->n;
+    const SolveSource src = solve_source(h, slot);
+    const SrcDev S = to_dev(src);
+    T.n = n;
+    T.backward = src.backward;
+    T.unit_diag = src.unit_diag;
+
+    // ---- levels
+    T.level.alloc(n);
+    ILUB_CUDA(cudaMemsetAsync(T.level.p, 0xff, sizeof(int) * n, s));
+    DevBuf<int> ctr;
+    ctr.alloc(4);
+    ILUB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int) * 4, s));
+    cudaDeviceProp prop;
+    ILUB_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    const long long spin = (long long)opt.spin_limit_ms * (long long)prop.clockRate;  // kHz * ms = cycles
+    {
+        int occ = 0;
+        ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels, 256, 0));
+        const int grid = std::max(1, occ * h->sm_count);
+        k_levels<<<grid, 256, 0, s>>>(S, n, T.level.p, ctr.p, ctr.p + 1, spin * 4, h->status.p);
+        h->launches++;
+    }
+    read_status(h, s);
+    int hctr[2];
+    ILUB_CUDA(cudaMemcpy(hctr, ctr.p, sizeof(hctr), cudaMemcpyDeviceToHost));
+    T.nlevels = hctr[1];
+
+    // ---- partition + (part, level, row) order
+    int nparts = (int)(h->sm_count * opt.ctas_per_sm);
+    const int64_t max_parts_by_rows = ((int64_t)n + 31) / 32;
+    if (nparts > max_parts_by_rows) nparts = (int)std::max<int64_t>(1, max_parts_by_rows);
+    T.nparts = nparts;
+    DevBuf<long long> wsum;
+    wsum.alloc(n);
+    DevBuf<unsigned long long> keys, keys2;
+    DevBuf<int> rowsb, rows2;
+    keys.alloc(n);
+    keys2.alloc(n);
+    rowsb.alloc(n);
+    rows2.alloc(n);
+    cub::CountingInputIterator<int> cnt_it(0);
+    WeightOp wop{S};
+    cub::TransformInputIterator<long long, WeightOp, cub::CountingInputIterator<int>> w_it(cnt_it, wop);
+    size_t tb1 = 0, tb2 = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tb1, w_it, wsum.p, n, s);
+    cub::DoubleBuffer<unsigned long long> dk(keys.p, keys2.p);
+    cub::DoubleBuffer<int> dv(rowsb.p, rows2.p);
+    const int end_bit = 32 + bits_for((unsigned)nparts);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, n, 0, end_bit, s);
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(std::max(tb1, tb2));
+    size_t tb = tmp.n;
+    ILUB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, w_it, wsum.p, n, s));
+    k_partition<<<blocks_for(n, 256), 256, 0, s>>>(n, wsum.p, S, nparts, T.level.p, keys.p, rowsb.p);
+    tb = tmp.n;
+    ILUB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, n, 0, end_bit, s));
+    T.order.alloc(n);
+    ILUB_CUDA(cudaMemcpyAsync(T.order.p, dv.Current(), sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+    DevBuf<int> rstart;
+    rstart.alloc(nparts + 1);
+    T.part_chunk_ptr.alloc(nparts + 1);
+    k_part_bounds<<<1, 256, 0, s>>>(n, nparts, dk.Current(), rstart.p, T.part_chunk_ptr.p);
+    int nchunks = 0;
+    ILUB_CUDA(cudaMemcpyAsync(&nchunks, T.part_chunk_ptr.p + nparts, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    T.nchunks = nchunks;
+    const int64_t nlane = (int64_t)nchunks * 32;
+    T.rows.alloc(nlane);
+    T.rowpos.alloc(n);
+    T.rlen.alloc(nlane);
+    T.diag.alloc(nlane);
+    T.diagpos.alloc(nlane);
+    T.ckind.alloc(nchunks);
+    T.chunk_ptr.alloc(nchunks + 1);
+    ILUB_CUDA(cudaMemsetAsync(T.rows.p, 0xff, sizeof(int) * nlane, s));
+    k_place_rows<<<blocks_for(n, 256), 256, 0, s>>>(n, dk.Current(), T.order.p, rstart.p, T.part_chunk_ptr.p,
+                                                    T.rows.p, T.rowpos.p);
+    // ---- chunk shapes
+    DevBuf<int> cslabs;
+    cslabs.alloc(nchunks + 1);
+    ILUB_CUDA(cudaMemsetAsync(cslabs.p, 0, sizeof(int) * (nchunks + 1), s));
+    ILUB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int) * 4, s));
+    k_chunk_shape<<<blocks_for(nlane, 256), 256, 0, s>>>(nchunks, S, T.rows.p, (int)opt.wcap, T.rlen.p, cslabs.p,
+                                                         T.ckind.p, ctr.p + 2, ctr.p + 3);
+    size_t tb3 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb3, cslabs.p, T.chunk_ptr.p, nchunks + 1, s);
+    DevBuf<unsigned char> tmp3;
+    tmp3.alloc(tb3);
+    ILUB_CUDA(cub::DeviceScan::ExclusiveSum(tmp3.p, tb3, cslabs.p, T.chunk_ptr.p, nchunks + 1, s));
+    int hshape[4];
+    int nsl = 0;
+    ILUB_CUDA(cudaMemcpyAsync(hshape, ctr.p, sizeof(hshape), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaMemcpyAsync(&nsl, T.chunk_ptr.p + nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    T.maxw_a = hshape[2];
+    T.any_kind_b = hshape[3];
+    T.nslabs = nsl;
+    {   // launch configuration of the sync-free kernel; `near` is baked into the encoded indices below
+        int W = (int)std::min<int64_t>(32, std::max<int64_t>(1, opt.warps_per_cta));
+        int RC = 64;
+        while (RC * 2 <= opt.ring_chunks) RC *= 2;
+        int near = (int)std::min<int64_t>(opt.near_window, RC / 2);
+        int stages = (int)std::min<int64_t>(2, std::max<int64_t>(1, opt.stages));
+        const int slabs = std::max(1, T.maxw_a);
+        const size_t budget = (size_t)227 * 1024 / (size_t)std::max<int64_t>(1, opt.ctas_per_sm) - 1024;
+        auto need = [&]() {
+            return (size_t)RC * 256 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + (size_t)RC * 4 + 128 + 128;
+        };
+        while (need() > budget) {
+            if (stages > 1) stages = 1;
+            else if (RC > 64) { RC /= 2; near = std::min(near, RC / 2); }
+            else if (W > 2) W /= 2;
+            else throw Error{ILUB_ERR_INVALID, "sync-free solve does not fit in shared memory (lower wcap)"};
+        }
+        T.cfg_warps = W;
+        T.cfg_ring_chunks = RC;
+        T.cfg_near = near;
+        T.cfg_stages = stages;
+        T.cfg_stage_slabs = slabs;
+        T.cfg_smem = need();
+    }
+    const int64_t nent = (int64_t)nsl * 32;
+    ILUB_REQUIRE(nent < (int64_t)1 << 31, ILUB_ERR_SIZE, "packed solve layout exceeds 2^31 entries");
+    T.idx.alloc(nent);
+    T.srcpos.alloc(nent);
+    T.val.alloc(nent);
+    k_chunk_fill<<<blocks_for(nlane, 256), 256, 0, s>>>(nchunks, S, T.rows.p, T.rlen.p, T.chunk_ptr.p, T.rowpos.p,
+                                                        T.part_chunk_ptr.p, nparts, T.cfg_near, T.ckind.p,
+                                                        T.idx.p, T.srcpos.p, T.diagpos.p);
+    T.gflag.alloc(n);
+    ILUB_CUDA(cudaMemsetAsync(T.gflag.p, 0, n, s));
+    T.epoch = 0;
+    h->launches += 8;
+    ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here
+    T.built = true;
+}
+
+void pack_solve_values(ilub_handle* h, int slot, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    if (!T.built) return;
+    const int64_t nent = T.nslabs * 32;
+    const int64_t nlane = (int64_t)T.nchunks * 32;
+    if (nent > 0) k_pack_values<<<blocks_for(nent, 256), 256, 0, s>>>(nent, T.srcpos.p, h->lu.p, T.val.p);
+    k_pack_diag<<<blocks_for(nlane, 256), 256, 0, s>>>(nlane, T.diagpos.p, h->lu.p, T.diag.p);
+    h->launches += 2;
+}
+
+void build_level_sets(ilub_handle* h, int slot, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    if (T.lvl_built) return;
+    const int n = h->n;
+    T.lvl_ptr.alloc(T.nlevels + 1);
+    T.lvl_rows.alloc(n);
+    DevBuf<int> k1, k2, v1, v2;
+    k1.alloc(n);
+    k2.alloc(n);
+    v1.alloc(n);
+    v2.alloc(n);
+    ILUB_CUDA(cudaMemcpyAsync(k1.p, T.level.p, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+    k_iota<<<blocks_for(n, 256), 256, 0, s>>>(n, v1.p);
+    cub::DoubleBuffer<int> dk(k1.p, k2.p), dv(v1.p, v2.p);
+    size_t tb = 0;
+    const int eb = bits_for((unsigned)std::max(1, T.nlevels));
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, n, 0, eb, s);
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(tb);
+    ILUB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, n, 0, eb, s));
+    ILUB_CUDA(cudaMemcpyAsync(T.lvl_rows.p, dv.Current(), sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+    k_level_ptr<<<blocks_for(T.nlevels + 1, 256), 256, 0, s>>>(n, T.nlevels, dk.Current(), T.lvl_ptr.p);
+    h->launches += 3;
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    T.lvl_built = true;
+}
+
+void expand_batched(ilub_handle* h, const int* ptr1, const int* idx1, int32_t n1, int64_t nnz1, int32_t nsys,
+                    cudaStream_t s) {
+    const int64_t nnz = nnz1 * nsys;
+    const int64_t n = (int64_t)n1 * nsys;
+    const int64_t work = std::max(nnz, n + 1);
+    k_expand_batched<<<blocks_for(work, 256), 256, 0, s>>>(n1, nnz1, nsys, ptr1, idx1, h->ptr.p, h->idx.p);
+    h->launches++;
+}
+
+}  // namespace ilub

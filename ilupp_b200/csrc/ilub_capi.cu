@@ -1,0 +1,475 @@
+// The C ABI of libilub.so (include/ilub.h): argument checking, host<->device staging, error
+// translation.  No numerical work happens here.
+#include <chrono>
+#include <cstring>
+#include <memory>
+
+#include "ilub_common.cuh"
+
+using namespace ilub;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return ILUB_OK;
+    } catch (const Error& e) {
+        g_last_error = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return ILUB_ERR_INVALID;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return ILUB_ERR_INVALID;
+    }
+}
+
+cudaMemcpyKind to_dev(int where) { return where == ILUB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
+cudaMemcpyKind from_dev(int where) { return where == ILUB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost; }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        ILUB_CUDA(cudaGetDevice(&prev));
+        if (prev != dev) ILUB_CUDA(cudaSetDevice(dev));
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// slots of the two solves of apply (transpose = 0) / apply_trans (transpose = 1), in order
+void apply_slots(const ilub_handle* h, int transpose, int& first, int& second) {
+    if (h->kind == KIND_ICHOL0) {  // LL^T class: L then L^T either way (preconditioner_implementation.h:381-394)
+        first = 0;
+        second = 3;
+        return;
+    }
+    const bool gather = (h->is_csr != 0) != (transpose != 0);
+    if (gather) {  // fwd-gather(Lc), bwd-gather(Uc)
+        first = 0;
+        second = 1;
+    } else {       // fwd-scatter(Uc) = Uc^T forward, bwd-scatter(Lc) = Lc^T backward
+        first = 2;
+        second = 3;
+    }
+}
+
+void ensure_solve(ilub_handle* h, int slot, cudaStream_t s) {
+    if (h->solve[slot].built) return;
+    analyse_solve(h, slot, s);
+    pack_solve_values(h, slot, s);
+}
+
+int slot_of(const ilub_handle* h, int which_solve) {
+    int a, b;
+    apply_slots(h, which_solve >= 2 ? 1 : 0, a, b);
+    return (which_solve & 1) ? b : a;
+}
+
+void create_common(int kind, const double* data, const int32_t* indices, const int32_t* indptr, int32_t n1,
+                   int64_t nnz1, int32_t nsys, int is_csr, int where, int device, void* stream, ilub_handle** out) {
+    ILUB_REQUIRE(out != nullptr, ILUB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    ILUB_REQUIRE(data && indices && indptr, ILUB_ERR_INVALID, "null matrix array");
+    ILUB_REQUIRE(n1 > 0, ILUB_ERR_INVALID, "matrix has size 0!");  // binding.cpp:80-81
+    ILUB_REQUIRE(nnz1 >= 0 && nsys >= 1, ILUB_ERR_INVALID, "bad nnz / nsys");
+    ILUB_REQUIRE(where == ILUB_HOST || where == ILUB_DEVICE, ILUB_ERR_INVALID, "bad `where`");
+    const int64_t n64 = (int64_t)n1 * nsys, nnz64 = nnz1 * nsys;
+    ILUB_REQUIRE(n64 < ((int64_t)1 << 31) - 64 && nnz64 < ((int64_t)1 << 31) - 64, ILUB_ERR_SIZE,
+                 "problem exceeds 32-bit indexing (reference Integer is int32, declarations.h:49-53)");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    ILUB_REQUIRE(ce == cudaSuccess && ndev > 0, ILUB_ERR_CUDA,
+                 std::string("no CUDA device available (libilub has no CPU fallback): ") + cudaGetErrorString(ce));
+    ILUB_REQUIRE(device >= 0 && device < ndev, ILUB_ERR_INVALID, "bad device ordinal");
+    DeviceGuard guard(device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    std::unique_ptr<ilub_handle> h(new ilub_handle());
+    h->kind = kind;
+    h->is_csr = is_csr ? 1 : 0;
+    h->device = device;
+    h->n = (int32_t)n64;
+    h->nnz = nnz64;
+    h->nsys = nsys;
+    cudaDeviceProp prop;
+    ILUB_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 4; ++i) ILUB_CUDA(cudaEventCreate(&h->ev[i]));
+    h->ptr.alloc(n64 + 1);
+    h->idx.alloc(nnz64);
+    h->a.alloc(nnz64);
+    h->lu.alloc(nnz64);
+    if (nsys == 1) {
+        ILUB_CUDA(cudaMemcpyAsync(h->ptr.p, indptr, sizeof(int) * (n64 + 1), to_dev(where), s));
+        ILUB_CUDA(cudaMemcpyAsync(h->idx.p, indices, sizeof(int) * nnz64, to_dev(where), s));
+    } else {
+        DevBuf<int> p1, i1;
+        p1.alloc(n1 + 1);
+        i1.alloc(nnz1);
+        ILUB_CUDA(cudaMemcpyAsync(p1.p, indptr, sizeof(int) * (n1 + 1), to_dev(where), s));
+        ILUB_CUDA(cudaMemcpyAsync(i1.p, indices, sizeof(int) * nnz1, to_dev(where), s));
+        // the single-system pointer array must be consistent with nnz1 before we replicate it
+        int last = 0;
+        ILUB_CUDA(cudaMemcpyAsync(&last, p1.p + n1, sizeof(int), cudaMemcpyDeviceToHost, s));
+        ILUB_CUDA(cudaStreamSynchronize(s));
+        ILUB_REQUIRE(last == nnz1, ILUB_ERR_INVALID, "indptr[n] != nnz");
+        expand_batched(h.get(), p1.p, i1.p, n1, nnz1, nsys, s);
+        ILUB_CUDA(cudaStreamSynchronize(s));
+    }
+    ILUB_CUDA(cudaMemcpyAsync(h->a.p, data, sizeof(double) * nnz64, to_dev(where), s));
+    if (nsys == 1) {
+        int ends[1] = {0};
+        ILUB_CUDA(cudaMemcpyAsync(ends, h->ptr.p + n64, sizeof(int), cudaMemcpyDeviceToHost, s));
+        ILUB_CUDA(cudaStreamSynchronize(s));
+        ILUB_REQUIRE(ends[0] == nnz64, ILUB_ERR_INVALID, "indptr[n] != nnz");
+    }
+
+    ILUB_CUDA(cudaEventRecord(h->ev[0], s));
+    validate_and_find_diag(h.get(), s);
+    int first, second;
+    apply_slots(h.get(), 0, first, second);
+    analyse_solve(h.get(), 0, s);  // the factorisation DAG (= L solve DAG) is always needed
+    analyse_solve(h.get(), first, s);
+    analyse_solve(h.get(), second, s);
+    ILUB_CUDA(cudaEventRecord(h->ev[1], s));
+    factor_numeric(h.get(), s);
+    ILUB_CUDA(cudaEventRecord(h->ev[2], s));
+    for (int k = 0; k < 4; ++k) pack_solve_values(h.get(), k, s);
+    ILUB_CUDA(cudaEventRecord(h->ev[3], s));
+    read_status(h.get(), s);  // syncs; throws on watchdog
+    float ms01 = 0, ms12 = 0, ms23 = 0;
+    cudaEventElapsedTime(&ms01, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&ms12, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&ms23, h->ev[2], h->ev[3]);
+    h->timings[0] = ms01;
+    h->timings[1] = ms12;
+    h->timings[2] = ms23;
+    h->timings[3] = ms01 + ms12 + ms23;
+    *out = h.release();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ilub_last_error(void) { return g_last_error.c_str(); }
+int ilub_version(void) { return 100; }
+int ilub_index_size(void) { return (int)sizeof(int32_t); }
+
+int ilub_device_count(int* count) {
+    return guarded([&] {
+        ILUB_REQUIRE(count, ILUB_ERR_INVALID, "count is null");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            *count = 0;
+            throw Error{ILUB_ERR_CUDA, cudaGetErrorString(e)};
+        }
+        *count = n;
+    });
+}
+
+int ilub_create_ilu0(const double* data, const int32_t* indices, const int32_t* indptr, int32_t n, int64_t nnz,
+                     int is_csr, int where, int device, void* stream, ilub_handle** out) {
+    return guarded([&] { create_common(KIND_ILU0, data, indices, indptr, n, nnz, 1, is_csr, where, device, stream, out); });
+}
+int ilub_create_ichol0(const double* data, const int32_t* indices, const int32_t* indptr, int32_t n, int64_t nnz,
+                       int is_csr, int where, int device, void* stream, ilub_handle** out) {
+    return guarded(
+        [&] { create_common(KIND_ICHOL0, data, indices, indptr, n, nnz, 1, is_csr, where, device, stream, out); });
+}
+int ilub_create_ilu0_batched(const double* values, const int32_t* indices, const int32_t* indptr, int32_t n,
+                             int64_t nnz, int32_t nsys, int is_csr, int where, int device, void* stream,
+                             ilub_handle** out) {
+    return guarded(
+        [&] { create_common(KIND_ILU0, values, indices, indptr, n, nnz, nsys, is_csr, where, device, stream, out); });
+}
+int ilub_create_ichol0_batched(const double* values, const int32_t* indices, const int32_t* indptr, int32_t n,
+                               int64_t nnz, int32_t nsys, int is_csr, int where, int device, void* stream,
+                               ilub_handle** out) {
+    return guarded([&] {
+        create_common(KIND_ICHOL0, values, indices, indptr, n, nnz, nsys, is_csr, where, device, stream, out);
+    });
+}
+
+int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && data, ILUB_ERR_INVALID, "null argument");
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        ILUB_CUDA(cudaEventRecord(h->ev[1], s));
+        ILUB_CUDA(cudaMemcpyAsync(h->a.p, data, sizeof(double) * h->nnz, to_dev(where), s));
+        factor_numeric(h, s);
+        ILUB_CUDA(cudaEventRecord(h->ev[2], s));
+        for (int k = 0; k < 4; ++k) pack_solve_values(h, k, s);
+        ILUB_CUDA(cudaEventRecord(h->ev[3], s));
+        read_status(h, s);
+        float ms12 = 0, ms23 = 0;
+        cudaEventElapsedTime(&ms12, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&ms23, h->ev[2], h->ev[3]);
+        h->timings[0] = 0;
+        h->timings[1] = ms12;
+        h->timings[2] = ms23;
+        h->timings[3] = ms12 + ms23;
+    });
+}
+
+int ilub_destroy(ilub_handle* h) {
+    return guarded([&] {
+        if (!h) return;
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < 4; ++i)
+            if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+        delete h;
+    });
+}
+
+int ilub_check_vector(const ilub_handle* h, int64_t len) {
+    return guarded([&] {
+        ILUB_REQUIRE(h, ILUB_ERR_INVALID, "null handle");
+        ILUB_REQUIRE(len == h->n, ILUB_ERR_SIZE, "vector has wrong size for preconditioner!");
+    });
+}
+
+int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nrhs, int where, void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && x, ILUB_ERR_INVALID, "null argument");
+        ILUB_REQUIRE(nrhs >= 1, ILUB_ERR_INVALID, "nrhs must be >= 1");
+        ILUB_REQUIRE(ldx >= h->n, ILUB_ERR_SIZE, "vector has wrong size for preconditioner!");
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        int first, second;
+        apply_slots(h, transpose, first, second);
+        ensure_solve(h, first, s);
+        ensure_solve(h, second, s);
+        if (where == ILUB_DEVICE) {
+            run_solve(h, first, x, ldx, nrhs, s);
+            run_solve(h, second, x, ldx, nrhs, s);
+        } else {
+            const size_t cnt = (size_t)h->n * nrhs;
+            h->work.ensure(cnt);
+            for (int c = 0; c < nrhs; ++c)
+                ILUB_CUDA(cudaMemcpyAsync(h->work.p + (size_t)c * h->n, x + (size_t)c * ldx, sizeof(double) * h->n,
+                                          cudaMemcpyHostToDevice, s));
+            run_solve(h, first, h->work.p, h->n, nrhs, s);
+            run_solve(h, second, h->work.p, h->n, nrhs, s);
+            for (int c = 0; c < nrhs; ++c)
+                ILUB_CUDA(cudaMemcpyAsync(x + (size_t)c * ldx, h->work.p + (size_t)c * h->n, sizeof(double) * h->n,
+                                          cudaMemcpyDeviceToHost, s));
+            read_status(h, s);
+        }
+    });
+}
+
+int ilub_total_nnz(const ilub_handle* h, int64_t* out) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && out, ILUB_ERR_INVALID, "null argument");
+        // preconditioner.h:164,208-209,246-247: left_nnz + right_nnz as stored (explicit unit diagonal included)
+        *out = h->kind == KIND_ICHOL0 ? h->nnz_lower + h->n : h->nnz_lower + h->nnz_upper + 2 * (int64_t)h->n;
+    });
+}
+int ilub_dim(const ilub_handle* h, int32_t* n) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && n, ILUB_ERR_INVALID, "null argument");
+        *n = h->n;
+    });
+}
+int ilub_num_factors(const ilub_handle* h, int* count) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && count, ILUB_ERR_INVALID, "null argument");
+        *count = h->kind == KIND_ICHOL0 ? 1 : 2;
+    });
+}
+
+// which factor arrays does reported factor `which` consist of?  mode as in extract_factor
+static int factor_mode(const ilub_handle* h, int which) {
+    if (h->kind == KIND_ICHOL0) return 2;
+    // CSR input: L = unit lower (0), U = upper (1).  CSC input: ILU0.hpp:100-105 swaps them.
+    return (h->is_csr != 0) == (which == ILUB_FACTOR_LEFT) ? 0 : 1;
+}
+
+int ilub_factor_dims(const ilub_handle* h, int which, int64_t* nnz, int* is_csr) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && nnz && is_csr, ILUB_ERR_INVALID, "null argument");
+        ILUB_REQUIRE(which == 0 || (which == 1 && h->kind == KIND_ILU0), ILUB_ERR_INVALID, "no such factor");
+        const int mode = factor_mode(h, which);
+        *nnz = (mode == 1 ? h->nnz_upper : h->nnz_lower) + h->n;
+        *is_csr = h->kind == KIND_ICHOL0 ? 1 : h->is_csr;  // IChol.hpp:67-68: always ROW
+    });
+}
+
+int ilub_get_factor(ilub_handle* h, int which, double* data, int32_t* indices, int32_t* indptr, int where,
+                    void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && data && indices && indptr, ILUB_ERR_INVALID, "null argument");
+        ILUB_REQUIRE(which == 0 || (which == 1 && h->kind == KIND_ILU0), ILUB_ERR_INVALID, "no such factor");
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const int mode = factor_mode(h, which);
+        const int64_t nnz = (mode == 1 ? h->nnz_upper : h->nnz_lower) + h->n;
+        if (where == ILUB_DEVICE) {
+            extract_factor(h, mode, data, indices, indptr, s);
+        } else {
+            DevBuf<double> d;
+            DevBuf<int> i, p;
+            d.alloc(nnz);
+            i.alloc(nnz);
+            p.alloc(h->n + 1);
+            extract_factor(h, mode, d.p, i.p, p.p, s);
+            ILUB_CUDA(cudaMemcpyAsync(data, d.p, sizeof(double) * nnz, cudaMemcpyDeviceToHost, s));
+            ILUB_CUDA(cudaMemcpyAsync(indices, i.p, sizeof(int) * nnz, cudaMemcpyDeviceToHost, s));
+            ILUB_CUDA(cudaMemcpyAsync(indptr, p.p, sizeof(int) * (h->n + 1), cudaMemcpyDeviceToHost, s));
+            ILUB_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+int ilub_get_levels(ilub_handle* h, int which_solve, int32_t* nlevels, int32_t* level_of_row, int where,
+                    void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h, ILUB_ERR_INVALID, "null handle");
+        ILUB_REQUIRE(which_solve >= 0 && which_solve < 4, ILUB_ERR_INVALID, "bad which_solve");
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const int slot = slot_of(h, which_solve);
+        ensure_solve(h, slot, s);
+        if (nlevels) *nlevels = h->solve[slot].nlevels;
+        if (level_of_row) {
+            ILUB_CUDA(cudaMemcpyAsync(level_of_row, h->solve[slot].level.p, sizeof(int) * h->n, from_dev(where), s));
+            if (where == ILUB_HOST) ILUB_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+int ilub_get_level_sets(ilub_handle* h, int which_solve, int32_t* level_ptr, int32_t* level_rows, int where,
+                        void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && level_ptr && level_rows, ILUB_ERR_INVALID, "null argument");
+        ILUB_REQUIRE(which_solve >= 0 && which_solve < 4, ILUB_ERR_INVALID, "bad which_solve");
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const int slot = slot_of(h, which_solve);
+        ensure_solve(h, slot, s);
+        build_level_sets(h, slot, s);
+        TriSolve& T = h->solve[slot];
+        ILUB_CUDA(cudaMemcpyAsync(level_ptr, T.lvl_ptr.p, sizeof(int) * (T.nlevels + 1), from_dev(where), s));
+        ILUB_CUDA(cudaMemcpyAsync(level_rows, T.lvl_rows.p, sizeof(int) * h->n, from_dev(where), s));
+        if (where == ILUB_HOST) ILUB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int ilub_spmv(ilub_handle* h, const double* x, double* y, int where, void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && x && y, ILUB_ERR_INVALID, "null argument");
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        if (where == ILUB_DEVICE) {
+            spmv(h, x, y, s);
+        } else {
+            DevBuf<double> dx, dy;
+            dx.alloc(h->n);
+            dy.alloc(h->n);
+            ILUB_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * h->n, cudaMemcpyHostToDevice, s));
+            spmv(h, dx.p, dy.p, s);
+            ILUB_CUDA(cudaMemcpyAsync(y, dy.p, sizeof(double) * h->n, cudaMemcpyDeviceToHost, s));
+            ILUB_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+int ilub_bicgstab(ilub_handle* h, const double* b, double* x, double rtol, double atol, int32_t max_iter,
+                  int32_t* iters, double* rel_achieved, double* abs_achieved, int where, void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && b && x && iters && rel_achieved && abs_achieved, ILUB_ERR_INVALID, "null argument");
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        int first, second;
+        apply_slots(h, 0, first, second);
+        ensure_solve(h, first, s);
+        ensure_solve(h, second, s);
+        int ok;
+        if (where == ILUB_DEVICE) {
+            ok = bicgstab(h, b, x, rtol, atol, max_iter, iters, rel_achieved, abs_achieved, s);
+        } else {
+            DevBuf<double> db, dx;
+            db.alloc(h->n);
+            dx.alloc(h->n);
+            ILUB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * h->n, cudaMemcpyHostToDevice, s));
+            ok = bicgstab(h, db.p, dx.p, rtol, atol, max_iter, iters, rel_achieved, abs_achieved, s);
+            ILUB_CUDA(cudaMemcpyAsync(x, dx.p, sizeof(double) * h->n, cudaMemcpyDeviceToHost, s));
+        }
+        read_status(h, s);
+        if (!ok) throw Error{ILUB_ERR_NOT_CONVERGED, "did not converge"};
+    });
+}
+
+int ilub_set_option(const char* key, int64_t value) {
+    return guarded([&] {
+        ILUB_REQUIRE(key, ILUB_ERR_INVALID, "null key");
+        Options& o = options();
+        const std::string k(key);
+        if (k == "factor_algo") o.factor_algo = value;
+        else if (k == "solve_algo") o.solve_algo = value;
+        else if (k == "exact") o.exact = value;
+        else if (k == "ctas_per_sm") o.ctas_per_sm = value;
+        else if (k == "warps_per_cta") o.warps_per_cta = value;
+        else if (k == "near_window") o.near_window = value;
+        else if (k == "ring_chunks") o.ring_chunks = value;
+        else if (k == "wcap") o.wcap = value;
+        else if (k == "stages") o.stages = value;
+        else if (k == "spin_limit_ms") o.spin_limit_ms = value;
+        else if (k == "partition") o.partition = value;
+        else if (k == "factor_group") o.factor_group = value;
+        else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
+    });
+}
+int ilub_get_option(const char* key, int64_t* value) {
+    return guarded([&] {
+        ILUB_REQUIRE(key && value, ILUB_ERR_INVALID, "null argument");
+        const Options& o = options();
+        const std::string k(key);
+        if (k == "factor_algo") *value = o.factor_algo;
+        else if (k == "solve_algo") *value = o.solve_algo;
+        else if (k == "exact") *value = o.exact;
+        else if (k == "ctas_per_sm") *value = o.ctas_per_sm;
+        else if (k == "warps_per_cta") *value = o.warps_per_cta;
+        else if (k == "near_window") *value = o.near_window;
+        else if (k == "ring_chunks") *value = o.ring_chunks;
+        else if (k == "wcap") *value = o.wcap;
+        else if (k == "stages") *value = o.stages;
+        else if (k == "spin_limit_ms") *value = o.spin_limit_ms;
+        else if (k == "partition") *value = o.partition;
+        else if (k == "factor_group") *value = o.factor_group;
+        else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
+    });
+}
+
+int ilub_get_timings(const ilub_handle* h, double out_ms[4]) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && out_ms, ILUB_ERR_INVALID, "null argument");
+        for (int i = 0; i < 4; ++i) out_ms[i] = h->timings[i];
+    });
+}
+int ilub_get_stats(const ilub_handle* h, int64_t out[8]) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && out, ILUB_ERR_INVALID, "null argument");
+        out[0] = h->n;
+        out[1] = h->nnz;
+        out[2] = h->kind == KIND_ICHOL0 ? h->nnz_lower + h->n : h->nnz_lower + h->nnz_upper + 2 * (int64_t)h->n;
+        for (int k = 0; k < 4; ++k) {
+            const int slot = slot_of(h, k);
+            out[3 + k] = h->solve[slot].built ? h->solve[slot].nlevels : 0;
+        }
+        out[7] = h->launches;
+    });
+}
+
+}  // extern "C"

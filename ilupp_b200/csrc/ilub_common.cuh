@@ -1,0 +1,234 @@
+// Internal declarations shared by the libilub translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "ilub.h"
+
+namespace ilub {
+
+// ------------------------------------------------------------------------------------------------
+// errors: thrown inside the library, converted to status codes at the C ABI (ilub_capi.cu)
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define ILUB_CUDA(expr)                                                                                  \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            throw ::ilub::Error{ILUB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)};     \
+    } while (0)
+
+#define ILUB_REQUIRE(cond, code, text)                      \
+    do {                                                    \
+        if (!(cond)) throw ::ilub::Error{(code), (text)};   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device buffer (plain cudaMalloc; freed with the handle)
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess)
+            throw Error{ILUB_ERR_ALLOC, "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes: " +
+                                            cudaGetErrorString(e)};
+        n = count;
+    }
+    void ensure(size_t count) {
+        if (count > n) alloc(count);
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+struct Options {
+    int64_t factor_algo = 0;    // 0 sync-free, 1 level-scheduled
+    int64_t solve_algo = 0;     // 0 sync-free, 1 level-scheduled
+    int64_t exact = 1;          // IEEE mul/sub/div in reference order
+    int64_t ctas_per_sm = 1;
+    int64_t warps_per_cta = 16;
+    int64_t near_window = 96;   // chunks; dependencies this close (same CTA) go through shared memory
+    int64_t ring_chunks = 256;  // shared-memory x ring, in 32-row chunks (power of two, >= 2*near_window)
+    int64_t wcap = 8;           // widest lane-per-row chunk (slabs); wider chunks are warp-cooperative
+    int64_t stages = 2;         // TMA staging depth per warp
+    int64_t spin_limit_ms = 1500;
+    int64_t partition = 0;      // 0 contiguous index ranges balanced by work
+    int64_t factor_group = 0;   // lanes per row in the factorisation kernels (0 = auto)
+};
+Options& options();
+
+constexpr int kLanes = 32;
+// dependency encoding inside a packed chunk (int32):
+//   e >= 0                      global path: original row index (value from x[e] once gflag[e] == epoch)
+//   e <  0, bit 30 clear        shared-memory path: low 30 bits = position in this CTA's processing order
+//   e <  0, bit 30 set          same-chunk dependency: low 5 bits = producing lane
+constexpr unsigned kLocalBit = 0x80000000u;
+constexpr unsigned kIntraBit = 0x40000000u;
+
+// One triangular solve packed in solve order (see DESIGN.md "data layout in HBM").
+struct TriSolve {
+    bool built = false;
+    int n = 0;
+    int nparts = 0;
+    int nchunks = 0;
+    int64_t nslabs = 0;     // 32-entry slabs of idx/val
+    int maxw_a = 0;         // widest lane-per-row chunk
+    int nlevels = 0;
+    bool backward = false;
+    bool unit_diag = false;
+    int any_kind_b = 0;
+    DevBuf<int> level;            // [n] level of every row in this solve's DAG
+    DevBuf<int> order;            // [n] rows sorted by (part, level, row)
+    DevBuf<int> rowpos;           // [n] (chunk << 5 | lane) of every row
+    DevBuf<int> part_chunk_ptr;   // [nparts + 1]
+    DevBuf<int> chunk_ptr;        // [nchunks + 1] slab offset of every chunk
+    DevBuf<unsigned char> ckind;  // [nchunks] bit0: warp-cooperative (kind B); bit1: has same-chunk deps
+    DevBuf<int> rows;             // [nchunks * 32] original row per lane (-1 = padding)
+    DevBuf<int> rlen;             // [nchunks * 32] number of off-diagonal entries per lane
+    DevBuf<int> idx;              // [nslabs * 32] encoded dependencies
+    DevBuf<int> srcpos;           // [nslabs * 32] position of the value in the factor value array (-1 pad)
+    DevBuf<double> val;           // [nslabs * 32]
+    DevBuf<double> diag;          // [nchunks * 32]
+    DevBuf<int> diagpos;          // [nchunks * 32] position of the diagonal value (-1: unit / padding)
+    DevBuf<unsigned char> gflag;  // [n] epoch flags of the global dependency path
+    unsigned epoch = 0;
+    // launch configuration of the sync-free kernel, fixed at analysis (near is baked into idx)
+    int cfg_warps = 16, cfg_ring_chunks = 256, cfg_near = 96, cfg_stages = 2, cfg_stage_slabs = 1;
+    size_t cfg_smem = 0;
+    // level-set listing for the level-scheduled variant / ilub_get_level_sets (built on demand)
+    DevBuf<int> lvl_ptr, lvl_rows;
+    bool lvl_built = false;
+};
+
+// Transposed pattern of the strict lower or strict upper triangle (for scatter-form solves).
+struct Transposed {
+    bool built = false;
+    DevBuf<int> tptr;  // [n + 1]
+    DevBuf<int> tidx;  // [nt] original row k of entry (k, i), ascending k inside every i
+    DevBuf<int> tpos;  // [nt] position of that entry in the CSR value array
+    int64_t nt = 0;
+};
+
+// How to read one triangular solve out of the CSR arrays (ptr, idx, lu, dpos).
+struct SolveSource {
+    const int* beg_a = nullptr;  // entries of row i: [beg_a[i] + beg_off, end_a[i] + end_off)
+    int beg_off = 0;
+    const int* end_a = nullptr;
+    int end_off = 0;
+    const int* dep_idx = nullptr;  // dependency row per entry
+    const int* val_pos = nullptr;  // position of the value in lu per entry (nullptr: the entry position itself)
+    const int* diag_pos = nullptr; // dpos (nullptr with unit_diag)
+    bool unit_diag = false;
+    bool backward = false;         // rows resolve in descending order
+    bool reverse_entries = false;  // accumulate the stored entries last-to-first (bwd-scatter order)
+};
+
+// device-side view of a SolveSource
+struct SrcDev {
+    const int* beg_a;
+    int beg_off;
+    const int* end_a;
+    int end_off;
+    const int* dep_idx;
+    const int* val_pos;
+    const int* diag_pos;
+    int reverse;
+    int backward;
+};
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ int src_beg(const SrcDev& S, int i) { return S.beg_a[i] + S.beg_off; }
+__host__ __device__ __forceinline__ int src_end(const SrcDev& S, int i) { return S.end_a[i] + S.end_off; }
+#endif
+inline SrcDev to_dev(const SolveSource& s) {
+    SrcDev d;
+    d.beg_a = s.beg_a;
+    d.beg_off = s.beg_off;
+    d.end_a = s.end_a;
+    d.end_off = s.end_off;
+    d.dep_idx = s.dep_idx;
+    d.val_pos = s.val_pos;
+    d.diag_pos = s.diag_pos;
+    d.reverse = s.reverse_entries ? 1 : 0;
+    d.backward = s.backward ? 1 : 0;
+    return d;
+}
+
+enum Kind { KIND_ILU0 = 0, KIND_ICHOL0 = 1 };
+
+}  // namespace ilub
+
+// The opaque handle of the C ABI.
+struct ilub_handle {
+    int kind = 0;        // ilub::Kind
+    int is_csr = 1;      // orientation label of the input (CSC input = CSR arrays of A^T)
+    int device = 0;
+    int sm_count = 148;
+    int32_t n = 0;       // dimension (nsys * n_one for batches)
+    int64_t nnz = 0;
+    int32_t nsys = 1;
+    // the matrix as given (CSR-read arrays), kept for spmv / bicgstab / refactor
+    ilub::DevBuf<int> ptr, idx;
+    ilub::DevBuf<double> a;
+    // factor values on A's pattern (ILU0: L strictly below, U on/above; IChol0: L on tril, rest unused)
+    ilub::DevBuf<double> lu;
+    ilub::DevBuf<int> dpos;  // [n] position of the diagonal entry of every row
+    int64_t nnz_lower = 0;   // strictly lower entries
+    int64_t nnz_upper = 0;   // strictly upper entries
+    ilub::Transposed t_upper, t_lower;
+    // solves: [0] first of apply, [1] second of apply, [2] first of apply_trans, [3] second of apply_trans
+    ilub::TriSolve solve[4];
+    ilub::DevBuf<unsigned char> fflag;  // factorisation row flags
+    unsigned fepoch = 0;
+    ilub::DevBuf<int> status;           // device status word(s) written by kernels (watchdog / structure errors)
+    ilub::DevBuf<double> work;          // vector workspace (host-side apply, bicgstab)
+    ilub::DevBuf<double> scal;          // device scalars for bicgstab
+    double timings[4] = {0, 0, 0, 0};
+    int64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace ilub {
+
+// ---- analysis (ilub_analysis.cu)
+void validate_and_find_diag(ilub_handle* h, cudaStream_t s);
+void build_transposed(ilub_handle* h, bool upper, cudaStream_t s);
+SolveSource solve_source(ilub_handle* h, int which);
+void analyse_solve(ilub_handle* h, int which, cudaStream_t s);            // levels + partition + layout
+void pack_solve_values(ilub_handle* h, int which, cudaStream_t s);        // (re)fill val/diag from lu
+void build_level_sets(ilub_handle* h, int which, cudaStream_t s);
+int read_status(ilub_handle* h, cudaStream_t s);                          // syncs the stream
+void expand_batched(ilub_handle* h, const int* ptr1, const int* idx1, int32_t n1, int64_t nnz1, int32_t nsys,
+                    cudaStream_t s);
+
+// ---- numeric factorisation (ilub_factor.cu)
+void factor_numeric(ilub_handle* h, cudaStream_t s);
+
+// ---- triangular solves (ilub_trsv.cu)
+void run_solve(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);
+void extract_factor(ilub_handle* h, int which, double* data, int* indices, int* indptr, cudaStream_t s);
+
+// ---- Krylov (ilub_krylov.cu)
+void spmv(ilub_handle* h, const double* x, double* y, cudaStream_t s);
+int bicgstab(ilub_handle* h, const double* b, double* x, double rtol, double atol, int max_iter, int* iters,
+             double* rel, double* abs_, cudaStream_t s);
+
+}  // namespace ilub

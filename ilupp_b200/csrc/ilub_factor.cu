@@ -1,0 +1,281 @@
+// Numeric ILU(0) / IChol(0) on the pattern of A -- replaces compute_ilu0 + sparse_vec_update
+// (ILU0.hpp:8-66) and compute_ichol0 + sparse_dot_product (IChol.hpp:15-59).
+//
+// Two schedules over the same per-row routine:
+//   sync-free      one persistent launch; a group of G lanes owns a row, rows are taken in
+//                  (CTA part, level, row) order -- the order of the L solve -- and a row waits for
+//                  the rows of its strictly-lower columns through acquire/release epoch flags;
+//   level-scheduled one launch per level of the L DAG, no flags.
+// The reference's two-pointer merges become lane-parallel intersections: every lane of the group
+// takes entries of row i and binary-searches their column in row k (ILU0) / row j (IChol0).
+// Operation order per entry is the reference's (updates in ascending k; IChol0 dot product summed
+// in ascending column order via an ordered shuffle reduction), so with `exact` arithmetic the
+// factors are bit-for-bit those of the reference compiled without FMA contraction.
+#include "ilub_common.cuh"
+#include "ilub_ptx.cuh"
+
+namespace ilub {
+namespace {
+
+struct FactorParams {
+    int n;
+    const int* ptr;
+    const int* idx;
+    const int* dpos;
+    const double* a;
+    double* lu;
+    // sync-free schedule
+    const int* part_chunk_ptr;
+    const int* rows;  // chunk-lane -> row (-1 padding)
+    unsigned char* fflag;
+    unsigned epoch;
+    // level schedule
+    const int* lvl_rows;
+    int lvl_begin, lvl_end;
+    int* status;
+    long long spin_limit;
+};
+
+// first position in [b, e) with idx >= c
+__device__ __forceinline__ int lower_bound(const int* __restrict__ idx, int b, int e, int c) {
+    while (b < e) {
+        const int m = (b + e) >> 1;
+        if (__ldg(idx + m) < c)
+            b = m + 1;
+        else
+            e = m;
+    }
+    return b;
+}
+
+template <bool SYNCFREE>
+__device__ __forceinline__ bool wait_row(const FactorParams& P, int k, long long& t0) {
+    if (!SYNCFREE) return true;
+    unsigned spins = 0;
+    while (ld_acquire_gpu_u8(P.fflag + k) != P.epoch) {
+        if ((++spins & 63u) == 0) {
+            if (t0 == 0) t0 = clock64();
+            if (clock64() - t0 > P.spin_limit || *(volatile int*)P.status != 0) {
+                atomicCAS(P.status, 0, 101);
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+// ILU(0) of one row by a group of G lanes (gl = lane in group, gmask = the group's lanes)
+template <int G, bool SYNCFREE, bool EXACT>
+__device__ __forceinline__ bool ilu0_row(const FactorParams& P, int i, int gl, unsigned gmask) {
+    const int p0 = P.ptr[i], p1 = P.ptr[i + 1], dp = P.dpos[i];
+    for (int p = p0 + gl; p < p1; p += G) P.lu[p] = P.a[p];  // ILU0.hpp:37
+    long long t0 = 0;
+    for (int kk = p0; kk < dp; ++kk) {  // ILU0.hpp:47-62, ascending k
+        const int k = __ldg(P.idx + kk);
+        if (!wait_row<SYNCFREE>(P, k, t0)) return false;
+        const int dk = P.dpos[k], ek = P.ptr[k + 1];
+        const double ukk = __ldcg(P.lu + dk);
+        const int owner = (kk - p0) % G;
+        double mine = 0.0;
+        if (gl == owner) mine = P.lu[kk];
+        const double wkk = __shfl_sync(gmask, mine, owner, G);
+        const double lik = EXACT ? __ddiv_rn(wkk, ukk) : wkk / ukk;  // ILU0.hpp:52
+        // U[i, k+1:] -= L_ik * U[k, k+1:]   (ILU0.hpp:55-59): my entries right of kk
+        int p = p0 + gl;
+        if (p <= kk) p += ((kk - p) / G + 1) * G;
+        for (; p < p1; p += G) {
+            const int c = __ldg(P.idx + p);
+            const int q = lower_bound(P.idx, dk + 1, ek, c);
+            if (q < ek && __ldg(P.idx + q) == c) P.lu[p] = sub_mul<EXACT>(P.lu[p], lik, __ldcg(P.lu + q));
+        }
+        if (gl == owner) P.lu[kk] = lik;  // ILU0.hpp:61
+    }
+    return true;
+}
+
+// IChol(0) of one row: entries [p0, dp] of the CSR-read arrays are row i of tril(A), diagonal last
+template <int G, bool SYNCFREE, bool EXACT>
+__device__ __forceinline__ bool ichol0_row(const FactorParams& P, int i, int gl, unsigned gmask, int gshift) {
+    const int p0 = P.ptr[i], dp = P.dpos[i];
+    long long t0 = 0;
+    for (int k = p0; k <= dp; ++k) {  // IChol.hpp:39-57
+        const int j = __ldg(P.idx + k);
+        int jb = p0, je = dp;
+        double ljj = 0.0;
+        if (j < i) {
+            if (!wait_row<SYNCFREE>(P, j, t0)) return false;
+            jb = P.ptr[j];
+            je = P.dpos[j];
+            ljj = __ldcg(P.lu + je);  // diagonal is the last entry of row j of L (IChol.hpp:50)
+        }
+        // dp = sum over common columns of (row i \ diag) and (row j \ diag), ascending column
+        double sum = 0.0;
+        for (int pb = p0; pb < k; pb += G) {
+            const int p = pb + gl;
+            double prod = 0.0;
+            bool hit = false;
+            if (p < k) {
+                if (j == i) {
+                    const double v = P.lu[p];
+                    prod = EXACT ? __dmul_rn(v, v) : v * v;
+                    hit = true;
+                } else {
+                    const int c = __ldg(P.idx + p);
+                    const int q = lower_bound(P.idx, jb, je, c);
+                    if (q < je && __ldg(P.idx + q) == c) {
+                        const double v = P.lu[p], u = __ldcg(P.lu + q);
+                        prod = EXACT ? __dmul_rn(v, u) : v * u;
+                        hit = true;
+                    }
+                }
+            }
+            unsigned m = (__ballot_sync(gmask, hit) & gmask) >> gshift;
+            while (m) {  // ordered accumulation, IChol.hpp:18-27
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const double t = __shfl_sync(gmask, prod, src, G);
+                sum = EXACT ? __dadd_rn(sum, t) : sum + t;
+            }
+        }
+        const double aij = P.a[k];
+        double v;
+        if (j < i)
+            v = EXACT ? __ddiv_rn(__dsub_rn(aij, sum), ljj) : (aij - sum) / ljj;  // IChol.hpp:49-51
+        else
+            v = EXACT ? __dsqrt_rn(__dsub_rn(aij, sum)) : sqrt(aij - sum);        // IChol.hpp:52-53
+        if (gl == (k - p0) % G) P.lu[k] = v;
+        __syncwarp(gmask);
+    }
+    return true;
+}
+
+template <int G, bool ICHOL, bool SYNCFREE, bool EXACT>
+__global__ void __launch_bounds__(512) k_factor(FactorParams P) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int gshift = (lane / G) * G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gshift);
+    const int gidx = threadIdx.x / G;
+    const int ng = blockDim.x / G;
+    if (SYNCFREE) {
+        const int64_t s0 = (int64_t)P.part_chunk_ptr[blockIdx.x] * 32;
+        const int64_t s1 = (int64_t)P.part_chunk_ptr[blockIdx.x + 1] * 32;
+        for (int64_t s = s0 + gidx; s < s1; s += ng) {
+            const int i = P.rows[s];
+            if (i < 0) continue;
+            bool ok;
+            if (ICHOL)
+                ok = ichol0_row<G, true, EXACT>(P, i, gl, gmask, gshift);
+            else
+                ok = ilu0_row<G, true, EXACT>(P, i, gl, gmask);
+            if (!ok) return;
+            __syncwarp(gmask);
+            if (gl == 0) {
+                __threadfence();
+                st_relaxed_gpu_u8(P.fflag + i, P.epoch);
+            }
+        }
+    } else {
+        const int64_t s = (int64_t)P.lvl_begin + (int64_t)blockIdx.x * ng + gidx;
+        if (s < P.lvl_end) {
+            const int i = P.lvl_rows[s];
+            if (ICHOL)
+                ichol0_row<G, false, EXACT>(P, i, gl, gmask, gshift);
+            else
+                ilu0_row<G, false, EXACT>(P, i, gl, gmask);
+        }
+    }
+}
+
+template <int G, bool ICHOL, bool SYNCFREE>
+void launch_g(bool exact, int grid, int block, cudaStream_t s, const FactorParams& P) {
+    if (exact)
+        k_factor<G, ICHOL, SYNCFREE, true><<<grid, block, 0, s>>>(P);
+    else
+        k_factor<G, ICHOL, SYNCFREE, false><<<grid, block, 0, s>>>(P);
+}
+
+template <bool ICHOL, bool SYNCFREE>
+void launch(int G, bool exact, int grid, int block, cudaStream_t s, const FactorParams& P) {
+    switch (G) {
+        case 4: launch_g<4, ICHOL, SYNCFREE>(exact, grid, block, s, P); break;
+        case 8: launch_g<8, ICHOL, SYNCFREE>(exact, grid, block, s, P); break;
+        case 16: launch_g<16, ICHOL, SYNCFREE>(exact, grid, block, s, P); break;
+        default: launch_g<32, ICHOL, SYNCFREE>(exact, grid, block, s, P); break;
+    }
+}
+
+}  // namespace
+
+void factor_numeric(ilub_handle* h, cudaStream_t s) {
+    const Options& opt = options();
+    TriSolve& T = h->solve[0];  // the factorisation DAG equals the L-solve DAG
+    ILUB_REQUIRE(T.built, ILUB_ERR_INVALID, "factor_numeric before analysis");
+    const bool ichol = h->kind == KIND_ICHOL0;
+    FactorParams P;
+    P.n = h->n;
+    P.ptr = h->ptr.p;
+    P.idx = h->idx.p;
+    P.dpos = h->dpos.p;
+    P.a = h->a.p;
+    P.lu = h->lu.p;
+    P.part_chunk_ptr = T.part_chunk_ptr.p;
+    P.rows = T.rows.p;
+    P.status = h->status.p;
+    cudaDeviceProp prop;
+    ILUB_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    P.spin_limit = (long long)opt.spin_limit_ms * (long long)prop.clockRate * 4;
+    int G = (int)opt.factor_group;
+    if (G != 4 && G != 8 && G != 16 && G != 32) {
+        const double avg = (double)h->nnz / (double)h->n;
+        G = avg <= 10 ? 8 : (avg <= 24 ? 16 : 32);
+    }
+    const bool exact = opt.exact != 0;
+    if (opt.factor_algo == 0) {
+        if (h->fflag.n < (size_t)h->n) {
+            h->fflag.alloc(h->n);
+            ILUB_CUDA(cudaMemsetAsync(h->fflag.p, 0, h->n, s));
+            h->fepoch = 0;
+        }
+        if (++h->fepoch > 255) {
+            ILUB_CUDA(cudaMemsetAsync(h->fflag.p, 0, h->n, s));
+            h->fepoch = 1;
+        }
+        P.fflag = h->fflag.p;
+        P.epoch = h->fepoch;
+        P.lvl_rows = nullptr;
+        P.lvl_begin = P.lvl_end = 0;
+        // persistent: one CTA per part, all co-resident (T.nparts <= SMs * ctas_per_sm)
+        const int block = 512;
+        if (ichol)
+            launch<true, true>(G, exact, T.nparts, block, s, P);
+        else
+            launch<false, true>(G, exact, T.nparts, block, s, P);
+        h->launches++;
+    } else {
+        build_level_sets(h, 0, s);
+        std::vector<int> lptr(T.nlevels + 1);
+        ILUB_CUDA(cudaMemcpyAsync(lptr.data(), T.lvl_ptr.p, sizeof(int) * (T.nlevels + 1), cudaMemcpyDeviceToHost, s));
+        ILUB_CUDA(cudaStreamSynchronize(s));
+        P.fflag = nullptr;
+        P.epoch = 0;
+        P.lvl_rows = T.lvl_rows.p;
+        const int block = 256;
+        const int ng = block / G;
+        for (int l = 0; l < T.nlevels; ++l) {
+            P.lvl_begin = lptr[l];
+            P.lvl_end = lptr[l + 1];
+            const int cnt = P.lvl_end - P.lvl_begin;
+            if (cnt <= 0) continue;
+            const int grid = (cnt + ng - 1) / ng;
+            if (ichol)
+                launch<true, false>(G, exact, grid, block, s, P);
+            else
+                launch<false, false>(G, exact, grid, block, s, P);
+            h->launches++;
+        }
+    }
+    ILUB_CUDA(cudaGetLastError());
+}
+
+}  // namespace ilub

@@ -1,0 +1,416 @@
+// Sparse triangular solves behind apply() / apply_trans() -- replaces the four sequential loops of
+// matrix_sparse::triangular_solve (sparse_implementation.h:4040-4087).
+//
+// Sync-free kernel (default).  One persistent CTA per row partition, all CTAs co-resident.  The
+// CTA's rows are packed in (level, row) order into 32-row chunks; warp w takes chunks w, w+W, ...
+// A chunk's index/value slabs are staged into shared memory ahead of time with 1-D bulk async
+// copies (TMA engine, mbarrier completion) so that only the x-gather sits on the dependency
+// critical path.  Every lane owns one row and walks its dependencies in the reference's
+// accumulation order in a non-blocking "try-advance" loop:
+//   * dependency in the same chunk        -> value passed lane to lane with a shuffle
+//   * dependency in a recent chunk of the
+//     same CTA (<= near chunks back)      -> x ring + per-chunk tag in shared memory
+//                                            (st.release.cta / ld.acquire.cta)
+//   * anything else (other CTA, far back) -> x in global memory + per-row epoch flag
+//                                            (st.release.gpu / ld.acquire.gpu)
+// Forward progress: chunks are ordered by (level, row) inside a CTA and every warp takes its
+// chunks in ascending order, so the globally smallest unfinished row (by level, row) is always at
+// the head of a resident warp and has all dependencies satisfied.  A clock64 watchdog turns any
+// violation of that argument into ILUB_ERR_WATCHDOG instead of a hang.
+//
+// Level-scheduled kernel (option solve_algo = 1): one launch per level over the CSR-read arrays.
+#include <algorithm>
+#include <climits>
+#include <cub/cub.cuh>
+
+#include "ilub_common.cuh"
+#include "ilub_ptx.cuh"
+
+namespace ilub {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+struct TrsvParams {
+    const int* part_chunk_ptr;
+    const int* chunk_ptr;
+    const unsigned char* ckind;
+    const int* rows;
+    const int* rlen;
+    const int* idx;
+    const double* val;
+    const double* diag;
+    double* x;
+    unsigned char* gflag;
+    unsigned epoch;
+    int ring_mask;  // ring rows - 1
+    int rc;         // ring chunks
+    int near;
+    int nstages;
+    int stage_slabs;
+    int unit_diag;
+    int* status;
+    long long spin_limit;
+};
+
+struct Watchdog {
+    long long t0 = 0;
+    unsigned spins = 0;
+    int* status;
+    long long limit;
+    __device__ __forceinline__ Watchdog(int* st, long long lim) : status(st), limit(lim) {}
+    // true => give up (another CTA failed or we ran out of time)
+    __device__ __forceinline__ bool expired(int code) {
+        if ((++spins & 127u) != 0) return false;
+        if (t0 == 0) t0 = clock64();
+        if (*(volatile int*)status != 0) return true;
+        if (clock64() - t0 > limit) {
+            atomicCAS(status, 0, code);
+            return true;
+        }
+        return false;
+    }
+};
+
+template <bool EXACT>
+__global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int R = P.ring_mask + 1;
+    double* xring = reinterpret_cast<double*>(smem);
+    unsigned char* stage_base = smem + (size_t)R * 8;
+    const int stage_bytes = P.stage_slabs * 384;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + (size_t)W * P.nstages * stage_bytes);
+    int* cflag = reinterpret_cast<int*>(mbar + W * P.nstages);
+    int* warp_cur = cflag + P.rc;
+
+    const int c0 = P.part_chunk_ptr[blockIdx.x];
+    const int nloc = P.part_chunk_ptr[blockIdx.x + 1] - c0;
+    for (int i = threadIdx.x; i < P.rc; i += blockDim.x) cflag[i] = -1;
+    if (threadIdx.x < 32) warp_cur[threadIdx.x] = (threadIdx.x < W && threadIdx.x < nloc) ? threadIdx.x : INT_MAX;
+    if (lane == 0) {
+        for (int s = 0; s < P.nstages; ++s) mbar_init(&mbar[warp * P.nstages + s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp >= nloc) return;
+
+    const int rc_mask = P.rc - 1;
+    unsigned phasebits = 0;
+    int done_cache = 0;
+    Watchdog wd(P.status, P.spin_limit);
+
+    // lane 0: start the bulk copies of local chunk lc into this warp's stage (it % nstages)
+    auto issue = [&](int lc, int it) {
+        const int c = c0 + lc;
+        const int cp = P.chunk_ptr[c];
+        const int w = P.chunk_ptr[c + 1] - cp;
+        if ((P.ckind[c] & 1) == 0 && w > 0) {
+            const int st = it % P.nstages;
+            unsigned char* sb = stage_base + (size_t)(warp * P.nstages + st) * stage_bytes;
+            uint64_t* bar = &mbar[warp * P.nstages + st];
+            mbar_arrive_expect_tx(bar, (unsigned)w * 384u);
+            bulk_g2s(sb, P.val + (size_t)cp * 32, (unsigned)w * 256u, bar);
+            bulk_g2s(sb + (size_t)P.stage_slabs * 256, P.idx + (size_t)cp * 32, (unsigned)w * 128u, bar);
+        }
+    };
+
+    if (lane == 0)
+        for (int k = 0; k + 1 < P.nstages; ++k)
+            if (warp + k * W < nloc) issue(warp + k * W, k);
+
+    int it = 0;
+    for (int lc = warp; lc < nloc; lc += W, ++it) {
+        __syncwarp();
+        if (lane == 0) {
+            const int la = lc + (P.nstages - 1) * W;
+            if (la < nloc) issue(la, it + P.nstages - 1);
+        }
+        const int c = c0 + lc;
+        const int cp = P.chunk_ptr[c];
+        const int w = P.chunk_ptr[c + 1] - cp;
+        const unsigned kind = P.ckind[c];
+        const int r = P.rows[c * 32 + lane];
+        const int len = P.rlen[c * 32 + lane];
+        const double d = P.unit_diag ? 1.0 : P.diag[c * 32 + lane];
+        double acc = r >= 0 ? __ldcg(P.x + r) : 0.0;
+        double xfin = 0.0;
+
+        if ((kind & 1) == 0) {
+            // ------------------------------------------------------------ lane-per-row chunk
+            const int st = it % P.nstages;
+            const unsigned char* sb = stage_base + (size_t)(warp * P.nstages + st) * stage_bytes;
+            const double* sval = reinterpret_cast<const double*>(sb);
+            const int* sidx = reinterpret_cast<const int*>(sb + (size_t)P.stage_slabs * 256);
+            if (w > 0) {
+                uint64_t* bar = &mbar[warp * P.nstages + st];
+                const unsigned par = (phasebits >> st) & 1u;
+                while (!mbar_try_wait(bar, par))
+                    if (wd.expired(102)) return;
+                phasebits ^= 1u << st;
+            }
+            const double dinv = EXACT ? 0.0 : 1.0 / d;
+            const bool has_intra = (kind & 2) != 0;
+            int j = 0;
+            bool fin = false;
+            while (true) {
+                if (has_intra) {
+                    const int e = (!fin && j < len) ? sidx[j * 32 + lane] : 0;
+                    const bool wi = ((unsigned)e & (kLocalBit | kIntraBit)) == (kLocalBit | kIntraBit);
+                    const unsigned finmask = __ballot_sync(FULL, fin);
+                    const double xs = __shfl_sync(FULL, xfin, e & 31);
+                    if (wi && ((finmask >> (e & 31)) & 1u)) {
+                        acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], xs);
+                        ++j;
+                    }
+                }
+                if (!fin) {
+                    while (j < len) {
+                        const int e = sidx[j * 32 + lane];
+                        double xv;
+                        if (e >= 0) {
+                            if (ld_acquire_gpu_u8(P.gflag + e) != P.epoch) break;
+                            xv = ld_relaxed_gpu_f64(P.x + e);
+                        } else if (((unsigned)e & kIntraBit) == 0) {
+                            const int lp = e & 0x3fffffff;
+                            const int dc = lp >> 5;
+                            if (ld_acquire_cta_s32(&cflag[dc & rc_mask]) != dc) break;
+                            xv = xring[lp & P.ring_mask];
+                        } else {
+                            break;  // same-chunk dependency: exchanged at the top of the next round
+                        }
+                        acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], xv);
+                        ++j;
+                    }
+                    if (j >= len) {
+                        xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
+                        fin = true;
+                    }
+                }
+                if (__all_sync(FULL, fin)) break;
+                if (wd.expired(103)) return;
+            }
+        } else {
+            // ------------------------------------------------------------ warp-cooperative chunk
+            int off = len;  // exclusive scan of len
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(FULL, off, s);
+                if (lane >= s) off += t;
+            }
+            off -= len;
+            const size_t base = (size_t)cp * 32;
+            for (int rr = 0; rr < 32; ++rr) {
+                const int rrow = __shfl_sync(FULL, r, rr);
+                if (rrow < 0) continue;
+                const int rl = __shfl_sync(FULL, len, rr);
+                const int ro = __shfl_sync(FULL, off, rr);
+                double part = 0.0;
+                for (int tb = 0; tb < rl; tb += 32) {
+                    const int t = tb + lane;
+                    const bool active = t < rl;
+                    const int e = active ? __ldg(P.idx + base + ro + t) : 0;
+                    const double v = active ? __ldg(P.val + base + ro + t) : 0.0;
+                    const bool wi = active && ((unsigned)e & (kLocalBit | kIntraBit)) == (kLocalBit | kIntraBit);
+                    const double xs = __shfl_sync(FULL, xfin, e & 31);  // producers are earlier lanes: final
+                    double xv = wi ? xs : 0.0;
+                    bool ok = !active || wi;
+                    while (true) {
+                        if (!ok) {
+                            if (e >= 0) {
+                                if (ld_acquire_gpu_u8(P.gflag + e) == P.epoch) {
+                                    xv = ld_relaxed_gpu_f64(P.x + e);
+                                    ok = true;
+                                }
+                            } else {
+                                const int lp = e & 0x3fffffff;
+                                const int dc = lp >> 5;
+                                if (ld_acquire_cta_s32(&cflag[dc & rc_mask]) == dc) {
+                                    xv = xring[lp & P.ring_mask];
+                                    ok = true;
+                                }
+                            }
+                        }
+                        if (__all_sync(FULL, ok)) break;
+                        if (wd.expired(104)) return;
+                    }
+                    if (active) part = add_mul<EXACT>(part, v, xv);
+                }
+                for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
+                if (lane == rr) {
+                    const double t = acc - part;
+                    xfin = P.unit_diag ? t : (EXACT ? __ddiv_rn(t, d) : t / d);
+                }
+            }
+        }
+
+        // ---------------------------------------------------------------- publish
+        // ring slot of chunk lc - rc may be overwritten once every chunk that could still read it
+        // through shared memory (ids <= lc - rc + near) has completed
+        const int need = lc - P.rc + P.near + 1;
+        if (need > done_cache) {
+            while (true) {
+                int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
+                v = __reduce_min_sync(FULL, v);
+                done_cache = v;
+                if (v >= need) break;
+                if (wd.expired(105)) return;
+            }
+        }
+        xring[(lc * 32 + lane) & P.ring_mask] = xfin;
+        __syncwarp();
+        if (lane == 0) st_release_cta_s32(&cflag[lc & rc_mask], lc);
+        if (r >= 0) {
+            st_relaxed_gpu_f64(P.x + r, xfin);
+            st_release_gpu_u8(P.gflag + r, P.epoch);
+        }
+        __syncwarp();
+        if (lane == 0) st_release_cta_s32(&warp_cur[warp], lc + W < nloc ? lc + W : INT_MAX);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// level-scheduled variant: thread per row of one level, straight from the CSR-read arrays
+template <bool EXACT>
+__global__ void k_trsv_level(SrcDev S, const double* __restrict__ lu, int unit_diag, const int* __restrict__ lvl_rows,
+                             int begin, int end, double* x) {
+    const int s = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= end) return;
+    const int row = lvl_rows[s];
+    const int b = src_beg(S, row), e = src_end(S, row);
+    double acc = x[row];
+    for (int j = 0; j < e - b; ++j) {
+        const int q = S.reverse ? e - 1 - j : b + j;
+        const int vp = S.val_pos ? S.val_pos[q] : q;
+        acc = sub_mul<EXACT>(acc, lu[vp], __ldcg(x + S.dep_idx[q]));
+    }
+    if (!unit_diag) {
+        const double d = lu[S.diag_pos[row]];
+        acc = EXACT ? __ddiv_rn(acc, d) : acc / d;
+    }
+    x[row] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference-layout factor extraction (wrap_matrix / factors_info, binding.cpp:118-175)
+//   mode 0: unit lower  = strict lower of lu + explicit 1.0 diagonal LAST   (ILU0.hpp:82-98)
+//   mode 1: upper       = diagonal FIRST + strict upper
+//   mode 2: lower incl. diagonal (IChol0 L, diagonal last)
+__global__ void k_factor_counts(int n, const int* __restrict__ ptr, const int* __restrict__ dpos, int mode,
+                                int* __restrict__ outptr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    outptr[i + 1] = mode == 1 ? ptr[i + 1] - dpos[i] : dpos[i] - ptr[i] + 1;
+    if (i == 0) outptr[0] = 0;
+}
+__global__ void k_factor_fill(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+                              const int* __restrict__ dpos, const double* __restrict__ lu, int mode,
+                              const int* __restrict__ outptr, int* __restrict__ oidx, double* __restrict__ oval) {
+    // 8 lanes per row
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = t >> 3;
+    const int gl = (int)(t & 7);
+    if (i >= n) return;
+    const int b = mode == 1 ? dpos[i] : ptr[i];
+    const int e = mode == 1 ? ptr[i + 1] : dpos[i] + 1;
+    const int o = outptr[i];
+    for (int p = b + gl; p < e; p += 8) {
+        oidx[o + p - b] = idx[p];
+        oval[o + p - b] = (mode == 0 && p == dpos[i]) ? 1.0 : lu[p];
+    }
+}
+
+inline int blocks_for(int64_t work, int threads) { return (int)((work + threads - 1) / threads); }
+
+}  // namespace
+
+void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    ILUB_REQUIRE(T.built, ILUB_ERR_INVALID, "solve not analysed");
+    const Options& opt = options();
+    const bool exact = opt.exact != 0;
+    cudaDeviceProp prop;
+    ILUB_CUDA(cudaGetDeviceProperties(&prop, h->device));
+    if (opt.solve_algo == 1) {
+        build_level_sets(h, slot, s);
+        std::vector<int> lptr(T.nlevels + 1);
+        ILUB_CUDA(cudaMemcpyAsync(lptr.data(), T.lvl_ptr.p, sizeof(int) * (T.nlevels + 1), cudaMemcpyDeviceToHost, s));
+        ILUB_CUDA(cudaStreamSynchronize(s));
+        const SolveSource src = solve_source(h, slot);
+        const SrcDev S = to_dev(src);
+        for (int c = 0; c < nrhs; ++c) {
+            double* xc = x + (int64_t)c * ldx;
+            for (int l = 0; l < T.nlevels; ++l) {
+                const int cnt = lptr[l + 1] - lptr[l];
+                if (cnt <= 0) continue;
+                if (exact)
+                    k_trsv_level<true><<<blocks_for(cnt, 128), 128, 0, s>>>(S, h->lu.p, src.unit_diag ? 1 : 0,
+                                                                              T.lvl_rows.p, lptr[l], lptr[l + 1], xc);
+                else
+                    k_trsv_level<false><<<blocks_for(cnt, 128), 128, 0, s>>>(S, h->lu.p, src.unit_diag ? 1 : 0,
+                                                                               T.lvl_rows.p, lptr[l], lptr[l + 1], xc);
+                h->launches++;
+            }
+        }
+        ILUB_CUDA(cudaGetLastError());
+        return;
+    }
+
+    TrsvParams P;
+    P.part_chunk_ptr = T.part_chunk_ptr.p;
+    P.chunk_ptr = T.chunk_ptr.p;
+    P.ckind = T.ckind.p;
+    P.rows = T.rows.p;
+    P.rlen = T.rlen.p;
+    P.idx = T.idx.p;
+    P.val = T.val.p;
+    P.diag = T.diag.p;
+    P.gflag = T.gflag.p;
+    P.ring_mask = T.cfg_ring_chunks * 32 - 1;
+    P.rc = T.cfg_ring_chunks;
+    P.near = T.cfg_near;
+    P.nstages = T.cfg_stages;
+    P.stage_slabs = T.cfg_stage_slabs;
+    P.unit_diag = T.unit_diag ? 1 : 0;
+    P.status = h->status.p;
+    P.spin_limit = (long long)opt.spin_limit_ms * (long long)prop.clockRate;
+    static thread_local bool attr_set[2] = {false, false};
+    if (!attr_set[exact ? 1 : 0]) {
+        if (exact)
+            ILUB_CUDA(cudaFuncSetAttribute(k_trsv_syncfree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024));
+        else
+            ILUB_CUDA(cudaFuncSetAttribute(k_trsv_syncfree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024));
+        attr_set[exact ? 1 : 0] = true;
+    }
+    for (int c = 0; c < nrhs; ++c) {
+        if (++T.epoch > 255) {
+            ILUB_CUDA(cudaMemsetAsync(T.gflag.p, 0, T.n, s));
+            T.epoch = 1;
+        }
+        P.epoch = T.epoch;
+        P.x = x + (int64_t)c * ldx;
+        if (exact)
+            k_trsv_syncfree<true><<<T.nparts, T.cfg_warps * 32, T.cfg_smem, s>>>(P);
+        else
+            k_trsv_syncfree<false><<<T.nparts, T.cfg_warps * 32, T.cfg_smem, s>>>(P);
+        h->launches++;
+    }
+    ILUB_CUDA(cudaGetLastError());
+}
+
+void extract_factor(ilub_handle* h, int mode, double* data, int* indices, int* indptr, cudaStream_t s) {
+    const int n = h->n;
+    k_factor_counts<<<blocks_for(n, 256), 256, 0, s>>>(n, h->ptr.p, h->dpos.p, mode, indptr);
+    size_t tb = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tb, indptr, indptr, n + 1, s);
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(tb);
+    ILUB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, indptr, indptr, n + 1, s));
+    k_factor_fill<<<blocks_for((int64_t)n * 8, 256), 256, 0, s>>>(n, h->ptr.p, h->idx.p, h->dpos.p, h->lu.p, mode,
+                                                                  indptr, indices, data);
+    h->launches += 3;
+    ILUB_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace ilub
