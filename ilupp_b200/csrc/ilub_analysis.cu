@@ -508,9 +508,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     DevBuf<int> ctr;
     ctr.alloc(4);
     ILUB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int) * 4, s));
-    cudaDeviceProp prop;
-    ILUB_CUDA(cudaGetDeviceProperties(&prop, h->device));
-    const long long spin = (long long)opt.spin_limit_ms * (long long)prop.clockRate;  // kHz * ms = cycles
+    const long long spin = (long long)opt.spin_limit_ms * h->clock_khz;  // kHz * ms = cycles
     {
         int occ = 0;
         ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels, 256, 0));

@@ -101,6 +101,7 @@ void create_common(int kind, const double* data, const int32_t* indices, const i
     cudaDeviceProp prop;
     ILUB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
+    h->clock_khz = prop.clockRate > 0 ? prop.clockRate : 1965000;
     for (int i = 0; i < 4; ++i) ILUB_CUDA(cudaEventCreate(&h->ev[i]));
     h->ptr.alloc(n64 + 1);
     h->idx.alloc(nnz64);

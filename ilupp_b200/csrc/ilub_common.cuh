@@ -182,6 +182,7 @@ struct ilub_handle {
     int is_csr = 1;      // orientation label of the input (CSC input = CSR arrays of A^T)
     int device = 0;
     int sm_count = 148;
+    long long clock_khz = 1965000;  // SM clock (cycles per ms) for the watchdog limits
     int32_t n = 0;       // dimension (nsys * n_one for batches)
     int64_t nnz = 0;
     int32_t nsys = 1;

@@ -222,9 +222,7 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
     P.part_chunk_ptr = T.part_chunk_ptr.p;
     P.rows = T.rows.p;
     P.status = h->status.p;
-    cudaDeviceProp prop;
-    ILUB_CUDA(cudaGetDeviceProperties(&prop, h->device));
-    P.spin_limit = (long long)opt.spin_limit_ms * (long long)prop.clockRate * 4;
+    P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz * 4;
     int G = (int)opt.factor_group;
     if (G != 4 && G != 8 && G != 16 && G != 32) {
         const double avg = (double)h->nnz / (double)h->n;

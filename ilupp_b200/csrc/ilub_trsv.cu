@@ -328,8 +328,6 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     ILUB_REQUIRE(T.built, ILUB_ERR_INVALID, "solve not analysed");
     const Options& opt = options();
     const bool exact = opt.exact != 0;
-    cudaDeviceProp prop;
-    ILUB_CUDA(cudaGetDeviceProperties(&prop, h->device));
     if (opt.solve_algo == 1) {
         build_level_sets(h, slot, s);
         std::vector<int> lptr(T.nlevels + 1);
@@ -372,7 +370,7 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.stage_slabs = T.cfg_stage_slabs;
     P.unit_diag = T.unit_diag ? 1 : 0;
     P.status = h->status.p;
-    P.spin_limit = (long long)opt.spin_limit_ms * (long long)prop.clockRate;
+    P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz;
     static thread_local bool attr_set[2] = {false, false};
     if (!attr_set[exact ? 1 : 0]) {
         if (exact)
