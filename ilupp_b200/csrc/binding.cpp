@@ -208,7 +208,7 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
         .def_property_readonly("special_info", [](const P&) { return std::string(); })
         .def("print_info",
              [](const P& pr) {
-                 int64_t s[8];
+                 int64_t s[16];
                  check(ilub_get_stats(pr.h, s));
                  py::print("B200 zero-fill preconditioner: n =", s[0], "nnz(A) =", s[1], "total_nnz =", s[2]);
              })
@@ -257,7 +257,7 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
              [](const P& pr, py::buffer A_data) {
                  py::buffer_info info = A_data.request();
                  check_is_real_array(info, "A_data");
-                 int64_t s[8];
+                 int64_t s[16];
                  check(ilub_get_stats(pr.h, s));
                  if (info.shape[0] != s[1]) throw std::runtime_error("indices and data should have the same size!");
                  int st;
@@ -327,7 +327,7 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
                                    return py::make_tuple(t[0], t[1], t[2], t[3]);
                                })
         .def_property_readonly("stats", [](const P& pr) {
-            int64_t s[8];
+            int64_t s[16];
             check(ilub_get_stats(pr.h, s));
             py::dict d;
             d["n"] = s[0];
@@ -335,6 +335,13 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
             d["total_nnz"] = s[2];
             d["levels"] = py::make_tuple(s[3], s[4], s[5], s[6]);
             d["launches"] = s[7];
+            d["nparts"] = s[8];
+            d["part_mode"] = s[9];
+            d["grid"] = py::make_tuple(s[10], s[11]);
+            d["nchunks"] = s[12];
+            d["nslabs"] = s[13];
+            d["warps"] = s[14];
+            d["smem"] = s[15];
             return d;
         });
 }

@@ -7,6 +7,8 @@
 // and the implicit "rows in index order" schedule of triangular_solve (:4040-4087).  The level
 // sets themselves have no reference counterpart.
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <cub/cub.cuh>
 
 #include "ilub_common.cuh"
@@ -166,18 +168,97 @@ struct WeightOp {
     }
 };
 
-__global__ void k_partition(int n, const long long* __restrict__ wsum /*inclusive*/, SrcDev S, int nparts,
-                            const int* __restrict__ level, unsigned long long* __restrict__ keys,
-                            int* __restrict__ rows) {
+constexpr int kPartShift = 33;  // sort key = part << 33 | level << 1 | has-remote-dependency
+
+struct PartPlan {
+    int mode;    // 0 contiguous ranges, 2 strips (2-D), 3 pencils (3-D)
+    int nparts;
+    int sy, sz;  // detected strides: y = (i % sz) / sy, z = i / sz   (mode 2: sz unused, y = i / sy)
+    int ny, nz, gy, gz;
+};
+
+__global__ void k_assign_parts(int n, const long long* __restrict__ wsum /*inclusive*/, SrcDev S, PartPlan pl,
+                               int* __restrict__ part) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const long long total = wsum[n - 1];
-    const long long w = (long long)(src_end(S, i) - src_beg(S, i)) + 2;
-    const long long start = wsum[i] - w;
-    int p = (int)((__int128)start * nparts / total);
-    if (p >= nparts) p = nparts - 1;
-    keys[i] = ((unsigned long long)(unsigned)p << 32) | (unsigned)level[i];
+    int p;
+    if (pl.mode == 0) {  // contiguous row ranges balanced by work (entries + per-row overhead)
+        const long long total = wsum[n - 1];
+        const long long w = (long long)(src_end(S, i) - src_beg(S, i)) + 2;
+        const long long start = wsum[i] - w;
+        p = (int)((__int128)start * pl.nparts / total);
+    } else if (pl.mode == 2) {  // strips of grid lines
+        const int y = i / pl.sy;
+        p = (int)((long long)y * pl.gy / pl.ny);
+    } else {  // pencils along the fastest axis: a (y, z) tile for every x
+        const int z = i / pl.sz;
+        const int y = (i - z * pl.sz) / pl.sy;
+        const int ty = (int)((long long)y * pl.gy / pl.ny);
+        const int tz = (int)((long long)z * pl.gz / pl.nz);
+        p = tz * pl.gy + ty;
+    }
+    if (p >= pl.nparts) p = pl.nparts - 1;
+    part[i] = p;
+}
+
+// rows that read another part's result go last inside their level so that chunks are (mostly) either
+// purely local or "remote" -- a warp polling global memory does not slow down local hand-offs
+__global__ void k_sort_keys(int n, SrcDev S, const int* __restrict__ part, const int* __restrict__ level,
+                            unsigned long long* __restrict__ keys, int* __restrict__ rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = part[i];
+    unsigned remote = 0;
+    for (int q = src_beg(S, i); q < src_end(S, i); ++q)
+        if (part[S.dep_idx[q]] != p) {
+            remote = 1;
+            break;
+        }
+    keys[i] = ((unsigned long long)(unsigned)p << kPartShift) | ((unsigned long long)(unsigned)level[i] << 1) | remote;
     rows[i] = i;
+}
+
+// 64 sample rows; the one with the most dependencies reports its (absolute) offsets: out[0] = count, out[1..8]
+__global__ void k_sample_offsets(int n, SrcDev S, int* out) {
+    __shared__ unsigned long long best;
+    if (threadIdx.x == 0) best = 0;
+    __syncthreads();
+    const long long step = n / 64 > 0 ? n / 64 : 1;
+    long long r = (long long)threadIdx.x * step + step / 2 + (long long)threadIdx.x * 37;
+    const int row = (int)(r % n);
+    const int cnt = src_end(S, row) - src_beg(S, row);
+    atomicMax(&best, ((unsigned long long)(unsigned)cnt << 32) | (unsigned)(63 - threadIdx.x));
+    __syncthreads();
+    if ((unsigned)(63 - threadIdx.x) == (unsigned)(best & 0xffffffffu)) {
+        out[0] = cnt;
+        for (int k = 0; k < cnt && k < 8; ++k) {
+            int d = S.dep_idx[src_beg(S, row) + k] - row;
+            out[1 + k] = d < 0 ? -d : d;
+        }
+    }
+}
+
+// how many dependency entries sit at one of the (<= 3) candidate offsets?
+__global__ void k_count_offsets(int n, SrcDev S, int no, int o0, int o1, int o2, unsigned long long* out /*[2]*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long hit = 0, tot = 0;
+    if (i < n) {
+        for (int q = src_beg(S, i); q < src_end(S, i); ++q) {
+            int d = S.dep_idx[q] - i;
+            if (d < 0) d = -d;
+            ++tot;
+            if (d == o0 || (no > 1 && d == o1) || (no > 2 && d == o2)) ++hit;
+        }
+    }
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    hit = BR(tmp).Sum(hit);
+    __syncthreads();
+    tot = BR(tmp).Sum(tot);
+    if (threadIdx.x == 0) {
+        atomicAdd(&out[0], hit);
+        atomicAdd(&out[1], tot);
+    }
 }
 
 // rows of part p occupy sorted positions [rstart[p], rstart[p+1]); chunks [pcp[p], pcp[p+1])
@@ -188,7 +269,7 @@ __global__ void k_part_bounds(int n, int nparts, const unsigned long long* __res
         int lo = 0, hi = n;  // first sorted position whose part >= p
         while (lo < hi) {
             const int mid = lo + ((hi - lo) >> 1);
-            if ((int)(skeys[mid] >> 32) < p)
+            if ((int)(skeys[mid] >> kPartShift) < p)
                 lo = mid + 1;
             else
                 hi = mid;
@@ -211,7 +292,7 @@ __global__ void k_place_rows(int n, const unsigned long long* __restrict__ skeys
                              int* __restrict__ rowpos) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const int p = (int)(skeys[s] >> 32);
+    const int p = (int)(skeys[s] >> kPartShift);
     const int rank = s - rstart[p];
     const int pos = ((pcp[p] + (rank >> 5)) << 5) | (rank & 31);
     const int row = order[s];
@@ -247,7 +328,8 @@ __global__ void k_chunk_shape(int nchunks, SrcDev S, const int* __restrict__ row
 __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows, const int* __restrict__ rlen,
                              const int* __restrict__ chunk_ptr, const int* __restrict__ rowpos,
                              const int* __restrict__ pcp, int nparts, int near, unsigned char* __restrict__ ckind,
-                             int* __restrict__ idx, int* __restrict__ srcpos, int* __restrict__ diagpos) {
+                             int* __restrict__ idx, int* __restrict__ srcpos, int* __restrict__ diagpos,
+                             unsigned char* __restrict__ pub) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= nchunks) return;
@@ -303,11 +385,22 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
             enc = kLocalBit | (unsigned)(pd - (cfirst << 5));
         } else {
             enc = (unsigned)d;
+            pub[d] = 1;  // row d must publish through the mailbox
         }
         idx[at] = (int)enc;
         srcpos[at] = S.val_pos ? S.val_pos[q] : q;
     }
     if (__any_sync(0xffffffffu, intra) && lane == 0) ckind[c] |= 2;
+}
+
+__global__ void k_pubmask(int nchunks, const int* __restrict__ rows, const unsigned char* __restrict__ pub,
+                          unsigned* __restrict__ pubmask) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= nchunks) return;
+    const int row = rows[c * 32 + lane];
+    const unsigned m = __ballot_sync(0xffffffffu, row >= 0 && pub[row] != 0);
+    if (lane == 0) pubmask[c] = m;
 }
 
 __global__ void k_pack_values(int64_t nent, const int* __restrict__ srcpos, const double* __restrict__ lu,
@@ -489,6 +582,69 @@ SolveSource solve_source(ilub_handle* h, int slot) {
     return S;
 }
 
+static PartPlan plan_partition(ilub_handle* h, const SrcDev& S, int64_t nent, cudaStream_t s) {
+    const Options& opt = options();
+    const int n = h->n;
+    PartPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    const int64_t maxp = (int64_t)h->sm_count * std::max<int64_t>(1, opt.ctas_per_sm);
+    const int64_t bytes = 12 * nent + 16 * (int64_t)n;
+    int64_t target = opt.nparts > 0 ? opt.nparts : std::max<int64_t>(1, bytes / (std::max<int64_t>(1, opt.part_kb) * 1024));
+    target = std::min(target, maxp);
+    target = std::min<int64_t>(target, std::max<int64_t>(1, ((int64_t)n + 31) / 32));
+    pl.mode = 0;
+    pl.nparts = (int)target;
+    if (opt.partition == 1 || target == 1) return pl;
+    DevBuf<int> dout;
+    DevBuf<unsigned long long> dcnt;
+    dout.alloc(16);
+    dcnt.alloc(2);
+    ILUB_CUDA(cudaMemsetAsync(dout.p, 0, sizeof(int) * 16, s));
+    ILUB_CUDA(cudaMemsetAsync(dcnt.p, 0, 16, s));
+    k_sample_offsets<<<1, 64, 0, s>>>(n, S, dout.p);
+    int ho[16];
+    ILUB_CUDA(cudaMemcpyAsync(ho, dout.p, sizeof(ho), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    h->launches++;
+    const int cnt = ho[0];
+    if (cnt < 1 || cnt > 3) return pl;
+    int off[3] = {0, 0, 0};
+    for (int k = 0; k < cnt; ++k) off[k] = ho[1 + k];
+    std::sort(off, off + cnt);
+    for (int k = 1; k < cnt; ++k)
+        if (off[k] == off[k - 1]) return pl;
+    k_count_offsets<<<blocks_for(n, 256), 256, 0, s>>>(n, S, cnt, off[0], off[1], off[2], dcnt.p);
+    unsigned long long hc[2];
+    ILUB_CUDA(cudaMemcpyAsync(hc, dcnt.p, 16, cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    h->launches++;
+    if (hc[1] == 0 || (double)hc[0] < 0.97 * (double)hc[1]) return pl;
+    if (cnt == 1) {
+        if (off[0] == 1) pl.nparts = 1;  // a single chain: no parallelism to partition
+        return pl;
+    }
+    if (cnt == 2) {
+        pl.mode = 2;
+        pl.sy = off[1];
+        pl.ny = (n + pl.sy - 1) / pl.sy;
+        pl.gy = (int)std::min<int64_t>(target, pl.ny);
+        pl.gz = 1;
+        pl.nparts = pl.gy;
+        return pl;
+    }
+    pl.mode = 3;
+    pl.sy = off[1];
+    pl.sz = off[2];
+    pl.ny = (pl.sz + pl.sy - 1) / pl.sy;
+    pl.nz = (n + pl.sz - 1) / pl.sz;
+    int g = (int)std::floor(std::sqrt((double)target));
+    pl.gy = std::max(1, std::min(g, pl.ny));
+    pl.gz = (int)std::max<int64_t>(1, std::min<int64_t>(target / pl.gy, pl.nz));
+    pl.gy = (int)std::max<int64_t>(1, std::min<int64_t>(target / pl.gz, pl.ny));
+    pl.nparts = pl.gy * pl.gz;
+    return pl;
+}
+
 void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     TriSolve& T = h->solve[slot];
     if (T.built) return;
@@ -521,19 +677,25 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     ILUB_CUDA(cudaMemcpy(hctr, ctr.p, sizeof(hctr), cudaMemcpyDeviceToHost));
     T.nlevels = hctr[1];
 
-    // ---- partition + (part, level, row) order
-    int nparts = (int)(h->sm_count * opt.ctas_per_sm);
-    const int64_t max_parts_by_rows = ((int64_t)n + 31) / 32;
-    if (nparts > max_parts_by_rows) nparts = (int)std::max<int64_t>(1, max_parts_by_rows);
+    // ---- partition + (part, level, remote, row) order
+    const int64_t nent_est = (slot == 0 || slot == 3) ? h->nnz_lower : h->nnz_upper;
+    const PartPlan pl = plan_partition(h, S, nent_est, s);
+    const int nparts = pl.nparts;
     T.nparts = nparts;
+    T.part_mode = pl.mode;
+    T.stride_y = pl.sy;
+    T.stride_z = pl.sz;
+    T.grid_y = pl.gy;
+    T.grid_z = pl.gz;
     DevBuf<long long> wsum;
     wsum.alloc(n);
     DevBuf<unsigned long long> keys, keys2;
-    DevBuf<int> rowsb, rows2;
+    DevBuf<int> rowsb, rows2, part;
     keys.alloc(n);
     keys2.alloc(n);
     rowsb.alloc(n);
     rows2.alloc(n);
+    part.alloc(n);
     cub::CountingInputIterator<int> cnt_it(0);
     WeightOp wop{S};
     cub::TransformInputIterator<long long, WeightOp, cub::CountingInputIterator<int>> w_it(cnt_it, wop);
@@ -541,13 +703,14 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     cub::DeviceScan::InclusiveSum(nullptr, tb1, w_it, wsum.p, n, s);
     cub::DoubleBuffer<unsigned long long> dk(keys.p, keys2.p);
     cub::DoubleBuffer<int> dv(rowsb.p, rows2.p);
-    const int end_bit = 32 + bits_for((unsigned)nparts);
+    const int end_bit = kPartShift + bits_for((unsigned)nparts);
     cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, n, 0, end_bit, s);
     DevBuf<unsigned char> tmp;
     tmp.alloc(std::max(tb1, tb2));
     size_t tb = tmp.n;
-    ILUB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, w_it, wsum.p, n, s));
-    k_partition<<<blocks_for(n, 256), 256, 0, s>>>(n, wsum.p, S, nparts, T.level.p, keys.p, rowsb.p);
+    if (pl.mode == 0) ILUB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, w_it, wsum.p, n, s));
+    k_assign_parts<<<blocks_for(n, 256), 256, 0, s>>>(n, wsum.p, S, pl, part.p);
+    k_sort_keys<<<blocks_for(n, 256), 256, 0, s>>>(n, S, part.p, T.level.p, keys.p, rowsb.p);
     tb = tmp.n;
     ILUB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, n, 0, end_bit, s));
     T.order.alloc(n);
@@ -620,11 +783,16 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     T.idx.alloc(nent);
     T.srcpos.alloc(nent);
     T.val.alloc(nent);
+    DevBuf<unsigned char> pub;
+    pub.alloc(n);
+    ILUB_CUDA(cudaMemsetAsync(pub.p, 0, n, s));
     k_chunk_fill<<<blocks_for(nlane, 256), 256, 0, s>>>(nchunks, S, T.rows.p, T.rlen.p, T.chunk_ptr.p, T.rowpos.p,
                                                         T.part_chunk_ptr.p, nparts, T.cfg_near, T.ckind.p,
-                                                        T.idx.p, T.srcpos.p, T.diagpos.p);
-    T.gflag.alloc(n);
-    ILUB_CUDA(cudaMemsetAsync(T.gflag.p, 0, n, s));
+                                                        T.idx.p, T.srcpos.p, T.diagpos.p, pub.p);
+    T.pubmask.alloc(nchunks);
+    k_pubmask<<<blocks_for(nlane, 256), 256, 0, s>>>(nchunks, T.rows.p, pub.p, T.pubmask.p);
+    T.mail.alloc(n);
+    ILUB_CUDA(cudaMemsetAsync(T.mail.p, 0, sizeof(ulonglong2) * (size_t)n, s));
     T.epoch = 0;
     h->launches += 8;
     ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here

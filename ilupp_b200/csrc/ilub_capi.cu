@@ -428,6 +428,8 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "stages") o.stages = value;
         else if (k == "spin_limit_ms") o.spin_limit_ms = value;
         else if (k == "partition") o.partition = value;
+        else if (k == "nparts") o.nparts = value;
+        else if (k == "part_kb") o.part_kb = value;
         else if (k == "factor_group") o.factor_group = value;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
     });
@@ -448,6 +450,8 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "stages") *value = o.stages;
         else if (k == "spin_limit_ms") *value = o.spin_limit_ms;
         else if (k == "partition") *value = o.partition;
+        else if (k == "nparts") *value = o.nparts;
+        else if (k == "part_kb") *value = o.part_kb;
         else if (k == "factor_group") *value = o.factor_group;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
     });
@@ -459,7 +463,7 @@ int ilub_get_timings(const ilub_handle* h, double out_ms[4]) {
         for (int i = 0; i < 4; ++i) out_ms[i] = h->timings[i];
     });
 }
-int ilub_get_stats(const ilub_handle* h, int64_t out[8]) {
+int ilub_get_stats(const ilub_handle* h, int64_t out[16]) {
     return guarded([&] {
         ILUB_REQUIRE(h && out, ILUB_ERR_INVALID, "null argument");
         out[0] = h->n;
@@ -470,6 +474,15 @@ int ilub_get_stats(const ilub_handle* h, int64_t out[8]) {
             out[3 + k] = h->solve[slot].built ? h->solve[slot].nlevels : 0;
         }
         out[7] = h->launches;
+        const TriSolve& T = h->solve[slot_of(h, 0)];
+        out[8] = T.nparts;
+        out[9] = T.part_mode;
+        out[10] = T.grid_y;
+        out[11] = T.grid_z;
+        out[12] = T.nchunks;
+        out[13] = T.nslabs;
+        out[14] = T.cfg_warps;
+        out[15] = (int64_t)T.cfg_smem;
     });
 }
 

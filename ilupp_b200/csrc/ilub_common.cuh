@@ -71,14 +71,17 @@ struct Options {
     int64_t wcap = 8;           // widest lane-per-row chunk (slabs); wider chunks are warp-cooperative
     int64_t stages = 2;         // TMA staging depth per warp
     int64_t spin_limit_ms = 1500;
-    int64_t partition = 0;      // 0 contiguous index ranges balanced by work
+    int64_t partition = 0;      // 0 auto (geometric strips/pencils when strides are detected), 1 contiguous ranges
+    int64_t nparts = 0;         // 0 auto, else number of CTAs/parts to aim for
+    int64_t part_kb = 256;      // auto nparts: aim for at least this many KB of solve data per CTA
     int64_t factor_group = 0;   // lanes per row in the factorisation kernels (0 = auto)
 };
 Options& options();
 
 constexpr int kLanes = 32;
 // dependency encoding inside a packed chunk (int32):
-//   e >= 0                      global path: original row index (value from x[e] once gflag[e] == epoch)
+//   e >= 0                      global path: original row index (value + epoch tag read from mail[e] in one
+//                               128-bit access)
 //   e <  0, bit 30 clear        shared-memory path: low 30 bits = position in this CTA's processing order
 //   e <  0, bit 30 set          same-chunk dependency: low 5 bits = producing lane
 constexpr unsigned kLocalBit = 0x80000000u;
@@ -109,8 +112,11 @@ struct TriSolve {
     DevBuf<double> val;           // [nslabs * 32]
     DevBuf<double> diag;          // [nchunks * 32]
     DevBuf<int> diagpos;          // [nchunks * 32] position of the diagonal value (-1: unit / padding)
-    DevBuf<unsigned char> gflag;  // [n] epoch flags of the global dependency path
-    unsigned epoch = 0;
+    DevBuf<unsigned> pubmask;     // [nchunks] lanes whose row is read through the global path by someone
+    DevBuf<ulonglong2> mail;      // [n] {x bits, epoch tag}: the global dependency path (one 16-B atomic access)
+    unsigned long long epoch = 0;
+    int part_mode = 0;            // 0 contiguous ranges, 2 / 3: strips / pencils from detected strides
+    int stride_y = 0, stride_z = 0, grid_y = 1, grid_z = 1;
     // launch configuration of the sync-free kernel, fixed at analysis (near is baked into idx)
     int cfg_warps = 16, cfg_ring_chunks = 256, cfg_near = 96, cfg_stages = 2, cfg_stage_slabs = 1;
     size_t cfg_smem = 0;

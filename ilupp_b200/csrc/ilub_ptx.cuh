@@ -29,6 +29,23 @@ __device__ __forceinline__ double ld_relaxed_gpu_f64(const double* p) {
 __device__ __forceinline__ void st_relaxed_gpu_f64(double* p, double v) {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// one architecturally atomic 16-byte access (PTX .b128 scalar type): value and epoch tag travel together,
+// so the global dependency path needs no fence and no second load
+__device__ __forceinline__ void st_mail(ulonglong2* p, double x, unsigned long long tag) {
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.gpu.global.b128 [%0], q;\n\t}" ::"l"(p),
+                 "l"(__double_as_longlong(x)), "l"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ bool ld_mail(const ulonglong2* p, unsigned long long tag, double& x) {
+    long long xb;
+    unsigned long long t;
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.gpu.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(xb), "=l"(t)
+                 : "l"(p)
+                 : "memory");
+    x = __longlong_as_double(xb);
+    return t == tag;
+}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // ---- shared memory, cta scope ----------------------------------------------------------------

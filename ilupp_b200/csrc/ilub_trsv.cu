@@ -11,8 +11,8 @@
 //   * dependency in a recent chunk of the
 //     same CTA (<= near chunks back)      -> x ring + per-chunk tag in shared memory
 //                                            (st.release.cta / ld.acquire.cta)
-//   * anything else (other CTA, far back) -> x in global memory + per-row epoch flag
-//                                            (st.release.gpu / ld.acquire.gpu)
+//   * anything else (other CTA, far back) -> 16-byte mailbox {x, epoch tag} in global memory, written
+//                                            and polled with single atomic .b128 accesses (no fence)
 // Forward progress: chunks are ordered by (level, row) inside a CTA and every warp takes its
 // chunks in ascending order, so the globally smallest unfinished row (by level, row) is always at
 // the head of a resident warp and has all dependencies satisfied.  A clock64 watchdog turns any
@@ -40,9 +40,10 @@ struct TrsvParams {
     const int* idx;
     const double* val;
     const double* diag;
+    const unsigned* pubmask;
     double* x;
-    unsigned char* gflag;
-    unsigned epoch;
+    ulonglong2* mail;
+    unsigned long long epoch;
     int ring_mask;  // ring rows - 1
     int rc;         // ring chunks
     int near;
@@ -153,24 +154,32 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
             const bool has_intra = (kind & 2) != 0;
             int j = 0;
             bool fin = false;
+            // the current dependency (index, value) is kept in registers: a poll only re-reads the flag
+            int e = 0;
+            double v = 0.0;
+            if (len > 0) {
+                e = sidx[lane];
+                v = sval[lane];
+            }
             while (true) {
                 if (has_intra) {
-                    const int e = (!fin && j < len) ? sidx[j * 32 + lane] : 0;
-                    const bool wi = ((unsigned)e & (kLocalBit | kIntraBit)) == (kLocalBit | kIntraBit);
+                    const bool wi = !fin && j < len && ((unsigned)e & (kLocalBit | kIntraBit)) == (kLocalBit | kIntraBit);
                     const unsigned finmask = __ballot_sync(FULL, fin);
                     const double xs = __shfl_sync(FULL, xfin, e & 31);
                     if (wi && ((finmask >> (e & 31)) & 1u)) {
-                        acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], xs);
+                        acc = sub_mul<EXACT>(acc, v, xs);
                         ++j;
+                        if (j < len) {
+                            e = sidx[j * 32 + lane];
+                            v = sval[j * 32 + lane];
+                        }
                     }
                 }
                 if (!fin) {
                     while (j < len) {
-                        const int e = sidx[j * 32 + lane];
                         double xv;
                         if (e >= 0) {
-                            if (ld_acquire_gpu_u8(P.gflag + e) != P.epoch) break;
-                            xv = ld_relaxed_gpu_f64(P.x + e);
+                            if (!ld_mail(P.mail + e, P.epoch, xv)) break;
                         } else if (((unsigned)e & kIntraBit) == 0) {
                             const int lp = e & 0x3fffffff;
                             const int dc = lp >> 5;
@@ -179,8 +188,12 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                         } else {
                             break;  // same-chunk dependency: exchanged at the top of the next round
                         }
-                        acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], xv);
+                        acc = sub_mul<EXACT>(acc, v, xv);
                         ++j;
+                        if (j < len) {
+                            e = sidx[j * 32 + lane];
+                            v = sval[j * 32 + lane];
+                        }
                     }
                     if (j >= len) {
                         xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
@@ -217,10 +230,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                     while (true) {
                         if (!ok) {
                             if (e >= 0) {
-                                if (ld_acquire_gpu_u8(P.gflag + e) == P.epoch) {
-                                    xv = ld_relaxed_gpu_f64(P.x + e);
-                                    ok = true;
-                                }
+                                if (ld_mail(P.mail + e, P.epoch, xv)) ok = true;
                             } else {
                                 const int lp = e & 0x3fffffff;
                                 const int dc = lp >> 5;
@@ -260,8 +270,8 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
         __syncwarp();
         if (lane == 0) st_release_cta_s32(&cflag[lc & rc_mask], lc);
         if (r >= 0) {
-            st_relaxed_gpu_f64(P.x + r, xfin);
-            st_release_gpu_u8(P.gflag + r, P.epoch);
+            P.x[r] = xfin;
+            if ((P.pubmask[c] >> lane) & 1u) st_mail(P.mail + r, xfin, P.epoch);
         }
         __syncwarp();
         if (lane == 0) st_release_cta_s32(&warp_cur[warp], lc + W < nloc ? lc + W : INT_MAX);
@@ -362,7 +372,8 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.idx = T.idx.p;
     P.val = T.val.p;
     P.diag = T.diag.p;
-    P.gflag = T.gflag.p;
+    P.pubmask = T.pubmask.p;
+    P.mail = T.mail.p;
     P.ring_mask = T.cfg_ring_chunks * 32 - 1;
     P.rc = T.cfg_ring_chunks;
     P.near = T.cfg_near;
@@ -382,11 +393,7 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
         attr_set[exact ? 1 : 0] = true;
     }
     for (int c = 0; c < nrhs; ++c) {
-        if (++T.epoch > 255) {
-            ILUB_CUDA(cudaMemsetAsync(T.gflag.p, 0, T.n, s));
-            T.epoch = 1;
-        }
-        P.epoch = T.epoch;
+        P.epoch = ++T.epoch;  // 64-bit tag: never wraps, the mailbox is never reset
         P.x = x + (int64_t)c * ldx;
         if (exact)
             k_trsv_syncfree<true><<<T.nparts, T.cfg_warps * 32, T.cfg_smem, s>>>(P);

@@ -157,8 +157,10 @@ ILUB_API int ilub_get_option(const char* key, int64_t* value);
  * [0] symbolic analysis, [1] numeric factorisation, [2] solve-layout packing, [3] total */
 ILUB_API int ilub_get_timings(const ilub_handle* h, double out_ms[4]);
 /* structure statistics: [0] n, [1] nnz(A), [2] total_nnz, [3..6] levels of the four solves (0 if not built),
- * [7] kernels launched by this handle so far */
-ILUB_API int ilub_get_stats(const ilub_handle* h, int64_t out[8]);
+ * [7] kernels launched by this handle so far; of the first solve of apply(): [8] CTAs (row parts),
+ * [9] partition mode (0 contiguous ranges, 2 strips, 3 pencils), [10] x [11] tile grid, [12] 32-row chunks,
+ * [13] 32-entry slabs, [14] warps per CTA, [15] dynamic shared memory bytes */
+ILUB_API int ilub_get_stats(const ilub_handle* h, int64_t out[16]);
 
 #ifdef __cplusplus
 }
