@@ -378,10 +378,8 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
         const int pd = rowpos[d];
         const int dc = pd >> 5;
         unsigned enc;
-        if (dc == c) {
-            enc = kLocalBit | kIntraBit | (unsigned)(pd & 31);
-            intra = true;
-        } else if (dc >= cfirst && dc < c && c - dc <= near) {
+        if (dc >= cfirst && dc <= c && c - dc <= near) {
+            if (dc == c) intra = true;
             enc = kLocalBit | (unsigned)(pd - (cfirst << 5));
         } else {
             enc = (unsigned)d;
@@ -763,7 +761,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         const int slabs = std::max(1, T.maxw_a);
         const size_t budget = (size_t)227 * 1024 / (size_t)std::max<int64_t>(1, opt.ctas_per_sm) - 1024;
         auto need = [&]() {
-            return (size_t)RC * 256 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + (size_t)RC * 4 + 128 + 128;
+            return (size_t)RC * 512 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + 128 + 128;
         };
         while (need() > budget) {
             if (stages > 1) stages = 1;

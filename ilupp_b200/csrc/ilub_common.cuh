@@ -66,7 +66,7 @@ struct Options {
     int64_t exact = 1;          // IEEE mul/sub/div in reference order
     int64_t ctas_per_sm = 1;
     int64_t warps_per_cta = 16;
-    int64_t near_window = 96;   // chunks; dependencies this close (same CTA) go through shared memory
+    int64_t near_window = 112;  // chunks; dependencies this close (same CTA) go through shared memory
     int64_t ring_chunks = 256;  // shared-memory x ring, in 32-row chunks (power of two, >= 2*near_window)
     int64_t wcap = 8;           // widest lane-per-row chunk (slabs); wider chunks are warp-cooperative
     int64_t stages = 2;         // TMA staging depth per warp
@@ -82,8 +82,8 @@ constexpr int kLanes = 32;
 // dependency encoding inside a packed chunk (int32):
 //   e >= 0                      global path: original row index (value + epoch tag read from mail[e] in one
 //                               128-bit access)
-//   e <  0, bit 30 clear        shared-memory path: low 30 bits = position in this CTA's processing order
-//   e <  0, bit 30 set          same-chunk dependency: low 5 bits = producing lane
+//   e <  0                      shared-memory path: low 30 bits = position in this CTA's processing order
+//                               (value + tag read from the x ring in one 128-bit access)
 constexpr unsigned kLocalBit = 0x80000000u;
 constexpr unsigned kIntraBit = 0x40000000u;
 

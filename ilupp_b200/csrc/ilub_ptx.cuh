@@ -67,6 +67,23 @@ __device__ __forceinline__ void st_release_cta_s32(int* p, int v) {
 __device__ __forceinline__ void st_relaxed_cta_s32(int* p, int v) {
     asm volatile("st.relaxed.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
+// x ring entries {x bits, tag}: one atomic 16-byte shared-memory access, no flag array, no fence
+__device__ __forceinline__ void st_ring(ulonglong2* p, double x, unsigned long long tag) {
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.cta.shared.b128 [%0], q;\n\t}" ::"r"(
+                     smem_u32(p)),
+                 "l"(__double_as_longlong(x)), "l"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ bool ld_ring(const ulonglong2* p, unsigned long long tag, double& x) {
+    long long xb;
+    unsigned long long t;
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.cta.shared.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(xb), "=l"(t)
+                 : "r"(smem_u32(p))
+                 : "memory");
+    x = __longlong_as_double(xb);
+    return t == tag;
+}
 __device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 // ---- mbarrier + bulk async copy (TMA engine, 1-D) ----------------------------------------------

@@ -73,21 +73,28 @@ struct Watchdog {
     }
 };
 
+// one dependency poll: mailbox (global, e >= 0) or x ring (shared, e < 0); true when the value is there
+__device__ __forceinline__ bool poll_dep(int e, const ulonglong2* mail, unsigned long long epoch,
+                                         const ulonglong2* ring, int ring_mask, double& xv) {
+    if (e >= 0) return ld_mail(mail + e, epoch, xv);
+    const int lp = e & 0x3fffffff;
+    return ld_ring(ring + (lp & ring_mask), (unsigned long long)lp + 1ull, xv);
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = P.ring_mask + 1;
-    double* xring = reinterpret_cast<double*>(smem);
-    unsigned char* stage_base = smem + (size_t)R * 8;
+    ulonglong2* ring = reinterpret_cast<ulonglong2*>(smem);  // {x bits, local position + 1}
+    unsigned char* stage_base = smem + (size_t)R * 16;
     const int stage_bytes = P.stage_slabs * 384;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + (size_t)W * P.nstages * stage_bytes);
-    int* cflag = reinterpret_cast<int*>(mbar + W * P.nstages);
-    int* warp_cur = cflag + P.rc;
+    int* warp_cur = reinterpret_cast<int*>(mbar + W * P.nstages);
 
     const int c0 = P.part_chunk_ptr[blockIdx.x];
     const int nloc = P.part_chunk_ptr[blockIdx.x + 1] - c0;
-    for (int i = threadIdx.x; i < P.rc; i += blockDim.x) cflag[i] = -1;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) ring[i] = make_ulonglong2(0ull, 0ull);
     if (threadIdx.x < 32) warp_cur[threadIdx.x] = (threadIdx.x < W && threadIdx.x < nloc) ? threadIdx.x : INT_MAX;
     if (lane == 0) {
         for (int s = 0; s < P.nstages; ++s) mbar_init(&mbar[warp * P.nstages + s], 1);
@@ -96,7 +103,6 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
     __syncthreads();
     if (warp >= nloc) return;
 
-    const int rc_mask = P.rc - 1;
     unsigned phasebits = 0;
     int done_cache = 0;
     Watchdog wd(P.status, P.spin_limit);
@@ -116,26 +122,48 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
         }
     };
 
-    if (lane == 0)
-        for (int k = 0; k + 1 < P.nstages; ++k)
-            if (warp + k * W < nloc) issue(warp + k * W, k);
+    // software pipeline over this warp's chunks: chunk metadata and the right-hand side of the NEXT chunk
+    // are loaded while the current one is being resolved
+    int lc = warp;
+    if (lane == 0) issue(lc, 0);
+    int r = P.rows[(size_t)(c0 + lc) * 32 + lane];
+    int len = P.rlen[(size_t)(c0 + lc) * 32 + lane];
+    double d = P.unit_diag ? 1.0 : P.diag[(size_t)(c0 + lc) * 32 + lane];
+    double acc = r >= 0 ? __ldcg(P.x + r) : 0.0;
 
-    int it = 0;
-    for (int lc = warp; lc < nloc; lc += W, ++it) {
-        __syncwarp();
-        if (lane == 0) {
-            const int la = lc + (P.nstages - 1) * W;
-            if (la < nloc) issue(la, it + P.nstages - 1);
-        }
+    for (int it = 0; lc < nloc; lc += W, ++it) {
         const int c = c0 + lc;
+        const int nlc = lc + W;
+        const bool has_next = nlc < nloc;
+        __syncwarp();
+        if (has_next && lane == 0 && P.nstages > 1) issue(nlc, it + 1);
+        int r1 = -1, len1 = 0;
+        double d1 = 1.0;
+        if (has_next) {
+            r1 = P.rows[(size_t)(c0 + nlc) * 32 + lane];
+            len1 = P.rlen[(size_t)(c0 + nlc) * 32 + lane];
+            if (!P.unit_diag) d1 = P.diag[(size_t)(c0 + nlc) * 32 + lane];
+        }
         const int cp = P.chunk_ptr[c];
         const int w = P.chunk_ptr[c + 1] - cp;
         const unsigned kind = P.ckind[c];
-        const int r = P.rows[c * 32 + lane];
-        const int len = P.rlen[c * 32 + lane];
-        const double d = P.unit_diag ? 1.0 : P.diag[c * 32 + lane];
-        double acc = r >= 0 ? __ldcg(P.x + r) : 0.0;
+        const unsigned pubm = P.pubmask[c];
         double xfin = 0.0;
+
+        // the ring slots of chunk lc are those of chunk lc - rc: they may be overwritten once every chunk
+        // that could still read them through shared memory (ids <= lc - rc + near) has completed
+        const int need = lc - P.rc + P.near + 1;
+        if (need > done_cache) {
+            while (true) {
+                int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
+                v = __reduce_min_sync(FULL, v);
+                done_cache = v;
+                if (v >= need) break;
+                if (wd.expired(105)) return;
+            }
+        }
+        ulonglong2* myslot = ring + ((lc * 32 + lane) & P.ring_mask);
+        const unsigned long long mytag = (unsigned long long)(lc * 32 + lane) + 1ull;
 
         if ((kind & 1) == 0) {
             // ------------------------------------------------------------ lane-per-row chunk
@@ -151,52 +179,42 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                 phasebits ^= 1u << st;
             }
             const double dinv = EXACT ? 0.0 : 1.0 / d;
-            const bool has_intra = (kind & 2) != 0;
             int j = 0;
             bool fin = false;
-            // the current dependency (index, value) is kept in registers: a poll only re-reads the flag
-            int e = 0;
-            double v = 0.0;
-            if (len > 0) {
-                e = sidx[lane];
-                v = sval[lane];
-            }
             while (true) {
-                if (has_intra) {
-                    const bool wi = !fin && j < len && ((unsigned)e & (kLocalBit | kIntraBit)) == (kLocalBit | kIntraBit);
-                    const unsigned finmask = __ballot_sync(FULL, fin);
-                    const double xs = __shfl_sync(FULL, xfin, e & 31);
-                    if (wi && ((finmask >> (e & 31)) & 1u)) {
-                        acc = sub_mul<EXACT>(acc, v, xs);
-                        ++j;
-                        if (j < len) {
-                            e = sidx[j * 32 + lane];
-                            v = sval[j * 32 + lane];
-                        }
-                    }
-                }
                 if (!fin) {
-                    while (j < len) {
-                        double xv;
-                        if (e >= 0) {
-                            if (!ld_mail(P.mail + e, P.epoch, xv)) break;
-                        } else if (((unsigned)e & kIntraBit) == 0) {
-                            const int lp = e & 0x3fffffff;
-                            const int dc = lp >> 5;
-                            if (ld_acquire_cta_s32(&cflag[dc & rc_mask]) != dc) break;
-                            xv = xring[lp & P.ring_mask];
-                        } else {
-                            break;  // same-chunk dependency: exchanged at the top of the next round
-                        }
-                        acc = sub_mul<EXACT>(acc, v, xv);
-                        ++j;
-                        if (j < len) {
-                            e = sidx[j * 32 + lane];
-                            v = sval[j * 32 + lane];
-                        }
+                    // poll a window of up to 4 dependencies at once, consume them in the stored order
+                    const int nw = len - j;
+                    int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+                    double x0, x1, x2, x3;
+                    bool k0 = false, k1 = false, k2 = false, k3 = false;
+                    if (nw > 0) e0 = sidx[(j + 0) * 32 + lane];
+                    if (nw > 1) e1 = sidx[(j + 1) * 32 + lane];
+                    if (nw > 2) e2 = sidx[(j + 2) * 32 + lane];
+                    if (nw > 3) e3 = sidx[(j + 3) * 32 + lane];
+                    if (nw > 0) k0 = poll_dep(e0, P.mail, P.epoch, ring, P.ring_mask, x0);
+                    if (nw > 1) k1 = poll_dep(e1, P.mail, P.epoch, ring, P.ring_mask, x1);
+                    if (nw > 2) k2 = poll_dep(e2, P.mail, P.epoch, ring, P.ring_mask, x2);
+                    if (nw > 3) k3 = poll_dep(e3, P.mail, P.epoch, ring, P.ring_mask, x3);
+                    if (k0) {
+                        acc = sub_mul<EXACT>(acc, sval[(j + 0) * 32 + lane], x0);
+                        if (k1) {
+                            acc = sub_mul<EXACT>(acc, sval[(j + 1) * 32 + lane], x1);
+                            if (k2) {
+                                acc = sub_mul<EXACT>(acc, sval[(j + 2) * 32 + lane], x2);
+                                if (k3) {
+                                    acc = sub_mul<EXACT>(acc, sval[(j + 3) * 32 + lane], x3);
+                                    j += 4;
+                                } else
+                                    j += 3;
+                            } else
+                                j += 2;
+                        } else
+                            j += 1;
                     }
                     if (j >= len) {
                         xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
+                        if (r >= 0) st_ring(myslot, xfin, mytag);
                         fin = true;
                     }
                 }
@@ -223,23 +241,10 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                     const bool active = t < rl;
                     const int e = active ? __ldg(P.idx + base + ro + t) : 0;
                     const double v = active ? __ldg(P.val + base + ro + t) : 0.0;
-                    const bool wi = active && ((unsigned)e & (kLocalBit | kIntraBit)) == (kLocalBit | kIntraBit);
-                    const double xs = __shfl_sync(FULL, xfin, e & 31);  // producers are earlier lanes: final
-                    double xv = wi ? xs : 0.0;
-                    bool ok = !active || wi;
+                    double xv = 0.0;
+                    bool ok = !active;
                     while (true) {
-                        if (!ok) {
-                            if (e >= 0) {
-                                if (ld_mail(P.mail + e, P.epoch, xv)) ok = true;
-                            } else {
-                                const int lp = e & 0x3fffffff;
-                                const int dc = lp >> 5;
-                                if (ld_acquire_cta_s32(&cflag[dc & rc_mask]) == dc) {
-                                    xv = xring[lp & P.ring_mask];
-                                    ok = true;
-                                }
-                            }
-                        }
+                        if (!ok) ok = poll_dep(e, P.mail, P.epoch, ring, P.ring_mask, xv);
                         if (__all_sync(FULL, ok)) break;
                         if (wd.expired(104)) return;
                     }
@@ -249,32 +254,27 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                 if (lane == rr) {
                     const double t = acc - part;
                     xfin = P.unit_diag ? t : (EXACT ? __ddiv_rn(t, d) : t / d);
+                    st_ring(myslot, xfin, mytag);
                 }
+                __syncwarp();
             }
         }
 
-        // ---------------------------------------------------------------- publish
-        // ring slot of chunk lc - rc may be overwritten once every chunk that could still read it
-        // through shared memory (ids <= lc - rc + near) has completed
-        const int need = lc - P.rc + P.near + 1;
-        if (need > done_cache) {
-            while (true) {
-                int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
-                v = __reduce_min_sync(FULL, v);
-                done_cache = v;
-                if (v >= need) break;
-                if (wd.expired(105)) return;
-            }
-        }
-        xring[(lc * 32 + lane) & P.ring_mask] = xfin;
-        __syncwarp();
-        if (lane == 0) st_release_cta_s32(&cflag[lc & rc_mask], lc);
+        // ---------------------------------------------------------------- publish to global memory
         if (r >= 0) {
             P.x[r] = xfin;
-            if ((P.pubmask[c] >> lane) & 1u) st_mail(P.mail + r, xfin, P.epoch);
+            if ((pubm >> lane) & 1u) st_mail(P.mail + r, xfin, P.epoch);
         }
         __syncwarp();
-        if (lane == 0) st_release_cta_s32(&warp_cur[warp], lc + W < nloc ? lc + W : INT_MAX);
+        if (lane == 0) {
+            st_release_cta_s32(&warp_cur[warp], has_next ? nlc : INT_MAX);
+            if (has_next && P.nstages == 1) issue(nlc, it + 1);
+        }
+        // rotate the software pipeline
+        r = r1;
+        len = len1;
+        d = d1;
+        acc = r >= 0 ? __ldcg(P.x + r) : 0.0;
     }
 }
 
