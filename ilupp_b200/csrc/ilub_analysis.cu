@@ -329,7 +329,8 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
                              const int* __restrict__ chunk_ptr, const int* __restrict__ rowpos,
                              const int* __restrict__ pcp, int nparts, int near, unsigned char* __restrict__ ckind,
                              int* __restrict__ idx, int* __restrict__ srcpos, int* __restrict__ diagpos,
-                             unsigned char* __restrict__ pub) {
+                             unsigned char* __restrict__ pub, const int* __restrict__ level,
+                             int* __restrict__ gate) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= nchunks) return;
@@ -364,6 +365,9 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
         }
     }
     bool intra = false;
+    const int lv = row >= 0 ? level[row] : 0x7fffffff;
+    const int lvmin = __reduce_min_sync(0xffffffffu, lv);
+    int g = -1;  // last local chunk (CTA numbering) feeding the rows of this chunk's lowest level
     const int b = row >= 0 ? src_beg(S, row) : 0;
     const int e = b + len;
     for (int j = 0; j < (kind ? len : w); ++j) {
@@ -380,6 +384,7 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
         unsigned enc;
         if (dc >= cfirst && dc <= c && c - dc <= near) {
             if (dc == c) intra = true;
+            if (lv == lvmin) g = max(g, dc - cfirst);
             enc = kLocalBit | (unsigned)(pd - (cfirst << 5));
         } else {
             enc = (unsigned)d;
@@ -389,6 +394,8 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
         srcpos[at] = S.val_pos ? S.val_pos[q] : q;
     }
     if (__any_sync(0xffffffffu, intra) && lane == 0) ckind[c] |= 2;
+    g = __reduce_max_sync(0xffffffffu, g + 1) - 1;
+    if (lane == 0) gate[c] = g;
 }
 
 __global__ void k_pubmask(int nchunks, const int* __restrict__ rows, const unsigned char* __restrict__ pub,
@@ -781,12 +788,13 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     T.idx.alloc(nent);
     T.srcpos.alloc(nent);
     T.val.alloc(nent);
+    T.gate.alloc(nchunks);
     DevBuf<unsigned char> pub;
     pub.alloc(n);
     ILUB_CUDA(cudaMemsetAsync(pub.p, 0, n, s));
     k_chunk_fill<<<blocks_for(nlane, 256), 256, 0, s>>>(nchunks, S, T.rows.p, T.rlen.p, T.chunk_ptr.p, T.rowpos.p,
                                                         T.part_chunk_ptr.p, nparts, T.cfg_near, T.ckind.p,
-                                                        T.idx.p, T.srcpos.p, T.diagpos.p, pub.p);
+                                                        T.idx.p, T.srcpos.p, T.diagpos.p, pub.p, T.level.p, T.gate.p);
     T.pubmask.alloc(nchunks);
     k_pubmask<<<blocks_for(nlane, 256), 256, 0, s>>>(nchunks, T.rows.p, pub.p, T.pubmask.p);
     T.mail.alloc(n);

@@ -429,6 +429,7 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "spin_limit_ms") o.spin_limit_ms = value;
         else if (k == "partition") o.partition = value;
         else if (k == "nparts") o.nparts = value;
+        else if (k == "gate_slack") o.gate_slack = value;
         else if (k == "part_kb") o.part_kb = value;
         else if (k == "factor_group") o.factor_group = value;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
@@ -451,6 +452,7 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "spin_limit_ms") *value = o.spin_limit_ms;
         else if (k == "partition") *value = o.partition;
         else if (k == "nparts") *value = o.nparts;
+        else if (k == "gate_slack") *value = o.gate_slack;
         else if (k == "part_kb") *value = o.part_kb;
         else if (k == "factor_group") *value = o.factor_group;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};

@@ -69,6 +69,7 @@ struct Options {
     int64_t near_window = 112;  // chunks; dependencies this close (same CTA) go through shared memory
     int64_t ring_chunks = 256;  // shared-memory x ring, in 32-row chunks (power of two, >= 2*near_window)
     int64_t wcap = 8;           // widest lane-per-row chunk (slabs); wider chunks are warp-cooperative
+    int64_t gate_slack = 2;     // start fine-grained polling this many chunks before the gate chunk completes
     int64_t stages = 2;         // TMA staging depth per warp
     int64_t spin_limit_ms = 1500;
     int64_t partition = 0;      // 0 auto (geometric strips/pencils when strides are detected), 1 contiguous ranges
@@ -112,6 +113,7 @@ struct TriSolve {
     DevBuf<double> val;           // [nslabs * 32]
     DevBuf<double> diag;          // [nchunks * 32]
     DevBuf<int> diagpos;          // [nchunks * 32] position of the diagonal value (-1: unit / padding)
+    DevBuf<int> gate;             // [nchunks] last local chunk feeding this chunk's lowest level (-1: none)
     DevBuf<unsigned> pubmask;     // [nchunks] lanes whose row is read through the global path by someone
     DevBuf<ulonglong2> mail;      // [n] {x bits, epoch tag}: the global dependency path (one 16-B atomic access)
     unsigned long long epoch = 0;

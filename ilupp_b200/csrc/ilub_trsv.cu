@@ -41,6 +41,8 @@ struct TrsvParams {
     const double* val;
     const double* diag;
     const unsigned* pubmask;
+    const int* gate;
+    int slack;
     double* x;
     ulonglong2* mail;
     unsigned long long epoch;
@@ -150,15 +152,19 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
         const unsigned pubm = P.pubmask[c];
         double xfin = 0.0;
 
-        // the ring slots of chunk lc are those of chunk lc - rc: they may be overwritten once every chunk
-        // that could still read them through shared memory (ids <= lc - rc + near) has completed
-        const int need = lc - P.rc + P.near + 1;
+        // (1) the ring slots of chunk lc are those of chunk lc - rc: they may be overwritten once every
+        //     chunk that could still read them through shared memory (ids <= lc - rc + near) has completed;
+        // (2) gate: do not start fine-grained polling (16-byte shared-memory reads by every lane) before
+        //     the chunks feeding this chunk's lowest level are (almost) done -- far-away warps sleep on the
+        //     cheap per-warp progress words instead of saturating the shared-memory pipe.
+        const int need = max(lc - P.rc + P.near + 1, P.gate[c] - P.slack + 1);
         if (need > done_cache) {
             while (true) {
                 int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
                 v = __reduce_min_sync(FULL, v);
                 done_cache = v;
                 if (v >= need) break;
+                __nanosleep(40);
                 if (wd.expired(105)) return;
             }
         }
@@ -181,36 +187,56 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
             const double dinv = EXACT ? 0.0 : 1.0 / d;
             int j = 0;
             bool fin = false;
+            // the dependency a lane is waiting for stays in registers: a failed round costs one 16-byte poll
+            int e = 0;
+            double v = 0.0;
+            if (len > 0) {
+                e = sidx[lane];
+                v = sval[lane];
+            }
             while (true) {
                 if (!fin) {
-                    // poll a window of up to 4 dependencies at once, consume them in the stored order
-                    const int nw = len - j;
-                    int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-                    double x0, x1, x2, x3;
-                    bool k0 = false, k1 = false, k2 = false, k3 = false;
-                    if (nw > 0) e0 = sidx[(j + 0) * 32 + lane];
-                    if (nw > 1) e1 = sidx[(j + 1) * 32 + lane];
-                    if (nw > 2) e2 = sidx[(j + 2) * 32 + lane];
-                    if (nw > 3) e3 = sidx[(j + 3) * 32 + lane];
-                    if (nw > 0) k0 = poll_dep(e0, P.mail, P.epoch, ring, P.ring_mask, x0);
-                    if (nw > 1) k1 = poll_dep(e1, P.mail, P.epoch, ring, P.ring_mask, x1);
-                    if (nw > 2) k2 = poll_dep(e2, P.mail, P.epoch, ring, P.ring_mask, x2);
-                    if (nw > 3) k3 = poll_dep(e3, P.mail, P.epoch, ring, P.ring_mask, x3);
-                    if (k0) {
-                        acc = sub_mul<EXACT>(acc, sval[(j + 0) * 32 + lane], x0);
-                        if (k1) {
-                            acc = sub_mul<EXACT>(acc, sval[(j + 1) * 32 + lane], x1);
-                            if (k2) {
-                                acc = sub_mul<EXACT>(acc, sval[(j + 2) * 32 + lane], x2);
-                                if (k3) {
-                                    acc = sub_mul<EXACT>(acc, sval[(j + 3) * 32 + lane], x3);
-                                    j += 4;
-                                } else
-                                    j += 3;
-                            } else
-                                j += 2;
-                        } else
-                            j += 1;
+                    double xv;
+                    if (j < len && poll_dep(e, P.mail, P.epoch, ring, P.ring_mask, xv)) {
+                        acc = sub_mul<EXACT>(acc, v, xv);
+                        ++j;
+                        // burst: the remaining dependencies are usually there too -- poll up to three at once,
+                        // consume them in the stored order (the reference's accumulation order)
+                        while (j < len) {
+                            const int nw = len - j;
+                            const int e0 = sidx[j * 32 + lane];
+                            const int e1 = nw > 1 ? sidx[(j + 1) * 32 + lane] : 0;
+                            const int e2 = nw > 2 ? sidx[(j + 2) * 32 + lane] : 0;
+                            double x0, x1 = 0.0, x2 = 0.0;
+                            const bool k0 = poll_dep(e0, P.mail, P.epoch, ring, P.ring_mask, x0);
+                            const bool k1 = nw > 1 && poll_dep(e1, P.mail, P.epoch, ring, P.ring_mask, x1);
+                            const bool k2 = nw > 2 && poll_dep(e2, P.mail, P.epoch, ring, P.ring_mask, x2);
+                            if (!k0) {
+                                e = e0;
+                                v = sval[j * 32 + lane];
+                                break;
+                            }
+                            acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], x0);
+                            ++j;
+                            if (!k1) {
+                                if (nw > 1) {
+                                    e = e1;
+                                    v = sval[j * 32 + lane];
+                                }
+                                break;
+                            }
+                            acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], x1);
+                            ++j;
+                            if (!k2) {
+                                if (nw > 2) {
+                                    e = e2;
+                                    v = sval[j * 32 + lane];
+                                }
+                                break;
+                            }
+                            acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], x2);
+                            ++j;
+                        }
                     }
                     if (j >= len) {
                         xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
@@ -373,6 +399,8 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.val = T.val.p;
     P.diag = T.diag.p;
     P.pubmask = T.pubmask.p;
+    P.gate = T.gate.p;
+    P.slack = (int)opt.gate_slack;
     P.mail = T.mail.p;
     P.ring_mask = T.cfg_ring_chunks * 32 - 1;
     P.rc = T.cfg_ring_chunks;
