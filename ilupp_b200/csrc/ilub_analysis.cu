@@ -364,7 +364,7 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
             srcpos[base + t] = -1;
         }
     }
-    bool intra = false;
+    bool intra = false, remote = false;
     const int lv = row >= 0 ? level[row] : 0x7fffffff;
     const int lvmin = __reduce_min_sync(0xffffffffu, lv);
     int g = -1;  // last local chunk (CTA numbering) feeding the rows of this chunk's lowest level
@@ -388,12 +388,14 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
             enc = kLocalBit | (unsigned)(pd - (cfirst << 5));
         } else {
             enc = (unsigned)d;
+            remote = true;
             pub[d] = 1;  // row d must publish through the mailbox
         }
         idx[at] = (int)enc;
         srcpos[at] = S.val_pos ? S.val_pos[q] : q;
     }
-    if (__any_sync(0xffffffffu, intra) && lane == 0) ckind[c] |= 2;
+    const bool any_intra = __any_sync(0xffffffffu, intra), any_remote = __any_sync(0xffffffffu, remote);
+    if (lane == 0) ckind[c] = (unsigned char)(kind | (any_intra ? 2 : 0) | (any_remote ? 4 : 0));
     g = __reduce_max_sync(0xffffffffu, g + 1) - 1;
     if (lane == 0) gate[c] = g;
 }

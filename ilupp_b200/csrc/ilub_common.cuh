@@ -69,7 +69,7 @@ struct Options {
     int64_t near_window = 112;  // chunks; dependencies this close (same CTA) go through shared memory
     int64_t ring_chunks = 256;  // shared-memory x ring, in 32-row chunks (power of two, >= 2*near_window)
     int64_t wcap = 8;           // widest lane-per-row chunk (slabs); wider chunks are warp-cooperative
-    int64_t gate_slack = 2;     // start fine-grained polling this many chunks before the gate chunk completes
+    int64_t gate_slack = 8;     // start fine-grained polling this many chunks before the gate chunk completes
     int64_t stages = 2;         // TMA staging depth per warp
     int64_t spin_limit_ms = 1500;
     int64_t partition = 0;      // 0 auto (geometric strips/pencils when strides are detected), 1 contiguous ranges
@@ -87,6 +87,7 @@ constexpr int kLanes = 32;
 //                               (value + tag read from the x ring in one 128-bit access)
 constexpr unsigned kLocalBit = 0x80000000u;
 constexpr unsigned kIntraBit = 0x40000000u;
+constexpr unsigned kReadyBit = 0x40000000u;  // run-time only: staged coefficient already holds v*x
 
 // One triangular solve packed in solve order (see DESIGN.md "data layout in HBM").
 struct TriSolve {
@@ -105,7 +106,7 @@ struct TriSolve {
     DevBuf<int> rowpos;           // [n] (chunk << 5 | lane) of every row
     DevBuf<int> part_chunk_ptr;   // [nparts + 1]
     DevBuf<int> chunk_ptr;        // [nchunks + 1] slab offset of every chunk
-    DevBuf<unsigned char> ckind;  // [nchunks] bit0: warp-cooperative (kind B); bit1: has same-chunk deps
+    DevBuf<unsigned char> ckind;  // [nchunks] bit0: warp-cooperative (kind B); bit1: has same-chunk deps; bit2: has mailbox deps
     DevBuf<int> rows;             // [nchunks * 32] original row per lane (-1 = padding)
     DevBuf<int> rlen;             // [nchunks * 32] number of off-diagonal entries per lane
     DevBuf<int> idx;              // [nslabs * 32] encoded dependencies

@@ -79,6 +79,10 @@ struct Watchdog {
 __device__ __forceinline__ bool poll_dep(int e, const ulonglong2* mail, unsigned long long epoch,
                                          const ulonglong2* ring, int ring_mask, double& xv) {
     if (e >= 0) return ld_mail(mail + e, epoch, xv);
+    if ((unsigned)e & kReadyBit) {  // remote value already folded into the staged coefficient
+        xv = 1.0;
+        return true;
+    }
     const int lp = e & 0x3fffffff;
     return ld_ring(ring + (lp & ring_mask), (unsigned long long)lp + 1ull, xv);
 }
@@ -137,6 +141,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
         const int c = c0 + lc;
         const int nlc = lc + W;
         const bool has_next = nlc < nloc;
+        fence_proxy_async();  // generic-proxy writes into a stage (remote prefetch) before the next bulk copy into it
         __syncwarp();
         if (has_next && lane == 0 && P.nstages > 1) issue(nlc, it + 1);
         int r1 = -1, len1 = 0;
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
         const int w = P.chunk_ptr[c + 1] - cp;
         const unsigned kind = P.ckind[c];
         const unsigned pubm = P.pubmask[c];
+        const bool pubm_remote = (kind & 4) != 0;  // chunk has mailbox dependencies
         double xfin = 0.0;
 
         // (1) the ring slots of chunk lc are those of chunk lc - rc: they may be overwritten once every
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                 v = __reduce_min_sync(FULL, v);
                 done_cache = v;
                 if (v >= need) break;
-                __nanosleep(40);
+                if (need - v > 4) __nanosleep(64);
                 if (wd.expired(105)) return;
             }
         }
@@ -185,6 +191,31 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                 phasebits ^= 1u << st;
             }
             const double dinv = EXACT ? 0.0 : 1.0 / d;
+            // Remote prefetch: resolve mailbox dependencies up front (a few bounded attempts, all lanes and
+            // slabs in parallel) and fold them into the staged coefficient (v := v*x, index := READY), so
+            // that the ordered hand-off loop below never waits on an L2 round trip in the middle of a
+            // chain.  Anything not there yet is simply polled in place later -- no blocking, no deadlock.
+            if (pubm_remote) {
+                int* widx = const_cast<int*>(sidx);
+                double* wval = const_cast<double*>(sval);
+                for (int attempt = 0; attempt < 4; ++attempt) {
+                    bool pending = false;
+                    for (int jj = 0; jj < len; ++jj) {
+                        const int ee = widx[jj * 32 + lane];
+                        if (ee >= 0) {
+                            double xr;
+                            if (ld_mail(P.mail + ee, P.epoch, xr)) {
+                                const double vv = wval[jj * 32 + lane];
+                                wval[jj * 32 + lane] = EXACT ? __dmul_rn(vv, xr) : vv * xr;
+                                widx[jj * 32 + lane] = (int)(kLocalBit | kReadyBit);
+                            } else {
+                                pending = true;
+                            }
+                        }
+                    }
+                    if (!__any_sync(FULL, pending)) break;
+                }
+            }
             int j = 0;
             bool fin = false;
             // the dependency a lane is waiting for stays in registers: a failed round costs one 16-byte poll
@@ -286,15 +317,18 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
             }
         }
 
-        // ---------------------------------------------------------------- publish to global memory
+        // ---------------------------------------------------------------- progress word, then global memory
+        // (the release fence of the progress word must not wait for the global stores below)
+        __syncwarp();
+        if (lane == 0) st_release_cta_s32(&warp_cur[warp], has_next ? nlc : INT_MAX);
         if (r >= 0) {
             P.x[r] = xfin;
             if ((pubm >> lane) & 1u) st_mail(P.mail + r, xfin, P.epoch);
         }
-        __syncwarp();
-        if (lane == 0) {
-            st_release_cta_s32(&warp_cur[warp], has_next ? nlc : INT_MAX);
-            if (has_next && P.nstages == 1) issue(nlc, it + 1);
+        if (has_next && P.nstages == 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) issue(nlc, it + 1);
         }
         // rotate the software pipeline
         r = r1;

@@ -1,0 +1,22 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+B="timeout 120 python scripts/bench_apply.py"
+{
+timeout 600 python scripts/dev_gpu_check.py quick 2>&1 | grep -E "FAIL|Traceback|Error|apply:|rror" | tail -30
+$B p3d128 ichol0 check=1
+$B p3d128 ichol0 exact=0 check=1
+$B p3d128 ichol0 exact=0 gate_slack=2
+$B p3d128 ichol0 exact=0 gate_slack=1000
+$B p3d128 ichol0 exact=0 warps_per_cta=32
+$B p3d128 ichol0 exact=0 warps_per_cta=8
+$B p3d128 ilu0 exact=0
+$B p2d256 ilu0 exact=0
+$B p2d256 ilu0 exact=0 nparts=4
+$B p2d256 ilu0 exact=0 nparts=4 gate_slack=1000
+$B p2d256 ilu0 exact=0 nparts=2 warps_per_cta=8
+$B p3d64 ichol0 exact=0
+$B cd3d160 ilu0 exact=0 check=1
+} 2>&1 | tee gpurun_out/sweep5.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_trsv_syncfree -s 6 -c 1 -o gpurun_out/trsv_r1c python scripts/bench_apply.py p3d128 ichol0 exact=0 reps=3 > gpurun_out/ncu3.log 2>&1
+tail -2 gpurun_out/ncu3.log
