@@ -15,6 +15,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <iostream>
 #include <memory>
@@ -23,6 +24,8 @@
 #include <typeinfo>
 
 #include "ilub.h"
+
+extern "C" int ilub_debug_chunks(ilub_handle* h, int which_solve, int32_t* nchunks, int32_t* rows, long long* trace);
 
 namespace py = pybind11;
 
@@ -320,6 +323,16 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
              },
              py::arg("b"), py::arg("x"), py::arg("rtol") = 1e-4, py::arg("atol") = 1e-4, py::arg("max_iter") = 500,
              py::arg("stream") = 0)
+        .def("debug_chunks",
+             [](const P& pr, int which) {
+                 int32_t nch = 0;
+                 check(ilub_debug_chunks(pr.h, which, &nch, nullptr, nullptr));
+                 py::array_t<Integer> rows((py::ssize_t)nch * 32);
+                 py::array_t<long long> trace((py::ssize_t)nch * 4);
+                 std::fill(trace.mutable_data(), trace.mutable_data() + (size_t)nch * 4, 0LL);
+                 check(ilub_debug_chunks(pr.h, which, &nch, rows.mutable_data(), trace.mutable_data()));
+                 return py::make_tuple(rows, trace);
+             })
         .def_property_readonly("timings_ms",
                                [](const P& pr) {
                                    double t[4];

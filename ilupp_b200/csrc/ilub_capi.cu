@@ -429,6 +429,7 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "spin_limit_ms") o.spin_limit_ms = value;
         else if (k == "partition") o.partition = value;
         else if (k == "nparts") o.nparts = value;
+        else if (k == "trace") o.trace = value;
         else if (k == "gate_slack") o.gate_slack = value;
         else if (k == "part_kb") o.part_kb = value;
         else if (k == "factor_group") o.factor_group = value;
@@ -456,6 +457,21 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "part_kb") *value = o.part_kb;
         else if (k == "factor_group") *value = o.factor_group;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
+    });
+}
+
+/* debug (not part of the supported ABI): chunk -> row map and per-chunk clock stamps of one solve */
+ILUB_API int ilub_debug_chunks(ilub_handle* h, int which_solve, int32_t* nchunks, int32_t* rows, long long* trace) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && nchunks, ILUB_ERR_INVALID, "null argument");
+        DeviceGuard guard(h->device);
+        TriSolve& T = h->solve[slot_of(h, which_solve)];
+        ILUB_REQUIRE(T.built, ILUB_ERR_INVALID, "solve not built");
+        *nchunks = T.nchunks;
+        ILUB_CUDA(cudaDeviceSynchronize());
+        if (rows) ILUB_CUDA(cudaMemcpy(rows, T.rows.p, sizeof(int) * (size_t)T.nchunks * 32, cudaMemcpyDeviceToHost));
+        if (trace && T.trace.n >= (size_t)T.nchunks * 4)
+            ILUB_CUDA(cudaMemcpy(trace, T.trace.p, sizeof(long long) * (size_t)T.nchunks * 4, cudaMemcpyDeviceToHost));
     });
 }
 

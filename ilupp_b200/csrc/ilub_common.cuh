@@ -75,6 +75,7 @@ struct Options {
     int64_t partition = 0;      // 0 auto (geometric strips/pencils when strides are detected), 1 contiguous ranges
     int64_t nparts = 0;         // 0 auto, else number of CTAs/parts to aim for
     int64_t part_kb = 256;      // auto nparts: aim for at least this many KB of solve data per CTA
+    int64_t trace = 0;          // debug: record per-chunk clock stamps in the sync-free solve
     int64_t factor_group = 0;   // lanes per row in the factorisation kernels (0 = auto)
 };
 Options& options();
@@ -124,6 +125,7 @@ struct TriSolve {
     int cfg_warps = 16, cfg_ring_chunks = 256, cfg_near = 96, cfg_stages = 2, cfg_stage_slabs = 1;
     size_t cfg_smem = 0;
     // level-set listing for the level-scheduled variant / ilub_get_level_sets (built on demand)
+    DevBuf<long long> trace;      // debug stamps (option trace)
     DevBuf<int> lvl_ptr, lvl_rows;
     bool lvl_built = false;
 };

@@ -54,6 +54,7 @@ struct TrsvParams {
     int unit_diag;
     int* status;
     long long spin_limit;
+    long long* trace;  // debug: 4 clock64 stamps per chunk (start, gate passed, data staged, resolved)
 };
 
 struct Watchdog {
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
             len1 = P.rlen[(size_t)(c0 + nlc) * 32 + lane];
             if (!P.unit_diag) d1 = P.diag[(size_t)(c0 + nlc) * 32 + lane];
         }
+        if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 0] = clock64();
         const int cp = P.chunk_ptr[c];
         const int w = P.chunk_ptr[c + 1] - cp;
         const unsigned kind = P.ckind[c];
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                 if (wd.expired(105)) return;
             }
         }
+        if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 1] = clock64();
         ulonglong2* myslot = ring + ((lc * 32 + lane) & P.ring_mask);
         const unsigned long long mytag = (unsigned long long)(lc * 32 + lane) + 1ull;
 
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                     if (wd.expired(102)) return;
                 phasebits ^= 1u << st;
             }
+            if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 2] = clock64();
             const double dinv = EXACT ? 0.0 : 1.0 / d;
             // Remote prefetch: resolve mailbox dependencies up front (a few bounded attempts, all lanes and
             // slabs in parallel) and fold them into the staged coefficient (v := v*x, index := READY), so
@@ -317,6 +321,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
             }
         }
 
+        if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 3] = clock64();
         // ---------------------------------------------------------------- progress word, then global memory
         // (the release fence of the progress word must not wait for the global stores below)
         __syncwarp();
@@ -444,6 +449,8 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.unit_diag = T.unit_diag ? 1 : 0;
     P.status = h->status.p;
     P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz;
+    if (opt.trace && T.trace.n < (size_t)T.nchunks * 4) T.trace.alloc((size_t)T.nchunks * 4);
+    P.trace = opt.trace ? T.trace.p : nullptr;
     static thread_local bool attr_set[2] = {false, false};
     if (!attr_set[exact ? 1 : 0]) {
         if (exact)
