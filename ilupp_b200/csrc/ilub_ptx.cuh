@@ -84,6 +84,18 @@ __device__ __forceinline__ bool ld_ring(const ulonglong2* p, unsigned long long 
     x = __longlong_as_double(xb);
     return t == tag;
 }
+__device__ __forceinline__ void ld_b128_cta(uint32_t saddr, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.cta.shared.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(lo), "=l"(hi)
+                 : "r"(saddr)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_b128_gpu(const ulonglong2* p, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.gpu.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+                 : "=l"(lo), "=l"(hi)
+                 : "l"(p)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 // ---- mbarrier + bulk async copy (TMA engine, 1-D) ----------------------------------------------

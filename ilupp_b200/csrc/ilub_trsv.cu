@@ -74,6 +74,16 @@ struct Watchdog {
         }
         return false;
     }
+    // unconditional variant for callers that already rate-limit
+    __device__ __forceinline__ bool expired_now(int code) {
+        if (t0 == 0) t0 = clock64();
+        if (*(volatile int*)status != 0) return true;
+        if (clock64() - t0 > limit) {
+            atomicCAS(status, 0, code);
+            return true;
+        }
+        return false;
+    }
 };
 
 // one dependency poll: mailbox (global, e >= 0) or x ring (shared, e < 0); true when the value is there
@@ -220,67 +230,67 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                     if (!__any_sync(FULL, pending)) break;
                 }
             }
+            // ---- ordered hand-off loop.  Per lane: the dependency it is waiting for lives in registers as
+            // (address, expected tag, coefficient).  The warp spins in a TIGHT loop (one 16-byte load, one
+            // compare, one vote) until some lane's dependency has arrived; only then does it run the heavier
+            // progress code for the lanes that can move.
             int j = 0;
             bool fin = false;
-            // the dependency a lane is waiting for stays in registers: a failed round costs one 16-byte poll
-            int e = 0;
+            bool is_glob = false;
+            uint32_t saddr = 0;
+            const ulonglong2* gaddr = P.mail;
+            unsigned long long etag = 0ull;
             double v = 0.0;
-            if (len > 0) {
-                e = sidx[lane];
-                v = sval[lane];
-            }
-            while (true) {
-                if (!fin) {
-                    double xv;
-                    if (j < len && poll_dep(e, P.mail, P.epoch, ring, P.ring_mask, xv)) {
-                        acc = sub_mul<EXACT>(acc, v, xv);
+            // walk forward from dependency j: consume everything already available, park on the first that is not
+            auto advance = [&]() {
+                while (j < len) {
+                    const int e_ = sidx[j * 32 + lane];
+                    const double v_ = sval[j * 32 + lane];
+                    double x_;
+                    if (poll_dep(e_, P.mail, P.epoch, ring, P.ring_mask, x_)) {
+                        acc = sub_mul<EXACT>(acc, v_, x_);
                         ++j;
-                        // burst: the remaining dependencies are usually there too -- poll up to three at once,
-                        // consume them in the stored order (the reference's accumulation order)
-                        while (j < len) {
-                            const int nw = len - j;
-                            const int e0 = sidx[j * 32 + lane];
-                            const int e1 = nw > 1 ? sidx[(j + 1) * 32 + lane] : 0;
-                            const int e2 = nw > 2 ? sidx[(j + 2) * 32 + lane] : 0;
-                            double x0, x1 = 0.0, x2 = 0.0;
-                            const bool k0 = poll_dep(e0, P.mail, P.epoch, ring, P.ring_mask, x0);
-                            const bool k1 = nw > 1 && poll_dep(e1, P.mail, P.epoch, ring, P.ring_mask, x1);
-                            const bool k2 = nw > 2 && poll_dep(e2, P.mail, P.epoch, ring, P.ring_mask, x2);
-                            if (!k0) {
-                                e = e0;
-                                v = sval[j * 32 + lane];
-                                break;
-                            }
-                            acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], x0);
-                            ++j;
-                            if (!k1) {
-                                if (nw > 1) {
-                                    e = e1;
-                                    v = sval[j * 32 + lane];
-                                }
-                                break;
-                            }
-                            acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], x1);
-                            ++j;
-                            if (!k2) {
-                                if (nw > 2) {
-                                    e = e2;
-                                    v = sval[j * 32 + lane];
-                                }
-                                break;
-                            }
-                            acc = sub_mul<EXACT>(acc, sval[j * 32 + lane], x2);
-                            ++j;
+                    } else {
+                        v = v_;
+                        is_glob = e_ >= 0;
+                        if (is_glob) {
+                            gaddr = P.mail + e_;
+                            etag = P.epoch;
+                        } else {
+                            const int lp = e_ & 0x3fffffff;
+                            saddr = smem_u32(ring + (lp & P.ring_mask));
+                            etag = (unsigned long long)lp + 1ull;
                         }
-                    }
-                    if (j >= len) {
-                        xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
-                        if (r >= 0) st_ring(myslot, xfin, mytag);
-                        fin = true;
+                        return;
                     }
                 }
-                if (__all_sync(FULL, fin)) break;
-                if (wd.expired(103)) return;
+                xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
+                if (r >= 0) st_ring(myslot, xfin, mytag);
+                fin = true;
+            };
+            advance();
+            while (!__all_sync(FULL, fin)) {
+                double xv = 0.0;
+                bool ok = false;
+                unsigned spins = 0;
+                while (true) {  // tight wait
+                    if (!fin) {
+                        unsigned long long xb, t;
+                        if (is_glob)
+                            ld_b128_gpu(gaddr, xb, t);
+                        else
+                            ld_b128_cta(saddr, xb, t);
+                        ok = (t == etag);
+                        xv = __longlong_as_double((long long)xb);
+                    }
+                    if (__any_sync(FULL, ok)) break;
+                    if ((++spins & 0xfffu) == 0 && wd.expired_now(103)) return;
+                }
+                if (ok) {
+                    acc = sub_mul<EXACT>(acc, v, xv);
+                    ++j;
+                    advance();
+                }
             }
         } else {
             // ------------------------------------------------------------ warp-cooperative chunk
