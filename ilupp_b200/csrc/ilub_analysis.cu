@@ -367,7 +367,7 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
     bool intra = false, remote = false;
     const int lv = row >= 0 ? level[row] : 0x7fffffff;
     const int lvmin = __reduce_min_sync(0xffffffffu, lv);
-    int g = -1;  // last local chunk (CTA numbering) feeding the rows of this chunk's lowest level
+    int g = -1;  // last local position (CTA numbering) feeding the rows of this chunk's lowest level
     const int b = row >= 0 ? src_beg(S, row) : 0;
     const int e = b + len;
     for (int j = 0; j < (kind ? len : w); ++j) {
@@ -384,7 +384,7 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
         unsigned enc;
         if (dc >= cfirst && dc <= c && c - dc <= near) {
             if (dc == c) intra = true;
-            if (lv == lvmin) g = max(g, dc - cfirst);
+            if (lv == lvmin) g = max(g, pd - (cfirst << 5));
             enc = kLocalBit | (unsigned)(pd - (cfirst << 5));
         } else {
             enc = (unsigned)d;

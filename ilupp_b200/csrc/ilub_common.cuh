@@ -115,7 +115,7 @@ struct TriSolve {
     DevBuf<double> val;           // [nslabs * 32]
     DevBuf<double> diag;          // [nchunks * 32]
     DevBuf<int> diagpos;          // [nchunks * 32] position of the diagonal value (-1: unit / padding)
-    DevBuf<int> gate;             // [nchunks] last local chunk feeding this chunk's lowest level (-1: none)
+    DevBuf<int> gate;             // [nchunks] gate row: last local position feeding this chunk's lowest level (-1: none)
     DevBuf<unsigned> pubmask;     // [nchunks] lanes whose row is read through the global path by someone
     DevBuf<ulonglong2> mail;      // [n] {x bits, epoch tag}: the global dependency path (one 16-B atomic access)
     unsigned long long epoch = 0;

@@ -170,20 +170,35 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
         const bool pubm_remote = (kind & 4) != 0;  // chunk has mailbox dependencies
         double xfin = 0.0;
 
-        // (1) the ring slots of chunk lc are those of chunk lc - rc: they may be overwritten once every
-        //     chunk that could still read them through shared memory (ids <= lc - rc + near) has completed;
-        // (2) gate: do not start fine-grained polling (16-byte shared-memory reads by every lane) before
-        //     the chunks feeding this chunk's lowest level are (almost) done -- far-away warps sleep on the
-        //     cheap per-warp progress words instead of saturating the shared-memory pipe.
-        const int need = max(lc - P.rc + P.near + 1, P.gate[c] - P.slack + 1);
+        // (1) ring safety: the ring slots of chunk lc are those of chunk lc - rc; they may be overwritten once
+        //     every chunk that could still read them through shared memory (ids <= lc - rc + near) is done.
+        const int need = lc - P.rc + P.near + 1;
         if (need > done_cache) {
             while (true) {
                 int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
                 v = __reduce_min_sync(FULL, v);
                 done_cache = v;
                 if (v >= need) break;
-                if (need - v > 4) __nanosleep(64);
+                __nanosleep(64);
                 if (wd.expired(105)) return;
+            }
+        }
+        // (2) gate row: the last row (in processing order) that feeds this chunk's lowest level.  Until it is
+        //     published nothing in this chunk can finish, so the whole warp waits on that ONE ring entry
+        //     (same address for all lanes: a broadcast, one shared-memory wavefront per poll) instead of
+        //     32 lanes polling 32 different entries and saturating the shared-memory pipe for the warps
+        //     that are on the critical path.  The gate row has a strictly lower level than every row of
+        //     this chunk, so blocking on it cannot create a cycle.
+        const int gate_lp = P.gate[c];
+        if (gate_lp >= 0 && P.slack >= 0) {
+            const uint32_t ga = smem_u32(ring + (gate_lp & P.ring_mask));
+            const unsigned long long gt = (unsigned long long)gate_lp + 1ull;
+            unsigned spins = 0;
+            while (true) {
+                unsigned long long xb, t;
+                ld_b128_cta(ga, xb, t);
+                if (t == gt) break;
+                if ((++spins & 0xfffu) == 0 && wd.expired_now(106)) return;
             }
         }
         if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 1] = clock64();

@@ -6,8 +6,8 @@ B="timeout 120 python scripts/bench_apply.py"
 timeout 600 python scripts/dev_gpu_check.py quick 2>&1 | grep -E "FAIL|Traceback|Error|apply:|rror" | tail -30
 $B p3d128 ichol0 check=1
 $B p3d128 ichol0 exact=0 check=1
-$B p3d128 ichol0 exact=0 gate_slack=2
-$B p3d128 ichol0 exact=0 gate_slack=1000
+$B p3d128 ichol0 exact=0 gate_slack=-1
+$B p3d128 ichol0 exact=0 gate_slack=-1 warps_per_cta=32
 $B p3d128 ichol0 exact=0 warps_per_cta=32
 $B p3d128 ichol0 exact=0 warps_per_cta=8
 $B p3d128 ilu0 exact=0
