@@ -190,17 +190,28 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
         //     that are on the critical path.  The gate row has a strictly lower level than every row of
         //     this chunk, so blocking on it cannot create a cycle.
         const int gate_lp = P.gate[c];
-        if (gate_lp >= 0 && P.slack >= 0) {
+        auto wait_gate = [&]() -> bool {
+            if (gate_lp < 0 || P.slack < 0) return true;
             const uint32_t ga = smem_u32(ring + (gate_lp & P.ring_mask));
             const unsigned long long gt = (unsigned long long)gate_lp + 1ull;
+            const int gate_chunk = gate_lp >> 5;
             unsigned spins = 0;
             while (true) {
-                unsigned long long xb, t;
-                ld_b128_cta(ga, xb, t);
-                if (t == gt) break;
-                if ((++spins & 0xfffu) == 0 && wd.expired_now(106)) return;
+                bool open = false;
+                if (lane == 0) {  // one lane polls: one shared-memory wavefront per round
+                    unsigned long long xb, t;
+                    ld_b128_cta(ga, xb, t);
+                    open = (t == gt);
+                }
+                if (__any_sync(FULL, open)) return true;
+                if (gate_chunk - done_cache > P.slack) {  // far from the frontier: look at the progress words, sleep
+                    int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
+                    done_cache = __reduce_min_sync(FULL, v);
+                    if (gate_chunk - done_cache > P.slack) __nanosleep(100);
+                }
+                if ((++spins & 0x3ffu) == 0 && wd.expired_now(106)) return false;
             }
-        }
+        };
         if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 1] = clock64();
         ulonglong2* myslot = ring + ((lc * 32 + lane) & P.ring_mask);
         const unsigned long long mytag = (unsigned long long)(lc * 32 + lane) + 1ull;
@@ -218,7 +229,6 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                     if (wd.expired(102)) return;
                 phasebits ^= 1u << st;
             }
-            if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 2] = clock64();
             const double dinv = EXACT ? 0.0 : 1.0 / d;
             // Remote prefetch: resolve mailbox dependencies up front (a few bounded attempts, all lanes and
             // slabs in parallel) and fold them into the staged coefficient (v := v*x, index := READY), so
@@ -245,11 +255,44 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                     if (!__any_sync(FULL, pending)) break;
                 }
             }
+            // the first (up to) four dependencies of the lane go to registers while the warp is still waiting
+            // at its gate: once the gate opens they are polled all at once (one shared-memory round trip)
+            int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+            double c0v = 0.0, c1v = 0.0, c2v = 0.0, c3v = 0.0;
+            if (len > 0) { q0 = sidx[lane];       c0v = sval[lane]; }
+            if (len > 1) { q1 = sidx[32 + lane];  c1v = sval[32 + lane]; }
+            if (len > 2) { q2 = sidx[64 + lane];  c2v = sval[64 + lane]; }
+            if (len > 3) { q3 = sidx[96 + lane];  c3v = sval[96 + lane]; }
+            if (!wait_gate()) return;
+            if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 2] = clock64();
+            int j = 0;
+            {
+                double y0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+                const bool k0 = len > 0 && poll_dep(q0, P.mail, P.epoch, ring, P.ring_mask, y0);
+                const bool k1 = len > 1 && poll_dep(q1, P.mail, P.epoch, ring, P.ring_mask, y1);
+                const bool k2 = len > 2 && poll_dep(q2, P.mail, P.epoch, ring, P.ring_mask, y2);
+                const bool k3 = len > 3 && poll_dep(q3, P.mail, P.epoch, ring, P.ring_mask, y3);
+                if (k0) {
+                    acc = sub_mul<EXACT>(acc, c0v, y0);
+                    j = 1;
+                    if (k1) {
+                        acc = sub_mul<EXACT>(acc, c1v, y1);
+                        j = 2;
+                        if (k2) {
+                            acc = sub_mul<EXACT>(acc, c2v, y2);
+                            j = 3;
+                            if (k3) {
+                                acc = sub_mul<EXACT>(acc, c3v, y3);
+                                j = 4;
+                            }
+                        }
+                    }
+                }
+            }
             // ---- ordered hand-off loop.  Per lane: the dependency it is waiting for lives in registers as
             // (address, expected tag, coefficient).  The warp spins in a TIGHT loop (one 16-byte load, one
             // compare, one vote) until some lane's dependency has arrived; only then does it run the heavier
             // progress code for the lanes that can move.
-            int j = 0;
             bool fin = false;
             bool is_glob = false;
             uint32_t saddr = 0;
@@ -309,6 +352,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
             }
         } else {
             // ------------------------------------------------------------ warp-cooperative chunk
+            if (!wait_gate()) return;
             int off = len;  // exclusive scan of len
             for (int s = 1; s < 32; s <<= 1) {
                 const int t = __shfl_up_sync(FULL, off, s);

@@ -7,7 +7,7 @@ timeout 600 python scripts/dev_gpu_check.py quick 2>&1 | grep -E "FAIL|Traceback
 $B p3d128 ichol0 check=1
 $B p3d128 ichol0 exact=0 check=1
 $B p3d128 ichol0 exact=0 gate_slack=-1
-$B p3d128 ichol0 exact=0 gate_slack=-1 warps_per_cta=32
+$B p3d128 ichol0 exact=0 gate_slack=2
 $B p3d128 ichol0 exact=0 warps_per_cta=32
 $B p3d128 ichol0 exact=0 warps_per_cta=8
 $B p3d128 ilu0 exact=0
