@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 ILU(0)/IChol(0) path (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--no-batched]
+
+One "step" = one preconditioner application (both triangular solves, one right-hand side) of the
+IChol(0) factor of the 3-D 7-point Poisson matrix 128^3 (BASELINE.json configs[1]), on every GPU for its
+own right-hand side (multi-RHS apply distributed per GPU: weak scaling, no data-path collective).
+metric = algorithmic apply bandwidth in GB/s (12*(nnz(L)+nnz(L^T)) + 8*(n+1) + 32*n bytes
+per apply).  `value` is measured with inputs resident in HBM (CUDA events on the launching stream);
+`e2e` is the same metric through the public API with HOST (pinned) buffers, host<->device copies inside
+the timed region.  The JSON line also carries factor ms, the BASELINE config-5 batched throughput
+(4096 systems sharded over the ranks), the roofline of the dominant kernel and the reference's own CPU
+path timed on this box (cpu_baseline).
+
+--impl reference times the UNMODIFIED reference C++ (oracle/_ref, built from /root/reference/src) on
+the host cores for the same metric and workload (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ichol0_apply_bandwidth"
+UNIT = "GB/s"
+WORKLOAD = "IChol0Preconditioner apply, 3-D 7-point Poisson 128^3 (n=2,097,152, nnz=14,581,760), fp64, 1 RHS per GPU"
+GRID = 128
+
+
+def apply_bytes(total_nnz, n, ichol=True):
+    nnz_lu = 2 * total_nnz if ichol else total_nnz
+    return 12 * nnz_lu + 8 * (n + 1) + 32 * n
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_apply(steps, warmup):
+    """The reference's own C++ ILU0/IChol0 path on the host (oracle/_ref when built, else the C port)."""
+    import oracle
+    from ilupp_b200 import problems as P
+    A = P.poisson3d(GRID)
+    n = A.shape[0]
+    kind = "reference" if oracle.ref is not None else "port"
+    t0 = time.perf_counter()
+    if oracle.ref is not None:
+        R = oracle.ref.IChol0(A)
+        total_nnz = R.total_nnz
+        apply_inplace = R.apply_inplace
+    else:
+        L = oracle.port.ichol0(A)
+        total_nnz = L.nnz
+        Lp, Li, Lx = L.indptr.astype(np.int32), L.indices.astype(np.int32), L.data
+
+        def apply_inplace(y):
+            oracle.port.lib.oracle_apply_llt(n, Lp, Li, Lx, y)
+    factor_s = time.perf_counter() - t0
+    b = P.rhs(n, 0)
+    y = b.copy()
+    for _ in range(warmup):
+        y[:] = b
+        apply_inplace(y)
+    ts = []
+    for _ in range(steps):
+        y[:] = b
+        t = time.perf_counter()
+        apply_inplace(y)
+        ts.append(time.perf_counter() - t)
+    by = apply_bytes(total_nnz, n)
+    return {"kind": kind, "cores": 1, "factor_ms": factor_s * 1e3, "apply_ms": float(np.mean(ts)) * 1e3,
+            "gbs": by / float(np.mean(ts)) / 1e9, "steps": steps,
+            "sample": "1 IChol0 factorisation + %d applies of the full 128^3 workload, single thread "
+                      "(the reference has no threading), %d host cores present" % (steps, os.cpu_count())}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_apply(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": res["gbs"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["apply_ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "host": "reference C++ (%s), 1 thread" % res["kind"]},
+            "factor_ms": res["factor_ms"],
+            "cpu_baseline": {"value": res["gbs"], "unit": UNIT, "cores": 1, "kind": res["kind"], "sample": res["sample"]},
+            "e2e": {"value": res["gbs"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import ilupp_b200 as ilupp
+    from ilupp_b200 import problems as P
+    from ilupp_b200.sharding import barrier, init_process_group, max_over_ranks, shard_range, sum_over_ranks
+
+    rank, local, world = init_process_group()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ilupp.set_option("exact", args.exact)
+    peak, peak_src = measured_peaks()
+
+    A = P.poisson3d(GRID)
+    n = A.shape[0]
+    t0 = time.perf_counter()
+    B = ilupp.IChol0Preconditioner(A, device=local)
+    create_wall_ms = (time.perf_counter() - t0) * 1e3
+    sym_ms, num_ms, pack_ms, tot_ms = B.timings_ms
+    # numeric-only re-factorisation (unchanged pattern), device-resident values
+    a_dev = torch.from_numpy(A.data).to(dev)
+    B.refactor(a_dev)
+    torch.cuda.synchronize()
+    refactor_ms = B.timings_ms[3]
+    total_nnz = B.total_nnz
+    by = apply_bytes(total_nnz, n)
+
+    b = P.rhs(n, rank)
+    x0 = torch.from_numpy(b).to(dev)
+    x = x0.clone()
+    stream = torch.cuda.current_stream()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for _ in range(args.warmup):
+        x.copy_(x0)
+        B.apply(x)
+    torch.cuda.synchronize()
+    launches0 = B.stats["launches"]
+    barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        t_wall0 = time.perf_counter()
+        for k in range(args.steps):
+            x.copy_(x0)               # restore the right-hand side (not timed: outside the event pair)
+            evs[k][0].record(stream)
+            B.apply(x)                # two launches of the sync-free SpTRSV kernel on `stream`
+            evs[k][1].record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t_wall0
+    barrier()
+    launches = B.stats["launches"] - launches0
+    step_ms = np.array([a.elapsed_time(bq) for a, bq in evs])
+    my_total_ms = float(step_ms.sum())
+    total_ms = max_over_ranks(my_total_ms, dev)
+    ms_per_step = total_ms / args.steps
+    value = world * by / (ms_per_step * 1e-3) / 1e9
+    clocks = clk.summary()
+
+    # ---- e2e: public API with host (pinned) buffers, copies inside the timed region
+    hb = torch.from_numpy(b).pin_memory()
+    hx = torch.empty_like(hb).pin_memory()
+    hx_np = hx.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        hx.copy_(hb)
+        B.apply(hx_np)
+    barrier()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(e2e_steps):
+        B.apply(hx_np)                # H2D 8n bytes + apply + D2H 8n bytes, returns when the result is on the host
+    e2e_s = max_over_ranks(time.perf_counter() - t, dev) / e2e_steps
+    e2e_value = world * by / e2e_s / 1e9
+
+    # ---- parity gate in the same run (rank 0): apply() against the CPU oracle on the same arrays
+    parity = None
+    cpu = None
+    if rank == 0:
+        import oracle
+        Lo = oracle.port.ichol0(A)
+        yo = oracle.port.apply_llt(Lo, b)
+        y = b.copy()
+        B.apply(y)
+        (L,) = B.factors()
+        parity = {"apply_relerr": float(np.abs(y - yo).max() / np.abs(yo).max()),
+                  "factor_relerr": float(np.abs(L.data - Lo.data).max() / np.abs(Lo.data).max()),
+                  "pattern_equal": bool(np.array_equal(L.indices, Lo.indices) and np.array_equal(L.indptr, Lo.indptr)),
+                  "bit_exact": bool(np.array_equal(y, yo))}
+        if world == 1 or True:
+            c = cpu_reference_apply(steps=40 if not args.quick else 5, warmup=2)
+            cpu = {"value": c["gbs"], "unit": UNIT, "cores": 1, "kind": c["kind"], "sample": c["sample"],
+                   "apply_ms": c["apply_ms"], "factor_ms": c["factor_ms"]}
+
+    # ---- BASELINE config 5: 4096 independent 2-D Poisson 128^2 systems, ILU0 factor + 16-RHS apply, sharded
+    batched = None
+    if not args.no_batched:
+        nsys_total = args.batched_systems
+        lo, hi = shard_range(nsys_total, rank, world)
+        pat, vals = P.batched_poisson2d(hi - lo, 128, first=lo)
+        n1 = pat.shape[0]
+        torch.cuda.synchronize()
+        barrier()
+        t = time.perf_counter()
+        Bb = ilupp.ILU0PreconditionerBatched(pat, vals, device=local)
+        create_s = time.perf_counter() - t
+        X = torch.randn((16, (hi - lo) * n1), dtype=torch.float64, device=dev).t()   # column-major (n, 16)
+        Bb.apply(X[:, :1])
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        Bb.apply(X)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        apply_ms = max_over_ranks(e0.elapsed_time(e1), dev)
+        fac_ms = max_over_ranks(Bb.timings_ms[1], dev)
+        sym_b = max_over_ranks(Bb.timings_ms[0], dev)
+        batched = {"systems": nsys_total, "rhs_per_system": 16, "n_per_system": n1,
+                   "factor_numeric_ms": fac_ms, "symbolic_ms": sym_b, "apply16_ms": apply_ms,
+                   "solves_per_s": nsys_total * 16 / (apply_ms * 1e-3),
+                   "systems_per_s": nsys_total / ((fac_ms + apply_ms) * 1e-3), "scaling": "strong"}
+        del Bb, X
+
+    if rank == 0:
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "trsv_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        kernel_ms = ms_per_step / 2.0            # one apply = forward + backward launch of the same kernel
+        achieved = (by / 2.0) / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bytes_per_apply": by, "total_nnz": int(total_nnz),
+                       "levels_per_solve": list(B.stats["levels"][:2]), "arithmetic": "exact (reference op order)" if args.exact else "fma + reciprocal diagonal",
+                       "l2": "inputs larger than L2: each apply streams %.0f MB of factor data (L2 = 126 MB)" % (by / 1e6),
+                       "partition": {"ctas": B.stats["nparts"], "mode": B.stats["part_mode"], "grid": list(B.stats["grid"])},
+                       "parallelism": "replicated factors, one RHS per GPU" if world > 1 else "single GPU"},
+            "pct_hbm_peak": 100.0 * value / world / peak,
+            "factor_ms": {"symbolic": sym_ms, "numeric": num_ms, "pack": pack_ms, "total": tot_ms,
+                          "refactor_numeric_plus_pack": refactor_ms, "create_wall_incl_h2d": create_wall_ms},
+            "roofline": {"bound": "hbm", "kernel": "k_trsv_syncfree", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": by / 2.0, "avg_launch_ms": kernel_ms,
+                         "second_bound": "dependency critical path: %d levels per solve" % B.stats["levels"][0]},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                    "ms_per_step": e2e_s * 1e3, "api": "IChol0Preconditioner.apply(numpy array in pinned host memory)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "parity": parity,
+            "batched": batched,
+            "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exact", type=int, default=0, help="1: reference operation order (bit-exact paths), 0: fma")
+    ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--batched-systems", type=int, default=4096)
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ilub.h declares; argument checking and the
+host-side mirror of the reference interface behave like the reference (no compute call needs a GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "ilupp_b200", "libilub.so")
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ilub.h")).read()
+    return sorted(set(re.findall(r"ILUB_API\s+[\w\s\*]+?\b(ilub_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = _declared_symbols()
+    for must in ("ilub_create_ilu0", "ilub_create_ichol0", "ilub_apply", "ilub_destroy", "ilub_total_nnz",
+                 "ilub_get_factor", "ilub_get_levels", "ilub_spmv", "ilub_bicgstab", "ilub_create_ilu0_batched",
+                 "ilub_refactor", "ilub_last_error", "ilub_index_size"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "libilub.so not built: run __graft_entry__.build()"
+    lib = C.CDLL(LIB)
+    missing = [s for s in _declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    lib.ilub_index_size.restype = C.c_int
+    assert lib.ilub_index_size() == 4                       # reference default Integer (declarations.h:49-53)
+    lib.ilub_version.restype = C.c_int
+    assert lib.ilub_version() >= 100
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = C.CDLL(LIB)
+    lib.ilub_last_error.restype = C.c_char_p
+    h = C.c_void_p()
+    # null arrays / n == 0 are rejected before any CUDA call
+    rc = lib.ilub_create_ilu0(None, None, None, C.c_int32(4), C.c_int64(4), 1, 0, 0, None, C.byref(h))
+    assert rc == 1 and b"null" in lib.ilub_last_error()
+    d = (C.c_double * 1)(1.0)
+    i = (C.c_int32 * 1)(0)
+    p = (C.c_int32 * 2)(0, 1)
+    rc = lib.ilub_create_ilu0(d, i, p, C.c_int32(0), C.c_int64(0), 1, 0, 0, None, C.byref(h))
+    assert rc == 1 and b"matrix has size 0!" in lib.ilub_last_error()   # binding.cpp:80-81
+    assert lib.ilub_set_option(b"no_such_option", C.c_int64(1)) == 1
+    v = C.c_int64()
+    assert lib.ilub_set_option(b"exact", C.c_int64(1)) == 0 and lib.ilub_get_option(b"exact", C.byref(v)) == 0
+    assert v.value == 1
+    assert lib.ilub_apply(None, 0, None, C.c_int64(1), C.c_int32(1), 0, None) == 1
+
+
+def test_python_layer_errors_match_reference():
+    import ilupp_b200 as ilupp
+    A = scipy.sparse.random(6, 6, density=0.5, random_state=0, format="coo")
+    with pytest.raises(TypeError, match="A must be a csr_matrix or a csc_matrix"):   # ilupp/__init__.py:60-65
+        ilupp.ILU0Preconditioner(A)
+    with pytest.raises(ValueError, match="A must be a square matrix!"):               # :67-68
+        ilupp.ILU0Preconditioner(scipy.sparse.csr_matrix(np.ones((3, 4))))
+    B = scipy.sparse.identity(5, format="csr")
+    B.indices = B.indices.astype(np.int64)
+    B.indptr = B.indptr.astype(np.int64)
+    with pytest.raises(TypeError, match="8 bytes per index"):                         # :47-53
+        ilupp._matrix_fields(B)
+    # in-place sort of the caller's matrix (:70)
+    M = scipy.sparse.csr_matrix((np.array([1.0, 2.0, 3.0]), np.array([1, 0, 1], np.int32), np.array([0, 2, 3], np.int32)),
+                                shape=(2, 2))
+    assert not np.array_equal(M.indices, [0, 1, 1])
+    ilupp._matrix_fields(M)
+    assert np.array_equal(M.indices, [0, 1, 1]) and np.array_equal(M.data, [2.0, 1.0, 3.0])
+
+
+def test_binding_buffer_checks_match_reference_messages():
+    import ilupp_b200 as ilupp
+    m = ilupp._ilupp
+    assert m.index_size() == 4
+    d = np.ones(3)
+    i = np.array([0, 1, 2], np.int32)
+    p = np.array([0, 1, 2, 3], np.int32)
+    with pytest.raises(RuntimeError, match=r"Expected d \(d\) array for A_data, got f!"):   # binding.cpp:42-51
+        m.ILU0Preconditioner(d.astype(np.float32), i, p, True)
+    with pytest.raises(RuntimeError, match="Expected integer type with length 4 for A_indices"):
+        m.ILU0Preconditioner(d, i.astype(np.int64), p, True)
+    with pytest.raises(RuntimeError, match="matrix has size 0!"):                            # :80-81
+        m.ILU0Preconditioner(np.zeros(0), np.zeros(0, np.int32), np.zeros(1, np.int32), True)
+    with pytest.raises(RuntimeError, match="indices and data should have the same size!"):   # :82-83
+        m.ILU0Preconditioner(d[:2], i, p, True)
+    with pytest.raises(RuntimeError, match="Expected 1D array for A_data!"):
+        m.ILU0Preconditioner(np.ones((3, 1)), i, p, True)
+    with pytest.raises(RuntimeError, match="Expected contiguous array for A_data!"):
+        m.ILU0Preconditioner(np.ones(6)[::2], i, p, True)
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product path must fail loudly, never compute on the CPU."""
+    import ilupp_b200 as ilupp
+    if ilupp._ilupp.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        ilupp.ILU0Preconditioner(scipy.sparse.identity(4, format="csr"))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ilupp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in text and "ilub_oracle" not in text and "oracle/" not in text, f

@@ -1,0 +1,420 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path through the public API / C ABI against
+  - the committed golden fixtures from the unmodified reference (tests/golden),
+  - the CPU oracle (oracle/ilub_oracle.c) on seeded inputs,
+  - the reference's own hot-path test cases (test/tests.py),
+  - size-independent properties at the BASELINE.json sizes.
+Bars (BASELINE.json north_star): sparsity pattern and level sets bit-exact; factor values and apply()
+outputs within 1e-12 relative (max norm).  With option exact=1 (default) lane-per-row paths are
+additionally bit-for-bit equal to the reference compiled without FMA contraction."""
+import numpy as np
+import pytest
+import scipy.sparse
+
+import oracle
+from ilupp_b200 import problems as P
+from helpers import (example_laplace, golden_factor, golden_matrix, ichol0_dense, ilu0_dense, laplace2d_matrix,
+                     laplace_matrix, load_golden, random_matrix, relerr, same_pattern)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ilupp():
+    import ilupp_b200
+    assert ilupp_b200._ilupp.device_count() > 0, "no CUDA device: the gpu tests must run on the B200 box"
+    ilupp_b200.set_option("exact", 1)
+    ilupp_b200.set_option("solve_algo", 0)
+    ilupp_b200.set_option("factor_algo", 0)
+    return ilupp_b200
+
+
+CASES = [(p, f) for p in ("laplace", "laplace2d", "random", "nonsym_tridiag") for f in ("csr", "csc")]
+
+
+# ---- golden fixtures ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("prob,fmt", CASES)
+def test_golden_ilu0(ilupp, prob, fmt):
+    g = load_golden("%s_%s" % (prob, fmt))
+    A = golden_matrix(g)
+    B = ilupp.ILU0Preconditioner(A)
+    L, U = B.factors()
+    Lg, Ug = golden_factor(g, "ilu0_L"), golden_factor(g, "ilu0_U")
+    assert same_pattern(L, Lg) and same_pattern(U, Ug)
+    assert relerr(L.data, Lg.data) <= TOL and relerr(U.data, Ug.data) <= TOL
+    assert np.array_equal(L.data, Lg.data) and np.array_equal(U.data, Ug.data)
+    assert B.total_nnz == int(g["ilu0_total_nnz"])
+    y = g["b"].copy()
+    B.apply(y)
+    assert relerr(y, g["ilu0_apply"]) <= TOL and np.array_equal(y, g["ilu0_apply"])
+    y = g["b"].copy()
+    B.apply_trans(y)
+    assert relerr(y, g["ilu0_apply_trans"]) <= TOL and np.array_equal(y, g["ilu0_apply_trans"])
+
+
+@pytest.mark.parametrize("prob,fmt", CASES)
+def test_golden_ichol0(ilupp, prob, fmt):
+    g = load_golden("%s_%s" % (prob, fmt))
+    S = golden_matrix(g, "S")
+    B = ilupp.IChol0Preconditioner(S)
+    (L,) = B.factors()
+    Lg = golden_factor(g, "ichol0_L")
+    assert L.format == "csr" and same_pattern(L, Lg)
+    assert np.array_equal(L.data, Lg.data, equal_nan=True)
+    assert B.total_nnz == int(g["ichol0_total_nnz"])
+    for fn in (B.apply, B.apply_trans):
+        y = g["b"].copy()
+        fn(y)
+        assert np.array_equal(y, g["ichol0_apply"], equal_nan=True)
+
+
+def test_golden_bicgstab(ilupp):
+    g = load_golden("bicgstab_convdiff12")
+    n = g["A_indptr"].size - 1
+    A = scipy.sparse.csr_matrix((g["A_data"], g["A_indices"], g["A_indptr"]), shape=(n, n))
+    x, (it, rel, ab) = ilupp.solve(A, g["b"], rtol=1e-8, atol=1e-8, max_iter=2000, info=True)
+    # parallel reductions reorder the dot products: iteration count within +-2, solution to solver tolerance
+    assert abs(it - int(g["iters"])) <= 2
+    assert relerr(x, g["x"]) < 1e-7 and rel < 1e-8 and ab < 1e-8
+
+
+# ---- the reference's own hot-path tests (test/tests.py) through the drop-in API -------------------------
+@pytest.mark.parametrize("cls", ["ILU0Preconditioner", "IChol0Preconditioner"])
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_ref_solve_in_one_step(ilupp, cls, fmt):  # tests.py:197-207,286-299
+    A, b, x_exact = example_laplace(50, fmt)
+    Pr = getattr(ilupp, cls)(A)
+    x = b.copy()
+    Pr.apply(x)
+    assert np.allclose(x, x_exact)
+    assert np.allclose(Pr.T @ (A.T @ x_exact), x_exact)
+    assert np.allclose(Pr @ b, x_exact) and np.allclose(Pr.dot(b), x_exact)
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_ref_factors_correct(ilupp, fmt):  # tests.py:229-259
+    A = laplace_matrix(50, fmt)
+    L, U = ilupp.ILU0Preconditioner(A).factors()
+    assert all(i >= j for i, j in zip(*L.nonzero())) and all(i <= j for i, j in zip(*U.nonzero()))
+    assert np.allclose(A.toarray(), (L @ U).toarray())
+    (Lc,) = ilupp.IChol0Preconditioner(A).factors()
+    assert np.allclose(A.toarray(), (Lc @ Lc.T).toarray())
+
+
+def test_ref_total_nnz_and_repr(ilupp):  # tests.py:301-306 + SURVEY appendix A
+    A = laplace_matrix(50)
+    B = ilupp.ILU0Preconditioner(A)
+    assert B.total_nnz == 2 * (2 * 50 - 1)
+    assert ilupp.IChol0Preconditioner(A).total_nnz == 2 * 50 - 1
+    assert repr(B) == "<50x50 ILU0Preconditioner with nnz=198, dtype=float64>"
+    assert B.pr.exists is True and B.pr.special_info == "" and B.pr.memory == 0.0
+    assert B.shape == (50, 50)
+
+
+@pytest.mark.parametrize("gen", [laplace_matrix, laplace2d_matrix, random_matrix])
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_ref_standalone_factorisations(ilupp, gen, fmt):  # tests.py:324-338
+    A = gen(50, fmt)
+    X, Xr = ilupp.ilu0(A), ilu0_dense(A)
+    assert all(Xi.format == fmt for Xi in X)
+    assert all(np.allclose(Xi.toarray(), Ri) for Xi, Ri in zip(X, Xr))
+    S = ((A + A.T) / 2).asformat(fmt)
+    Lc = ilupp.ichol0(S)
+    assert Lc.format == "csr" and np.allclose(Lc.toarray(), ichol0_dense(S))
+
+
+def test_layout_conventions(ilupp):  # explicit unit diagonals and their position
+    A = laplace_matrix(50, "csr")
+    L, U = ilupp.ilu0(A)
+    assert np.array_equal(L.indices[L.indptr[1]:L.indptr[2]], [0, 1])      # unit diagonal LAST
+    assert np.array_equal(U.indices[U.indptr[1]:U.indptr[2]], [1, 2])      # diagonal FIRST
+    assert L.data[L.indptr[2] - 1] == 1.0
+    Lc, Uc = ilupp.ilu0(A.tocsc())
+    assert Lc.format == "csc" and Uc.format == "csc"
+    assert not np.allclose(Lc.diagonal(), 1.0) and np.allclose(Uc.diagonal(), 1.0)   # ILU0.hpp:100-105
+    assert L.has_sorted_indices and U.has_sorted_indices
+
+
+# ---- seeded inputs against the CPU oracle ---------------------------------------------------------------
+PROBLEMS = [
+    ("poisson2d_40", lambda: P.poisson2d(40), True),
+    ("poisson3d_13", lambda: P.poisson3d(13), True),
+    ("convdiff3d_12", lambda: P.convdiff3d(12), False),
+    ("powerlaw_6000", lambda: P.irregular_powerlaw(6000, 7, seed=3), False),
+    ("powerlaw_wide_12000", lambda: P.irregular_powerlaw(12000, 19, seed=4), False),   # warp-cooperative chunks
+    ("dense_small_24", lambda: scipy.sparse.csr_matrix(np.random.default_rng(0).random((24, 24)) + 24 * np.eye(24)), False),
+    ("one_by_one", lambda: scipy.sparse.csr_matrix(np.array([[2.5]])), True),
+    ("diagonal_70", lambda: scipy.sparse.diags([np.arange(1.0, 71.0)], [0]).tocsr(), True),
+]
+
+
+@pytest.mark.parametrize("name,gen,sym", PROBLEMS, ids=[p[0] for p in PROBLEMS])
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_oracle_parity(ilupp, name, gen, sym, fmt):
+    A = gen().asformat(fmt)
+    A.indices = A.indices.astype(np.int32)
+    A.indptr = A.indptr.astype(np.int32)
+    n = A.shape[0]
+    b = P.rhs(n, 2)
+    B = ilupp.ILU0Preconditioner(A)
+    L, U = B.factors()
+    Lo, Uo = oracle.port.ilu0(A)
+    assert same_pattern(L, Lo) and same_pattern(U, Uo)
+    assert relerr(L.data, Lo.data) <= TOL and relerr(U.data, Uo.data) <= TOL
+    assert np.array_equal(L.data, Lo.data) and np.array_equal(U.data, Uo.data)
+    assert B.total_nnz == Lo.nnz + Uo.nnz
+    for tr in (False, True):
+        y = b.copy()
+        (B.apply_trans if tr else B.apply)(y)
+        assert relerr(y, oracle.port.apply_lu(Lo, Uo, b, tr)) <= TOL
+    # level sets: bit-exact against the CPU restatement (no reference counterpart)
+    Mc = A if fmt == "csr" else A.T.tocsr()
+    Mc.sort_indices()
+    for which in range(4):
+        lev, nlev = B.levels(which)
+        gather = (fmt == "csr") == (which < 2)
+        lo, nlo = oracle.port.levels(Mc.indptr, Mc.indices, lower=(which % 2 == 0), transposed=not gather)
+        assert nlev == nlo and np.array_equal(lev, lo)
+        lptr, lrows = B.level_sets(which)
+        order = np.lexsort((np.arange(n), lo))                      # canonical listing: (level, row)
+        assert np.array_equal(lrows, order) and lptr[0] == 0 and lptr[-1] == n
+        assert np.array_equal(np.diff(lptr), np.bincount(lo, minlength=nlo))
+    assert relerr(B.pr.spmv(b), oracle.port.spmv(A, b)) <= 1e-14
+    X = P.rhs(n, 5, k=4)
+    Y = B @ X                                                       # native multi-RHS
+    for c in range(4):
+        assert relerr(Y[:, c], oracle.port.apply_lu(Lo, Uo, X[:, c])) <= TOL
+    if sym:
+        Cc = ilupp.IChol0Preconditioner(A)
+        (Lc,) = Cc.factors()
+        Lco = oracle.port.ichol0(A)
+        assert same_pattern(Lc, Lco) and np.array_equal(Lc.data, Lco.data)
+        y = b.copy()
+        Cc.apply(y)
+        assert relerr(y, oracle.port.apply_llt(Lco, b)) <= TOL
+
+
+@pytest.mark.parametrize("opts", [{"solve_algo": 1, "factor_algo": 1}, {"exact": 0}, {"warps_per_cta": 4, "nparts": 3},
+                                  {"partition": 1}, {"stages": 1, "wcap": 2}, {"ring_chunks": 64, "near_window": 8}],
+                         ids=["level-scheduled", "fma", "few-warps", "contiguous", "one-stage-narrow", "small-ring"])
+def test_kernel_variants(ilupp, opts):
+    """every schedule / arithmetic variant meets the same parity bar"""
+    defaults = {k: ilupp.get_option(k) for k in opts}
+    try:
+        for k, v in opts.items():
+            ilupp.set_option(k, v)
+        for A in (P.poisson3d(11), P.irregular_powerlaw(5000, 9, seed=8), P.convdiff3d(10).tocsc()):
+            A.indices = A.indices.astype(np.int32)
+            A.indptr = A.indptr.astype(np.int32)
+            b = P.rhs(A.shape[0], 4)
+            B = ilupp.ILU0Preconditioner(A)
+            Lo, Uo = oracle.port.ilu0(A)
+            L, U = B.factors()
+            assert same_pattern(L, Lo) and same_pattern(U, Uo)
+            assert relerr(L.data, Lo.data) <= TOL and relerr(U.data, Uo.data) <= TOL
+            for tr in (False, True):
+                y = b.copy()
+                (B.apply_trans if tr else B.apply)(y)
+                assert relerr(y, oracle.port.apply_lu(Lo, Uo, b, tr)) <= TOL
+    finally:
+        for k, v in defaults.items():
+            ilupp.set_option(k, v)
+
+
+# ---- behaviours at the boundary ---------------------------------------------------------------------------
+def test_apply_shapes_and_errors(ilupp):
+    A = P.poisson2d(8)
+    B = ilupp.ILU0Preconditioner(A)
+    n = A.shape[0]
+    b = P.rhs(n, 0)
+    y1 = B @ b
+    y2 = (B @ b.reshape(n, 1))
+    assert y1.shape == (n,) and y2.shape == (n, 1) and np.array_equal(y1, y2.ravel())
+    x = b.reshape(n, 1).copy()
+    B.apply(x)                                           # in place through ravel() (ilupp/__init__.py:144-146)
+    assert np.array_equal(x.ravel(), y1)
+    with pytest.raises(RuntimeError, match="vector has wrong size for preconditioner!"):    # binding.cpp:241-242
+        B.apply(np.zeros(n + 1))
+    with pytest.raises(RuntimeError, match=r"Expected d \(d\) array for b, got f!"):
+        B.apply(np.zeros(n, np.float32))
+    import scipy.sparse.linalg as spla
+    xs, info = spla.gmres(A, b, M=B, atol=1e-10, restart=30)     # usable as scipy preconditioner
+    assert info == 0 and np.linalg.norm(A @ xs - b) < 1e-8 * np.linalg.norm(b)
+
+
+def test_structure_validation(ilupp):
+    # structurally missing diagonal: undefined behaviour in the reference (ILU0.hpp:31,39-44); refused here
+    M = scipy.sparse.csr_matrix((np.array([1.0, 2.0, 3.0]), np.array([0, 1, 0], np.int32), np.array([0, 2, 3], np.int32)),
+                                shape=(2, 2))
+    with pytest.raises(RuntimeError, match="missing diagonal"):
+        ilupp._ilupp.ILU0Preconditioner(M.data, M.indices, M.indptr, True)
+    # duplicate column indices break the reference's two-pointer merges; refused here
+    with pytest.raises(RuntimeError, match="not strictly ascending"):
+        ilupp._ilupp.ILU0Preconditioner(np.ones(4), np.array([0, 0, 0, 1], np.int32), np.array([0, 2, 4], np.int32), True)
+    with pytest.raises(RuntimeError, match="out of range"):
+        ilupp._ilupp.ILU0Preconditioner(np.ones(2), np.array([0, 5], np.int32), np.array([0, 1, 2], np.int32), True)
+
+
+def test_nan_inf_propagate_like_the_reference(ilupp):
+    A = (-P.poisson2d(6)).tocsr()                                   # not SPD: NaN factor, no error
+    (L,) = ilupp.IChol0Preconditioner(A).factors()
+    Lo = oracle.port.ichol0(A)
+    assert np.array_equal(np.isnan(L.data), np.isnan(Lo.data)) and np.isnan(L.data).any()
+    Z = scipy.sparse.csr_matrix((np.array([0.0, 1.0, 1.0, 0.0]), np.array([0, 1, 0, 1], np.int32),
+                                 np.array([0, 2, 4], np.int32)), shape=(2, 2))
+    L, U = ilupp.ilu0(Z)                                            # stored zero pivot: inf, no error
+    Lo, Uo = oracle.port.ilu0(Z)
+    assert np.array_equal(L.data, Lo.data, equal_nan=True) and np.array_equal(U.data, Uo.data, equal_nan=True)
+    # a NaN right-hand side entry propagates and does not hang the sync-free kernels
+    A = P.poisson2d(12)
+    B = ilupp.ILU0Preconditioner(A)
+    b = np.ones(A.shape[0])
+    b[5] = np.nan
+    y = b.copy()
+    B.apply(y)
+    Lo, Uo = oracle.port.ilu0(A)
+    assert np.array_equal(np.isnan(y), np.isnan(oracle.port.apply_lu(Lo, Uo, b)))
+
+
+def test_refactor_and_batched(ilupp):
+    A = P.poisson2d(16)
+    B = ilupp.ILU0Preconditioner(A)
+    A2 = A.copy()
+    A2.data = A2.data * (1.0 + 0.1 * np.random.default_rng(0).random(A2.nnz))
+    B.refactor(A2)
+    L, U = B.factors()
+    Lo, Uo = oracle.port.ilu0(A2)
+    assert np.array_equal(L.data, Lo.data) and np.array_equal(U.data, Uo.data)
+    pat, vals = P.batched_poisson2d(5, 12)
+    n1 = pat.shape[0]
+    Bb = ilupp.ILU0PreconditionerBatched(pat, vals)
+    assert Bb.shape == (5 * n1, 5 * n1)
+    X = P.rhs(5 * n1, 9)
+    y = X.copy()
+    Bb.apply(y)
+    for s in range(5):
+        As = pat.copy()
+        As.data = vals[s].copy()
+        Lo, Uo = oracle.port.ilu0(As)
+        assert np.array_equal(y[s * n1:(s + 1) * n1], oracle.port.apply_lu(Lo, Uo, X[s * n1:(s + 1) * n1]))
+
+
+def test_torch_device_tensors(ilupp):
+    import torch
+    A = P.poisson3d(10)
+    B = ilupp.IChol0Preconditioner(A)
+    b = P.rhs(A.shape[0], 0)
+    x = torch.from_numpy(b).cuda()
+    B.apply(x)                                          # zero-copy, asynchronous on the current stream
+    y = b.copy()
+    B.apply(y)
+    assert np.array_equal(x.cpu().numpy(), y)
+    X = torch.from_numpy(np.asfortranarray(P.rhs(A.shape[0], 1, k=3))).cuda()    # column-major (n, k)
+    Xh = X.cpu().numpy().copy()
+    B.apply(X.t().contiguous().t())                     # strides (1, n)
+    with pytest.raises(RuntimeError):
+        B.apply(torch.zeros(7, dtype=torch.float64, device="cuda"))
+
+
+# ---- BASELINE.json sizes: parity against the oracle + size-independent properties -------------------------
+def test_baseline_config1_poisson2d_256(ilupp):
+    A = P.poisson2d(256)
+    b = P.rhs(A.shape[0], 0)
+    for fmt in ("csr", "csc"):
+        M = A.asformat(fmt)
+        B = ilupp.ILU0Preconditioner(M)
+        assert B.total_nnz == 392192
+        Lo, Uo = oracle.port.ilu0(M)
+        L, U = B.factors()
+        assert same_pattern(L, Lo) and same_pattern(U, Uo) and relerr(L.data, Lo.data) <= TOL and relerr(U.data, Uo.data) <= TOL
+        y = b.copy()
+        B.apply(y)
+        assert relerr(y, oracle.port.apply_lu(Lo, Uo, b)) <= TOL
+        lev, nlev = B.levels(0)
+        assert nlev == 511
+        if fmt == "csr":
+            i = np.arange(A.shape[0])
+            assert np.array_equal(lev, i % 256 + i // 256)            # closed form
+
+
+def test_baseline_config2_poisson3d_128(ilupp):
+    N = 128
+    A = P.poisson3d(N)
+    n = A.shape[0]
+    B = ilupp.IChol0Preconditioner(A)
+    assert B.total_nnz == 8339456
+    lev, nlev = B.levels(0)
+    i = np.arange(n)
+    assert nlev == 3 * N - 2 and np.array_equal(lev, i % N + (i // N) % N + i // (N * N))
+    (L,) = B.factors()
+    Lo = oracle.port.ichol0(A)                                        # ~0.2 s on the host
+    assert same_pattern(L, Lo) and relerr(L.data, Lo.data) <= TOL
+    b = P.rhs(n, 0)
+    y = b.copy()
+    B.apply(y)
+    assert relerr(y, oracle.port.apply_llt(Lo, b)) <= TOL
+    # size-independent properties: L L^T y == b, and linearity of the apply
+    r = L @ (L.T @ y)
+    assert relerr(r, b) < 1e-10
+    b2 = P.rhs(n, 1)
+    y2 = b2.copy()
+    B.apply(y2)
+    y3 = (2.0 * b + b2).copy()
+    B.apply(y3)
+    assert relerr(y3, 2.0 * y + y2) < 1e-12
+
+
+def test_baseline_config3_convdiff_bicgstab(ilupp):
+    A = P.convdiff3d(48)                                              # reduced size of config 3 (oracle in seconds)
+    n = A.shape[0]
+    b = A @ np.ones(n)
+    x, (it, rel, ab) = ilupp.solve(A, b, rtol=1e-8, atol=1e-8, max_iter=2000, info=True)
+    Lo, Uo = oracle.port.ilu0(A)
+    xo, ito, relo, abo, ok = oracle.port.bicgstab(A, b, (Lo, Uo), 1e-8, 1e-8, 2000)
+    assert ok and abs(it - ito) <= 2
+    assert np.abs(x - 1.0).max() < 1e-6 and relerr(x, xo) < 1e-6
+    # one preconditioned mat-vec, tight: L^-1 A U^-1 p
+    B = ilupp.ILU0Preconditioner(A)
+    p = P.rhs(n, 3)
+    t = oracle.port.trsv("bwd_gather", Uo, p)
+    t = oracle.port.spmv(A, t)
+    t = oracle.port.trsv("fwd_gather", Lo, t)
+    # GPU: same composition through the public pieces
+    L, U = B.factors()
+    assert relerr(B.pr.spmv(oracle.port.trsv("bwd_gather", U, p)), oracle.port.spmv(A, oracle.port.trsv("bwd_gather", Uo, p))) <= 1e-13
+    with pytest.raises(RuntimeError, match="did not converge"):
+        ilupp.solve(A, b, rtol=1e-14, atol=1e-14, max_iter=2)
+    with pytest.raises(RuntimeError, match="right-hand side has wrong size!"):
+        ilupp.solve(A, b[:-1])
+
+
+def test_baseline_config4_irregular(ilupp):
+    A = P.irregular_powerlaw(60000, 19, seed=1234)                    # reduced n (oracle factor in seconds)
+    b = P.rhs(A.shape[0], 0)
+    B = ilupp.ILU0Preconditioner(A)
+    Lo, Uo = oracle.port.ilu0(A)
+    L, U = B.factors()
+    assert same_pattern(L, Lo) and same_pattern(U, Uo)
+    assert relerr(L.data, Lo.data) <= TOL and relerr(U.data, Uo.data) <= TOL
+    y = b.copy()
+    B.apply(y)
+    assert relerr(y, oracle.port.apply_lu(Lo, Uo, b)) <= TOL
+    lev, nlev = B.levels(0)
+    lo, nlo = oracle.port.levels(A.indptr, A.indices, lower=True)
+    assert nlev == nlo and np.array_equal(lev, lo)
+
+
+def test_baseline_config5_batched(ilupp):
+    nsys, N = 24, 128
+    pat, vals = P.batched_poisson2d(nsys, N)
+    n1 = pat.shape[0]
+    Bb = ilupp.ILU0PreconditionerBatched(pat, vals)
+    assert Bb.total_nnz == nsys * 97792
+    X = P.rhs(nsys * n1, 10**6, k=16)
+    Y = Bb @ X
+    for s in (0, 7, nsys - 1):
+        As = pat.copy()
+        As.data = vals[s].copy()
+        Lo, Uo = oracle.port.ilu0(As)
+        for c in (0, 15):
+            assert relerr(Y[s * n1:(s + 1) * n1, c], oracle.port.apply_lu(Lo, Uo, X[s * n1:(s + 1) * n1, c])) <= TOL
