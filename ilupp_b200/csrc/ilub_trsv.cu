@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                 const int rl = __shfl_sync(FULL, len, rr);
                 const int ro = __shfl_sync(FULL, off, rr);
                 double part = 0.0;
+                double run = __shfl_sync(FULL, acc, rr);  // EXACT: running value b - sum, in stored order
                 for (int tb = 0; tb < rl; tb += 32) {
                     const int t = tb + lane;
                     const bool active = t < rl;
@@ -378,11 +379,20 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                         if (__all_sync(FULL, ok)) break;
                         if (wd.expired(104)) return;
                     }
-                    if (active) part = add_mul<EXACT>(part, v, xv);
+                    if (EXACT) {
+                        // the reference's sequential accumulation: one rounded product per entry, subtracted
+                        // in stored order (ordered shuffle pass instead of a tree)
+                        const double prod = active ? __dmul_rn(v, xv) : 0.0;
+                        const int cnt = min(32, rl - tb);
+                        for (int l = 0; l < cnt; ++l) run = __dsub_rn(run, __shfl_sync(FULL, prod, l));
+                    } else if (active) {
+                        part = fma(v, xv, part);
+                    }
                 }
-                for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
+                if (!EXACT)
+                    for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(FULL, part, s);
                 if (lane == rr) {
-                    const double t = acc - part;
+                    const double t = EXACT ? run : acc - part;
                     xfin = P.unit_diag ? t : (EXACT ? __ddiv_rn(t, d) : t / d);
                     st_ring(myslot, xfin, mytag);
                 }
