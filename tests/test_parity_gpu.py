@@ -238,7 +238,7 @@ def test_apply_shapes_and_errors(ilupp):
     with pytest.raises(RuntimeError, match=r"Expected d \(d\) array for b, got f!"):
         B.apply(np.zeros(n, np.float32))
     import scipy.sparse.linalg as spla
-    xs, info = spla.gmres(A, b, M=B, atol=1e-10, restart=30)     # usable as scipy preconditioner
+    xs, info = spla.gmres(A, b, M=B, rtol=1e-12, atol=1e-12, restart=30)     # usable as scipy preconditioner
     assert info == 0 and np.linalg.norm(A @ xs - b) < 1e-8 * np.linalg.norm(b)
 
 
