@@ -300,6 +300,47 @@ __global__ void k_place_rows(int n, const unsigned long long* __restrict__ skeys
     rowpos[row] = pos;
 }
 
+// ---- chunk assignment.  A "group" is a maximal run of sorted rows that must start a new chunk: a new part
+// always does; with level alignment every (part, level) pair does, so that a chunk never mixes levels and has
+// no internal dependencies (the straight-line fast path of the solve kernel relies on that).
+__global__ void k_group_start(int n, const unsigned long long* __restrict__ skeys, int align_levels,
+                              int* __restrict__ gstart) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int sh = align_levels ? 1 : kPartShift;   // drop the "remote" bit / everything below the part
+    const bool head = s == 0 || (skeys[s] >> sh) != (skeys[s - 1] >> sh);
+    gstart[s] = head ? s : 0;
+}
+__global__ void k_new_chunk(int n, const int* __restrict__ gstart, int* __restrict__ newchunk) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    newchunk[s] = ((s - gstart[s]) & 31) == 0 ? 1 : 0;
+}
+// pcp[p] = chunk of the first row of part p (parts are contiguous in sorted order; empty parts collapse)
+__global__ void k_part_chunks(int n, int nparts, const unsigned long long* __restrict__ skeys,
+                              const int* __restrict__ chunk_incl, int* __restrict__ pcp) {
+    for (int p = threadIdx.x; p <= nparts; p += blockDim.x) {
+        int lo = 0, hi = n;  // first sorted position whose part >= p
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if ((int)(skeys[mid] >> kPartShift) < p)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        pcp[p] = lo < n ? chunk_incl[lo] - 1 : chunk_incl[n - 1];
+    }
+}
+__global__ void k_place_rows2(int n, const int* __restrict__ order, const int* __restrict__ gstart,
+                              const int* __restrict__ chunk_incl, int* __restrict__ rows, int* __restrict__ rowpos) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int pos = ((chunk_incl[s] - 1) << 5) | ((s - gstart[s]) & 31);
+    const int row = order[s];
+    rows[pos] = row;
+    rowpos[row] = pos;
+}
+
 // one warp per chunk: lengths, width, kind, slab count
 __global__ void k_chunk_shape(int nchunks, SrcDev S, const int* __restrict__ rows, int wcap,
                               int* __restrict__ rlen, int* __restrict__ cslabs, unsigned char* __restrict__ ckind,
@@ -367,6 +408,7 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
     bool intra = false, remote = false;
     const int lv = row >= 0 ? level[row] : 0x7fffffff;
     const int lvmin = __reduce_min_sync(0xffffffffu, lv);
+    const int lvmax = __reduce_max_sync(0xffffffffu, row >= 0 ? lv : -1);
     int g = -1;  // last local position (CTA numbering) feeding the rows of this chunk's lowest level
     const int b = row >= 0 ? src_beg(S, row) : 0;
     const int e = b + len;
@@ -395,7 +437,8 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
         srcpos[at] = S.val_pos ? S.val_pos[q] : q;
     }
     const bool any_intra = __any_sync(0xffffffffu, intra), any_remote = __any_sync(0xffffffffu, remote);
-    if (lane == 0) ckind[c] = (unsigned char)(kind | (any_intra ? 2 : 0) | (any_remote ? 4 : 0));
+    if (lane == 0)
+        ckind[c] = (unsigned char)(kind | (any_intra ? 2 : 0) | (any_remote ? 4 : 0) | (lvmin == lvmax ? 8 : 0));
     g = __reduce_max_sync(0xffffffffu, g + 1) - 1;
     if (lane == 0) gate[c] = g;
 }
@@ -722,12 +765,32 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     ILUB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, n, 0, end_bit, s));
     T.order.alloc(n);
     ILUB_CUDA(cudaMemcpyAsync(T.order.p, dv.Current(), sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
-    DevBuf<int> rstart;
-    rstart.alloc(nparts + 1);
+    // chunk assignment (level-aligned when the (part, level) groups are big enough to fill chunks)
+    const double avg_group = (double)n / ((double)std::max(1, T.nlevels) * (double)nparts);
+    const int align = opt.level_align == 1 || (opt.level_align != 0 && avg_group >= (double)opt.align_min_rows) ? 1 : 0;
+    T.level_aligned = align;
+    DevBuf<int> gstart, newchunk, chunk_incl;
+    gstart.alloc(n);
+    newchunk.alloc(n);
+    chunk_incl.alloc(n);
+    k_group_start<<<blocks_for(n, 256), 256, 0, s>>>(n, dk.Current(), align, gstart.p);
+    {
+        size_t tbm = 0, tbs = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, tbm, gstart.p, gstart.p, cub::Max(), n, s);
+        cub::DeviceScan::InclusiveSum(nullptr, tbs, newchunk.p, chunk_incl.p, n, s);
+        DevBuf<unsigned char> tmpc;
+        tmpc.alloc(std::max(tbm, tbs));
+        size_t tbx = tmpc.n;
+        ILUB_CUDA(cub::DeviceScan::InclusiveScan(tmpc.p, tbx, gstart.p, gstart.p, cub::Max(), n, s));
+        k_new_chunk<<<blocks_for(n, 256), 256, 0, s>>>(n, gstart.p, newchunk.p);
+        tbx = tmpc.n;
+        ILUB_CUDA(cub::DeviceScan::InclusiveSum(tmpc.p, tbx, newchunk.p, chunk_incl.p, n, s));
+        ILUB_CUDA(cudaStreamSynchronize(s));
+    }
     T.part_chunk_ptr.alloc(nparts + 1);
-    k_part_bounds<<<1, 256, 0, s>>>(n, nparts, dk.Current(), rstart.p, T.part_chunk_ptr.p);
+    k_part_chunks<<<1, 256, 0, s>>>(n, nparts, dk.Current(), chunk_incl.p, T.part_chunk_ptr.p);
     int nchunks = 0;
-    ILUB_CUDA(cudaMemcpyAsync(&nchunks, T.part_chunk_ptr.p + nparts, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaMemcpyAsync(&nchunks, chunk_incl.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     ILUB_CUDA(cudaStreamSynchronize(s));
     T.nchunks = nchunks;
     const int64_t nlane = (int64_t)nchunks * 32;
@@ -739,8 +802,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     T.ckind.alloc(nchunks);
     T.chunk_ptr.alloc(nchunks + 1);
     ILUB_CUDA(cudaMemsetAsync(T.rows.p, 0xff, sizeof(int) * nlane, s));
-    k_place_rows<<<blocks_for(n, 256), 256, 0, s>>>(n, dk.Current(), T.order.p, rstart.p, T.part_chunk_ptr.p,
-                                                    T.rows.p, T.rowpos.p);
+    k_place_rows2<<<blocks_for(n, 256), 256, 0, s>>>(n, T.order.p, gstart.p, chunk_incl.p, T.rows.p, T.rowpos.p);
     // ---- chunk shapes
     DevBuf<int> cslabs;
     cslabs.alloc(nchunks + 1);
@@ -762,7 +824,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     T.any_kind_b = hshape[3];
     T.nslabs = nsl;
     {   // launch configuration of the sync-free kernel; `near` is baked into the encoded indices below
-        int W = (int)std::min<int64_t>(32, std::max<int64_t>(1, opt.warps_per_cta));
+        int W = (int)std::min<int64_t>(16, std::max<int64_t>(1, opt.warps_per_cta));  // kernel: __launch_bounds__(512)
         int RC = 64;
         while (RC * 2 <= opt.ring_chunks) RC *= 2;
         int near = (int)std::min<int64_t>(opt.near_window, RC / 2);

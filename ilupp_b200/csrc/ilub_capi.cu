@@ -430,6 +430,9 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "partition") o.partition = value;
         else if (k == "nparts") o.nparts = value;
         else if (k == "trace") o.trace = value;
+        else if (k == "fastpath") o.fastpath = value;
+        else if (k == "level_align") o.level_align = value;
+        else if (k == "align_min_rows") o.align_min_rows = value;
         else if (k == "gate_slack") o.gate_slack = value;
         else if (k == "part_kb") o.part_kb = value;
         else if (k == "factor_group") o.factor_group = value;

@@ -75,6 +75,9 @@ struct Options {
     int64_t partition = 0;      // 0 auto (geometric strips/pencils when strides are detected), 1 contiguous ranges
     int64_t nparts = 0;         // 0 auto, else number of CTAs/parts to aim for
     int64_t part_kb = 256;      // auto nparts: aim for at least this many KB of solve data per CTA
+    int64_t level_align = 2;    // chunks never mix levels: 0 never, 1 always, 2 when (part, level) groups average >= align_min_rows
+    int64_t align_min_rows = 16;
+    int64_t fastpath = 1;       // straight-line path for single-level lane-per-row chunks
     int64_t trace = 0;          // debug: record per-chunk clock stamps in the sync-free solve
     int64_t factor_group = 0;   // lanes per row in the factorisation kernels (0 = auto)
 };
@@ -107,7 +110,7 @@ struct TriSolve {
     DevBuf<int> rowpos;           // [n] (chunk << 5 | lane) of every row
     DevBuf<int> part_chunk_ptr;   // [nparts + 1]
     DevBuf<int> chunk_ptr;        // [nchunks + 1] slab offset of every chunk
-    DevBuf<unsigned char> ckind;  // [nchunks] bit0: warp-cooperative (kind B); bit1: has same-chunk deps; bit2: has mailbox deps
+    DevBuf<unsigned char> ckind;  // [nchunks] bit0: warp-cooperative (kind B); bit1: has same-chunk deps; bit2: has mailbox deps; bit3: single level
     DevBuf<int> rows;             // [nchunks * 32] original row per lane (-1 = padding)
     DevBuf<int> rlen;             // [nchunks * 32] number of off-diagonal entries per lane
     DevBuf<int> idx;              // [nslabs * 32] encoded dependencies
@@ -119,6 +122,7 @@ struct TriSolve {
     DevBuf<unsigned> pubmask;     // [nchunks] lanes whose row is read through the global path by someone
     DevBuf<ulonglong2> mail;      // [n] {x bits, epoch tag}: the global dependency path (one 16-B atomic access)
     unsigned long long epoch = 0;
+    int level_aligned = 0;
     int part_mode = 0;            // 0 contiguous ranges, 2 / 3: strips / pencils from detected strides
     int stride_y = 0, stride_z = 0, grid_y = 1, grid_z = 1;
     // launch configuration of the sync-free kernel, fixed at analysis (near is baked into idx)

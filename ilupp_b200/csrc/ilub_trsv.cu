@@ -54,6 +54,7 @@ struct TrsvParams {
     int unit_diag;
     int* status;
     long long spin_limit;
+    int fastpath;
     long long* trace;  // debug: 4 clock64 stamps per chunk (start, gate passed, data staged, resolved)
 };
 
@@ -99,7 +100,7 @@ __device__ __forceinline__ bool poll_dep(int e, const ulonglong2* mail, unsigned
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
+__global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = P.ring_mask + 1;
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
             // slabs in parallel) and fold them into the staged coefficient (v := v*x, index := READY), so
             // that the ordered hand-off loop below never waits on an L2 round trip in the middle of a
             // chain.  Anything not there yet is simply polled in place later -- no blocking, no deadlock.
+            bool remote_pending = false;
             if (pubm_remote) {
                 int* widx = const_cast<int*>(sidx);
                 double* wval = const_cast<double*>(sval);
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                             }
                         }
                     }
-                    if (!__any_sync(FULL, pending)) break;
+                    remote_pending = __any_sync(FULL, pending);
+                    if (!remote_pending) break;
                 }
             }
             // the first (up to) four dependencies of the lane go to registers while the warp is still waiting
@@ -266,6 +269,43 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
             if (!wait_gate()) return;
             if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 2] = clock64();
             int j = 0;
+            if ((kind & 8) && w <= 4 && !remote_pending && P.fastpath) {
+                // ---- straight-line fast path: a single-level chunk has no internal dependencies and every
+                // dependency sits at a lower level, so the whole warp may block until all of them have arrived:
+                // up to four 16-byte ring polls in flight per lane, one vote, then the multiply-subtract chain
+                // in the stored order, the diagonal and one 16-byte publish.  This is the per-level critical path.
+                const bool n0 = len > 0 && !((unsigned)q0 & kReadyBit), n1 = len > 1 && !((unsigned)q1 & kReadyBit);
+                const bool n2 = len > 2 && !((unsigned)q2 & kReadyBit), n3 = len > 3 && !((unsigned)q3 & kReadyBit);
+                const uint32_t rb = smem_u32(ring);
+                const uint32_t a0 = rb + (((unsigned)q0 & (unsigned)P.ring_mask) << 4);
+                const uint32_t a1 = rb + (((unsigned)q1 & (unsigned)P.ring_mask) << 4);
+                const uint32_t a2 = rb + (((unsigned)q2 & (unsigned)P.ring_mask) << 4);
+                const uint32_t a3 = rb + (((unsigned)q3 & (unsigned)P.ring_mask) << 4);
+                const unsigned g0 = ((unsigned)q0 & 0x3fffffffu) + 1u, g1 = ((unsigned)q1 & 0x3fffffffu) + 1u;
+                const unsigned g2 = ((unsigned)q2 & 0x3fffffffu) + 1u, g3 = ((unsigned)q3 & 0x3fffffffu) + 1u;
+                double y0 = 1.0, y1 = 1.0, y2 = 1.0, y3 = 1.0;
+                unsigned spins = 0;
+                while (true) {
+                    bool ok = true;
+                    unsigned long long xb0, xb1, xb2, xb3, u0, u1, u2, u3;
+                    if (n0) ld_b128_cta(a0, xb0, u0);
+                    if (n1) ld_b128_cta(a1, xb1, u1);
+                    if (n2) ld_b128_cta(a2, xb2, u2);
+                    if (n3) ld_b128_cta(a3, xb3, u3);
+                    if (n0) { ok = ok && ((unsigned)u0 == g0); y0 = __longlong_as_double((long long)xb0); }
+                    if (n1) { ok = ok && ((unsigned)u1 == g1); y1 = __longlong_as_double((long long)xb1); }
+                    if (n2) { ok = ok && ((unsigned)u2 == g2); y2 = __longlong_as_double((long long)xb2); }
+                    if (n3) { ok = ok && ((unsigned)u3 == g3); y3 = __longlong_as_double((long long)xb3); }
+                    if (__all_sync(FULL, ok)) break;
+                    if ((++spins & 0xfffu) == 0 && wd.expired_now(107)) return;
+                }
+                if (len > 0) acc = sub_mul<EXACT>(acc, c0v, y0);
+                if (len > 1) acc = sub_mul<EXACT>(acc, c1v, y1);
+                if (len > 2) acc = sub_mul<EXACT>(acc, c2v, y2);
+                if (len > 3) acc = sub_mul<EXACT>(acc, c3v, y3);
+                xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
+                if (r >= 0) st_ring(myslot, xfin, mytag);
+            } else {
             {
                 double y0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
                 const bool k0 = len > 0 && poll_dep(q0, P.mail, P.epoch, ring, P.ring_mask, y0);
@@ -350,6 +390,7 @@ __global__ void __launch_bounds__(1024, 1) k_trsv_syncfree(TrsvParams P) {
                     advance();
                 }
             }
+            }  // generic path
         } else {
             // ------------------------------------------------------------ warp-cooperative chunk
             if (!wait_gate()) return;
@@ -519,6 +560,7 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.pubmask = T.pubmask.p;
     P.gate = T.gate.p;
     P.slack = (int)opt.gate_slack;
+    P.fastpath = (int)opt.fastpath;
     P.mail = T.mail.p;
     P.ring_mask = T.cfg_ring_chunks * 32 - 1;
     P.rc = T.cfg_ring_chunks;
