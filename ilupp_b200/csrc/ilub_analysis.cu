@@ -832,7 +832,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         const int slabs = std::max(1, T.maxw_a);
         const size_t budget = (size_t)227 * 1024 / (size_t)std::max<int64_t>(1, opt.ctas_per_sm) - 1024;
         auto need = [&]() {
-            return (size_t)RC * 512 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + 128 + 128;
+            return (size_t)RC * 512 + 128 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + 128 + 128;
         };
         while (need() > budget) {
             if (stages > 1) stages = 1;

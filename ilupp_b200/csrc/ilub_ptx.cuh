@@ -74,6 +74,11 @@ __device__ __forceinline__ void st_ring(ulonglong2* p, double x, unsigned long l
                  "l"(__double_as_longlong(x)), "l"(tag)
                  : "memory");
 }
+__device__ __forceinline__ void st_ring_s(uint32_t saddr, double x, unsigned long long tag) {
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.cta.shared.b128 [%0], q;\n\t}" ::"r"(saddr),
+                 "l"(__double_as_longlong(x)), "l"(tag)
+                 : "memory");
+}
 __device__ __forceinline__ bool ld_ring(const ulonglong2* p, unsigned long long tag, double& x) {
     long long xb;
     unsigned long long t;

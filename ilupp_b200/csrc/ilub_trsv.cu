@@ -99,13 +99,37 @@ __device__ __forceinline__ bool poll_dep(int e, const ulonglong2* mail, unsigned
     return ld_ring(ring + (lp & ring_mask), (unsigned long long)lp + 1ull, xv);
 }
 
+// Critical path of a single-level lane-per-row chunk: NW ring polls in flight per lane (absent / pre-folded
+// dependencies point at two always-ready dummy entries), one vote, NW multiply-subtracts in stored order.
+template <int NW, bool EXACT>
+__device__ __forceinline__ bool fast_resolve(const uint32_t (&a)[4], const unsigned (&g)[4], const double (&cv)[4],
+                                             double& acc, Watchdog& wd) {
+    unsigned spins = 0;
+    double y[NW];
+    while (true) {
+        unsigned long long xb[NW], u[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) ld_b128_cta(a[k], xb[k], u[k]);
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) ok = ok && ((unsigned)u[k] == g[k]);
+#pragma unroll
+        for (int k = 0; k < NW; ++k) y[k] = __longlong_as_double((long long)xb[k]);
+        if (__all_sync(0xffffffffu, ok)) break;
+        if ((++spins & 0xfffu) == 0 && wd.expired_now(107)) return false;
+    }
+#pragma unroll
+    for (int k = 0; k < NW; ++k) acc = sub_mul<EXACT>(acc, cv[k], y[k]);
+    return true;
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = P.ring_mask + 1;
     ulonglong2* ring = reinterpret_cast<ulonglong2*>(smem);  // {x bits, local position + 1}
-    unsigned char* stage_base = smem + (size_t)R * 16;
+    unsigned char* stage_base = smem + (size_t)(R + 8) * 16;  // 8 spare entries: [R] = {0.0, ~0}, [R+1] = {1.0, ~0}
     const int stage_bytes = P.stage_slabs * 384;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + (size_t)W * P.nstages * stage_bytes);
     int* warp_cur = reinterpret_cast<int*>(mbar + W * P.nstages);
@@ -113,6 +137,10 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
     const int c0 = P.part_chunk_ptr[blockIdx.x];
     const int nloc = P.part_chunk_ptr[blockIdx.x + 1] - c0;
     for (int i = threadIdx.x; i < R; i += blockDim.x) ring[i] = make_ulonglong2(0ull, 0ull);
+    if (threadIdx.x == 0) {
+        ring[R] = make_ulonglong2(0ull, 0xffffffffffffffffull);
+        ring[R + 1] = make_ulonglong2((unsigned long long)__double_as_longlong(1.0), 0xffffffffffffffffull);
+    }
     if (threadIdx.x < 32) warp_cur[threadIdx.x] = (threadIdx.x < W && threadIdx.x < nloc) ? threadIdx.x : INT_MAX;
     if (lane == 0) {
         for (int s = 0; s < P.nstages; ++s) mbar_init(&mbar[warp * P.nstages + s], 1);
@@ -194,23 +222,27 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
         auto wait_gate = [&]() -> bool {
             if (gate_lp < 0 || P.slack < 0) return true;
             const uint32_t ga = smem_u32(ring + (gate_lp & P.ring_mask));
-            const unsigned long long gt = (unsigned long long)gate_lp + 1ull;
+            const unsigned gt = (unsigned)gate_lp + 1u;
             const int gate_chunk = gate_lp >> 5;
+            // far from the frontier: watch the per-warp progress words and sleep
+            while (gate_chunk - done_cache > P.slack) {
+                int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
+                done_cache = __reduce_min_sync(FULL, v);
+                if (gate_chunk - done_cache <= P.slack) break;
+                __nanosleep(100);
+                if (wd.expired(106)) return false;
+            }
+            // near: one lane polls the gate row (one shared-memory wavefront per round)
             unsigned spins = 0;
             while (true) {
                 bool open = false;
-                if (lane == 0) {  // one lane polls: one shared-memory wavefront per round
+                if (lane == 0) {
                     unsigned long long xb, t;
                     ld_b128_cta(ga, xb, t);
-                    open = (t == gt);
+                    open = ((unsigned)t == gt);
                 }
                 if (__any_sync(FULL, open)) return true;
-                if (gate_chunk - done_cache > P.slack) {  // far from the frontier: look at the progress words, sleep
-                    int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
-                    done_cache = __reduce_min_sync(FULL, v);
-                    if (gate_chunk - done_cache > P.slack) __nanosleep(100);
-                }
-                if ((++spins & 0x3ffu) == 0 && wd.expired_now(106)) return false;
+                if ((++spins & 0xfffu) == 0 && wd.expired_now(106)) return false;
             }
         };
         if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 1] = clock64();
@@ -266,45 +298,47 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
             if (len > 1) { q1 = sidx[32 + lane];  c1v = sval[32 + lane]; }
             if (len > 2) { q2 = sidx[64 + lane];  c2v = sval[64 + lane]; }
             if (len > 3) { q3 = sidx[96 + lane];  c3v = sval[96 + lane]; }
+            // everything the fast path needs is computed BEFORE the gate: what runs after it is the critical path
+            uint32_t fa[4];
+            unsigned fg[4];
+            double fc[4];
+            {
+                const uint32_t rb = smem_u32(ring);
+                const int qq[4] = {q0, q1, q2, q3};
+                const double cc[4] = {c0v, c1v, c2v, c3v};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < len) {
+                        if ((unsigned)qq[k] & kReadyBit) {
+                            fa[k] = rb + ((unsigned)(R + 1) << 4);
+                            fg[k] = 0xffffffffu;
+                        } else {
+                            fa[k] = rb + (((unsigned)qq[k] & (unsigned)P.ring_mask) << 4);
+                            fg[k] = ((unsigned)qq[k] & 0x3fffffffu) + 1u;
+                        }
+                        fc[k] = cc[k];
+                    } else {
+                        fa[k] = rb + ((unsigned)R << 4);
+                        fg[k] = 0xffffffffu;
+                        fc[k] = 0.0;
+                    }
+                    asm volatile("" : "+r"(fa[k]), "+r"(fg[k]));  // pin the values in registers before the gate
+                }
+            }
+            const uint32_t myslot_s = smem_u32(myslot);
+            const bool fast = (kind & 8) && w <= 4 && !remote_pending && P.fastpath;
             if (!wait_gate()) return;
             if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 2] = clock64();
             int j = 0;
-            if ((kind & 8) && w <= 4 && !remote_pending && P.fastpath) {
-                // ---- straight-line fast path: a single-level chunk has no internal dependencies and every
-                // dependency sits at a lower level, so the whole warp may block until all of them have arrived:
-                // up to four 16-byte ring polls in flight per lane, one vote, then the multiply-subtract chain
-                // in the stored order, the diagonal and one 16-byte publish.  This is the per-level critical path.
-                const bool n0 = len > 0 && !((unsigned)q0 & kReadyBit), n1 = len > 1 && !((unsigned)q1 & kReadyBit);
-                const bool n2 = len > 2 && !((unsigned)q2 & kReadyBit), n3 = len > 3 && !((unsigned)q3 & kReadyBit);
-                const uint32_t rb = smem_u32(ring);
-                const uint32_t a0 = rb + (((unsigned)q0 & (unsigned)P.ring_mask) << 4);
-                const uint32_t a1 = rb + (((unsigned)q1 & (unsigned)P.ring_mask) << 4);
-                const uint32_t a2 = rb + (((unsigned)q2 & (unsigned)P.ring_mask) << 4);
-                const uint32_t a3 = rb + (((unsigned)q3 & (unsigned)P.ring_mask) << 4);
-                const unsigned g0 = ((unsigned)q0 & 0x3fffffffu) + 1u, g1 = ((unsigned)q1 & 0x3fffffffu) + 1u;
-                const unsigned g2 = ((unsigned)q2 & 0x3fffffffu) + 1u, g3 = ((unsigned)q3 & 0x3fffffffu) + 1u;
-                double y0 = 1.0, y1 = 1.0, y2 = 1.0, y3 = 1.0;
-                unsigned spins = 0;
-                while (true) {
-                    bool ok = true;
-                    unsigned long long xb0, xb1, xb2, xb3, u0, u1, u2, u3;
-                    if (n0) ld_b128_cta(a0, xb0, u0);
-                    if (n1) ld_b128_cta(a1, xb1, u1);
-                    if (n2) ld_b128_cta(a2, xb2, u2);
-                    if (n3) ld_b128_cta(a3, xb3, u3);
-                    if (n0) { ok = ok && ((unsigned)u0 == g0); y0 = __longlong_as_double((long long)xb0); }
-                    if (n1) { ok = ok && ((unsigned)u1 == g1); y1 = __longlong_as_double((long long)xb1); }
-                    if (n2) { ok = ok && ((unsigned)u2 == g2); y2 = __longlong_as_double((long long)xb2); }
-                    if (n3) { ok = ok && ((unsigned)u3 == g3); y3 = __longlong_as_double((long long)xb3); }
-                    if (__all_sync(FULL, ok)) break;
-                    if ((++spins & 0xfffu) == 0 && wd.expired_now(107)) return;
-                }
-                if (len > 0) acc = sub_mul<EXACT>(acc, c0v, y0);
-                if (len > 1) acc = sub_mul<EXACT>(acc, c1v, y1);
-                if (len > 2) acc = sub_mul<EXACT>(acc, c2v, y2);
-                if (len > 3) acc = sub_mul<EXACT>(acc, c3v, y3);
+            if (fast) {
+                bool okf;
+                if (w <= 1) okf = fast_resolve<1, EXACT>(fa, fg, fc, acc, wd);
+                else if (w == 2) okf = fast_resolve<2, EXACT>(fa, fg, fc, acc, wd);
+                else if (w == 3) okf = fast_resolve<3, EXACT>(fa, fg, fc, acc, wd);
+                else okf = fast_resolve<4, EXACT>(fa, fg, fc, acc, wd);
+                if (!okf) return;
                 xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
-                if (r >= 0) st_ring(myslot, xfin, mytag);
+                if (r >= 0) st_ring_s(myslot_s, xfin, mytag);
             } else {
             {
                 double y0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
