@@ -366,12 +366,19 @@ __global__ void k_chunk_shape(int nchunks, SrcDev S, const int* __restrict__ row
     }
 }
 
-__global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows, const int* __restrict__ rlen,
-                             const int* __restrict__ chunk_ptr, const int* __restrict__ rowpos,
-                             const int* __restrict__ pcp, int nparts, int near, unsigned char* __restrict__ ckind,
-                             int* __restrict__ idx, int* __restrict__ srcpos, int* __restrict__ diagpos,
-                             unsigned char* __restrict__ pub, const int* __restrict__ level,
-                             int* __restrict__ gate) {
+// Pack one chunk.  mode 0: only count the chunk's remote edges (nrem[c]); mode 1: write everything, with the
+// halo position of every remote edge taken from hptr (exclusive scan of nrem).
+// Dependency encoding (see ilub_common.cuh): local ring position, or halo ring position for remote edges --
+// every remote (other CTA / too far back) edge gets its own halo entry, filled by the CTA's fetcher warps
+// from the producer's mailbox, so compute warps only ever poll shared memory.
+__global__ void k_chunk_fill(int mode, int nchunks, SrcDev S, const int* __restrict__ rows,
+                             const int* __restrict__ rlen, const int* __restrict__ chunk_ptr,
+                             const int* __restrict__ rowpos, const int* __restrict__ pcp, int nparts, int near,
+                             unsigned char* __restrict__ ckind, int* __restrict__ idx, int* __restrict__ srcpos,
+                             int* __restrict__ diagpos, unsigned char* __restrict__ pub,
+                             const int* __restrict__ level, int* __restrict__ gate, int* __restrict__ nrem,
+                             const int* __restrict__ hptr, int* __restrict__ halo_src,
+                             int* __restrict__ halo_cons, int halo_cap) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= nchunks) return;
@@ -388,6 +395,31 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
     const int row = rows[c * 32 + lane];
     const int len = rlen[c * 32 + lane];
     const int kind = ckind[c] & 1;
+    const int b = row >= 0 ? src_beg(S, row) : 0;
+    const int e = b + len;
+    // remote edges of this lane, and their first halo position inside the chunk
+    int myrem = 0;
+    for (int j = 0; j < len; ++j) {
+        const int q = S.reverse ? e - 1 - j : b + j;
+        const int dc = rowpos[S.dep_idx[q]] >> 5;
+        if (!(dc >= cfirst && dc <= c && c - dc <= near)) ++myrem;
+    }
+    int pre = myrem;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pre, d);
+        if (lane >= d) pre += t;
+    }
+    const int chunk_rem = __shfl_sync(0xffffffffu, pre, 31);
+    pre -= myrem;
+    // a chunk with more remote edges than a fraction of the halo ring polls the mailboxes directly instead
+    // (its edges could not all be resident in the ring at once)
+    const bool use_halo = chunk_rem <= halo_cap;
+    if (mode == 0) {
+        if (lane == 0) nrem[c] = use_halo ? chunk_rem : 0;
+        return;
+    }
+    const int hfirst = hptr[cfirst];           // halo positions are numbered per CTA
+    int hp = hptr[c] + pre;                    // global halo position of this lane's next remote edge
     const int64_t base = (int64_t)chunk_ptr[c] * 32;
     const int w = chunk_ptr[c + 1] - chunk_ptr[c];
     diagpos[c * 32 + lane] = (row >= 0 && S.diag_pos) ? S.diag_pos[row] : -1;
@@ -405,13 +437,11 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
             srcpos[base + t] = -1;
         }
     }
-    bool intra = false, remote = false;
+    bool intra = false;
     const int lv = row >= 0 ? level[row] : 0x7fffffff;
     const int lvmin = __reduce_min_sync(0xffffffffu, lv);
     const int lvmax = __reduce_max_sync(0xffffffffu, row >= 0 ? lv : -1);
     int g = -1;  // last local position (CTA numbering) feeding the rows of this chunk's lowest level
-    const int b = row >= 0 ? src_beg(S, row) : 0;
-    const int e = b + len;
     for (int j = 0; j < (kind ? len : w); ++j) {
         const int64_t at = kind ? base + off + j : base + (int64_t)j * 32 + lane;
         if (j >= len) {
@@ -428,17 +458,23 @@ __global__ void k_chunk_fill(int nchunks, SrcDev S, const int* __restrict__ rows
             if (dc == c) intra = true;
             if (lv == lvmin) g = max(g, pd - (cfirst << 5));
             enc = kLocalBit | (unsigned)(pd - (cfirst << 5));
-        } else {
-            enc = (unsigned)d;
-            remote = true;
+        } else if (use_halo) {
+            enc = kLocalBit | kHaloBit | (unsigned)(hp - hfirst);
+            halo_src[hp] = d;
+            halo_cons[hp] = c - cfirst;
+            ++hp;
             pub[d] = 1;  // row d must publish through the mailbox
+        } else {
+            enc = (unsigned)d;  // direct mailbox poll by the consumer
+            pub[d] = 1;
         }
         idx[at] = (int)enc;
         srcpos[at] = S.val_pos ? S.val_pos[q] : q;
     }
-    const bool any_intra = __any_sync(0xffffffffu, intra), any_remote = __any_sync(0xffffffffu, remote);
+    const bool any_intra = __any_sync(0xffffffffu, intra);
     if (lane == 0)
-        ckind[c] = (unsigned char)(kind | (any_intra ? 2 : 0) | (any_remote ? 4 : 0) | (lvmin == lvmax ? 8 : 0));
+        ckind[c] = (unsigned char)(kind | (any_intra ? 2 : 0) | (chunk_rem > 0 ? 4 : 0) | (lvmin == lvmax ? 8 : 0) |
+                                   ((chunk_rem > 0 && !use_halo) ? 16 : 0));
     g = __reduce_max_sync(0xffffffffu, g + 1) - 1;
     if (lane == 0) gate[c] = g;
 }
@@ -824,25 +860,31 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     T.any_kind_b = hshape[3];
     T.nslabs = nsl;
     {   // launch configuration of the sync-free kernel; `near` is baked into the encoded indices below
-        int W = (int)std::min<int64_t>(16, std::max<int64_t>(1, opt.warps_per_cta));  // kernel: __launch_bounds__(512)
-        int RC = 64;
+        int W = (int)std::min<int64_t>(16, std::max<int64_t>(2, opt.warps_per_cta));  // kernel: __launch_bounds__(512)
+        int F = (int)std::min<int64_t>(W - 1, std::max<int64_t>(1, opt.fetch_warps));
+        int RC = 32;
         while (RC * 2 <= opt.ring_chunks) RC *= 2;
         int near = (int)std::min<int64_t>(opt.near_window, RC / 2);
+        int HR = 256;
+        while (HR * 2 <= opt.halo_entries) HR *= 2;
         int stages = (int)std::min<int64_t>(2, std::max<int64_t>(1, opt.stages));
         const int slabs = std::max(1, T.maxw_a);
         const size_t budget = (size_t)227 * 1024 / (size_t)std::max<int64_t>(1, opt.ctas_per_sm) - 1024;
         auto need = [&]() {
-            return (size_t)RC * 512 + 128 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + 128 + 128;
+            return (size_t)RC * 512 + 128 + (size_t)HR * 16 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + 128 + 128;
         };
         while (need() > budget) {
             if (stages > 1) stages = 1;
             else if (RC > 64) { RC /= 2; near = std::min(near, RC / 2); }
-            else if (W > 2) W /= 2;
+            else if (HR > 256) HR /= 2;
+            else if (W > 4) { W /= 2; F = std::min(F, W - 1); }
             else throw Error{ILUB_ERR_INVALID, "sync-free solve does not fit in shared memory (lower wcap)"};
         }
         T.cfg_warps = W;
+        T.cfg_fetch = F;
         T.cfg_ring_chunks = RC;
         T.cfg_near = near;
+        T.cfg_halo = HR;
         T.cfg_stages = stages;
         T.cfg_stage_slabs = slabs;
         T.cfg_smem = need();
@@ -856,9 +898,32 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     DevBuf<unsigned char> pub;
     pub.alloc(n);
     ILUB_CUDA(cudaMemsetAsync(pub.p, 0, n, s));
-    k_chunk_fill<<<blocks_for(nlane, 256), 256, 0, s>>>(nchunks, S, T.rows.p, T.rlen.p, T.chunk_ptr.p, T.rowpos.p,
-                                                        T.part_chunk_ptr.p, nparts, T.cfg_near, T.ckind.p,
-                                                        T.idx.p, T.srcpos.p, T.diagpos.p, pub.p, T.level.p, T.gate.p);
+    // pass 0: count remote edges per chunk -> halo pointers; pass 1: fill
+    DevBuf<int> nrem;
+    nrem.alloc(nchunks + 1);
+    ILUB_CUDA(cudaMemsetAsync(nrem.p, 0, sizeof(int) * (nchunks + 1), s));
+    k_chunk_fill<<<blocks_for(nlane, 256), 256, 0, s>>>(0, nchunks, S, T.rows.p, T.rlen.p, T.chunk_ptr.p, T.rowpos.p,
+                                                        T.part_chunk_ptr.p, nparts, T.cfg_near, T.ckind.p, nullptr,
+                                                        nullptr, nullptr, nullptr, T.level.p, nullptr, nrem.p, nullptr,
+                                                        nullptr, nullptr);
+    T.hptr.alloc(nchunks + 1);
+    {
+        size_t tbh = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tbh, nrem.p, T.hptr.p, nchunks + 1, s);
+        DevBuf<unsigned char> tmph;
+        tmph.alloc(tbh);
+        ILUB_CUDA(cub::DeviceScan::ExclusiveSum(tmph.p, tbh, nrem.p, T.hptr.p, nchunks + 1, s));
+        int nh = 0;
+        ILUB_CUDA(cudaMemcpyAsync(&nh, T.hptr.p + nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+        ILUB_CUDA(cudaStreamSynchronize(s));
+        T.nhalo = nh;
+    }
+    T.halo_src.alloc(T.nhalo);
+    T.halo_cons.alloc(T.nhalo);
+    k_chunk_fill<<<blocks_for(nlane, 256), 256, 0, s>>>(1, nchunks, S, T.rows.p, T.rlen.p, T.chunk_ptr.p, T.rowpos.p,
+                                                        T.part_chunk_ptr.p, nparts, T.cfg_near, T.ckind.p, T.idx.p,
+                                                        T.srcpos.p, T.diagpos.p, pub.p, T.level.p, T.gate.p, nrem.p,
+                                                        T.hptr.p, T.halo_src.p, T.halo_cons.p, T.cfg_halo / 4);
     T.pubmask.alloc(nchunks);
     k_pubmask<<<blocks_for(nlane, 256), 256, 0, s>>>(nchunks, T.rows.p, pub.p, T.pubmask.p);
     T.mail.alloc(n);

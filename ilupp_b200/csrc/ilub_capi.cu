@@ -430,6 +430,8 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "partition") o.partition = value;
         else if (k == "nparts") o.nparts = value;
         else if (k == "trace") o.trace = value;
+        else if (k == "fetch_warps") o.fetch_warps = value;
+        else if (k == "halo_entries") o.halo_entries = value;
         else if (k == "fastpath") o.fastpath = value;
         else if (k == "level_align") o.level_align = value;
         else if (k == "align_min_rows") o.align_min_rows = value;

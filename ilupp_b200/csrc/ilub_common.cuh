@@ -66,9 +66,11 @@ struct Options {
     int64_t exact = 1;          // IEEE mul/sub/div in reference order
     int64_t ctas_per_sm = 1;
     int64_t warps_per_cta = 16;
-    int64_t near_window = 112;  // chunks; dependencies this close (same CTA) go through shared memory
-    int64_t ring_chunks = 256;  // shared-memory x ring, in 32-row chunks (power of two, >= 2*near_window)
+    int64_t near_window = 56;   // chunks; dependencies this close (same CTA) go through shared memory
+    int64_t ring_chunks = 128;  // shared-memory x ring, in 32-row chunks (power of two, >= 2*near_window)
     int64_t wcap = 8;           // widest lane-per-row chunk (slabs); wider chunks are warp-cooperative
+    int64_t fetch_warps = 2;    // warps per CTA that only move remote values from mailboxes into the halo ring
+    int64_t halo_entries = 2048;// halo ring size (remote edges in flight per CTA)
     int64_t gate_slack = 8;     // start fine-grained polling this many chunks before the gate chunk completes
     int64_t stages = 2;         // TMA staging depth per warp
     int64_t spin_limit_ms = 1500;
@@ -85,13 +87,15 @@ Options& options();
 
 constexpr int kLanes = 32;
 // dependency encoding inside a packed chunk (int32):
-//   e >= 0                      global path: original row index (value + epoch tag read from mail[e] in one
-//                               128-bit access)
-//   e <  0                      shared-memory path: low 30 bits = position in this CTA's processing order
-//                               (value + tag read from the x ring in one 128-bit access)
+//   bit 31 set, bit 30 clear    local ring: low 30 bits = position of the producing row in this CTA's order
+//   bit 31 set, bit 30 set      halo ring: low 30 bits = number of this remote edge in the CTA's edge order;
+//                               the CTA's fetcher warps copy the producer's mailbox entry there
+// Both are polled with one atomic 128-bit shared-memory load of {value, tag = position + 1}.
+//   bit 31 clear                direct mailbox poll: original row index (chunks with too many remote edges
+//                               for the halo ring; general path only)
 constexpr unsigned kLocalBit = 0x80000000u;
 constexpr unsigned kIntraBit = 0x40000000u;
-constexpr unsigned kReadyBit = 0x40000000u;  // run-time only: staged coefficient already holds v*x
+constexpr unsigned kHaloBit = 0x40000000u;
 
 // One triangular solve packed in solve order (see DESIGN.md "data layout in HBM").
 struct TriSolve {
@@ -110,7 +114,7 @@ struct TriSolve {
     DevBuf<int> rowpos;           // [n] (chunk << 5 | lane) of every row
     DevBuf<int> part_chunk_ptr;   // [nparts + 1]
     DevBuf<int> chunk_ptr;        // [nchunks + 1] slab offset of every chunk
-    DevBuf<unsigned char> ckind;  // [nchunks] bit0: warp-cooperative (kind B); bit1: has same-chunk deps; bit2: has mailbox deps; bit3: single level
+    DevBuf<unsigned char> ckind;  // [nchunks] bit0: warp-cooperative (kind B); bit1: has same-chunk deps; bit2: has mailbox deps; bit3: single level; bit4: direct mailbox polls
     DevBuf<int> rows;             // [nchunks * 32] original row per lane (-1 = padding)
     DevBuf<int> rlen;             // [nchunks * 32] number of off-diagonal entries per lane
     DevBuf<int> idx;              // [nslabs * 32] encoded dependencies
@@ -120,13 +124,18 @@ struct TriSolve {
     DevBuf<int> diagpos;          // [nchunks * 32] position of the diagonal value (-1: unit / padding)
     DevBuf<int> gate;             // [nchunks] gate row: last local position feeding this chunk's lowest level (-1: none)
     DevBuf<unsigned> pubmask;     // [nchunks] lanes whose row is read through the global path by someone
+    DevBuf<int> hptr;             // [nchunks + 1] first remote edge (halo position) of every chunk
+    DevBuf<int> halo_src;         // [nhalo] producing row of every remote edge
+    DevBuf<int> halo_cons;        // [nhalo] consuming chunk (CTA numbering) of every remote edge
+    int nhalo = 0;
     DevBuf<ulonglong2> mail;      // [n] {x bits, epoch tag}: the global dependency path (one 16-B atomic access)
     unsigned long long epoch = 0;
     int level_aligned = 0;
     int part_mode = 0;            // 0 contiguous ranges, 2 / 3: strips / pencils from detected strides
     int stride_y = 0, stride_z = 0, grid_y = 1, grid_z = 1;
     // launch configuration of the sync-free kernel, fixed at analysis (near is baked into idx)
-    int cfg_warps = 16, cfg_ring_chunks = 256, cfg_near = 96, cfg_stages = 2, cfg_stage_slabs = 1;
+    int cfg_warps = 16, cfg_fetch = 2, cfg_ring_chunks = 128, cfg_near = 56, cfg_halo = 2048, cfg_stages = 2,
+        cfg_stage_slabs = 1;
     size_t cfg_smem = 0;
     // level-set listing for the level-scheduled variant / ilub_get_level_sets (built on demand)
     DevBuf<long long> trace;      // debug stamps (option trace)

@@ -42,6 +42,11 @@ struct TrsvParams {
     const double* diag;
     const unsigned* pubmask;
     const int* gate;
+    const int* hptr;
+    const int* halo_src;
+    const int* halo_cons;
+    int halo_mask;
+    int nfetch;
     int slack;
     double* x;
     ulonglong2* mail;
@@ -87,20 +92,34 @@ struct Watchdog {
     }
 };
 
-// one dependency poll: mailbox (global, e >= 0) or x ring (shared, e < 0); true when the value is there
-__device__ __forceinline__ bool poll_dep(int e, const ulonglong2* mail, unsigned long long epoch,
-                                         const ulonglong2* ring, int ring_mask, double& xv) {
-    if (e >= 0) return ld_mail(mail + e, epoch, xv);
-    if ((unsigned)e & kReadyBit) {  // remote value already folded into the staged coefficient
-        xv = 1.0;
-        return true;
+// Shared-memory geometry of one CTA (all dependency polls are 16-byte shared-memory loads).
+struct SmemView {
+    uint32_t ring_s;   // shared address of the x ring  {x, local position + 1}
+    uint32_t halo_s;   // shared address of the halo ring {x, edge number + 1}
+    unsigned ring_mask, halo_mask;
+    // (address, expected tag) of an encoded dependency
+    __device__ __forceinline__ void locate(int e, uint32_t& addr, unsigned& tag) const {
+        const unsigned p = (unsigned)e & 0x3fffffffu;
+        const bool halo = ((unsigned)e & kHaloBit) != 0;
+        addr = (halo ? halo_s : ring_s) + ((p & (halo ? halo_mask : ring_mask)) << 4);
+        tag = p + 1u;
     }
-    const int lp = e & 0x3fffffff;
-    return ld_ring(ring + (lp & ring_mask), (unsigned long long)lp + 1ull, xv);
+};
+
+__device__ __forceinline__ bool poll_dep(int e, const SmemView& sv, const ulonglong2* mail, unsigned long long epoch,
+                                         double& xv) {
+    if (e >= 0) return ld_mail(mail + e, epoch, xv);  // direct mailbox poll (halo-heavy chunks only)
+    uint32_t a;
+    unsigned g;
+    sv.locate(e, a, g);
+    unsigned long long xb, t;
+    ld_b128_cta(a, xb, t);
+    xv = __longlong_as_double((long long)xb);
+    return (unsigned)t == g;
 }
 
-// Critical path of a single-level lane-per-row chunk: NW ring polls in flight per lane (absent / pre-folded
-// dependencies point at two always-ready dummy entries), one vote, NW multiply-subtracts in stored order.
+// Critical path of a single-level lane-per-row chunk: NW ring polls in flight per lane (absent dependencies
+// point at an always-ready dummy entry holding 0.0), one vote, NW multiply-subtracts in stored order.
 template <int NW, bool EXACT>
 __device__ __forceinline__ bool fast_resolve(const uint32_t (&a)[4], const unsigned (&g)[4], const double (&cv)[4],
                                              double& acc, Watchdog& wd) {
@@ -127,31 +146,93 @@ template <bool EXACT>
 __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int WC = W - P.nfetch;  // compute warps; the last nfetch warps are halo fetchers
     const int R = P.ring_mask + 1;
-    ulonglong2* ring = reinterpret_cast<ulonglong2*>(smem);  // {x bits, local position + 1}
-    unsigned char* stage_base = smem + (size_t)(R + 8) * 16;  // 8 spare entries: [R] = {0.0, ~0}, [R+1] = {1.0, ~0}
+    const int HR = P.halo_mask + 1;
+    ulonglong2* ring = reinterpret_cast<ulonglong2*>(smem);                  // [R + 8]; [R] = {0.0, ~0} dummy
+    ulonglong2* halo = ring + (R + 8);                                       // [HR]
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(halo + HR);
     const int stage_bytes = P.stage_slabs * 384;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + (size_t)W * P.nstages * stage_bytes);
-    int* warp_cur = reinterpret_cast<int*>(mbar + W * P.nstages);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + (size_t)WC * P.nstages * stage_bytes);
+    int* warp_cur = reinterpret_cast<int*>(mbar + WC * P.nstages);
 
     const int c0 = P.part_chunk_ptr[blockIdx.x];
     const int nloc = P.part_chunk_ptr[blockIdx.x + 1] - c0;
-    for (int i = threadIdx.x; i < R; i += blockDim.x) ring[i] = make_ulonglong2(0ull, 0ull);
-    if (threadIdx.x == 0) {
-        ring[R] = make_ulonglong2(0ull, 0xffffffffffffffffull);
-        ring[R + 1] = make_ulonglong2((unsigned long long)__double_as_longlong(1.0), 0xffffffffffffffffull);
-    }
-    if (threadIdx.x < 32) warp_cur[threadIdx.x] = (threadIdx.x < W && threadIdx.x < nloc) ? threadIdx.x : INT_MAX;
-    if (lane == 0) {
+    for (int i = threadIdx.x; i < R + 8 + HR; i += blockDim.x) ring[i] = make_ulonglong2(0ull, 0ull);
+    if (threadIdx.x < 32) warp_cur[threadIdx.x] = (threadIdx.x < WC && threadIdx.x < nloc) ? threadIdx.x : INT_MAX;
+    if (lane == 0 && warp < WC) {
         for (int s = 0; s < P.nstages; ++s) mbar_init(&mbar[warp * P.nstages + s], 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (warp >= nloc) return;
+    if (threadIdx.x == 0) ring[R] = make_ulonglong2(0ull, 0xffffffffffffffffull);
+    __syncthreads();
 
-    unsigned phasebits = 0;
-    int done_cache = 0;
     Watchdog wd(P.status, P.spin_limit);
+    SmemView sv;
+    sv.ring_s = smem_u32(ring);
+    sv.halo_s = smem_u32(halo);
+    sv.ring_mask = (unsigned)P.ring_mask;
+    sv.halo_mask = (unsigned)P.halo_mask;
+    int done_cache = 0;
+    auto refresh_done = [&]() {
+        int v = lane < WC ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
+        done_cache = __reduce_min_sync(FULL, v);
+    };
+
+    if (warp >= WC) {
+        // ================================================================== halo fetcher warps
+        // Remote edges (dependencies on rows of other CTAs, or too far back for the x ring) are numbered per
+        // CTA in the order their consumers are processed.  A fetcher takes 128 consecutive edges, polls the
+        // producers' 16-byte mailboxes in global memory {x, epoch} and drops each value into the halo ring
+        // {x, edge + 1}, far ahead of the compute warps -- which therefore never wait on an L2 round trip.
+        const int h0 = P.hptr[c0];
+        const int nh = P.hptr[c0 + nloc] - h0;
+        const int fid = warp - WC;
+        for (int pos = fid * 128; pos < nh; pos += P.nfetch * 128) {
+            int src[4], need = 0;
+            bool todo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int hp = pos + k * 32 + lane;
+                todo[k] = hp < nh;
+                src[k] = todo[k] ? P.halo_src[h0 + hp] : 0;
+                // the slot still belongs to edge hp - HR until that edge's consumer chunk has completed
+                if (todo[k] && hp >= HR) need = max(need, P.halo_cons[h0 + hp - HR] + 1);
+            }
+            need = __reduce_max_sync(FULL, need);
+            while (done_cache < need) {
+                refresh_done();
+                if (done_cache >= need) break;
+                __nanosleep(200);
+                if (wd.expired(108)) return;
+            }
+            unsigned spins = 0;
+            while (true) {
+                bool pending = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (todo[k]) {
+                        double xr;
+                        if (ld_mail(P.mail + src[k], P.epoch, xr)) {
+                            const unsigned hp = (unsigned)(pos + k * 32 + lane);
+                            st_ring_s(sv.halo_s + ((hp & sv.halo_mask) << 4), xr, (unsigned long long)hp + 1ull);
+                            todo[k] = false;
+                        } else {
+                            pending = true;
+                        }
+                    }
+                }
+                if (!__any_sync(FULL, pending)) break;
+                if ((++spins & 0xffu) == 0 && wd.expired_now(109)) return;
+            }
+        }
+        return;
+    }
+
+    // ====================================================================== compute warps
+    if (warp >= nloc) return;
+    unsigned phasebits = 0;
 
     // lane 0: start the bulk copies of local chunk lc into this warp's stage (it % nstages)
     auto issue = [&](int lc, int it) {
@@ -177,11 +258,10 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
     double d = P.unit_diag ? 1.0 : P.diag[(size_t)(c0 + lc) * 32 + lane];
     double acc = r >= 0 ? __ldcg(P.x + r) : 0.0;
 
-    for (int it = 0; lc < nloc; lc += W, ++it) {
+    for (int it = 0; lc < nloc; lc += WC, ++it) {
         const int c = c0 + lc;
-        const int nlc = lc + W;
+        const int nlc = lc + WC;
         const bool has_next = nlc < nloc;
-        fence_proxy_async();  // generic-proxy writes into a stage (remote prefetch) before the next bulk copy into it
         __syncwarp();
         if (has_next && lane == 0 && P.nstages > 1) issue(nlc, it + 1);
         int r1 = -1, len1 = 0;
@@ -196,43 +276,34 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
         const int w = P.chunk_ptr[c + 1] - cp;
         const unsigned kind = P.ckind[c];
         const unsigned pubm = P.pubmask[c];
-        const bool pubm_remote = (kind & 4) != 0;  // chunk has mailbox dependencies
+        const int gate_lp = P.gate[c];
         double xfin = 0.0;
 
         // (1) ring safety: the ring slots of chunk lc are those of chunk lc - rc; they may be overwritten once
         //     every chunk that could still read them through shared memory (ids <= lc - rc + near) is done.
         const int need = lc - P.rc + P.near + 1;
-        if (need > done_cache) {
-            while (true) {
-                int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
-                v = __reduce_min_sync(FULL, v);
-                done_cache = v;
-                if (v >= need) break;
-                __nanosleep(64);
-                if (wd.expired(105)) return;
-            }
+        while (need > done_cache) {
+            refresh_done();
+            if (done_cache >= need) break;
+            __nanosleep(64);
+            if (wd.expired(105)) return;
         }
         // (2) gate row: the last row (in processing order) that feeds this chunk's lowest level.  Until it is
-        //     published nothing in this chunk can finish, so the whole warp waits on that ONE ring entry
-        //     (same address for all lanes: a broadcast, one shared-memory wavefront per poll) instead of
-        //     32 lanes polling 32 different entries and saturating the shared-memory pipe for the warps
-        //     that are on the critical path.  The gate row has a strictly lower level than every row of
-        //     this chunk, so blocking on it cannot create a cycle.
-        const int gate_lp = P.gate[c];
+        //     published nothing in this chunk can finish, so the warp waits on that ONE ring entry (one lane
+        //     polls: one shared-memory wavefront per round) instead of 32 lanes polling 32 entries and
+        //     saturating the shared-memory pipe for the warps on the critical path.  The gate row has a
+        //     strictly lower level than every row of this chunk, so blocking on it cannot create a cycle.
         auto wait_gate = [&]() -> bool {
             if (gate_lp < 0 || P.slack < 0) return true;
-            const uint32_t ga = smem_u32(ring + (gate_lp & P.ring_mask));
+            const uint32_t ga = sv.ring_s + (((unsigned)gate_lp & sv.ring_mask) << 4);
             const unsigned gt = (unsigned)gate_lp + 1u;
             const int gate_chunk = gate_lp >> 5;
-            // far from the frontier: watch the per-warp progress words and sleep
-            while (gate_chunk - done_cache > P.slack) {
-                int v = lane < W ? ld_relaxed_cta_s32(&warp_cur[lane]) : INT_MAX;
-                done_cache = __reduce_min_sync(FULL, v);
+            while (gate_chunk - done_cache > P.slack) {  // far from the frontier: progress words + sleep
+                refresh_done();
                 if (gate_chunk - done_cache <= P.slack) break;
                 __nanosleep(100);
                 if (wd.expired(106)) return false;
             }
-            // near: one lane polls the gate row (one shared-memory wavefront per round)
             unsigned spins = 0;
             while (true) {
                 bool open = false;
@@ -246,7 +317,7 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
             }
         };
         if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 1] = clock64();
-        ulonglong2* myslot = ring + ((lc * 32 + lane) & P.ring_mask);
+        const uint32_t myslot_s = sv.ring_s + (((unsigned)(lc * 32 + lane) & sv.ring_mask) << 4);
         const unsigned long long mytag = (unsigned long long)(lc * 32 + lane) + 1ull;
 
         if ((kind & 1) == 0) {
@@ -263,74 +334,28 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
                 phasebits ^= 1u << st;
             }
             const double dinv = EXACT ? 0.0 : 1.0 / d;
-            // Remote prefetch: resolve mailbox dependencies up front (a few bounded attempts, all lanes and
-            // slabs in parallel) and fold them into the staged coefficient (v := v*x, index := READY), so
-            // that the ordered hand-off loop below never waits on an L2 round trip in the middle of a
-            // chain.  Anything not there yet is simply polled in place later -- no blocking, no deadlock.
-            bool remote_pending = false;
-            if (pubm_remote) {
-                int* widx = const_cast<int*>(sidx);
-                double* wval = const_cast<double*>(sval);
-                for (int attempt = 0; attempt < 4; ++attempt) {
-                    bool pending = false;
-                    for (int jj = 0; jj < len; ++jj) {
-                        const int ee = widx[jj * 32 + lane];
-                        if (ee >= 0) {
-                            double xr;
-                            if (ld_mail(P.mail + ee, P.epoch, xr)) {
-                                const double vv = wval[jj * 32 + lane];
-                                wval[jj * 32 + lane] = EXACT ? __dmul_rn(vv, xr) : vv * xr;
-                                widx[jj * 32 + lane] = (int)(kLocalBit | kReadyBit);
-                            } else {
-                                pending = true;
-                            }
-                        }
-                    }
-                    remote_pending = __any_sync(FULL, pending);
-                    if (!remote_pending) break;
-                }
-            }
-            // the first (up to) four dependencies of the lane go to registers while the warp is still waiting
-            // at its gate: once the gate opens they are polled all at once (one shared-memory round trip)
-            int q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-            double c0v = 0.0, c1v = 0.0, c2v = 0.0, c3v = 0.0;
-            if (len > 0) { q0 = sidx[lane];       c0v = sval[lane]; }
-            if (len > 1) { q1 = sidx[32 + lane];  c1v = sval[32 + lane]; }
-            if (len > 2) { q2 = sidx[64 + lane];  c2v = sval[64 + lane]; }
-            if (len > 3) { q3 = sidx[96 + lane];  c3v = sval[96 + lane]; }
             // everything the fast path needs is computed BEFORE the gate: what runs after it is the critical path
             uint32_t fa[4];
             unsigned fg[4];
             double fc[4];
-            {
-                const uint32_t rb = smem_u32(ring);
-                const int qq[4] = {q0, q1, q2, q3};
-                const double cc[4] = {c0v, c1v, c2v, c3v};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < len) {
-                        if ((unsigned)qq[k] & kReadyBit) {
-                            fa[k] = rb + ((unsigned)(R + 1) << 4);
-                            fg[k] = 0xffffffffu;
-                        } else {
-                            fa[k] = rb + (((unsigned)qq[k] & (unsigned)P.ring_mask) << 4);
-                            fg[k] = ((unsigned)qq[k] & 0x3fffffffu) + 1u;
-                        }
-                        fc[k] = cc[k];
-                    } else {
-                        fa[k] = rb + ((unsigned)R << 4);
-                        fg[k] = 0xffffffffu;
-                        fc[k] = 0.0;
-                    }
-                    asm volatile("" : "+r"(fa[k]), "+r"(fg[k]));  // pin the values in registers before the gate
+            for (int k = 0; k < 4; ++k) {
+                if (k < len && !(kind & 16)) {
+                    sv.locate(sidx[k * 32 + lane], fa[k], fg[k]);
+                    fc[k] = sval[k * 32 + lane];
+                } else {
+                    fa[k] = sv.ring_s + ((unsigned)R << 4);  // dummy entry {0.0, ~0}
+                    fg[k] = 0xffffffffu;
+                    fc[k] = 0.0;
                 }
+                asm volatile("" : "+r"(fa[k]), "+r"(fg[k]));  // pin the values in registers before the gate
             }
-            const uint32_t myslot_s = smem_u32(myslot);
-            const bool fast = (kind & 8) && w <= 4 && !remote_pending && P.fastpath;
+            const bool fast = (kind & 8) && !(kind & 16) && w <= 4 && P.fastpath;
             if (!wait_gate()) return;
             if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 2] = clock64();
-            int j = 0;
             if (fast) {
+                // ---- straight-line fast path: a single-level chunk has no internal dependencies and every
+                // dependency sits at a lower level, so the whole warp may block until all of them have arrived.
                 bool okf;
                 if (w <= 1) okf = fast_resolve<1, EXACT>(fa, fg, fc, acc, wd);
                 else if (w == 2) okf = fast_resolve<2, EXACT>(fa, fg, fc, acc, wd);
@@ -340,94 +365,66 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
                 xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
                 if (r >= 0) st_ring_s(myslot_s, xfin, mytag);
             } else {
-            {
-                double y0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-                const bool k0 = len > 0 && poll_dep(q0, P.mail, P.epoch, ring, P.ring_mask, y0);
-                const bool k1 = len > 1 && poll_dep(q1, P.mail, P.epoch, ring, P.ring_mask, y1);
-                const bool k2 = len > 2 && poll_dep(q2, P.mail, P.epoch, ring, P.ring_mask, y2);
-                const bool k3 = len > 3 && poll_dep(q3, P.mail, P.epoch, ring, P.ring_mask, y3);
-                if (k0) {
-                    acc = sub_mul<EXACT>(acc, c0v, y0);
-                    j = 1;
-                    if (k1) {
-                        acc = sub_mul<EXACT>(acc, c1v, y1);
-                        j = 2;
-                        if (k2) {
-                            acc = sub_mul<EXACT>(acc, c2v, y2);
-                            j = 3;
-                            if (k3) {
-                                acc = sub_mul<EXACT>(acc, c3v, y3);
-                                j = 4;
-                            }
-                        }
-                    }
-                }
-            }
-            // ---- ordered hand-off loop.  Per lane: the dependency it is waiting for lives in registers as
-            // (address, expected tag, coefficient).  The warp spins in a TIGHT loop (one 16-byte load, one
-            // compare, one vote) until some lane's dependency has arrived; only then does it run the heavier
-            // progress code for the lanes that can move.
-            bool fin = false;
-            bool is_glob = false;
-            uint32_t saddr = 0;
-            const ulonglong2* gaddr = P.mail;
-            unsigned long long etag = 0ull;
-            double v = 0.0;
-            // walk forward from dependency j: consume everything already available, park on the first that is not
-            auto advance = [&]() {
-                while (j < len) {
-                    const int e_ = sidx[j * 32 + lane];
-                    const double v_ = sval[j * 32 + lane];
-                    double x_;
-                    if (poll_dep(e_, P.mail, P.epoch, ring, P.ring_mask, x_)) {
-                        acc = sub_mul<EXACT>(acc, v_, x_);
-                        ++j;
-                    } else {
-                        v = v_;
-                        is_glob = e_ >= 0;
-                        if (is_glob) {
-                            gaddr = P.mail + e_;
-                            etag = P.epoch;
+                // ---- general ordered hand-off loop (chunks that mix levels, rows with more than 4 entries).
+                // Per lane the dependency it is waiting for lives in registers as (address, tag, coefficient);
+                // the warp spins in a tight loop (one 16-byte load, one compare, one vote) until some lane's
+                // dependency has arrived and only then runs the progress code for the lanes that can move.
+                int j = 0;
+                bool fin = false;
+                uint32_t saddr = sv.ring_s + ((unsigned)R << 4);
+                unsigned etag = 0u;
+                const ulonglong2* gaddr = nullptr;  // non-null: parked on a direct mailbox dependency
+                double v = 0.0;
+                auto advance = [&]() {
+                    while (j < len) {
+                        const int e_ = sidx[j * 32 + lane];
+                        const double v_ = sval[j * 32 + lane];
+                        double x_;
+                        if (poll_dep(e_, sv, P.mail, P.epoch, x_)) {
+                            acc = sub_mul<EXACT>(acc, v_, x_);
+                            ++j;
                         } else {
-                            const int lp = e_ & 0x3fffffff;
-                            saddr = smem_u32(ring + (lp & P.ring_mask));
-                            etag = (unsigned long long)lp + 1ull;
+                            v = v_;
+                            gaddr = e_ >= 0 ? P.mail + e_ : nullptr;
+                            if (e_ < 0) sv.locate(e_, saddr, etag);
+                            return;
                         }
-                        return;
                     }
-                }
-                xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
-                if (r >= 0) st_ring(myslot, xfin, mytag);
-                fin = true;
-            };
-            advance();
-            while (!__all_sync(FULL, fin)) {
-                double xv = 0.0;
-                bool ok = false;
-                unsigned spins = 0;
-                while (true) {  // tight wait
-                    if (!fin) {
-                        unsigned long long xb, t;
-                        if (is_glob)
-                            ld_b128_gpu(gaddr, xb, t);
-                        else
-                            ld_b128_cta(saddr, xb, t);
-                        ok = (t == etag);
-                        xv = __longlong_as_double((long long)xb);
+                    xfin = P.unit_diag ? acc : (EXACT ? __ddiv_rn(acc, d) : acc * dinv);
+                    if (r >= 0) st_ring_s(myslot_s, xfin, mytag);
+                    fin = true;
+                };
+                advance();
+                while (!__all_sync(FULL, fin)) {
+                    double xv = 0.0;
+                    bool ok = false;
+                    unsigned spins = 0;
+                    while (true) {  // tight wait
+                        if (!fin) {
+                            unsigned long long xb, t;
+                            if (gaddr) {
+                                ld_b128_gpu(gaddr, xb, t);
+                                ok = (t == P.epoch);
+                            } else {
+                                ld_b128_cta(saddr, xb, t);
+                                ok = ((unsigned)t == etag);
+                            }
+                            xv = __longlong_as_double((long long)xb);
+                        }
+                        if (__any_sync(FULL, ok)) break;
+                        if ((++spins & 0xfffu) == 0 && wd.expired_now(103)) return;
                     }
-                    if (__any_sync(FULL, ok)) break;
-                    if ((++spins & 0xfffu) == 0 && wd.expired_now(103)) return;
-                }
-                if (ok) {
-                    acc = sub_mul<EXACT>(acc, v, xv);
-                    ++j;
-                    advance();
+                    if (ok) {
+                        acc = sub_mul<EXACT>(acc, v, xv);
+                        ++j;
+                        advance();
+                    }
                 }
             }
-            }  // generic path
         } else {
             // ------------------------------------------------------------ warp-cooperative chunk
             if (!wait_gate()) return;
+            if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 2] = clock64();
             int off = len;  // exclusive scan of len
             for (int s = 1; s < 32; s <<= 1) {
                 const int t = __shfl_up_sync(FULL, off, s);
@@ -450,7 +447,7 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
                     double xv = 0.0;
                     bool ok = !active;
                     while (true) {
-                        if (!ok) ok = poll_dep(e, P.mail, P.epoch, ring, P.ring_mask, xv);
+                        if (!ok) ok = poll_dep(e, sv, P.mail, P.epoch, xv);
                         if (__all_sync(FULL, ok)) break;
                         if (wd.expired(104)) return;
                     }
@@ -469,7 +466,7 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
                 if (lane == rr) {
                     const double t = EXACT ? run : acc - part;
                     xfin = P.unit_diag ? t : (EXACT ? __ddiv_rn(t, d) : t / d);
-                    st_ring(myslot, xfin, mytag);
+                    st_ring_s(myslot_s, xfin, mytag);
                 }
                 __syncwarp();
             }
@@ -485,7 +482,6 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
             if ((pubm >> lane) & 1u) st_mail(P.mail + r, xfin, P.epoch);
         }
         if (has_next && P.nstages == 1) {
-            fence_proxy_async();
             __syncwarp();
             if (lane == 0) issue(nlc, it + 1);
         }
@@ -593,6 +589,11 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.diag = T.diag.p;
     P.pubmask = T.pubmask.p;
     P.gate = T.gate.p;
+    P.hptr = T.hptr.p;
+    P.halo_src = T.halo_src.p;
+    P.halo_cons = T.halo_cons.p;
+    P.halo_mask = T.cfg_halo - 1;
+    P.nfetch = T.cfg_fetch;
     P.slack = (int)opt.gate_slack;
     P.fastpath = (int)opt.fastpath;
     P.mail = T.mail.p;
