@@ -871,7 +871,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         const int slabs = std::max(1, T.maxw_a);
         const size_t budget = (size_t)227 * 1024 / (size_t)std::max<int64_t>(1, opt.ctas_per_sm) - 1024;
         auto need = [&]() {
-            return (size_t)RC * 512 + 128 + (size_t)HR * 16 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + 128 + 128;
+            return (size_t)RC * 512 + 128 + (size_t)HR * 16 + (size_t)W * stages * slabs * 384 + (size_t)W * stages * 8 + (size_t)RC * 8 + 128 + 128;
         };
         while (need() > budget) {
             if (stages > 1) stages = 1;
@@ -905,7 +905,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     k_chunk_fill<<<blocks_for(nlane, 256), 256, 0, s>>>(0, nchunks, S, T.rows.p, T.rlen.p, T.chunk_ptr.p, T.rowpos.p,
                                                         T.part_chunk_ptr.p, nparts, T.cfg_near, T.ckind.p, nullptr,
                                                         nullptr, nullptr, nullptr, T.level.p, nullptr, nrem.p, nullptr,
-                                                        nullptr, nullptr);
+                                                        nullptr, nullptr, T.cfg_halo / 4);
     T.hptr.alloc(nchunks + 1);
     {
         size_t tbh = 0;

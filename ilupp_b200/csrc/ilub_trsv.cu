@@ -154,16 +154,17 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
     unsigned char* stage_base = reinterpret_cast<unsigned char*>(halo + HR);
     const int stage_bytes = P.stage_slabs * 384;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + (size_t)WC * P.nstages * stage_bytes);
-    int* warp_cur = reinterpret_cast<int*>(mbar + WC * P.nstages);
+    uint64_t* cbar = mbar + WC * P.nstages;  // [rc] one count-1 barrier per ring chunk slot: phase k = chunk slot + k*rc
+    int* warp_cur = reinterpret_cast<int*>(cbar + P.rc);
 
     const int c0 = P.part_chunk_ptr[blockIdx.x];
     const int nloc = P.part_chunk_ptr[blockIdx.x + 1] - c0;
     for (int i = threadIdx.x; i < R + 8 + HR; i += blockDim.x) ring[i] = make_ulonglong2(0ull, 0ull);
     if (threadIdx.x < 32) warp_cur[threadIdx.x] = (threadIdx.x < WC && threadIdx.x < nloc) ? threadIdx.x : INT_MAX;
-    if (lane == 0 && warp < WC) {
+    if (lane == 0 && warp < WC)
         for (int s = 0; s < P.nstages; ++s) mbar_init(&mbar[warp * P.nstages + s], 1);
-        fence_mbar_init();
-    }
+    for (int i = threadIdx.x; i < P.rc; i += blockDim.x) mbar_init(&cbar[i], 1);
+    fence_mbar_init();
     __syncthreads();
     if (threadIdx.x == 0) ring[R] = make_ulonglong2(0ull, 0xffffffffffffffffull);
     __syncthreads();
@@ -295,26 +296,17 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
         //     strictly lower level than every row of this chunk, so blocking on it cannot create a cycle.
         auto wait_gate = [&]() -> bool {
             if (gate_lp < 0 || P.slack < 0) return true;
-            const uint32_t ga = sv.ring_s + (((unsigned)gate_lp & sv.ring_mask) << 4);
-            const unsigned gt = (unsigned)gate_lp + 1u;
+            // Hardware-suspended wait on the completion barrier of the gate chunk: no polling traffic from the
+            // (many) warps that are still far from the frontier, prompt wake-up when the chunk's warp arrives.
+            // Parity is unambiguous: ring safety (1) guarantees chunk gate - rc has completed, and chunk
+            // gate + rc cannot complete before this chunk does.
             const int gate_chunk = gate_lp >> 5;
-            while (gate_chunk - done_cache > P.slack) {  // far from the frontier: progress words + sleep
-                refresh_done();
-                if (gate_chunk - done_cache <= P.slack) break;
-                __nanosleep(100);
-                if (wd.expired(106)) return false;
-            }
+            uint64_t* gb = &cbar[gate_chunk & (P.rc - 1)];
+            const unsigned gpar = (unsigned)(gate_chunk / P.rc) & 1u;
             unsigned spins = 0;
-            while (true) {
-                bool open = false;
-                if (lane == 0) {
-                    unsigned long long xb, t;
-                    ld_b128_cta(ga, xb, t);
-                    open = ((unsigned)t == gt);
-                }
-                if (__any_sync(FULL, open)) return true;
-                if ((++spins & 0xfffu) == 0 && wd.expired_now(106)) return false;
-            }
+            while (!mbar_try_wait(gb, gpar))
+                if ((++spins & 0xffu) == 0 && wd.expired_now(106)) return false;
+            return true;
         };
         if (P.trace && lane == 0) P.trace[(size_t)c * 4 + 1] = clock64();
         const uint32_t myslot_s = sv.ring_s + (((unsigned)(lc * 32 + lane) & sv.ring_mask) << 4);
@@ -476,7 +468,10 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
         // ---------------------------------------------------------------- progress word, then global memory
         // (the release fence of the progress word must not wait for the global stores below)
         __syncwarp();
-        if (lane == 0) st_release_cta_s32(&warp_cur[warp], has_next ? nlc : INT_MAX);
+        if (lane == 0) {
+            mbar_arrive(&cbar[lc & (P.rc - 1)]);  // chunk complete: wakes the warps gated on it
+            st_release_cta_s32(&warp_cur[warp], has_next ? nlc : INT_MAX);
+        }
         if (r >= 0) {
             P.x[r] = xfin;
             if ((pubm >> lane) & 1u) st_mail(P.mail + r, xfin, P.epoch);
