@@ -210,14 +210,19 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
             }
             unsigned spins = 0;
             while (true) {
+                // all four mailbox loads of the lane are in flight together: one L2 round trip per poll round
+                unsigned long long xb[4], tg[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (todo[k]) ld_b128_gpu(P.mail + src[k], xb[k], tg[k]);
                 bool pending = false;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (todo[k]) {
-                        double xr;
-                        if (ld_mail(P.mail + src[k], P.epoch, xr)) {
+                        if (tg[k] == P.epoch) {
                             const unsigned hp = (unsigned)(pos + k * 32 + lane);
-                            st_ring_s(sv.halo_s + ((hp & sv.halo_mask) << 4), xr, (unsigned long long)hp + 1ull);
+                            st_ring_s(sv.halo_s + ((hp & sv.halo_mask) << 4), __longlong_as_double((long long)xb[k]),
+                                      (unsigned long long)hp + 1ull);
                             todo[k] = false;
                         } else {
                             pending = true;
@@ -468,14 +473,10 @@ __global__ void __launch_bounds__(512, 1) k_trsv_syncfree(TrsvParams P) {
         // ---------------------------------------------------------------- progress word, then global memory
         // (the release fence of the progress word must not wait for the global stores below)
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&cbar[lc & (P.rc - 1)]);  // chunk complete: wakes the warps gated on it
-            st_release_cta_s32(&warp_cur[warp], has_next ? nlc : INT_MAX);
-        }
-        if (r >= 0) {
-            P.x[r] = xfin;
-            if ((pubm >> lane) & 1u) st_mail(P.mail + r, xfin, P.epoch);
-        }
+        if (lane == 0) mbar_arrive(&cbar[lc & (P.rc - 1)]);  // chunk complete: wakes the warps gated on it
+        if (r >= 0 && ((pubm >> lane) & 1u)) st_mail(P.mail + r, xfin, P.epoch);  // remote consumers next
+        if (lane == 0) st_release_cta_s32(&warp_cur[warp], has_next ? nlc : INT_MAX);
+        if (r >= 0) P.x[r] = xfin;
         if (has_next && P.nstages == 1) {
             __syncwarp();
             if (lane == 0) issue(nlc, it + 1);
