@@ -763,6 +763,23 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     ILUB_CUDA(cudaMemcpy(hctr, ctr.p, sizeof(hctr), cudaMemcpyDeviceToHost));
     T.nlevels = hctr[1];
 
+    // ---- structured grids: line-systolic layout (ilub_systolic.cu).  The chunked sync-free layout below is then
+    //      only built for slot 0 (the factorisation kernels walk it) or on demand (option solve_algo = 2).
+    const bool sys_ok = opt.solve_algo != 2 && analyse_systolic(h, slot, s);
+    T.built = true;
+    if (!sys_ok || slot == 0) analyse_generic(h, slot, s);
+}
+
+void analyse_generic(ilub_handle* h, int slot, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    if (T.generic_built) return;
+    const Options& opt = options();
+    const int n = h->n;
+    const SolveSource src = solve_source(h, slot);
+    const SrcDev S = to_dev(src);
+    DevBuf<int> ctr;
+    ctr.alloc(4);
+
     // ---- partition + (part, level, remote, row) order
     const int64_t nent_est = (slot == 0 || slot == 3) ? h->nnz_lower : h->nnz_upper;
     const PartPlan pl = plan_partition(h, S, nent_est, s);
@@ -931,12 +948,14 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     T.epoch = 0;
     h->launches += 8;
     ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here
-    T.built = true;
+    T.generic_built = true;
 }
 
 void pack_solve_values(ilub_handle* h, int slot, cudaStream_t s) {
     TriSolve& T = h->solve[slot];
     if (!T.built) return;
+    if (T.sys.built) pack_systolic(h, slot, s);
+    if (!T.generic_built) return;
     const int64_t nent = T.nslabs * 32;
     const int64_t nlane = (int64_t)T.nchunks * 32;
     if (nent > 0) k_pack_values<<<blocks_for(nent, 256), 256, 0, s>>>(nent, T.srcpos.p, h->lu.p, T.val.p);

@@ -438,6 +438,8 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "gate_slack") o.gate_slack = value;
         else if (k == "part_kb") o.part_kb = value;
         else if (k == "factor_group") o.factor_group = value;
+        else if (k == "sys_pz") o.sys_pz = value;
+        else if (k == "sys_stages") o.sys_stages = value;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
     });
 }
@@ -461,6 +463,14 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "gate_slack") *value = o.gate_slack;
         else if (k == "part_kb") *value = o.part_kb;
         else if (k == "factor_group") *value = o.factor_group;
+        else if (k == "sys_pz") *value = o.sys_pz;
+        else if (k == "sys_stages") *value = o.sys_stages;
+        else if (k == "fetch_warps") *value = o.fetch_warps;
+        else if (k == "halo_entries") *value = o.halo_entries;
+        else if (k == "fastpath") *value = o.fastpath;
+        else if (k == "level_align") *value = o.level_align;
+        else if (k == "align_min_rows") *value = o.align_min_rows;
+        else if (k == "trace") *value = o.trace;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
     });
 }
@@ -506,6 +516,17 @@ int ilub_get_stats(const ilub_handle* h, int64_t out[16]) {
         out[13] = T.nslabs;
         out[14] = T.cfg_warps;
         out[15] = (int64_t)T.cfg_smem;
+        if (T.sys.built && options().solve_algo == 0) {  // line-systolic path: tasks instead of chunks
+            const SysSolve& Y = T.sys;
+            out[8] = (int64_t)Y.gyb * Y.gz;
+            out[9] = 4;
+            out[10] = Y.gyb;
+            out[11] = Y.gz;
+            out[12] = Y.ntasks;
+            out[13] = Y.nsteps_pad;
+            out[14] = Y.pyb * Y.pz + 2;
+            out[15] = (int64_t)Y.smem;
+        }
     });
 }
 

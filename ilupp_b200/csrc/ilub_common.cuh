@@ -62,7 +62,7 @@ struct DevBuf {
 
 struct Options {
     int64_t factor_algo = 0;    // 0 sync-free, 1 level-scheduled
-    int64_t solve_algo = 0;     // 0 sync-free, 1 level-scheduled
+    int64_t solve_algo = 0;     // 0 auto (line-systolic on structured grids, else sync-free), 1 level-scheduled, 2 sync-free
     int64_t exact = 1;          // IEEE mul/sub/div in reference order
     int64_t ctas_per_sm = 1;
     int64_t warps_per_cta = 16;
@@ -82,6 +82,8 @@ struct Options {
     int64_t fastpath = 1;       // straight-line path for single-level lane-per-row chunks
     int64_t trace = 0;          // debug: record per-chunk clock stamps in the sync-free solve
     int64_t factor_group = 0;   // lanes per row in the factorisation kernels (0 = auto)
+    int64_t sys_pz = 0;         // line-systolic: planes per CTA (0 = auto)
+    int64_t sys_stages = 0;     // line-systolic: coefficient stages per warp (0 = auto)
 };
 Options& options();
 
@@ -96,6 +98,28 @@ constexpr int kLanes = 32;
 constexpr unsigned kLocalBit = 0x80000000u;
 constexpr unsigned kIntraBit = 0x40000000u;
 constexpr unsigned kHaloBit = 0x40000000u;
+
+// Line-systolic layout of one triangular solve (ilub_systolic.cu): chosen at analysis when every dependency of
+// the solve sits at grid offset 1, nx or nx*ny of a lexicographically numbered nx x ny x nplanes grid.
+struct SysSolve {
+    bool built = false;
+    bool tried = false;
+    int nx = 0, ny = 0, nplanes = 0, nz1 = 1;  // nz1: planes per system (batches: nplanes = nz1 * nsys)
+    int nyb = 0;                                // 32-line blocks per plane
+    int nsteps_pad = 0;                         // (nx + 31) rounded up to the 8-step stage size
+    int pyb = 1, pz = 1, gyb = 1, gz = 1;       // CTA tile of tasks (line blocks x planes) and CTA grid
+    int zcoupled = 0;                           // planes depend on the previous plane (3-D)
+    int order_xyz = 0;                          // exact arithmetic: accumulate x, y, z (bwd-gather) instead of z, y, x
+    int ntasks = 0, ntasks1 = 0;                // tasks = (line block, plane); ntasks1: tasks of one system
+    int nstages = 3, rz = 8, ry = 64;
+    size_t smem = 0;
+    int nzchan = 0, nychan = 0;
+    int packed_exact = -1;                      // arithmetic mode the coefficients were packed for
+    DevBuf<int> srcpos;                         // [ntasks1][nsteps_pad][4][32] position in lu (-1: absent / unit)
+    DevBuf<double> coef;                        // [ntasks][nsteps_pad][4][32] {z, y, x, diagonal} per lane and step
+    DevBuf<ulonglong2> zmail, ymail;            // cross-CTA hand-off {x, epoch}
+    unsigned long long epoch = 0;
+};
 
 // One triangular solve packed in solve order (see DESIGN.md "data layout in HBM").
 struct TriSolve {
@@ -141,6 +165,8 @@ struct TriSolve {
     DevBuf<long long> trace;      // debug stamps (option trace)
     DevBuf<int> lvl_ptr, lvl_rows;
     bool lvl_built = false;
+    bool generic_built = false;   // the chunked sync-free layout above exists (always for slot 0: the factorisation uses it)
+    SysSolve sys;                 // line-systolic layout (structured grids), preferred when built
 };
 
 // Transposed pattern of the strict lower or strict upper triangle (for scatter-form solves).
@@ -237,7 +263,8 @@ namespace ilub {
 void validate_and_find_diag(ilub_handle* h, cudaStream_t s);
 void build_transposed(ilub_handle* h, bool upper, cudaStream_t s);
 SolveSource solve_source(ilub_handle* h, int which);
-void analyse_solve(ilub_handle* h, int which, cudaStream_t s);            // levels + partition + layout
+void analyse_solve(ilub_handle* h, int which, cudaStream_t s);            // levels + layout(s)
+void analyse_generic(ilub_handle* h, int which, cudaStream_t s);          // partition + chunked sync-free layout
 void pack_solve_values(ilub_handle* h, int which, cudaStream_t s);        // (re)fill val/diag from lu
 void build_level_sets(ilub_handle* h, int which, cudaStream_t s);
 int read_status(ilub_handle* h, cudaStream_t s);                          // syncs the stream
@@ -246,6 +273,11 @@ void expand_batched(ilub_handle* h, const int* ptr1, const int* idx1, int32_t n1
 
 // ---- numeric factorisation (ilub_factor.cu)
 void factor_numeric(ilub_handle* h, cudaStream_t s);
+
+// ---- line-systolic triangular solves on structured grids (ilub_systolic.cu)
+bool analyse_systolic(ilub_handle* h, int which, cudaStream_t s);         // false: structure not eligible
+void pack_systolic(ilub_handle* h, int which, cudaStream_t s);
+void run_systolic(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);
 
 // ---- triangular solves (ilub_trsv.cu)
 void run_solve(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);

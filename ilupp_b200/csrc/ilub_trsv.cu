@@ -574,6 +574,15 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
         return;
     }
 
+    if (opt.solve_algo != 2 && T.sys.built) {
+        run_systolic(h, slot, x, ldx, nrhs, s);
+        return;
+    }
+    if (!T.generic_built) {
+        analyse_generic(h, slot, s);
+        pack_solve_values(h, slot, s);
+    }
+
     TrsvParams P;
     P.part_chunk_ptr = T.part_chunk_ptr.p;
     P.chunk_ptr = T.chunk_ptr.p;
