@@ -36,7 +36,6 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr long long kAbsentBits = 0x7ff8dead00000001ll;  // quiet NaN with a payload arithmetic never produces
 constexpr int kStageSteps = 8;                            // steps per coefficient stage (8 KB)
 constexpr int kStageBytes = kStageSteps * 4 * 32 * 8;
-constexpr int kWin = 64;                                  // columns of the rhs / solution window per line
 constexpr int kMaxWarps = 6;                              // compute warps per CTA
 constexpr int kMaxYChan = 8;
 
@@ -115,7 +114,7 @@ __global__ void k_sys_pack(int64_t total, int per_task, int nyb, int nz1, int ns
         v = lu[(int64_t)pos + (int64_t)sys * nnz1];
         if (role == 3 && recip) v = 1.0 / v;
     } else {
-        v = role == 3 ? 1.0 : __longlong_as_double(kAbsentBits);
+        v = role == 3 ? 1.0 : (recip ? 0.0 : __longlong_as_double(kAbsentBits));  // fast mode: plain zero
     }
     coef[e] = v;
 }
@@ -131,69 +130,100 @@ struct SysParams {
     ulonglong2* zmail;
     ulonglong2* ymail;
     unsigned long long epoch;
-    int zcoupled, order_xyz, unit_diag;
-    int nst, rz, ry;
+    int order_xyz, unit_diag;
+    int nst, rz;
     int per_warp;  // shared-memory bytes per compute warp
     int* status;
-    long long spin_limit;
+    unsigned spin_iters;  // failed polls before a wait gives up (watchdog)
 };
 
-struct Dog {  // clock64 watchdog: a broken schedule becomes ILUB_ERR_WATCHDOG instead of a hang
-    long long t0 = 0;
-    unsigned spins = 0;
-    int* status;
-    long long limit;
-    __device__ __forceinline__ Dog(int* st, long long lim) : status(st), limit(lim) {}
-    __device__ __forceinline__ bool expired(int code) {
-        if ((++spins & 1023u) != 0) return false;
-        if (t0 == 0) t0 = clock64();
-        if (*(volatile int*)status != 0) return true;
-        if (clock64() - t0 > limit) {
-            atomicCAS(status, 0, code);
-            return true;
-        }
-        return false;
-    }
-};
+// Shared memory of one compute warp: [nst coefficient stages][rhs/solution window 32 x 65][z ring rz x 32][y ring 64]
+// Window: element (line l, column i) lives at xw[l*65 + ((i + l) & 63)], i.e. at the STEP it is resolved in, so a
+// lane's accesses inside an 8-step block are base + immediate; the odd row stride keeps them conflict-free.
+constexpr int kWinStride = 65;
+constexpr int kWinBytes = 32 * kWinStride * 8;
+constexpr int kRy = 64;
 
 __device__ __forceinline__ int ld_prog(const int* p) { return *(const volatile int*)p; }
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ void give_up(int* status, int code) { atomicCAS(status, 0, code); }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(256, 1) k_trsv_systolic(SysParams P) {
+__device__ __forceinline__ void ld_s128(uint32_t a, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.cta.shared.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}" : "=l"(lo), "=l"(hi) : "r"(a));
+}
+// one 16-byte store {x, tag} through a GENERIC address: the same instruction feeds a ring in this CTA's shared
+// memory or a mailbox in global memory
+__device__ __forceinline__ void st_gen128(void* p, double x, unsigned long long tag) {
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.gpu.b128 [%0], q;\n\t}" ::"l"(p),
+                 "l"(__double_as_longlong(x)), "l"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ void* smem_generic(uint32_t saddr) {
+    void* g;
+    asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tcvta.shared.u64 %0, t;\n\t}" : "=l"(g) : "r"(saddr));
+    return g;
+}
+
+// A wait that has failed `limit` polls (or sees another warp's failure) gives up: ILUB_ERR_WATCHDOG, not a hang.
+#define SYS_SPIN(spins, code)                                          \
+    if ((++(spins) & 0xfffu) == 0) {                                   \
+        if ((spins) >= P.spin_iters || *(volatile int*)P.status != 0) { \
+            give_up(P.status, code);                                   \
+            return;                                                    \
+        }                                                              \
+    }
+
+template <bool EXACT, bool ZC>
+__global__ void __launch_bounds__(256, 1) k_trsv_systolic(const __grid_constant__ SysParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = P.pyb * P.pz;
-    const int zbytes = P.zcoupled ? P.rz * 512 : 0;
-    const int ring_off = P.nst * kStageBytes + 32 * kWin * 8;  // zin ring, then yin ring
+    const int zbytes = ZC ? P.rz * 512 : 0;
+    const int win_off = P.nst * kStageBytes;
+    const int ring_off = win_off + kWinBytes;  // z ring, then y ring
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + (size_t)W * P.per_warp);
-    int* prog = reinterpret_cast<int*>(mbar + W * P.nst);
+    int* progh = reinterpret_cast<int*>(mbar + W * P.nst);  // completed half-blocks (4 steps) per compute warp; [W] = INT_MAX
+    const int cy = blockIdx.x % P.gyb, cz = blockIdx.x / P.gyb;
 
-    // rings start with tag 0 (never a valid tag), barriers armed, progress 0
+    // windows zeroed; rings zeroed (tag 0 = nothing yet) -- or, for a warp WITHOUT that input, pre-filled with
+    // {0.0, INT_MAX}: always ready, value zero, so the step loop needs no "do I have this input" branches
     for (int w = 0; w < W; ++w) {
-        ulonglong2* ring = reinterpret_cast<ulonglong2*>(smem + (size_t)w * P.per_warp + ring_off);
-        const int cnt = (zbytes + P.ry * 16) / 16;
-        for (int t = threadIdx.x; t < cnt; t += blockDim.x) ring[t] = make_ulonglong2(0ull, 0ull);
+        unsigned char* base = smem + (size_t)w * P.per_warp;
+        ulonglong2* win = reinterpret_cast<ulonglong2*>(base + win_off);
+        for (int t = threadIdx.x; t < kWinBytes / 16; t += blockDim.x) win[t] = make_ulonglong2(0ull, 0ull);
+        const int jbw = cy * P.pyb + w % P.pyb, pw = cz * P.pz + w / P.pyb;
+        const unsigned long long ztag = (ZC && (pw % P.nz1) != 0) ? 0ull : (unsigned long long)INT_MAX;
+        const unsigned long long ytag = jbw > 0 ? 0ull : (unsigned long long)INT_MAX;
+        ulonglong2* zr = reinterpret_cast<ulonglong2*>(base + ring_off);
+        for (int t = threadIdx.x; t < zbytes / 16; t += blockDim.x) zr[t] = make_ulonglong2(0ull, ztag);
+        ulonglong2* yr = reinterpret_cast<ulonglong2*>(base + ring_off + zbytes);
+        for (int t = threadIdx.x; t < kRy; t += blockDim.x) yr[t] = make_ulonglong2(0ull, ytag);
     }
     if (threadIdx.x < W * P.nst) mbar_init(&mbar[threadIdx.x], 1);
-    if (threadIdx.x < W) prog[threadIdx.x] = 0;
+    if (threadIdx.x <= W) progh[threadIdx.x] = threadIdx.x == W ? INT_MAX : 0;
     fence_mbar_init();
     __syncthreads();
 
-    const int cy = blockIdx.x % P.gyb, cz = blockIdx.x / P.gyb;
-    Dog dog(P.status, P.spin_limit);
+    const int zlag = P.rz / 4 - 1;  // a producer may run this many half-blocks ahead of its z consumer
+    const unsigned long long ehi = (P.epoch & 0xffffffffull) << 32;  // mailbox tag = {epoch, step + 1}
 
     if (warp == W) {
         // ============================================================ z fetcher: plane cz*pz - 1 -> warp 0
-        // (z-coupled tilings have pyb == 1: one remote z channel per CTA)
+        // (z-coupled tilings have pyb == 1: one remote z channel per CTA); four steps in flight per lane
         const int p = cz * P.pz, jb = cy * P.pyb;
-        if (!P.zcoupled || p >= P.nplanes || (p % P.nz1) == 0 || jb >= P.nyb) return;
+        if (!ZC || p >= P.nplanes || (p % P.nz1) == 0 || jb >= P.nyb) return;
         const size_t chan = (size_t)(cz - 1) * P.nyb + jb;
         const ulonglong2* src = P.zmail + chan * P.nsteps_pad * 32 + lane;
         const uint32_t zin = smem_u32(smem + ring_off) + lane * 16;
         const int rzm = P.rz - 1;
+        unsigned spins = 0;
         for (int s0 = 0; s0 < P.nsteps_pad; s0 += 4) {
-            while (s0 + 3 >= ld_prog(&prog[0]) + P.rz)
-                if (dog.expired(201)) return;
+            while (ld_prog(&progh[0]) < (s0 >> 2) - zlag) SYS_SPIN(spins, 201)
             bool done[4] = {false, false, false, false};
             while (true) {
                 unsigned long long xb[4], tg[4];
@@ -204,9 +234,8 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(SysParams P) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (!done[u]) {
-                        if (tg[u] == P.epoch) {
-                            st_ring_s(zin + (((s0 + u) & rzm) << 9), __longlong_as_double((long long)xb[u]),
-                                      (unsigned long long)(s0 + u) + 1ull);
+                        if (tg[u] == (ehi | (unsigned long long)(s0 + u + 1))) {
+                            st_ring_s(zin + (((s0 + u) & rzm) << 9), __longlong_as_double((long long)xb[u]), tg[u]);
                             done[u] = true;
                         } else {
                             pending = true;
@@ -214,14 +243,15 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(SysParams P) {
                     }
                 }
                 if (!__any_sync(FULL, pending)) break;
-                if (dog.expired(202)) return;
+                SYS_SPIN(spins, 202)
             }
         }
         return;
     }
     if (warp == W + 1) {
-        // ============================================================ y fetcher: line block cy*pyb - 1 -> lane 0 of
-        // the first line block of every plane of this CTA (up to kMaxYChan channels polled together)
+        // ============================================================ y fetcher: line block cy*pyb - 1 -> the first
+        // line block of every plane of this CTA (up to kMaxYChan channels polled together).  Entries are indexed
+        // by the PRODUCER's step; lanes take 32 consecutive steps of a channel.
         const int jb = cy * P.pyb;
         if (cy == 0 || jb >= P.nyb) return;
         int i0[kMaxYChan];
@@ -233,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(SysParams P) {
             done[c] = false;
             if (c < P.pz && cz * P.pz + c < P.nplanes) nch = c + 1;
         }
-        const int rym = P.ry - 1;
+        unsigned spins = 0;
         while (true) {
             unsigned long long xb[kMaxYChan], tg[kMaxYChan];
             bool can[kMaxYChan];
@@ -241,35 +271,36 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(SysParams P) {
 #pragma unroll
             for (int c = 0; c < kMaxYChan; ++c) {
                 can[c] = false;
-                if (c < nch && i0[c] < P.nx) {
+                if (c < nch && i0[c] < P.nsteps_pad) {
                     active = true;
-                    const int i = i0[c] + lane;
+                    const int sp = i0[c] + lane;
                     const int cons = c * P.pyb;  // warp (wy = 0, wz = c)
-                    can[c] = i < P.nx && !done[c] && i < ld_prog(&prog[cons]) + P.ry;
+                    // the slot's previous occupant (step sp - 64) is read by the consumer at its step sp - 96
+                    can[c] = sp < P.nsteps_pad && !done[c] && sp < 4 * ld_prog(&progh[cons]) + 96;
                     if (can[c]) {
                         const size_t chan = (size_t)(cz * P.pz + c) * (P.gyb - 1) + (cy - 1);
-                        ld_b128_gpu(P.ymail + chan * P.nx + i, xb[c], tg[c]);
+                        ld_b128_gpu(P.ymail + chan * P.nsteps_pad + sp, xb[c], tg[c]);
                     }
                 }
             }
             if (!active) break;
 #pragma unroll
             for (int c = 0; c < kMaxYChan; ++c) {
-                if (c < nch && i0[c] < P.nx) {
-                    const int i = i0[c] + lane;
-                    if (can[c] && tg[c] == P.epoch) {
+                if (c < nch && i0[c] < P.nsteps_pad) {
+                    const int sp = i0[c] + lane;
+                    if (can[c] && tg[c] == (ehi | (unsigned long long)(sp + 1))) {
                         const uint32_t yin =
-                            smem_u32(smem + (size_t)(c * P.pyb) * P.per_warp + ring_off + zbytes) + ((i & rym) << 4);
-                        st_ring_s(yin, __longlong_as_double((long long)xb[c]), (unsigned long long)i + 1ull);
+                            smem_u32(smem + (size_t)(c * P.pyb) * P.per_warp + ring_off + zbytes) + ((sp & (kRy - 1)) << 4);
+                        st_ring_s(yin, __longlong_as_double((long long)xb[c]), tg[c]);
                         done[c] = true;
                     }
-                    if (__all_sync(FULL, done[c] || i >= P.nx)) {
+                    if (__all_sync(FULL, done[c] || sp >= P.nsteps_pad)) {
                         i0[c] += 32;
                         done[c] = false;
                     }
                 }
             }
-            if (dog.expired(203)) return;
+            SYS_SPIN(spins, 203)
         }
         return;
     }
@@ -278,9 +309,9 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(SysParams P) {
     const int wy = warp % P.pyb, wz = warp / P.pyb;
     const int jb = cy * P.pyb + wy, p = cz * P.pz + wz;
     if (jb >= P.nyb || p >= P.nplanes) return;
+    const int nx = P.nx;
     const int task = p * P.nyb + jb;
-    const bool has_zin = P.zcoupled && (p % P.nz1) != 0;
-    const bool has_zout = P.zcoupled && ((p + 1) % P.nz1) != 0;
+    const bool has_zout = ZC && ((p + 1) % P.nz1) != 0;
     const bool zout_local = has_zout && wz + 1 < P.pz;
     const bool has_yin = jb > 0;
     const bool has_yout = jb + 1 < P.nyb;
@@ -288,172 +319,197 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(SysParams P) {
     const int j0 = jb * 32;
     const int nlines = min(32, P.ny - j0);
     const int nblocks = P.nsteps_pad / kStageSteps;
-    const int nrect = (P.nx + 7) >> 3;
-    const long long tile_base = ((long long)p * P.ny + j0) * P.nx;
+    const int nrect = (nx + 7) >> 3;
+    const long long tile_base = ((long long)p * P.ny + j0) * nx;
 
     unsigned char* mine = smem + (size_t)warp * P.per_warp;
-    const double* stage = reinterpret_cast<const double*>(mine);
-    double* xb = reinterpret_cast<double*>(mine + P.nst * kStageBytes);  // [32][kWin]
+    const uint32_t stage_s = smem_u32(mine) + lane * 8;
+    const uint32_t xw_s = smem_u32(mine + win_off);
+    const uint32_t xw_lane = xw_s + lane * (kWinStride * 8);
     const uint32_t zin_s = smem_u32(mine + ring_off) + lane * 16;
     const uint32_t yin_s = smem_u32(mine + ring_off + zbytes);
-    const uint32_t zout_s = smem_u32(smem + (size_t)(warp + P.pyb) * P.per_warp + ring_off) + lane * 16;
-    const uint32_t yout_s = smem_u32(smem + (size_t)(warp + 1) * P.per_warp + ring_off + zbytes);
+    // where this warp's hand-offs go: a ring of another warp of this CTA (generic address of shared memory) or
+    // a mailbox in global memory; the step loop issues the same generic 16-byte store either way
+    unsigned char* zdst0 = nullptr;
+    unsigned char* ydst0 = nullptr;
+    if (zout_local)
+        zdst0 = (unsigned char*)smem_generic(smem_u32(smem + (size_t)(warp + P.pyb) * P.per_warp + ring_off) + lane * 16);
+    else if (has_zout)
+        zdst0 = (unsigned char*)(P.zmail + ((size_t)((p + 1) / P.pz - 1) * P.nyb + jb) * P.nsteps_pad * 32 + lane);
+    if (yout_local)
+        ydst0 = (unsigned char*)smem_generic(smem_u32(smem + (size_t)(warp + 1) * P.per_warp + ring_off + zbytes));
+    else if (has_yout)
+        ydst0 = (unsigned char*)(P.ymail + ((size_t)p * (P.gyb - 1) + ((jb + 1) / P.pyb - 1)) * P.nsteps_pad);
+    const bool ypred = has_yout && lane == 31;
+    const int* zcons = zout_local ? &progh[warp + P.pyb] : &progh[W];  // [W] = INT_MAX: never blocks
+    const int* ycons = yout_local ? &progh[warp + 1] : &progh[W];
     uint64_t* bar = mbar + warp * P.nst;
-    const int rzm = P.rz - 1, rym = P.ry - 1;
-    ulonglong2* zmail_out = nullptr;
-    ulonglong2* ymail_out = nullptr;
-    if (has_zout && !zout_local)
-        zmail_out = P.zmail + ((size_t)((p + 1) / P.pz - 1) * P.nyb + jb) * P.nsteps_pad * 32 + lane;
-    if (has_yout && !yout_local) ymail_out = P.ymail + ((size_t)p * (P.gyb - 1) + ((jb + 1) / P.pyb - 1)) * P.nx;
+    const unsigned rzmask = (unsigned)P.rz - 1u;
     const double* coef_task = P.coef + (size_t)task * P.nsteps_pad * 128;
+    const int order_xyz = P.order_xyz, unit_diag = P.unit_diag, nst = P.nst;
+    unsigned spins = 0;
 
-    // rhs / solution rectangles: 32 lines x 8 columns, element e = q*32 + lane -> line e>>3, column e&7
+    // rhs / solution rectangles: 32 lines x 8 columns, element q of a lane = (line 4q + rl, column 8m + rc)
     const int rl = lane >> 3, rc = lane & 7;
-    auto row_of = [&](int line, int col) -> long long {
-        const long long rm = tile_base + (long long)line * P.nx + col;
-        return P.backward ? P.n - 1 - rm : rm;
-    };
+    const long long dir = P.backward ? -1 : 1;
+    const long long g0 = P.backward ? P.n - 1 - (tile_base + (long long)rl * nx + rc) : tile_base + (long long)rl * nx + rc;
+    double* const gp = P.x + g0;
+    const long long qstride = dir * 4 * nx;
+    const uint32_t xw_rl = xw_s + rl * (kWinStride * 8);
+    const bool full_lines = nlines == 32;
     double pre[8];
     auto rect_load = [&](int m) {
+        double* b = gp + dir * 8 * m;
+        if (full_lines && 8 * m + 8 <= nx) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int line = q * 4 + rl, col = m * 8 + rc;
-            pre[q] = (line < nlines && col < P.nx) ? __ldcs(P.x + row_of(line, col)) : 0.0;
+            for (int q = 0; q < 8; ++q) pre[q] = __ldcs(b + q * qstride);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pre[q] = (q * 4 + rl < nlines && m * 8 + rc < nx) ? __ldcs(b + q * qstride) : 0.0;
         }
     };
     auto rect_deposit = [&](int m) {
+        const int t0 = 8 * m + rc + rl;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) xb[(q * 4 + rl) * kWin + ((m * 8 + rc) & (kWin - 1))] = pre[q];
+        for (int q = 0; q < 8; ++q) sts_f64(xw_rl + q * (4 * kWinStride * 8) + (((t0 + 4 * q) & 63) << 3), pre[q]);
     };
     auto rect_drain = [&](int m) {
+        const int t0 = 8 * m + rc + rl;
+        double* b = gp + dir * 8 * m;
+        const bool guard = !(full_lines && 8 * m + 8 <= nx);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const int line = q * 4 + rl, col = m * 8 + rc;
-            const double v = xb[line * kWin + (col & (kWin - 1))];
-            if (line < nlines && col < P.nx) P.x[row_of(line, col)] = v;
+            const double v = lds_f64(xw_rl + q * (4 * kWinStride * 8) + (((t0 + 4 * q) & 63) << 3));
+            if (!guard || (q * 4 + rl < nlines && m * 8 + rc < nx)) b[q * qstride] = v;
         }
     };
-    auto issue_stage = [&](int b) {  // lane 0 only
-        uint64_t* bb = &bar[b % P.nst];
-        mbar_arrive_expect_tx(bb, (unsigned)kStageBytes);
-        bulk_g2s(mine + (size_t)(b % P.nst) * kStageBytes, coef_task + (size_t)b * (kStageBytes / 8),
-                 (unsigned)kStageBytes, bb);
+    auto issue_stage = [&](int b, int slot) {  // lane 0 only
+        mbar_arrive_expect_tx(&bar[slot], (unsigned)kStageBytes);
+        bulk_g2s(mine + (size_t)slot * kStageBytes, coef_task + (size_t)b * (kStageBytes / 8), (unsigned)kStageBytes, &bar[slot]);
     };
 
     if (lane == 0)
-        for (int b = 0; b < P.nst && b < nblocks; ++b) issue_stage(b);
+        for (int b = 0; b < nst && b < nblocks; ++b) issue_stage(b, b);
     rect_load(0);
     rect_deposit(0);
     if (nrect > 1) rect_load(1);
     __syncwarp();
 
+    // lane 0's offset-nx dependency of element i is produced by lane 31 of the previous line block at ITS step
+    // i + 31.  It is polled one step early (slot of producer step s + 32 while resolving step s: same slot
+    // alignment as everything else in the block) and carried in a register; element 0 is fetched here.
+    double ycur = 0.0;
+    if (has_yin) {
+        while (true) {
+            unsigned long long v, t;
+            ld_s128(yin_s + (31 << 4), v, t);
+            ycur = __longlong_as_double((long long)v);
+            if ((int)(unsigned)t >= 32) break;
+            SYS_SPIN(spins, 208)
+        }
+    }
+
     double xprev = 0.0;
-    int zlimit = 0, ylimit = 0;  // flow control: steps / elements the local consumer has room for
+    int slot = 0;
+    unsigned phase = 0;
+    int zseen = 0, yseen = 0;  // last progress read from the local z / y consumer
     for (int B = 0; B < nblocks; ++B) {
         if (B + 1 < nrect) rect_deposit(B + 1);
         if (B + 2 < nrect) rect_load(B + 2);
         if (B >= 5 && B - 5 < nrect) rect_drain(B - 5);
         __syncwarp();
-        {
-            const unsigned par = (unsigned)(B / P.nst) & 1u;
-            while (!mbar_try_wait(&bar[B % P.nst], par))
-                if (__any_sync(FULL, dog.expired(204))) return;
-        }
-        const double* st = stage + (size_t)(B % P.nst) * (kStageBytes / 8) + lane;
+        while (!mbar_try_wait(&bar[slot], phase)) SYS_SPIN(spins, 204)
+        const uint32_t st = stage_s + slot * kStageBytes;
+        const uint32_t wb = xw_lane + ((B & 7) << 6);
+        const uint32_t zb = zin_s + (((unsigned)(B * kStageSteps) & rzmask) << 9);
+        const uint32_t yb = yin_s + (((B + 4) & 7) << 7);  // slots of producer steps 8B + 32 ...
+        const bool ypoll = B + 4 < nblocks;                 // ... which exist until four blocks before the end
+        unsigned char* zdst = zout_local ? zdst0 + (((unsigned)(B * kStageSteps) & rzmask) << 9) : zdst0 + (size_t)B * (kStageSteps * 512);
+        unsigned char* ydst = yout_local ? ydst0 + ((B & 7) << 7) : ydst0 + (size_t)B * (kStageSteps * 16);
+        const int s0 = B * kStageSteps;
+        // coefficients / rhs of the block's first step (later steps are loaded one step ahead)
+        double cz_ = 0.0, cy_, cx_, dv, bb;
+        if (ZC) cz_ = lds_f64(st);
+        cy_ = lds_f64(st + 256);
+        cx_ = lds_f64(st + 512);
+        dv = lds_f64(st + 768);
+        bb = lds_f64(wb);
 #pragma unroll
         for (int u = 0; u < kStageSteps; ++u) {
-            const int s = B * kStageSteps + u;
-            const int i = s - lane;
-            const bool valid = lane < nlines && i >= 0 && i < P.nx;
-            double cz_ = st[u * 128], cy_ = st[u * 128 + 32], cx_ = st[u * 128 + 64];
-            const double dv = st[u * 128 + 96];
-            const double bb = valid ? xb[lane * kWin + (i & (kWin - 1))] : 0.0;
-            const bool az = __double_as_longlong(cz_) == kAbsentBits;
-            const bool ay = __double_as_longlong(cy_) == kAbsentBits;
-            const bool ax = __double_as_longlong(cx_) == kAbsentBits;
-            double xy = __shfl_up_sync(FULL, xprev, 1);
-            double xz = 0.0;
-            // ---- inputs from other warps: z ring (all lanes), y ring (lane 0)
-            const bool need_y = has_yin && lane == 0 && s < P.nx;
-            {
-                bool zok = !has_zin, yok = !need_y;
-                const uint32_t za = zin_s + ((s & rzm) << 9);
-                const uint32_t ya = yin_s + ((s & rym) << 4);
-                while (true) {
-                    unsigned long long vb, tg;
-                    if (!zok) {
-                        ld_b128_cta(za, vb, tg);
-                        if ((unsigned)tg == (unsigned)(s + 1)) {
-                            xz = __longlong_as_double((long long)vb);
-                            zok = true;
-                        }
-                    }
-                    if (!yok) {
-                        ld_b128_cta(ya, vb, tg);
-                        if ((unsigned)tg == (unsigned)(s + 1)) {
-                            xy = __longlong_as_double((long long)vb);
-                            yok = true;
-                        }
-                    }
-                    if (__all_sync(FULL, zok && yok)) break;
-                    if (__any_sync(FULL, dog.expired(205))) return;
+            const int tag = s0 + u + 1;
+            if ((u & 3) == 0) {
+                // flow control once per half-block: the local consumers' ring slots we are about to overwrite are free
+                const int h = 2 * B + (u >> 2);
+                while (zseen < h - zlag) {
+                    zseen = ld_prog(zcons);
+                    SYS_SPIN(spins, 206)
+                }
+                while (yseen < h - 23) {
+                    yseen = ld_prog(ycons);
+                    SYS_SPIN(spins, 207)
                 }
             }
-            if (lane == 0 && !need_y) xy = 0.0;
-            if (az) { cz_ = 0.0; xz = 0.0; }
-            if (ay) { cy_ = 0.0; xy = 0.0; }
-            const double xx = ax ? 0.0 : xprev;
-            if (ax) cx_ = 0.0;
+            const double czu = cz_, cyu = cy_, cxu = cx_, dvu = dv, bbu = bb;
+            if (u + 1 < kStageSteps) {  // next step's operands: independent of everything below
+                if (ZC) cz_ = lds_f64(st + (u + 1) * 1024);
+                cy_ = lds_f64(st + (u + 1) * 1024 + 256);
+                cx_ = lds_f64(st + (u + 1) * 1024 + 512);
+                dv = lds_f64(st + (u + 1) * 1024 + 768);
+                bb = lds_f64(wb + (u + 1) * 8);
+            }
+            double xy = __shfl_up_sync(FULL, xprev, 1);
+            if (lane == 0) xy = ycur;
+            // ---- inputs from other warps: z ring (own entry per lane, this step), y ring (one entry read by every
+            //      lane, next step).  Rings of inputs this warp does not have are pre-filled "always ready".
+            double xz = 0.0, ynext = 0.0;
+            while (true) {
+                unsigned long long vz = 0ull, tz = (unsigned long long)INT_MAX, vy = 0ull, ty = (unsigned long long)INT_MAX;
+                if (ZC) ld_s128(zb + u * 512, vz, tz);
+                if (ypoll) ld_s128(yb + u * 16, vy, ty);
+                xz = __longlong_as_double((long long)vz);
+                ynext = __longlong_as_double((long long)vy);
+                if (__all_sync(FULL, (int)(unsigned)tz >= tag && (int)(unsigned)ty >= tag + 32)) break;
+                SYS_SPIN(spins, 205)
+            }
             double xnew;
             if (EXACT) {
-                double acc = bb;
-                if (P.order_xyz) {
-                    if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_, xx));
-                    if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_, xy));
-                    if (!az) acc = __dsub_rn(acc, __dmul_rn(cz_, xz));
+                const bool az = !ZC || __double_as_longlong(czu) == kAbsentBits;
+                const bool ay = __double_as_longlong(cyu) == kAbsentBits;
+                const bool ax = __double_as_longlong(cxu) == kAbsentBits;
+                double acc = bbu;
+                if (order_xyz) {
+                    if (!ax) acc = __dsub_rn(acc, __dmul_rn(cxu, xprev));
+                    if (!ay) acc = __dsub_rn(acc, __dmul_rn(cyu, xy));
+                    if (!az) acc = __dsub_rn(acc, __dmul_rn(czu, xz));
                 } else {
-                    if (!az) acc = __dsub_rn(acc, __dmul_rn(cz_, xz));
-                    if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_, xy));
-                    if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_, xx));
+                    if (!az) acc = __dsub_rn(acc, __dmul_rn(czu, xz));
+                    if (!ay) acc = __dsub_rn(acc, __dmul_rn(cyu, xy));
+                    if (!ax) acc = __dsub_rn(acc, __dmul_rn(cxu, xprev));
                 }
-                xnew = P.unit_diag ? acc : __ddiv_rn(acc, dv);
+                xnew = unit_diag ? acc : __ddiv_rn(acc, dvu);
             } else {
-                double acc = fma(-cz_, xz, bb);
-                acc = fma(-cx_, xx, acc);
-                acc = fma(-cy_, xy, acc);
-                xnew = acc * dv;
+                // absent entries carry coefficient 0.0 and every operand that can reach them is finite
+                double acc = bbu;
+                if (ZC) acc = fma(-czu, xz, acc);
+                acc = fma(-cxu, xprev, acc);
+                acc = fma(-cyu, xy, acc);
+                xnew = acc * dvu;
             }
             xprev = xnew;
-            if (valid) xb[lane * kWin + (i & (kWin - 1))] = xnew;
-            // ---- outputs
-            if (has_zout) {
-                if (zout_local) {
-                    while (s >= zlimit) {
-                        zlimit = ld_prog(&prog[warp + P.pyb]) + P.rz;
-                        if (s < zlimit) break;
-                        if (__any_sync(FULL, dog.expired(206))) return;
-                    }
-                    st_ring_s(zout_s + ((s & rzm) << 9), xnew, (unsigned long long)s + 1ull);
-                } else {
-                    st_mail(zmail_out + (size_t)s * 32, xnew, P.epoch);
-                }
-            }
-            if (has_yout && lane == 31 && valid) {
-                if (yout_local) {
-                    while (i >= ylimit) {
-                        ylimit = ld_prog(&prog[warp + 1]) + P.ry;
-                        if (i < ylimit) break;
-                        if (dog.expired(207)) return;
-                    }
-                    st_ring_s(yout_s + ((i & rym) << 4), xnew, (unsigned long long)i + 1ull);
-                } else {
-                    st_mail(ymail_out + i, xnew, P.epoch);
-                }
-            }
-            if (lane == 0) *(volatile int*)&prog[warp] = s + 1;
+            ycur = ynext;
+            sts_f64(wb + u * 8, xnew);
+            // ---- hand-offs: {x, {epoch, step + 1}}
+            const unsigned long long tag64 = ehi | (unsigned long long)(unsigned)tag;
+            if (has_zout) st_gen128(zdst + u * 512, xnew, tag64);
+            if (ypred) st_gen128(ydst + u * 16, xnew, tag64);
+            if ((u & 3) == 3 && lane == 0) *(volatile int*)&progh[warp] = 2 * B + (u >> 2) + 1;
         }
         __syncwarp();
-        if (lane == 0 && B + P.nst < nblocks) issue_stage(B + P.nst);
+        if (lane == 0 && B + nst < nblocks) issue_stage(B + nst, slot);
+        if (++slot == nst) {
+            slot = 0;
+            phase ^= 1u;
+        }
     }
     __syncwarp();
     for (int m = max(0, nblocks - 5); m < nrect; ++m) rect_drain(m);
@@ -513,27 +569,29 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     // ---- tiling of tasks onto CTAs, shared-memory budget
     const int zc = G.sz > 0 ? 1 : 0;
     const int nplanes = G.nz1 * nsys;
-    const int rz = 8, ry = 64;
     const size_t budget = (size_t)227 * 1024 - 1024;
-    auto per_warp = [&](int nst) { return (size_t)nst * kStageBytes + 32 * kWin * 8 + (zc ? rz * 512 : 0) + ry * 16; };
-    auto max_warps = [&](int nst) { return (int)std::min<size_t>(kMaxWarps, budget / (per_warp(nst) + 64)); };
-    int pyb = 1, pz = 1, nst = 3;
+    auto per_warp = [&](int nst, int rz) { return (size_t)nst * kStageBytes + kWinBytes + (zc ? rz * 512 : 0) + kRy * 16; };
+    auto max_warps = [&](int nst, int rz) { return (int)std::min<size_t>(kMaxWarps, budget / (per_warp(nst, rz) + 64)); };
+    int pyb = 1, pz = 1, nst = 3, rz = 16;
     if (zc) {
         pz = 1;
         while ((int64_t)G.nyb * ((nplanes + pz - 1) / pz) > h->sm_count) ++pz;
         if (opt.sys_pz > 0) pz = (int)opt.sys_pz;
         pz = std::min(pz, nplanes);
-        if (pz > max_warps(2) || pz > kMaxYChan) return false;  // too large for one co-resident wave: generic path
-        nst = 4;
-        while (nst > 2 && pz > max_warps(nst)) --nst;
+        if (pz > max_warps(2, 8) || pz > kMaxYChan) return false;  // too large for one co-resident wave: generic path
+        // prefer three stages and the 16-step z ring, give up ring depth first, then a stage
+        if (pz <= max_warps(3, 16)) { nst = 3; rz = 16; }
+        else if (pz <= max_warps(3, 8)) { nst = 3; rz = 8; }
+        else if (pz <= max_warps(2, 16)) { nst = 2; rz = 16; }
+        else { nst = 2; rz = 8; }
     } else {
-        const int mw = max_warps(3);
+        const int mw = max_warps(3, 8);
         const int gyb = (G.nyb + mw - 1) / mw;
         pyb = (G.nyb + gyb - 1) / gyb;
         nst = 4;
-        while (nst > 3 && pyb > max_warps(nst)) --nst;
+        while (nst > 3 && pyb > max_warps(nst, 8)) --nst;
     }
-    if (opt.sys_stages >= 2 && opt.sys_stages <= 4 && pyb * pz <= max_warps((int)opt.sys_stages)) nst = (int)opt.sys_stages;
+    if (opt.sys_stages >= 2 && opt.sys_stages <= 4 && pyb * pz <= max_warps((int)opt.sys_stages, rz)) nst = (int)opt.sys_stages;
 
     // ---- (task, step, lane) map of one system; fails on anything that is not the grid stencil
     const size_t per_task = (size_t)G.nsteps_pad * 128;
@@ -566,13 +624,13 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     Y.ntasks = ntasks1 * nsys;
     Y.nstages = nst;
     Y.rz = rz;
-    Y.ry = ry;
-    Y.smem = (size_t)pyb * pz * per_warp(nst) + (size_t)pyb * pz * nst * 8 + kMaxWarps * 4 + 64;
+    Y.ry = kRy;
+    Y.smem = (size_t)pyb * pz * per_warp(nst, rz) + (size_t)pyb * pz * nst * 8 + (kMaxWarps + 1) * 4 + 64;
     Y.coef.alloc((size_t)Y.ntasks * per_task);
     Y.nzchan = zc ? G.nyb * std::max(0, Y.gz - 1) : 0;
     Y.nychan = nplanes * std::max(0, Y.gyb - 1);
     Y.zmail.alloc((size_t)Y.nzchan * G.nsteps_pad * 32);
-    Y.ymail.alloc((size_t)Y.nychan * G.nx);
+    Y.ymail.alloc((size_t)Y.nychan * G.nsteps_pad);
     ILUB_CUDA(cudaMemsetAsync(Y.zmail.p, 0, Y.zmail.bytes(), s));
     ILUB_CUDA(cudaMemsetAsync(Y.ymail.p, 0, Y.ymail.bytes(), s));
     Y.epoch = 0;
@@ -616,32 +674,29 @@ void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cu
     P.n = h->n;
     P.zmail = Y.zmail.p;
     P.ymail = Y.ymail.p;
-    P.zcoupled = Y.zcoupled;
     P.order_xyz = Y.order_xyz;
     P.unit_diag = T.unit_diag ? 1 : 0;
     P.nst = Y.nstages;
     P.rz = Y.rz;
-    P.ry = Y.ry;
-    P.per_warp = (int)((size_t)Y.nstages * kStageBytes + 32 * kWin * 8 + (Y.zcoupled ? Y.rz * 512 : 0) + Y.ry * 16);
+    P.per_warp = (int)((size_t)Y.nstages * kStageBytes + kWinBytes + (Y.zcoupled ? Y.rz * 512 : 0) + kRy * 16);
     P.status = h->status.p;
-    P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz;
-    static thread_local bool attr_set[2] = {false, false};
-    if (!attr_set[exact ? 1 : 0]) {
-        if (exact)
-            ILUB_CUDA(cudaFuncSetAttribute(k_trsv_systolic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        else
-            ILUB_CUDA(cudaFuncSetAttribute(k_trsv_systolic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[exact ? 1 : 0] = true;
+    // watchdog in failed polls (a poll round is >= ~40 cycles)
+    P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 16, (long long)opt.spin_limit_ms * h->clock_khz / 64));
+    typedef void (*kern_t)(const SysParams);
+    const kern_t kern = exact ? (Y.zcoupled ? (kern_t)k_trsv_systolic<true, true> : (kern_t)k_trsv_systolic<true, false>)
+                              : (Y.zcoupled ? (kern_t)k_trsv_systolic<false, true> : (kern_t)k_trsv_systolic<false, false>);
+    static thread_local bool attr_set[4] = {false, false, false, false};
+    const int ki = (exact ? 2 : 0) + (Y.zcoupled ? 1 : 0);
+    if (!attr_set[ki]) {
+        ILUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[ki] = true;
     }
     const int grid = Y.gyb * Y.gz;
     const int block = (Y.pyb * Y.pz + 2) * 32;
     for (int c = 0; c < nrhs; ++c) {
         P.epoch = ++Y.epoch;
         P.x = x + (int64_t)c * ldx;
-        if (exact)
-            k_trsv_systolic<true><<<grid, block, Y.smem, s>>>(P);
-        else
-            k_trsv_systolic<false><<<grid, block, Y.smem, s>>>(P);
+        kern<<<grid, block, Y.smem, s>>>(P);
         h->launches++;
     }
     ILUB_CUDA(cudaGetLastError());
