@@ -440,6 +440,7 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "factor_group") o.factor_group = value;
         else if (k == "sys_pz") o.sys_pz = value;
         else if (k == "sys_stages") o.sys_stages = value;
+        else if (k == "sys_cluster") o.sys_cluster = value;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
     });
 }
@@ -465,6 +466,7 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "factor_group") *value = o.factor_group;
         else if (k == "sys_pz") *value = o.sys_pz;
         else if (k == "sys_stages") *value = o.sys_stages;
+        else if (k == "sys_cluster") *value = o.sys_cluster;
         else if (k == "fetch_warps") *value = o.fetch_warps;
         else if (k == "halo_entries") *value = o.halo_entries;
         else if (k == "fastpath") *value = o.fastpath;
@@ -522,7 +524,7 @@ int ilub_get_stats(const ilub_handle* h, int64_t out[16]) {
             out[9] = 4;
             out[10] = Y.gyb;
             out[11] = Y.gz;
-            out[12] = Y.ntasks;
+            out[12] = Y.ntasks * 100 + Y.csize;  // tasks, cluster size in the last two digits
             out[13] = Y.nsteps_pad;
             out[14] = Y.pyb * Y.pz + 2;
             out[15] = (int64_t)Y.smem;

@@ -84,6 +84,7 @@ struct Options {
     int64_t factor_group = 0;   // lanes per row in the factorisation kernels (0 = auto)
     int64_t sys_pz = 0;         // line-systolic: planes per CTA (0 = auto)
     int64_t sys_stages = 0;     // line-systolic: coefficient stages per warp (0 = auto)
+    int64_t sys_cluster = 0;    // line-systolic: largest thread-block cluster to try (0 = auto: 8, 1 = no clusters)
 };
 Options& options();
 
@@ -108,6 +109,7 @@ struct SysSolve {
     int nyb = 0;                                // 32-line blocks per plane
     int nsteps_pad = 0;                         // (nx + 31) rounded up to the 8-step stage size
     int pyb = 1, pz = 1, gyb = 1, gz = 1;       // CTA tile of tasks (line blocks x planes) and CTA grid
+    int csize = 1, gzp = 1;                     // thread-block cluster along z (DSMEM hand-offs), gz padded to it
     int zcoupled = 0;                           // planes depend on the previous plane (3-D)
     int order_xyz = 0;                          // exact arithmetic: accumulate x, y, z (bwd-gather) instead of z, y, x
     int ntasks = 0, ntasks1 = 0;                // tasks = (line block, plane); ntasks1: tasks of one system

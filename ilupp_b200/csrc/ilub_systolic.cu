@@ -23,6 +23,8 @@
 // true division (bit-for-bit with a non-FMA build of the reference); otherwise FMA and a reciprocal diagonal.
 // Absent stencil entries are marked with a reserved NaN payload and skipped, so NaN / inf propagate exactly
 // as in the reference.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <climits>
 
@@ -36,7 +38,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr long long kAbsentBits = 0x7ff8dead00000001ll;  // quiet NaN with a payload arithmetic never produces
 constexpr int kStageSteps = 8;                            // steps per coefficient stage (8 KB)
 constexpr int kStageBytes = kStageSteps * 4 * 32 * 8;
-constexpr int kMaxWarps = 6;                              // compute warps per CTA
+constexpr int kMaxWarps = 6;                              // compute warps per CTA (each has a helper warp)
 constexpr int kMaxYChan = 8;
 
 inline int blocks_for(int64_t work, int threads) { return (int)((work + threads - 1) / threads); }
@@ -77,7 +79,8 @@ __global__ void k_sys_map(SysGeom G, SrcDev S, int* __restrict__ srcpos, int* fa
     const int task = k * G.nyb + (j >> 5);
     const int lane = j & 31;
     const int step = i + lane;
-    const size_t base = ((size_t)task * G.nsteps_pad + step) * 128 + lane;
+    // per step: [lane]{z, y} (64 values) then [lane]{x, diagonal}: role r sits at (r >> 1) * 64 + lane * 2 + (r & 1)
+    const size_t base = ((size_t)task * G.nsteps_pad + step) * 128 + lane * 2;
     bool bad = false;
     for (int q = src_beg(S, r); q < src_end(S, r); ++q) {
         const int dep = S.dep_idx[q];
@@ -90,9 +93,9 @@ __global__ void k_sys_map(SysGeom G, SrcDev S, int* __restrict__ srcpos, int* fa
             bad = true;
             break;
         }
-        srcpos[base + role * 32] = S.val_pos ? S.val_pos[q] : q;
+        srcpos[base + (role >> 1) * 64 + (role & 1)] = S.val_pos ? S.val_pos[q] : q;
     }
-    if (!G.unit_diag) srcpos[base + 3 * 32] = S.diag_pos[r];
+    if (!G.unit_diag) srcpos[base + 64 + 1] = S.diag_pos[r];
     if (bad) *fail = 1;
 }
 
@@ -108,7 +111,7 @@ __global__ void k_sys_pack(int64_t total, int per_task, int nyb, int nz1, int ns
     const int sysm = p / nz1, k = p - sysm * nz1;
     const int sys = backward ? nsys - 1 - sysm : sysm;
     const int pos = srcpos[(size_t)(k * nyb + jb) * per_task + rem];
-    const int role = (rem >> 5) & 3;
+    const int role = ((rem >> 6) & 1) * 2 + (rem & 1);
     double v;
     if (pos >= 0) {
         v = lu[(int64_t)pos + (int64_t)sys * nnz1];
@@ -124,7 +127,7 @@ struct SysParams {
     const double* coef;
     double* x;
     int nx, ny, nyb, nplanes, nz1, nsteps_pad;
-    int pyb, pz, gyb;
+    int pyb, pz, gyb, gz, gzp, csize;  // gzp: gz padded to the cluster size; CTA = blockIdx.x = cy * gzp + cz
     int backward;
     long long n;
     ulonglong2* zmail;
@@ -140,9 +143,11 @@ struct SysParams {
 // Shared memory of one compute warp: [nst coefficient stages][rhs/solution window 32 x 65][z ring rz x 32][y ring 64]
 // Window: element (line l, column i) lives at xw[l*65 + ((i + l) & 63)], i.e. at the STEP it is resolved in, so a
 // lane's accesses inside an 8-step block are base + immediate; the odd row stride keeps them conflict-free.
+// Coefficient stage: per step 1 KB = [lane]{z, y} (512 B) then [lane]{x, diagonal} (512 B): two 16-byte loads.
 constexpr int kWinStride = 65;
 constexpr int kWinBytes = 32 * kWinStride * 8;
 constexpr int kRy = 64;
+constexpr int kCtlInts = 4 * kMaxWarps + 4;  // progh[W] | hdep[W] | zcredit[W] | scratch[W] | always = INT_MAX
 
 __device__ __forceinline__ int ld_prog(const int* p) { return *(const volatile int*)p; }
 __device__ __forceinline__ double lds_f64(uint32_t a) {
@@ -150,24 +155,22 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void lds_2f64(uint32_t a, double& v0, double& v1) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a));
+}
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
 __device__ __forceinline__ void give_up(int* status, int code) { atomicCAS(status, 0, code); }
-
 __device__ __forceinline__ void ld_s128(uint32_t a, unsigned long long& lo, unsigned long long& hi) {
     asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.cta.shared.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}" : "=l"(lo), "=l"(hi) : "r"(a));
 }
 // one 16-byte store {x, tag} through a GENERIC address: the same instruction feeds a ring in this CTA's shared
-// memory or a mailbox in global memory
+// memory, a ring in another CTA of the cluster (distributed shared memory) or a mailbox in global memory
 __device__ __forceinline__ void st_gen128(void* p, double x, unsigned long long tag) {
     asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.gpu.b128 [%0], q;\n\t}" ::"l"(p),
                  "l"(__double_as_longlong(x)), "l"(tag)
                  : "memory");
 }
-__device__ __forceinline__ void* smem_generic(uint32_t saddr) {
-    void* g;
-    asm("{\n\t.reg .u64 t;\n\tcvt.u64.u32 t, %1;\n\tcvta.shared.u64 %0, t;\n\t}" : "=l"(g) : "r"(saddr));
-    return g;
-}
+__device__ __forceinline__ void st_gen_s32(int* p, int v) { asm volatile("st.relaxed.gpu.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // A wait that has failed `limit` polls (or sees another warp's failure) gives up: ILUB_ERR_WATCHDOG, not a hang.
 #define SYS_SPIN(spins, code)                                          \
@@ -178,178 +181,131 @@ __device__ __forceinline__ void* smem_generic(uint32_t saddr) {
         }                                                              \
     }
 
-template <bool EXACT, bool ZC>
-__global__ void __launch_bounds__(256, 1) k_trsv_systolic(const __grid_constant__ SysParams P) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = P.pyb * P.pz;
-    const int zbytes = ZC ? P.rz * 512 : 0;
-    const int win_off = P.nst * kStageBytes;
-    const int ring_off = win_off + kWinBytes;  // z ring, then y ring
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + (size_t)W * P.per_warp);
-    int* progh = reinterpret_cast<int*>(mbar + W * P.nst);  // completed half-blocks (4 steps) per compute warp; [W] = INT_MAX
-    const int cy = blockIdx.x % P.gyb, cz = blockIdx.x / P.gyb;
+struct SysCtx {  // where things live in this CTA's shared memory
+    unsigned char* smem;
+    uint64_t* mbar;
+    int* progh;    // [W] completed half-blocks (4 steps) of every compute warp
+    int* hdep;     // [W] rectangles the helper of every compute warp has deposited
+    int* zcredit;  // [W] progress of a z consumer that lives in the NEXT CTA of the cluster (it pushes it here)
+    int* scratch;  // [W] sink for progress pushes nobody needs
+    int* always;   // INT_MAX: "consumer" that never blocks
+    int W, zbytes, win_off, ring_off, cy, cz, crank;
+};
 
-    // windows zeroed; rings zeroed (tag 0 = nothing yet) -- or, for a warp WITHOUT that input, pre-filled with
-    // {0.0, INT_MAX}: always ready, value zero, so the step loop needs no "do I have this input" branches
-    for (int w = 0; w < W; ++w) {
-        unsigned char* base = smem + (size_t)w * P.per_warp;
-        ulonglong2* win = reinterpret_cast<ulonglong2*>(base + win_off);
-        for (int t = threadIdx.x; t < kWinBytes / 16; t += blockDim.x) win[t] = make_ulonglong2(0ull, 0ull);
-        const int jbw = cy * P.pyb + w % P.pyb, pw = cz * P.pz + w / P.pyb;
-        const unsigned long long ztag = (ZC && (pw % P.nz1) != 0) ? 0ull : (unsigned long long)INT_MAX;
-        const unsigned long long ytag = jbw > 0 ? 0ull : (unsigned long long)INT_MAX;
-        ulonglong2* zr = reinterpret_cast<ulonglong2*>(base + ring_off);
-        for (int t = threadIdx.x; t < zbytes / 16; t += blockDim.x) zr[t] = make_ulonglong2(0ull, ztag);
-        ulonglong2* yr = reinterpret_cast<ulonglong2*>(base + ring_off + zbytes);
-        for (int t = threadIdx.x; t < kRy; t += blockDim.x) yr[t] = make_ulonglong2(0ull, ytag);
-    }
-    if (threadIdx.x < W * P.nst) mbar_init(&mbar[threadIdx.x], 1);
-    if (threadIdx.x <= W) progh[threadIdx.x] = threadIdx.x == W ? INT_MAX : 0;
-    fence_mbar_init();
-    __syncthreads();
-
-    const int zlag = P.rz / 4 - 1;  // a producer may run this many half-blocks ahead of its z consumer
-    const unsigned long long ehi = (P.epoch & 0xffffffffull) << 32;  // mailbox tag = {epoch, step + 1}
-
-    if (warp == W) {
-        // ============================================================ z fetcher: plane cz*pz - 1 -> warp 0
-        // (z-coupled tilings have pyb == 1: one remote z channel per CTA); four steps in flight per lane
-        const int p = cz * P.pz, jb = cy * P.pyb;
-        if (!ZC || p >= P.nplanes || (p % P.nz1) == 0 || jb >= P.nyb) return;
-        const size_t chan = (size_t)(cz - 1) * P.nyb + jb;
-        const ulonglong2* src = P.zmail + chan * P.nsteps_pad * 32 + lane;
-        const uint32_t zin = smem_u32(smem + ring_off) + lane * 16;
-        const int rzm = P.rz - 1;
-        unsigned spins = 0;
-        for (int s0 = 0; s0 < P.nsteps_pad; s0 += 4) {
-            while (ld_prog(&progh[0]) < (s0 >> 2) - zlag) SYS_SPIN(spins, 201)
-            bool done[4] = {false, false, false, false};
-            while (true) {
-                unsigned long long xb[4], tg[4];
+// ---------------------------------------------------------------- z fetcher: last plane of CTA cz-1 (outside this
+// cluster) -> warp 0.  z-coupled tilings have pyb == 1: one remote z channel per CTA; four steps in flight per lane
+template <bool ZC>
+__device__ __forceinline__ void role_zfetch(const SysParams& P, const SysCtx& C, int lane) {
+    const int p = C.cz * P.pz, jb = C.cy * P.pyb;
+    if (!ZC || p >= P.nplanes || (p % P.nz1) == 0 || jb >= P.nyb || C.crank != 0) return;
+    const unsigned long long ehi = (P.epoch & 0xffffffffull) << 32;
+    const int zlag = P.rz / 4 - 1;
+    const size_t chan = (size_t)(C.cz - 1) * P.nyb + jb;
+    const ulonglong2* src = P.zmail + chan * P.nsteps_pad * 32 + lane;
+    const uint32_t zin = smem_u32(C.smem + C.ring_off) + lane * 16;
+    const int rzm = P.rz - 1;
+    unsigned spins = 0;
+    for (int s0 = 0; s0 < P.nsteps_pad; s0 += 4) {
+        while (ld_prog(&C.progh[0]) < (s0 >> 2) - zlag) SYS_SPIN(spins, 201)
+        bool done[4] = {false, false, false, false};
+        while (true) {
+            unsigned long long xb[4], tg[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (!done[u]) ld_b128_gpu(src + (size_t)(s0 + u) * 32, xb[u], tg[u]);
-                bool pending = false;
+            for (int u = 0; u < 4; ++u)
+                if (!done[u]) ld_b128_gpu(src + (size_t)(s0 + u) * 32, xb[u], tg[u]);
+            bool pending = false;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (!done[u]) {
-                        if (tg[u] == (ehi | (unsigned long long)(s0 + u + 1))) {
-                            st_ring_s(zin + (((s0 + u) & rzm) << 9), __longlong_as_double((long long)xb[u]), tg[u]);
-                            done[u] = true;
-                        } else {
-                            pending = true;
-                        }
+            for (int u = 0; u < 4; ++u) {
+                if (!done[u]) {
+                    if (tg[u] == (ehi | (unsigned long long)(s0 + u + 1))) {
+                        st_ring_s(zin + (((s0 + u) & rzm) << 9), __longlong_as_double((long long)xb[u]), tg[u]);
+                        done[u] = true;
+                    } else {
+                        pending = true;
                     }
                 }
-                if (!__any_sync(FULL, pending)) break;
-                SYS_SPIN(spins, 202)
             }
+            if (!__any_sync(FULL, pending)) break;
+            SYS_SPIN(spins, 202)
         }
-        return;
     }
-    if (warp == W + 1) {
-        // ============================================================ y fetcher: line block cy*pyb - 1 -> the first
-        // line block of every plane of this CTA (up to kMaxYChan channels polled together).  Entries are indexed
-        // by the PRODUCER's step; lanes take 32 consecutive steps of a channel.
-        const int jb = cy * P.pyb;
-        if (cy == 0 || jb >= P.nyb) return;
-        int i0[kMaxYChan];
-        bool done[kMaxYChan];
-        int nch = 0;
+}
+
+// ---------------------------------------------------------------- y fetcher: line block cy*pyb - 1 -> the first line
+// block of every plane of this CTA (up to kMaxYChan channels polled together).  Entries are indexed by the
+// PRODUCER's step; lanes take 32 consecutive steps of a channel.
+__device__ __forceinline__ void role_yfetch(const SysParams& P, const SysCtx& C, int lane) {
+    const int jb = C.cy * P.pyb;
+    if (C.cy == 0 || jb >= P.nyb) return;
+    const unsigned long long ehi = (P.epoch & 0xffffffffull) << 32;
+    int i0[kMaxYChan];
+    bool done[kMaxYChan];
+    int nch = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxYChan; ++c) {
+        i0[c] = 0;
+        done[c] = false;
+        if (c < P.pz && C.cz * P.pz + c < P.nplanes) nch = c + 1;
+    }
+    unsigned spins = 0;
+    while (true) {
+        unsigned long long xb[kMaxYChan], tg[kMaxYChan];
+        bool can[kMaxYChan];
+        bool active = false;
 #pragma unroll
         for (int c = 0; c < kMaxYChan; ++c) {
-            i0[c] = 0;
-            done[c] = false;
-            if (c < P.pz && cz * P.pz + c < P.nplanes) nch = c + 1;
-        }
-        unsigned spins = 0;
-        while (true) {
-            unsigned long long xb[kMaxYChan], tg[kMaxYChan];
-            bool can[kMaxYChan];
-            bool active = false;
-#pragma unroll
-            for (int c = 0; c < kMaxYChan; ++c) {
-                can[c] = false;
-                if (c < nch && i0[c] < P.nsteps_pad) {
-                    active = true;
-                    const int sp = i0[c] + lane;
-                    const int cons = c * P.pyb;  // warp (wy = 0, wz = c)
-                    // the slot's previous occupant (step sp - 64) is read by the consumer at its step sp - 96
-                    can[c] = sp < P.nsteps_pad && !done[c] && sp < 4 * ld_prog(&progh[cons]) + 96;
-                    if (can[c]) {
-                        const size_t chan = (size_t)(cz * P.pz + c) * (P.gyb - 1) + (cy - 1);
-                        ld_b128_gpu(P.ymail + chan * P.nsteps_pad + sp, xb[c], tg[c]);
-                    }
+            can[c] = false;
+            if (c < nch && i0[c] < P.nsteps_pad) {
+                active = true;
+                const int sp = i0[c] + lane;
+                const int cons = c * P.pyb;  // warp (wy = 0, wz = c)
+                // the slot's previous occupant (step sp - 64) is read by the consumer at its step sp - 96
+                can[c] = sp < P.nsteps_pad && !done[c] && sp < 4 * ld_prog(&C.progh[cons]) + 96;
+                if (can[c]) {
+                    const size_t chan = (size_t)(C.cz * P.pz + c) * (P.gyb - 1) + (C.cy - 1);
+                    ld_b128_gpu(P.ymail + chan * P.nsteps_pad + sp, xb[c], tg[c]);
                 }
             }
-            if (!active) break;
+        }
+        if (!active) break;
 #pragma unroll
-            for (int c = 0; c < kMaxYChan; ++c) {
-                if (c < nch && i0[c] < P.nsteps_pad) {
-                    const int sp = i0[c] + lane;
-                    if (can[c] && tg[c] == (ehi | (unsigned long long)(sp + 1))) {
-                        const uint32_t yin =
-                            smem_u32(smem + (size_t)(c * P.pyb) * P.per_warp + ring_off + zbytes) + ((sp & (kRy - 1)) << 4);
-                        st_ring_s(yin, __longlong_as_double((long long)xb[c]), tg[c]);
-                        done[c] = true;
-                    }
-                    if (__all_sync(FULL, done[c] || sp >= P.nsteps_pad)) {
-                        i0[c] += 32;
-                        done[c] = false;
-                    }
+        for (int c = 0; c < kMaxYChan; ++c) {
+            if (c < nch && i0[c] < P.nsteps_pad) {
+                const int sp = i0[c] + lane;
+                if (can[c] && tg[c] == (ehi | (unsigned long long)(sp + 1))) {
+                    const uint32_t yin =
+                        smem_u32(C.smem + (size_t)(c * P.pyb) * P.per_warp + C.ring_off + C.zbytes) + ((sp & (kRy - 1)) << 4);
+                    st_ring_s(yin, __longlong_as_double((long long)xb[c]), tg[c]);
+                    done[c] = true;
+                }
+                if (__all_sync(FULL, done[c] || sp >= P.nsteps_pad)) {
+                    i0[c] += 32;
+                    done[c] = false;
                 }
             }
-            SYS_SPIN(spins, 203)
         }
-        return;
+        SYS_SPIN(spins, 203)
     }
+}
 
-    // ================================================================ compute warps
-    const int wy = warp % P.pyb, wz = warp / P.pyb;
-    const int jb = cy * P.pyb + wy, p = cz * P.pz + wz;
+// ---------------------------------------------------------------- helper of compute warp w (same scheduler): moves the
+// right-hand side in and the solution out in coalesced 32 x 8 rectangles through the window, and keeps the TMA
+// coefficient stages filled.  Iteration k runs beside the compute warp's block k.
+__device__ __forceinline__ void role_helper(const SysParams& P, const SysCtx& C, int w, int lane) {
+    const int wy = w % P.pyb, wz = w / P.pyb;
+    const int jb = C.cy * P.pyb + wy, p = C.cz * P.pz + wz;
     if (jb >= P.nyb || p >= P.nplanes) return;
-    const int nx = P.nx;
-    const int task = p * P.nyb + jb;
-    const bool has_zout = ZC && ((p + 1) % P.nz1) != 0;
-    const bool zout_local = has_zout && wz + 1 < P.pz;
-    const bool has_yin = jb > 0;
-    const bool has_yout = jb + 1 < P.nyb;
-    const bool yout_local = has_yout && wy + 1 < P.pyb;
+    const int nx = P.nx, nst = P.nst;
     const int j0 = jb * 32;
     const int nlines = min(32, P.ny - j0);
     const int nblocks = P.nsteps_pad / kStageSteps;
     const int nrect = (nx + 7) >> 3;
     const long long tile_base = ((long long)p * P.ny + j0) * nx;
-
-    unsigned char* mine = smem + (size_t)warp * P.per_warp;
-    const uint32_t stage_s = smem_u32(mine) + lane * 8;
-    const uint32_t xw_s = smem_u32(mine + win_off);
-    const uint32_t xw_lane = xw_s + lane * (kWinStride * 8);
-    const uint32_t zin_s = smem_u32(mine + ring_off) + lane * 16;
-    const uint32_t yin_s = smem_u32(mine + ring_off + zbytes);
-    // where this warp's hand-offs go: a ring of another warp of this CTA (generic address of shared memory) or
-    // a mailbox in global memory; the step loop issues the same generic 16-byte store either way
-    unsigned char* zdst0 = nullptr;
-    unsigned char* ydst0 = nullptr;
-    if (zout_local)
-        zdst0 = (unsigned char*)smem_generic(smem_u32(smem + (size_t)(warp + P.pyb) * P.per_warp + ring_off) + lane * 16);
-    else if (has_zout)
-        zdst0 = (unsigned char*)(P.zmail + ((size_t)((p + 1) / P.pz - 1) * P.nyb + jb) * P.nsteps_pad * 32 + lane);
-    if (yout_local)
-        ydst0 = (unsigned char*)smem_generic(smem_u32(smem + (size_t)(warp + 1) * P.per_warp + ring_off + zbytes));
-    else if (has_yout)
-        ydst0 = (unsigned char*)(P.ymail + ((size_t)p * (P.gyb - 1) + ((jb + 1) / P.pyb - 1)) * P.nsteps_pad);
-    const bool ypred = has_yout && lane == 31;
-    const int* zcons = zout_local ? &progh[warp + P.pyb] : &progh[W];  // [W] = INT_MAX: never blocks
-    const int* ycons = yout_local ? &progh[warp + 1] : &progh[W];
-    uint64_t* bar = mbar + warp * P.nst;
-    const unsigned rzmask = (unsigned)P.rz - 1u;
-    const double* coef_task = P.coef + (size_t)task * P.nsteps_pad * 128;
-    const int order_xyz = P.order_xyz, unit_diag = P.unit_diag, nst = P.nst;
-    unsigned spins = 0;
-
-    // rhs / solution rectangles: 32 lines x 8 columns, element q of a lane = (line 4q + rl, column 8m + rc)
+    unsigned char* mine = C.smem + (size_t)w * P.per_warp;
+    const uint32_t xw_s = smem_u32(mine + C.win_off);
+    uint64_t* bar = C.mbar + w * nst;
+    const double* coef_task = P.coef + (size_t)(p * P.nyb + jb) * P.nsteps_pad * 128;
+    // element q of a lane = (line 4q + rl, column 8m + rc)
     const int rl = lane >> 3, rc = lane & 7;
     const long long dir = P.backward ? -1 : 1;
     const long long g0 = P.backward ? P.n - 1 - (tile_base + (long long)rl * nx + rc) : tile_base + (long long)rl * nx + rc;
@@ -380,20 +336,101 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(const __grid_constant_
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const double v = lds_f64(xw_rl + q * (4 * kWinStride * 8) + (((t0 + 4 * q) & 63) << 3));
-            if (!guard || (q * 4 + rl < nlines && m * 8 + rc < nx)) b[q * qstride] = v;
+            if (!guard || (q * 4 + rl < nlines && m * 8 + rc < nx)) __stcs(b + q * qstride, v);
         }
     };
-    auto issue_stage = [&](int b, int slot) {  // lane 0 only
+    auto issue_stage = [&](int b) {  // lane 0 only
+        const int slot = b % nst;
         mbar_arrive_expect_tx(&bar[slot], (unsigned)kStageBytes);
         bulk_g2s(mine + (size_t)slot * kStageBytes, coef_task + (size_t)b * (kStageBytes / 8), (unsigned)kStageBytes, &bar[slot]);
     };
 
     if (lane == 0)
-        for (int b = 0; b < nst && b < nblocks; ++b) issue_stage(b, b);
+        for (int b = 0; b < nst && b < nblocks; ++b) issue_stage(b);
+    // rectangles 0 and 1 before the compute warp may start; 2 stays in registers until iteration 0
     rect_load(0);
     rect_deposit(0);
-    if (nrect > 1) rect_load(1);
+    if (nrect > 1) {
+        rect_load(1);
+        rect_deposit(1);
+    }
+    if (nrect > 2) rect_load(2);
     __syncwarp();
+    fence_acq_rel_cta();
+    if (lane == 0) *(volatile int*)&C.hdep[w] = 2;
+
+    unsigned spins = 0;
+    const int last = max(nblocks, nrect + 4);
+    for (int k = 0; k <= last; ++k) {
+        // the compute warp has finished block k - 1
+        const int need = 2 * min(k, nblocks);
+        while (ld_prog(&C.progh[w]) < need) SYS_SPIN(spins, 209)
+        fence_acq_rel_cta();
+        if (lane == 0 && k >= 1 && k - 1 + nst < nblocks) issue_stage(k - 1 + nst);  // its stage slot is free again
+        if (k + 2 < nrect) rect_deposit(k + 2);  // window columns of rectangle k - 6, drained in iteration k - 1
+        if (k + 3 < nrect) rect_load(k + 3);
+        if (k >= 5 && k - 5 < nrect) rect_drain(k - 5);  // complete since block k - 1
+        __syncwarp();
+        fence_acq_rel_cta();
+        if (lane == 0) *(volatile int*)&C.hdep[w] = k + 3;
+    }
+}
+
+// ---------------------------------------------------------------- compute warp: one task, one wavefront level per step
+template <bool EXACT, bool ZC>
+__device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C, int warp, int lane) {
+    namespace cg = cooperative_groups;
+    const int W = C.W;
+    const int wy = warp % P.pyb, wz = warp / P.pyb;
+    const int jb = C.cy * P.pyb + wy, p = C.cz * P.pz + wz;
+    if (jb >= P.nyb || p >= P.nplanes) return;
+    const int nx = P.nx;
+    const bool has_zin = ZC && (p % P.nz1) != 0;
+    const bool has_zout = ZC && ((p + 1) % P.nz1) != 0;
+    const bool zout_local = has_zout && wz + 1 < P.pz;
+    const bool zout_dsmem = has_zout && !zout_local && C.crank + 1 < P.csize;  // next CTA of this cluster
+    const bool has_yin = jb > 0;
+    const bool has_yout = jb + 1 < P.nyb;
+    const bool yout_local = has_yout && wy + 1 < P.pyb;
+    const int nblocks = P.nsteps_pad / kStageSteps;
+    unsigned char* mine = C.smem + (size_t)warp * P.per_warp;
+    const uint32_t stage_s = smem_u32(mine) + lane * 16;
+    const uint32_t xw_lane = smem_u32(mine + C.win_off) + lane * (kWinStride * 8);
+    const uint32_t zin_s = smem_u32(mine + C.ring_off) + lane * 16;
+    const uint32_t yin_s = smem_u32(mine + C.ring_off + C.zbytes);
+    // where this warp's hand-offs go: a ring of another warp of this CTA, the ring of warp wy of the next CTA of
+    // the cluster, or a mailbox in global memory; the step loop issues the same generic 16-byte store either way
+    unsigned char* zdst0 = nullptr;
+    unsigned char* ydst0 = nullptr;
+    const int* zcons = C.always;  // progress word of whoever reads a RING we write (never blocks for mailboxes)
+    const int* ycons = C.always;
+    if (zout_local) {
+        zdst0 = C.smem + (size_t)(warp + P.pyb) * P.per_warp + C.ring_off + lane * 16;
+        zcons = &C.progh[warp + P.pyb];
+    } else if (zout_dsmem) {
+        unsigned char* mine_ring = C.smem + (size_t)wy * P.per_warp + C.ring_off + lane * 16;
+        zdst0 = (unsigned char*)cg::this_cluster().map_shared_rank((void*)mine_ring, C.crank + 1);
+        zcons = &C.zcredit[wy];
+    } else if (has_zout) {
+        zdst0 = (unsigned char*)(P.zmail + ((size_t)((p + 1) / P.pz - 1) * P.nyb + jb) * P.nsteps_pad * 32 + lane);
+    }
+    const bool zring = zout_local || zout_dsmem;
+    if (yout_local) {
+        ydst0 = C.smem + (size_t)(warp + 1) * P.per_warp + C.ring_off + C.zbytes;
+        ycons = &C.progh[warp + 1];
+    } else if (has_yout) {
+        ydst0 = (unsigned char*)(P.ymail + ((size_t)p * (P.gyb - 1) + ((jb + 1) / P.pyb - 1)) * P.nsteps_pad);
+    }
+    const bool ypred = has_yout && lane == 31;
+    // a z producer in the PREVIOUS CTA of the cluster needs our progress: pushed into its zcredit word
+    int* credit = &C.scratch[warp];
+    if (has_zin && wz == 0 && C.crank > 0) credit = (int*)cg::this_cluster().map_shared_rank((void*)&C.zcredit[wy], C.crank - 1);
+    uint64_t* bar = C.mbar + warp * P.nst;
+    const unsigned rzmask = (unsigned)P.rz - 1u;
+    const int zlag = P.rz / 4 - 1;  // a producer may run this many half-blocks ahead of its z consumer
+    const unsigned long long ehi = (P.epoch & 0xffffffffull) << 32;  // tag = {epoch, step + 1}
+    const int order_xyz = P.order_xyz, unit_diag = P.unit_diag, nst = P.nst;
+    unsigned spins = 0;
 
     // lane 0's offset-nx dependency of element i is produced by lane 31 of the previous line block at ITS step
     // i + 31.  It is polled one step early (slot of producer step s + 32 while resolving step s: same slot
@@ -412,33 +449,34 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(const __grid_constant_
     double xprev = 0.0;
     int slot = 0;
     unsigned phase = 0;
-    int zseen = 0, yseen = 0;  // last progress read from the local z / y consumer
+    int zseen = 0, yseen = 0, hseen = 0;  // last progress read from the z / y ring consumers and from the helper
     for (int B = 0; B < nblocks; ++B) {
-        if (B + 1 < nrect) rect_deposit(B + 1);
-        if (B + 2 < nrect) rect_load(B + 2);
-        if (B >= 5 && B - 5 < nrect) rect_drain(B - 5);
-        __syncwarp();
+        {   // rectangle B (all columns <= 8B + 7) is in the window
+            const int need = B + 1;  // also: every rectangle aliased by this block's window columns is drained
+            while (hseen < need) {
+                hseen = ld_prog(&C.hdep[warp]);
+                SYS_SPIN(spins, 210)
+            }
+        }
         while (!mbar_try_wait(&bar[slot], phase)) SYS_SPIN(spins, 204)
         const uint32_t st = stage_s + slot * kStageBytes;
         const uint32_t wb = xw_lane + ((B & 7) << 6);
         const uint32_t zb = zin_s + (((unsigned)(B * kStageSteps) & rzmask) << 9);
         const uint32_t yb = yin_s + (((B + 4) & 7) << 7);  // slots of producer steps 8B + 32 ...
         const bool ypoll = B + 4 < nblocks;                 // ... which exist until four blocks before the end
-        unsigned char* zdst = zout_local ? zdst0 + (((unsigned)(B * kStageSteps) & rzmask) << 9) : zdst0 + (size_t)B * (kStageSteps * 512);
+        unsigned char* zdst = zring ? zdst0 + (((unsigned)(B * kStageSteps) & rzmask) << 9) : zdst0 + (size_t)B * (kStageSteps * 512);
         unsigned char* ydst = yout_local ? ydst0 + ((B & 7) << 7) : ydst0 + (size_t)B * (kStageSteps * 16);
         const int s0 = B * kStageSteps;
-        // coefficients / rhs of the block's first step (later steps are loaded one step ahead)
-        double cz_ = 0.0, cy_, cx_, dv, bb;
-        if (ZC) cz_ = lds_f64(st);
-        cy_ = lds_f64(st + 256);
-        cx_ = lds_f64(st + 512);
-        dv = lds_f64(st + 768);
+        // operands of the block's first step (later steps are loaded one step ahead)
+        double cz_, cy_, cx_, dv, bb;
+        lds_2f64(st, cz_, cy_);
+        lds_2f64(st + 512, cx_, dv);
         bb = lds_f64(wb);
 #pragma unroll
         for (int u = 0; u < kStageSteps; ++u) {
             const int tag = s0 + u + 1;
             if ((u & 3) == 0) {
-                // flow control once per half-block: the local consumers' ring slots we are about to overwrite are free
+                // flow control once per half-block: the ring slots we are about to overwrite have been read
                 const int h = 2 * B + (u >> 2);
                 while (zseen < h - zlag) {
                     zseen = ld_prog(zcons);
@@ -451,10 +489,8 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(const __grid_constant_
             }
             const double czu = cz_, cyu = cy_, cxu = cx_, dvu = dv, bbu = bb;
             if (u + 1 < kStageSteps) {  // next step's operands: independent of everything below
-                if (ZC) cz_ = lds_f64(st + (u + 1) * 1024);
-                cy_ = lds_f64(st + (u + 1) * 1024 + 256);
-                cx_ = lds_f64(st + (u + 1) * 1024 + 512);
-                dv = lds_f64(st + (u + 1) * 1024 + 768);
+                lds_2f64(st + (u + 1) * 1024, cz_, cy_);
+                lds_2f64(st + (u + 1) * 1024 + 512, cx_, dv);
                 bb = lds_f64(wb + (u + 1) * 8);
             }
             double xy = __shfl_up_sync(FULL, xprev, 1);
@@ -502,22 +538,109 @@ __global__ void __launch_bounds__(256, 1) k_trsv_systolic(const __grid_constant_
             const unsigned long long tag64 = ehi | (unsigned long long)(unsigned)tag;
             if (has_zout) st_gen128(zdst + u * 512, xnew, tag64);
             if (ypred) st_gen128(ydst + u * 16, xnew, tag64);
-            if ((u & 3) == 3 && lane == 0) *(volatile int*)&progh[warp] = 2 * B + (u >> 2) + 1;
+            if ((u & 3) == 3 && lane == 0) {
+                const int hb = 2 * B + (u >> 2) + 1;
+                *(volatile int*)&C.progh[warp] = hb;
+                st_gen_s32(credit, hb);
+            }
         }
-        __syncwarp();
-        if (lane == 0 && B + nst < nblocks) issue_stage(B + nst, slot);
         if (++slot == nst) {
             slot = 0;
             phase ^= 1u;
         }
     }
-    __syncwarp();
-    for (int m = max(0, nblocks - 5); m < nrect; ++m) rect_drain(m);
+}
+
+template <bool EXACT, bool ZC>
+__global__ void __launch_bounds__(448, 1) k_trsv_systolic(const __grid_constant__ SysParams P) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SysCtx C;
+    C.smem = smem;
+    C.W = P.pyb * P.pz;
+    C.zbytes = ZC ? P.rz * 512 : 0;
+    C.win_off = P.nst * kStageBytes;
+    C.ring_off = C.win_off + kWinBytes;  // z ring, then y ring
+    C.mbar = reinterpret_cast<uint64_t*>(smem + (size_t)C.W * P.per_warp);
+    int* ctl = reinterpret_cast<int*>(C.mbar + C.W * P.nst);
+    C.progh = ctl;
+    C.hdep = ctl + kMaxWarps;
+    C.zcredit = ctl + 2 * kMaxWarps;
+    C.scratch = ctl + 3 * kMaxWarps;
+    C.always = ctl + 4 * kMaxWarps;
+    C.cy = blockIdx.x / P.gzp;
+    C.cz = blockIdx.x % P.gzp;
+    C.crank = (int)(blockIdx.x % P.csize);  // gzp is a multiple of the cluster size
+    const int W = C.W;
+
+    // windows zeroed; rings zeroed (tag 0 = nothing yet) -- or, for a warp WITHOUT that input, pre-filled with
+    // {0.0, INT_MAX}: always ready, value zero, so the step loop needs no "do I have this input" branches
+    for (int w = 0; w < W; ++w) {
+        unsigned char* base = smem + (size_t)w * P.per_warp;
+        ulonglong2* win = reinterpret_cast<ulonglong2*>(base + C.win_off);
+        for (int t = threadIdx.x; t < kWinBytes / 16; t += blockDim.x) win[t] = make_ulonglong2(0ull, 0ull);
+        const int jbw = C.cy * P.pyb + w % P.pyb, pw = C.cz * P.pz + w / P.pyb;
+        const unsigned long long ztag = (ZC && (pw % P.nz1) != 0) ? 0ull : (unsigned long long)INT_MAX;
+        const unsigned long long ytag = jbw > 0 ? 0ull : (unsigned long long)INT_MAX;
+        ulonglong2* zr = reinterpret_cast<ulonglong2*>(base + C.ring_off);
+        for (int t = threadIdx.x; t < C.zbytes / 16; t += blockDim.x) zr[t] = make_ulonglong2(0ull, ztag);
+        ulonglong2* yr = reinterpret_cast<ulonglong2*>(base + C.ring_off + C.zbytes);
+        for (int t = threadIdx.x; t < kRy; t += blockDim.x) yr[t] = make_ulonglong2(0ull, ytag);
+    }
+    if (threadIdx.x < W * P.nst) mbar_init(&C.mbar[threadIdx.x], 1);
+    if (threadIdx.x < kCtlInts) ctl[threadIdx.x] = threadIdx.x == 4 * kMaxWarps ? INT_MAX : 0;
+    fence_mbar_init();
+    __syncthreads();
+    cg::this_cluster().sync();  // every CTA of the cluster has initialised its rings before anyone writes into them
+
+    if (C.cz < P.gz) {
+        if (warp < W) role_compute<EXACT, ZC>(P, C, warp, lane);
+        else if (warp < 2 * W) role_helper(P, C, warp - W, lane);
+        else if (warp == 2 * W) role_zfetch<ZC>(P, C, lane);
+        else role_yfetch(P, C, lane);
+    }
+    // nobody leaves while a neighbour may still write into its shared memory
+    cg::this_cluster().sync();
 }
 
 }  // namespace
 
 // ================================================================================================== host
+typedef void (*sys_kern_t)(const SysParams);
+static sys_kern_t sys_kernel(bool exact, bool zc) {
+    const sys_kern_t k = exact ? (zc ? (sys_kern_t)k_trsv_systolic<true, true> : (sys_kern_t)k_trsv_systolic<true, false>)
+                               : (zc ? (sys_kern_t)k_trsv_systolic<false, true> : (sys_kern_t)k_trsv_systolic<false, false>);
+    static thread_local bool attr_set[4] = {false, false, false, false};
+    const int ki = (exact ? 2 : 0) + (zc ? 1 : 0);
+    if (!attr_set[ki]) {
+        ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[ki] = true;
+    }
+    return k;
+}
+// how many clusters of `csize` CTAs of this shape can be resident at once (0: not launchable)
+static int max_active_clusters(sys_kern_t k, int csize, int block, size_t smem) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(csize, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     TriSolve& T = h->solve[slot];
     SysSolve& Y = T.sys;
@@ -625,7 +748,25 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     Y.nstages = nst;
     Y.rz = rz;
     Y.ry = kRy;
-    Y.smem = (size_t)pyb * pz * per_warp(nst, rz) + (size_t)pyb * pz * nst * 8 + (kMaxWarps + 1) * 4 + 64;
+    Y.smem = (size_t)pyb * pz * per_warp(nst, rz) + (size_t)pyb * pz * nst * 8 + kCtlInts * 4 + 64;
+    // thread-block clusters along z: hand-offs between consecutive CTAs of a cluster go through distributed shared
+    // memory instead of a global mailbox.  Largest cluster whose padded grid is still co-resident.
+    Y.csize = 1;
+    Y.gzp = Y.gz;
+    if (zc && Y.gz > 1 && opt.sys_cluster != 1) {
+        const sys_kern_t k = sys_kernel(false, true);
+        const int block = (pyb * pz * 2 + 2) * 32;
+        for (int c = (int)std::min<int64_t>(8, opt.sys_cluster > 0 ? opt.sys_cluster : 8); c >= 2; --c) {
+            const int gzp = (Y.gz + c - 1) / c * c;
+            if (gzp - Y.gz >= c) continue;
+            const int need = Y.gyb * gzp / c;
+            if (need <= max_active_clusters(k, c, block, Y.smem)) {
+                Y.csize = c;
+                Y.gzp = gzp;
+                break;
+            }
+        }
+    }
     Y.coef.alloc((size_t)Y.ntasks * per_task);
     Y.nzchan = zc ? G.nyb * std::max(0, Y.gz - 1) : 0;
     Y.nychan = nplanes * std::max(0, Y.gyb - 1);
@@ -682,21 +823,27 @@ void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cu
     P.status = h->status.p;
     // watchdog in failed polls (a poll round is >= ~40 cycles)
     P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 16, (long long)opt.spin_limit_ms * h->clock_khz / 64));
-    typedef void (*kern_t)(const SysParams);
-    const kern_t kern = exact ? (Y.zcoupled ? (kern_t)k_trsv_systolic<true, true> : (kern_t)k_trsv_systolic<true, false>)
-                              : (Y.zcoupled ? (kern_t)k_trsv_systolic<false, true> : (kern_t)k_trsv_systolic<false, false>);
-    static thread_local bool attr_set[4] = {false, false, false, false};
-    const int ki = (exact ? 2 : 0) + (Y.zcoupled ? 1 : 0);
-    if (!attr_set[ki]) {
-        ILUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[ki] = true;
-    }
-    const int grid = Y.gyb * Y.gz;
-    const int block = (Y.pyb * Y.pz + 2) * 32;
+    const sys_kern_t kern = sys_kernel(exact, Y.zcoupled != 0);
+    P.gz = Y.gz;
+    P.gzp = Y.gzp;
+    P.csize = Y.csize;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(Y.gyb * Y.gzp, 1, 1);
+    cfg.blockDim = dim3((Y.pyb * Y.pz * 2 + 2) * 32, 1, 1);
+    cfg.dynamicSmemBytes = Y.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = Y.csize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
     for (int c = 0; c < nrhs; ++c) {
         P.epoch = ++Y.epoch;
         P.x = x + (int64_t)c * ldx;
-        kern<<<grid, block, Y.smem, s>>>(P);
+        ILUB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
         h->launches++;
     }
     ILUB_CUDA(cudaGetLastError());

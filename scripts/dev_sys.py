@@ -111,6 +111,11 @@ if mode in ("parity", "all"):
     ilupp.set_option("sys_stages", 2)
     case("p3d20-st2", P.poisson3d(20), True, ("csr",))
     ilupp.set_option("sys_stages", 0)
+    ilupp.set_option("sys_cluster", 1)
+    case("p3d20-nocluster", P.poisson3d(20), True, ("csr",))
+    ilupp.set_option("sys_cluster", 3)
+    case("p3d20-cluster3", P.poisson3d(20), True, ("csr",))
+    ilupp.set_option("sys_cluster", 0)
 if mode in ("time", "all"):
     ilupp.set_option("exact", 0)
     timing("p3d128", P.poisson3d(128), "ichol0")
