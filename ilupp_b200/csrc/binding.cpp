@@ -25,6 +25,7 @@
 
 #include "ilub.h"
 
+extern "C" int ilub_debug_sys_trace(ilub_handle* h, int which_solve, int32_t* dims, long long* trace);
 extern "C" int ilub_debug_chunks(ilub_handle* h, int which_solve, int32_t* nchunks, int32_t* rows, long long* trace);
 
 namespace py = pybind11;
@@ -323,6 +324,16 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
              },
              py::arg("b"), py::arg("x"), py::arg("rtol") = 1e-4, py::arg("atol") = 1e-4, py::arg("max_iter") = 500,
              py::arg("stream") = 0)
+        .def("debug_sys_trace",
+             [](const P& pr, int which) {
+                 int32_t dims[8];
+                 check(ilub_debug_sys_trace(pr.h, which, dims, nullptr));
+                 py::array_t<long long> trace((size_t)dims[0] * dims[1]);
+                 check(ilub_debug_sys_trace(pr.h, which, dims, trace.mutable_data()));
+                 py::list d;
+                 for (int k = 0; k < 8; ++k) d.append(dims[k]);
+                 return py::make_tuple(d, trace);
+             })
         .def("debug_chunks",
              [](const P& pr, int which) {
                  int32_t nch = 0;

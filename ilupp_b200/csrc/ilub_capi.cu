@@ -477,6 +477,28 @@ int ilub_get_option(const char* key, int64_t* value) {
     });
 }
 
+/* debug (not part of the supported ABI): per-task block time stamps of the line-systolic solve (option trace) */
+ILUB_API int ilub_debug_sys_trace(ilub_handle* h, int which_solve, int32_t* dims /*[8]*/, long long* trace) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && dims, ILUB_ERR_INVALID, "null argument");
+        DeviceGuard guard(h->device);
+        TriSolve& T = h->solve[slot_of(h, which_solve)];
+        ILUB_REQUIRE(T.built && T.sys.built, ILUB_ERR_INVALID, "no line-systolic solve");
+        const SysSolve& Y = T.sys;
+        dims[0] = Y.ntasks;
+        dims[1] = Y.nsteps_pad / 8 + 1;
+        dims[2] = Y.nyb;
+        dims[3] = Y.nplanes;
+        dims[4] = Y.pyb;
+        dims[5] = Y.pz;
+        dims[6] = Y.csize;
+        dims[7] = Y.nstages * 100 + Y.rz;
+        ILUB_CUDA(cudaDeviceSynchronize());
+        const size_t cnt = (size_t)dims[0] * dims[1];
+        if (trace && T.trace.n >= cnt) ILUB_CUDA(cudaMemcpy(trace, T.trace.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost));
+    });
+}
+
 /* debug (not part of the supported ABI): chunk -> row map and per-chunk clock stamps of one solve */
 ILUB_API int ilub_debug_chunks(ilub_handle* h, int which_solve, int32_t* nchunks, int32_t* rows, long long* trace) {
     return guarded([&] {

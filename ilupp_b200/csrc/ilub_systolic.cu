@@ -110,14 +110,18 @@ __global__ void k_sys_pack(int64_t total, int per_task, int nyb, int nz1, int ns
     const int p = task / nyb, jb = task - p * nyb;
     const int sysm = p / nz1, k = p - sysm * nz1;
     const int sys = backward ? nsys - 1 - sysm : sysm;
-    const int pos = srcpos[(size_t)(k * nyb + jb) * per_task + rem];
+    const size_t tbase = (size_t)(k * nyb + jb) * per_task;
+    const int pos = srcpos[tbase + rem];
     const int role = ((rem >> 6) & 1) * 2 + (rem & 1);
+    const int64_t soff = (int64_t)sys * nnz1;
     double v;
-    if (pos >= 0) {
-        v = lu[(int64_t)pos + (int64_t)sys * nnz1];
-        if (role == 3 && recip) v = 1.0 / v;
+    if (recip) {
+        // fast arithmetic: x = b/d - sum (c/d) x_dep  -> {c/d, ..., 1/d}; absent entries are plain zeros
+        const int dpos = srcpos[tbase + (rem & ~127) + 64 + (rem & 62) + 1];
+        const double dinv = dpos >= 0 ? 1.0 / lu[(int64_t)dpos + soff] : 1.0;
+        v = role == 3 ? dinv : (pos >= 0 ? lu[(int64_t)pos + soff] * dinv : 0.0);
     } else {
-        v = role == 3 ? 1.0 : (recip ? 0.0 : __longlong_as_double(kAbsentBits));  // fast mode: plain zero
+        v = pos >= 0 ? lu[(int64_t)pos + soff] : (role == 3 ? 1.0 : __longlong_as_double(kAbsentBits));
     }
     coef[e] = v;
 }
@@ -138,7 +142,14 @@ struct SysParams {
     int per_warp;  // shared-memory bytes per compute warp
     int* status;
     unsigned spin_iters;  // failed polls before a wait gives up (watchdog)
+    long long* trace;     // debug (option trace): %globaltimer at every block start of every task, and at its end
 };
+
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Shared memory of one compute warp: [nst coefficient stages][rhs/solution window 32 x 65][z ring rz x 32][y ring 64]
 // Window: element (line l, column i) lives at xw[l*65 + ((i + l) & 63)], i.e. at the STEP it is resolved in, so a
@@ -450,7 +461,9 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
     int slot = 0;
     unsigned phase = 0;
     int zseen = 0, yseen = 0, hseen = 0;  // last progress read from the z / y ring consumers and from the helper
+    long long* trace = P.trace ? P.trace + (size_t)(p * P.nyb + jb) * (nblocks + 1) : nullptr;
     for (int B = 0; B < nblocks; ++B) {
+        if (trace && lane == 0) trace[B] = global_ns();
         {   // rectangle B (all columns <= 8B + 7) is in the window
             const int need = B + 1;  // also: every rectangle aliased by this block's window columns is drained
             while (hseen < need) {
@@ -466,6 +479,7 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
         const bool ypoll = B + 4 < nblocks;                 // ... which exist until four blocks before the end
         unsigned char* zdst = zring ? zdst0 + (((unsigned)(B * kStageSteps) & rzmask) << 9) : zdst0 + (size_t)B * (kStageSteps * 512);
         unsigned char* ydst = yout_local ? ydst0 + ((B & 7) << 7) : ydst0 + (size_t)B * (kStageSteps * 16);
+        asm volatile("" : "+l"(zdst), "+l"(ydst));  // keep them in registers: no per-step re-derivation
         const int s0 = B * kStageSteps;
         // operands of the block's first step (later steps are loaded one step ahead)
         double cz_, cy_, cx_, dv, bb;
@@ -493,22 +507,21 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
                 lds_2f64(st + (u + 1) * 1024 + 512, cx_, dv);
                 bb = lds_f64(wb + (u + 1) * 8);
             }
-            double xy = __shfl_up_sync(FULL, xprev, 1);
-            if (lane == 0) xy = ycur;
             // ---- inputs from other warps: z ring (own entry per lane, this step), y ring (one entry read by every
             //      lane, next step).  Rings of inputs this warp does not have are pre-filled "always ready".
-            double xz = 0.0, ynext = 0.0;
-            while (true) {
-                unsigned long long vz = 0ull, tz = (unsigned long long)INT_MAX, vy = 0ull, ty = (unsigned long long)INT_MAX;
-                if (ZC) ld_s128(zb + u * 512, vz, tz);
-                if (ypoll) ld_s128(yb + u * 16, vy, ty);
-                xz = __longlong_as_double((long long)vz);
-                ynext = __longlong_as_double((long long)vy);
-                if (__all_sync(FULL, (int)(unsigned)tz >= tag && (int)(unsigned)ty >= tag + 32)) break;
-                SYS_SPIN(spins, 205)
-            }
-            double xnew;
+            unsigned long long vz = 0ull, tz = (unsigned long long)INT_MAX, vy = 0ull, ty = (unsigned long long)INT_MAX;
+            if (ZC) ld_s128(zb + u * 512, vz, tz);  // first poll goes out before anything else of the step
+            if (ypoll) ld_s128(yb + u * 16, vy, ty);
+            double xy = __shfl_up_sync(FULL, xprev, 1);
+            if (lane == 0) xy = ycur;
+            double xnew, ynext;
             if (EXACT) {
+                while (!__all_sync(FULL, (int)(unsigned)tz >= tag && (int)(unsigned)ty >= tag + 32)) {
+                    SYS_SPIN(spins, 205)
+                    if (ZC) ld_s128(zb + u * 512, vz, tz);
+                    if (ypoll) ld_s128(yb + u * 16, vy, ty);
+                }
+                const double xz = __longlong_as_double((long long)vz);
                 const bool az = !ZC || __double_as_longlong(czu) == kAbsentBits;
                 const bool ay = __double_as_longlong(cyu) == kAbsentBits;
                 const bool ax = __double_as_longlong(cxu) == kAbsentBits;
@@ -524,13 +537,21 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
                 }
                 xnew = unit_diag ? acc : __ddiv_rn(acc, dvu);
             } else {
-                // absent entries carry coefficient 0.0 and every operand that can reach them is finite
-                double acc = bbu;
-                if (ZC) acc = fma(-czu, xz, acc);
+                // coefficients are pre-divided by the diagonal (dvu = 1/d); absent entries carry 0.0 and every operand
+                // that can reach them is finite.  Only ONE fused multiply-add waits for the other warp's value, and it
+                // is issued speculatively: the vote on the tags resolves beside it.
+                double acc = bbu * dvu;
                 acc = fma(-cxu, xprev, acc);
                 acc = fma(-cyu, xy, acc);
-                xnew = acc * dvu;
+                while (true) {
+                    xnew = ZC ? fma(-czu, __longlong_as_double((long long)vz), acc) : acc;
+                    if (__all_sync(FULL, (int)(unsigned)tz >= tag && (int)(unsigned)ty >= tag + 32)) break;
+                    SYS_SPIN(spins, 205)
+                    if (ZC) ld_s128(zb + u * 512, vz, tz);
+                    if (ypoll) ld_s128(yb + u * 16, vy, ty);
+                }
             }
+            ynext = __longlong_as_double((long long)vy);
             xprev = xnew;
             ycur = ynext;
             sts_f64(wb + u * 8, xnew);
@@ -549,6 +570,7 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
             phase ^= 1u;
         }
     }
+    if (trace && lane == 0) trace[nblocks] = global_ns();
 }
 
 template <bool EXACT, bool ZC>
@@ -824,6 +846,9 @@ void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cu
     // watchdog in failed polls (a poll round is >= ~40 cycles)
     P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 16, (long long)opt.spin_limit_ms * h->clock_khz / 64));
     const sys_kern_t kern = sys_kernel(exact, Y.zcoupled != 0);
+    if (opt.trace && T.trace.n < (size_t)Y.ntasks * (Y.nsteps_pad / kStageSteps + 1))
+        T.trace.alloc((size_t)Y.ntasks * (Y.nsteps_pad / kStageSteps + 1));
+    P.trace = opt.trace ? T.trace.p : nullptr;
     P.gz = Y.gz;
     P.gzp = Y.gzp;
     P.csize = Y.csize;
