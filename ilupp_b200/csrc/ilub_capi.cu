@@ -486,7 +486,7 @@ ILUB_API int ilub_debug_sys_trace(ilub_handle* h, int which_solve, int32_t* dims
         ILUB_REQUIRE(T.built && T.sys.built, ILUB_ERR_INVALID, "no line-systolic solve");
         const SysSolve& Y = T.sys;
         dims[0] = Y.ntasks;
-        dims[1] = Y.nsteps_pad / 8 + 1;
+        dims[1] = 3 * (Y.nsteps_pad / 8 + 1);  // per task: time, failed polls, helper/stage wait cycles
         dims[2] = Y.nyb;
         dims[3] = Y.nplanes;
         dims[4] = Y.pyb;

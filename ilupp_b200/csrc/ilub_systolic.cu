@@ -461,9 +461,18 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
     int slot = 0;
     unsigned phase = 0;
     int zseen = 0, yseen = 0, hseen = 0;  // last progress read from the z / y ring consumers and from the helper
-    long long* trace = P.trace ? P.trace + (size_t)(p * P.nyb + jb) * (nblocks + 1) : nullptr;
+    long long* trace = P.trace ? P.trace + (size_t)(p * P.nyb + jb) * 3 * (nblocks + 1) : nullptr;
+    long long wait_cycles = 0;
     for (int B = 0; B < nblocks; ++B) {
-        if (trace && lane == 0) trace[B] = global_ns();
+        long long c0 = 0;
+        if (trace) {
+            if (lane == 0) {
+                trace[B] = global_ns();
+                trace[(nblocks + 1) + B] = spins;
+                trace[2 * (nblocks + 1) + B] = wait_cycles;
+            }
+            c0 = clock64();
+        }
         {   // rectangle B (all columns <= 8B + 7) is in the window
             const int need = B + 1;  // also: every rectangle aliased by this block's window columns is drained
             while (hseen < need) {
@@ -472,6 +481,7 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
             }
         }
         while (!mbar_try_wait(&bar[slot], phase)) SYS_SPIN(spins, 204)
+        if (trace) wait_cycles += clock64() - c0;
         const uint32_t st = stage_s + slot * kStageBytes;
         const uint32_t wb = xw_lane + ((B & 7) << 6);
         const uint32_t zb = zin_s + (((unsigned)(B * kStageSteps) & rzmask) << 9);
@@ -570,7 +580,11 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
             phase ^= 1u;
         }
     }
-    if (trace && lane == 0) trace[nblocks] = global_ns();
+    if (trace && lane == 0) {
+        trace[nblocks] = global_ns();
+        trace[(nblocks + 1) + nblocks] = spins;
+        trace[2 * (nblocks + 1) + nblocks] = wait_cycles;
+    }
 }
 
 template <bool EXACT, bool ZC>
@@ -846,8 +860,8 @@ void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cu
     // watchdog in failed polls (a poll round is >= ~40 cycles)
     P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 16, (long long)opt.spin_limit_ms * h->clock_khz / 64));
     const sys_kern_t kern = sys_kernel(exact, Y.zcoupled != 0);
-    if (opt.trace && T.trace.n < (size_t)Y.ntasks * (Y.nsteps_pad / kStageSteps + 1))
-        T.trace.alloc((size_t)Y.ntasks * (Y.nsteps_pad / kStageSteps + 1));
+    if (opt.trace && T.trace.n < (size_t)Y.ntasks * 3 * (Y.nsteps_pad / kStageSteps + 1))
+        T.trace.alloc((size_t)Y.ntasks * 3 * (Y.nsteps_pad / kStageSteps + 1));
     P.trace = opt.trace ? T.trace.p : nullptr;
     P.gz = Y.gz;
     P.gzp = Y.gzp;

@@ -26,15 +26,26 @@ print("apply (traced) %.1f us" % (e0.elapsed_time(e1) * 1e3))
 for which in (0, 1):
     dims, tr = B.pr.debug_sys_trace(which)
     ntasks, nper, nyb, nplanes, pyb, pz, csize, cfg = dims
-    tr = np.asarray(tr).reshape(ntasks, nper).astype(np.float64)
+    full = np.asarray(tr).reshape(ntasks, 3, nper // 3).astype(np.float64)
+    np.save("gpurun_out/tracefull_%s_%d.npy" % (name, which), full)
+    nper //= 3
+    tr = full[:, 0, :].copy()
+    sp = full[:, 1, :]
+    wc = full[:, 2, :]
     t0 = tr[:, 0].min()
     tr -= t0
+    print("  failed polls per task: median %.0f max %.0f ; per plane-group position (wz): %s" % (
+        np.median(sp[:, -1]), sp[:, -1].max(), [float(np.median(sp[:, -1].reshape(nplanes, nyb)[wz::pz, :])) for wz in range(pz)]))
+    print("  helper/stage wait per task (us): median %.1f max %.1f" % (np.median(wc[:, -1]) / 1965, wc[:, -1].max() / 1965))
     start, end = tr[:, 0], tr[:, -1]
     print("solve %d: tasks %d (nyb %d x planes %d), tile %dx%d, cluster %d, stages/rz %d | span %.1f us" % (
         which, ntasks, nyb, nplanes, pyb, pz, csize, cfg, end.max() / 1e3))
     dur = np.diff(tr, axis=1)
     print("  per-block duration (ns): median %.0f p10 %.0f p90 %.0f max %.0f -> %.0f ns/step" % (
         np.median(dur), np.percentile(dur, 10), np.percentile(dur, 90), dur.max(), np.median(dur) / 8))
+    T3 = tr.reshape(nplanes, nyb, nper)
+    print("  plane end-time slope (jb 0): %.0f ns/plane ; task duration plane 0: %.1f us, last plane: %.1f us" % (
+        (T3[-1, 0, -1] - T3[0, 0, -1]) / max(1, nplanes - 1), (T3[0, 0, -1] - T3[0, 0, 0]) / 1e3, (T3[-1, 0, -1] - T3[-1, 0, 0]) / 1e3))
     S = start.reshape(nplanes, nyb)
     E = end.reshape(nplanes, nyb)
     print("  task start (us) by plane for line block 0:", np.round(S[::max(1, nplanes // 16), 0] / 1e3, 1))
