@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 #include "ilub_common.cuh"
 #include "ilub_ptx.cuh"
@@ -731,18 +732,57 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     const size_t budget = (size_t)227 * 1024 - 1024;
     auto per_warp = [&](int nst, int rz) { return (size_t)nst * kStageBytes + kWinBytes + (zc ? rz * 512 : 0) + kRy * 16; };
     auto max_warps = [&](int nst, int rz) { return (int)std::min<size_t>(kMaxWarps, budget / (per_warp(nst, rz) + 64)); };
-    int pyb = 1, pz = 1, nst = 3, rz = 16;
+    int pyb = 1, pz = 1, nst = 3, rz = 16, csize = 1, gzp = 1;
+    auto fit_rings = [&](int warps, int& nst_, int& rz_) {  // three stages and the 16-step z ring if they fit
+        if (warps <= max_warps(3, 16)) { nst_ = 3; rz_ = 16; }
+        else if (warps <= max_warps(3, 8)) { nst_ = 3; rz_ = 8; }
+        else if (warps <= max_warps(2, 16)) { nst_ = 2; rz_ = 16; }
+        else { nst_ = 2; rz_ = 8; }
+    };
+    auto smem_of = [&](int warps, int nst_, int rz_) { return (size_t)warps * per_warp(nst_, rz_) + (size_t)warps * nst_ * 8 + kCtlInts * 4 + 64; };
     if (zc) {
-        pz = 1;
-        while ((int64_t)G.nyb * ((nplanes + pz - 1) / pz) > h->sm_count) ++pz;
-        if (opt.sys_pz > 0) pz = (int)opt.sys_pz;
-        pz = std::min(pz, nplanes);
-        if (pz > max_warps(2, 8) || pz > kMaxYChan) return false;  // too large for one co-resident wave: generic path
-        // prefer three stages and the 16-step z ring, give up ring depth first, then a stage
-        if (pz <= max_warps(3, 16)) { nst = 3; rz = 16; }
-        else if (pz <= max_warps(3, 8)) { nst = 3; rz = 8; }
-        else if (pz <= max_warps(2, 16)) { nst = 2; rz = 16; }
-        else { nst = 2; rz = 8; }
+        // planes per CTA: the fewest that keep the whole grid co-resident, then up to two more if that lets a
+        // larger thread-block cluster (fewer global-memory hand-offs on the z chain) stay co-resident
+        int pz0 = 1;
+        while ((int64_t)G.nyb * ((nplanes + pz0 - 1) / pz0) > h->sm_count) ++pz0;
+        if (opt.sys_pz > 0) pz0 = (int)opt.sys_pz;
+        pz0 = std::min(pz0, nplanes);
+        if (pz0 > max_warps(2, 8) || pz0 > kMaxYChan) return false;  // too large for one co-resident wave: generic path
+        const sys_kern_t k = sys_kernel(false, true);
+        ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        ILUB_CUDA(cudaFuncSetAttribute(sys_kernel(true, true), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        const int cmax = (int)std::min<int64_t>(16, opt.sys_cluster > 0 ? opt.sys_cluster : 16);
+        long best_cost = LONG_MAX;
+        for (int pzc = pz0; pzc <= std::min(pz0 + (opt.sys_pz > 0 ? 0 : 2), std::min(nplanes, std::min(max_warps(2, 8), kMaxYChan))); ++pzc) {
+            int nstc, rzc;
+            fit_rings(pzc, nstc, rzc);
+            const int gz = (nplanes + pzc - 1) / pzc;
+            const int block = (pzc * 2 + 2) * 32;
+            const size_t sm = smem_of(pzc, nstc, rzc);
+            for (int c = cmax; c >= 1; --c) {
+                const int gzpc = (gz + c - 1) / c * c;
+                if ((int64_t)G.nyb * gzpc > h->sm_count) continue;
+                if (c > 1 && G.nyb * gzpc / c > max_active_clusters(k, c, block, sm)) continue;
+                // cost model (ns on the z chain): global hop 1500, DSMEM hop 300, local hop 120; two compute warps
+                // on one scheduler slow every step of the task
+                const long glob = gzpc / c - 1, dsm = gz - 1 - glob, loc = nplanes - gz;
+                // (measured on 128^3: a fifth / sixth compute warp per SM costs more than the hops it saves)
+                const long cost = glob * 1500 + dsm * 300 + loc * 120 + (long)(pzc - pz0) * 15000 + (nstc < 3 ? 1000 : 0);
+                if (getenv("ILUB_DEBUG"))
+                    fprintf(stderr, "[ilub] tiling pz %d cluster %d: gz %d (padded %d), global %ld dsmem %ld, cost %ld\n", pzc, c, gz,
+                            gzpc, glob, dsm, cost);
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    pz = pzc;
+                    nst = nstc;
+                    rz = rzc;
+                    csize = c;
+                    gzp = gzpc;
+                }
+                break;  // largest admissible cluster for this pz
+            }
+        }
+        if (best_cost == LONG_MAX) return false;
     } else {
         const int mw = max_warps(3, 8);
         const int gyb = (G.nyb + mw - 1) / mw;
@@ -784,25 +824,11 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     Y.nstages = nst;
     Y.rz = rz;
     Y.ry = kRy;
-    Y.smem = (size_t)pyb * pz * per_warp(nst, rz) + (size_t)pyb * pz * nst * 8 + kCtlInts * 4 + 64;
-    // thread-block clusters along z: hand-offs between consecutive CTAs of a cluster go through distributed shared
-    // memory instead of a global mailbox.  Largest cluster whose padded grid is still co-resident.
-    Y.csize = 1;
-    Y.gzp = Y.gz;
-    if (zc && Y.gz > 1 && opt.sys_cluster != 1) {
-        const sys_kern_t k = sys_kernel(false, true);
-        const int block = (pyb * pz * 2 + 2) * 32;
-        for (int c = (int)std::min<int64_t>(8, opt.sys_cluster > 0 ? opt.sys_cluster : 8); c >= 2; --c) {
-            const int gzp = (Y.gz + c - 1) / c * c;
-            if (gzp - Y.gz >= c) continue;
-            const int need = Y.gyb * gzp / c;
-            if (need <= max_active_clusters(k, c, block, Y.smem)) {
-                Y.csize = c;
-                Y.gzp = gzp;
-                break;
-            }
-        }
-    }
+    Y.smem = smem_of(pyb * pz, nst, rz);
+    // thread-block cluster along z (chosen with the tiling above): hand-offs between consecutive CTAs of a cluster
+    // go through distributed shared memory instead of a global mailbox
+    Y.csize = zc ? csize : 1;
+    Y.gzp = zc ? gzp : Y.gz;
     Y.coef.alloc((size_t)Y.ntasks * per_task);
     Y.nzchan = zc ? G.nyb * std::max(0, Y.gz - 1) : 0;
     Y.nychan = nplanes * std::max(0, Y.gyb - 1);
