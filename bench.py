@@ -201,7 +201,7 @@ def run_ours(args):
         for k in range(args.steps):
             x.copy_(x0)               # restore the right-hand side (not timed: outside the event pair)
             evs[k][0].record(stream)
-            B.apply(x)                # two launches of the sync-free SpTRSV kernel on `stream`
+            B.apply(x)                # two launches of the line-systolic SpTRSV kernel on `stream`
             evs[k][1].record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t_wall0
@@ -300,7 +300,7 @@ def run_ours(args):
             "pct_hbm_peak": 100.0 * value / world / peak,
             "factor_ms": {"symbolic": sym_ms, "numeric": num_ms, "pack": pack_ms, "total": tot_ms,
                           "refactor_numeric_plus_pack": refactor_ms, "create_wall_incl_h2d": create_wall_ms},
-            "roofline": {"bound": "hbm", "kernel": "k_trsv_syncfree", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_trsv_systolic" if B.stats["part_mode"] == 4 else "k_trsv_syncfree", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": by / 2.0, "avg_launch_ms": kernel_ms,
                          "second_bound": "dependency critical path: %d levels per solve" % B.stats["levels"][0]},
