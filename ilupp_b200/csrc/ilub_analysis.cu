@@ -734,8 +734,10 @@ static PartPlan plan_partition(ilub_handle* h, const SrcDev& S, int64_t nent, cu
 void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     TriSolve& T = h->solve[slot];
     if (T.built) return;
-    if (slot == 2) build_transposed(h, true, s);
-    if (slot == 3) build_transposed(h, false, s);
+    if (slot == 2 || slot == 3) {
+        DebugTimer t("  transposed pattern", s);
+        build_transposed(h, slot == 2, s);
+    }
     const Options& opt = options();
     const int n = h->n;
     const SolveSource src = solve_source(h, slot);
@@ -752,6 +754,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     ILUB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int) * 4, s));
     const long long spin = (long long)opt.spin_limit_ms * h->clock_khz;  // kHz * ms = cycles
     {
+        DebugTimer t("  levels", s);
         int occ = 0;
         ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels, 256, 0));
         const int grid = std::max(1, occ * h->sm_count);
@@ -765,9 +768,16 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
 
     // ---- structured grids: line-systolic layout (ilub_systolic.cu).  The chunked sync-free layout below is then
     //      only built for slot 0 (the factorisation kernels walk it) or on demand (option solve_algo = 2).
-    const bool sys_ok = opt.solve_algo != 2 && analyse_systolic(h, slot, s);
+    bool sys_ok;
+    {
+        DebugTimer t("  systolic layout", s);
+        sys_ok = opt.solve_algo != 2 && analyse_systolic(h, slot, s);
+    }
     T.built = true;
-    if (!sys_ok || slot == 0) analyse_generic(h, slot, s);
+    if (!sys_ok) {  // (slot 0: the sync-free factorisation builds it on demand, factor_prepare)
+        DebugTimer t("  chunked layout", s);
+        analyse_generic(h, slot, s);
+    }
 }
 
 void analyse_generic(ilub_handle* h, int slot, cudaStream_t s) {

@@ -91,6 +91,7 @@ void create_common(int kind, const double* data, const int32_t* indices, const i
     ILUB_REQUIRE(device >= 0 && device < ndev, ILUB_ERR_INVALID, "bad device ordinal");
     DeviceGuard guard(device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    set_alloc_stream(s);
     std::unique_ptr<ilub_handle> h(new ilub_handle());
     h->kind = kind;
     h->is_csr = is_csr ? 1 : 0;
@@ -133,15 +134,35 @@ void create_common(int kind, const double* data, const int32_t* indices, const i
     }
 
     ILUB_CUDA(cudaEventRecord(h->ev[0], s));
-    validate_and_find_diag(h.get(), s);
+    {
+        DebugTimer t("validate + diagonal", s);
+        validate_and_find_diag(h.get(), s);
+    }
     int first, second;
     apply_slots(h.get(), 0, first, second);
-    analyse_solve(h.get(), 0, s);  // the factorisation DAG (= L solve DAG) is always needed
-    analyse_solve(h.get(), first, s);
-    analyse_solve(h.get(), second, s);
+    {
+        DebugTimer t("analyse slot 0", s);
+        analyse_solve(h.get(), 0, s);  // the factorisation DAG (= L solve DAG) is always needed
+    }
+    {
+        DebugTimer t("analyse first solve", s);
+        analyse_solve(h.get(), first, s);
+    }
+    {
+        DebugTimer t("analyse second solve", s);
+        analyse_solve(h.get(), second, s);
+    }
+    {
+        DebugTimer t("factorisation schedule", s);
+        factor_prepare(h.get(), s);
+    }
     ILUB_CUDA(cudaEventRecord(h->ev[1], s));
-    factor_numeric(h.get(), s);
+    {
+        DebugTimer t("numeric factorisation", s);
+        factor_numeric(h.get(), s);
+    }
     ILUB_CUDA(cudaEventRecord(h->ev[2], s));
+    DebugTimer tpack("pack", s);
     for (int k = 0; k < 4; ++k) pack_solve_values(h.get(), k, s);
     ILUB_CUDA(cudaEventRecord(h->ev[3], s));
     read_status(h.get(), s);  // syncs; throws on watchdog
@@ -205,6 +226,7 @@ int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream) {
         ILUB_REQUIRE(h && data, ILUB_ERR_INVALID, "null argument");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
         ILUB_CUDA(cudaEventRecord(h->ev[1], s));
         ILUB_CUDA(cudaMemcpyAsync(h->a.p, data, sizeof(double) * h->nnz, to_dev(where), s));
         factor_numeric(h, s);
@@ -229,7 +251,9 @@ int ilub_destroy(ilub_handle* h) {
         cudaDeviceSynchronize();
         for (int i = 0; i < 4; ++i)
             if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+        set_alloc_stream(kIdleStream);  // the device is idle: the handle's blocks can be reused on any stream
         delete h;
+        set_alloc_stream(nullptr);
     });
 }
 
@@ -247,6 +271,7 @@ int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nr
         ILUB_REQUIRE(ldx >= h->n, ILUB_ERR_SIZE, "vector has wrong size for preconditioner!");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
         int first, second;
         apply_slots(h, transpose, first, second);
         ensure_solve(h, first, s);
@@ -314,6 +339,7 @@ int ilub_get_factor(ilub_handle* h, int which, double* data, int32_t* indices, i
         ILUB_REQUIRE(which == 0 || (which == 1 && h->kind == KIND_ILU0), ILUB_ERR_INVALID, "no such factor");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
         const int mode = factor_mode(h, which);
         const int64_t nnz = (mode == 1 ? h->nnz_upper : h->nnz_lower) + h->n;
         if (where == ILUB_DEVICE) {
@@ -340,6 +366,7 @@ int ilub_get_levels(ilub_handle* h, int which_solve, int32_t* nlevels, int32_t* 
         ILUB_REQUIRE(which_solve >= 0 && which_solve < 4, ILUB_ERR_INVALID, "bad which_solve");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
         const int slot = slot_of(h, which_solve);
         ensure_solve(h, slot, s);
         if (nlevels) *nlevels = h->solve[slot].nlevels;
@@ -357,6 +384,7 @@ int ilub_get_level_sets(ilub_handle* h, int which_solve, int32_t* level_ptr, int
         ILUB_REQUIRE(which_solve >= 0 && which_solve < 4, ILUB_ERR_INVALID, "bad which_solve");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
         const int slot = slot_of(h, which_solve);
         ensure_solve(h, slot, s);
         build_level_sets(h, slot, s);
@@ -372,6 +400,7 @@ int ilub_spmv(ilub_handle* h, const double* x, double* y, int where, void* strea
         ILUB_REQUIRE(h && x && y, ILUB_ERR_INVALID, "null argument");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
         if (where == ILUB_DEVICE) {
             spmv(h, x, y, s);
         } else {
@@ -392,6 +421,7 @@ int ilub_bicgstab(ilub_handle* h, const double* b, double* x, double rtol, doubl
         ILUB_REQUIRE(h && b && x && iters && rel_achieved && abs_achieved, ILUB_ERR_INVALID, "null argument");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
         int first, second;
         apply_slots(h, 0, first, second);
         ensure_solve(h, first, s);

@@ -1,5 +1,8 @@
 // Internal declarations shared by the libilub translation units (not part of the C ABI).
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -31,7 +34,18 @@ struct Error {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// device buffer (plain cudaMalloc; freed with the handle)
+// device memory: a small caching allocator (ilub_capi.cu) in front of cudaMalloc / cudaFree.  The analysis phase
+// allocates and frees dozens of temporaries; plain cudaMalloc / cudaFree (device-synchronising, milliseconds each on
+// a busy allocator) made it 5-25x slower than its kernels.  A freed block is tagged with the stream the freeing
+// thread works on (set_alloc_stream) and is only handed out again for work on the same stream, so stream order keeps
+// a reused block safe without a device synchronisation.
+void* pool_alloc(size_t bytes);
+void pool_free(void* p) noexcept;
+void pool_trim() noexcept;                 // return every cached block to the driver
+void set_alloc_stream(cudaStream_t s);     // per thread: the stream subsequent allocations / frees are ordered on
+// tag for blocks freed while the device is known to be idle (after a device synchronisation): reusable on any stream
+static const cudaStream_t kIdleStream = (cudaStream_t)(intptr_t)-1;
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -41,17 +55,14 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr;
         n = 0;
     }
     void alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e != cudaSuccess)
-            throw Error{ILUB_ERR_ALLOC, "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes: " +
-                                            cudaGetErrorString(e)};
+        p = static_cast<T*>(pool_alloc(count * sizeof(T)));
         n = count;
     }
     void ensure(size_t count) {
@@ -60,8 +71,29 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// debug (env ILUB_DEBUG): wall-clock time of a host-side phase, stream synchronised at both ends
+struct DebugTimer {
+    const char* name;
+    cudaStream_t s;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    DebugTimer(const char* name_, cudaStream_t s_) : name(name_), s(s_), on(getenv("ILUB_DEBUG") != nullptr) {
+        if (on) {
+            cudaStreamSynchronize(s);
+            t0 = std::chrono::steady_clock::now();
+        }
+    }
+    ~DebugTimer() {
+        if (on) {
+            cudaStreamSynchronize(s);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            fprintf(stderr, "[ilub] %-28s %8.3f ms\n", name, ms);
+        }
+    }
+};
+
 struct Options {
-    int64_t factor_algo = 0;    // 0 sync-free, 1 level-scheduled
+    int64_t factor_algo = 0;    // 0 auto, 1 one launch per level, 2 sync-free, 3 level loop (one cooperative launch)
     int64_t solve_algo = 0;     // 0 auto (line-systolic on structured grids, else sync-free), 1 level-scheduled, 2 sync-free
     int64_t exact = 1;          // IEEE mul/sub/div in reference order
     int64_t ctas_per_sm = 1;
@@ -250,6 +282,7 @@ struct ilub_handle {
     // solves: [0] first of apply, [1] second of apply, [2] first of apply_trans, [3] second of apply_trans
     ilub::TriSolve solve[4];
     ilub::DevBuf<unsigned char> fflag;  // factorisation row flags
+    ilub::DevBuf<unsigned> fbarrier;    // grid barrier of the level-loop factorisation
     unsigned fepoch = 0;
     ilub::DevBuf<int> status;           // device status word(s) written by kernels (watchdog / structure errors)
     ilub::DevBuf<double> work;          // vector workspace (host-side apply, bicgstab)
@@ -269,6 +302,8 @@ void analyse_solve(ilub_handle* h, int which, cudaStream_t s);            // lev
 void analyse_generic(ilub_handle* h, int which, cudaStream_t s);          // partition + chunked sync-free layout
 void pack_solve_values(ilub_handle* h, int which, cudaStream_t s);        // (re)fill val/diag from lu
 void build_level_sets(ilub_handle* h, int which, cudaStream_t s);
+int factor_schedule(const ilub_handle* h);
+void factor_prepare(ilub_handle* h, cudaStream_t s);
 int read_status(ilub_handle* h, cudaStream_t s);                          // syncs the stream
 void expand_batched(ilub_handle* h, const int* ptr1, const int* idx1, int32_t n1, int64_t nnz1, int32_t nsys,
                     cudaStream_t s);

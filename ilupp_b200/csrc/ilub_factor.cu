@@ -11,6 +11,8 @@
 // Operation order per entry is the reference's (updates in ascending k; IChol0 dot product summed
 // in ascending column order via an ordered shuffle reduction), so with `exact` arithmetic the
 // factors are bit-for-bit those of the reference compiled without FMA contraction.
+#include <algorithm>
+
 #include "ilub_common.cuh"
 #include "ilub_ptx.cuh"
 
@@ -187,6 +189,76 @@ __global__ void __launch_bounds__(512) k_factor(FactorParams P) {
     }
 }
 
+// Level loop: ONE cooperative launch walks all levels of the L DAG; between two levels every CTA passes a
+// grid-wide barrier (a monotone arrival counter in global memory).  Right when levels are few and wide
+// (stencil matrices, block-diagonal batches): ~2 us per level instead of a dependency flag per row.
+template <int G, bool ICHOL, bool EXACT>
+__global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int* __restrict__ lvl_ptr, int nlevels,
+                                                       unsigned* barrier) {
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int gshift = (lane / G) * G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gshift);
+    const int ng = blockDim.x / G;
+    const int64_t g = (int64_t)blockIdx.x * ng + threadIdx.x / G;
+    const int64_t gstride = (int64_t)gridDim.x * ng;
+    long long t0 = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const int b = __ldg(lvl_ptr + l), e = __ldg(lvl_ptr + l + 1);
+        for (int64_t s = b + g; s < e; s += gstride) {
+            const int i = P.lvl_rows[s];
+            if (ICHOL)
+                ichol0_row<G, false, EXACT>(P, i, gl, gmask, gshift);
+            else
+                ilu0_row<G, false, EXACT>(P, i, gl, gmask);
+        }
+        if (l + 1 == nlevels) break;
+        // grid barrier: the rows of level l are visible (lu is read through L2) before anyone starts level l + 1
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(barrier, 1u);
+            const unsigned target = (unsigned)(l + 1) * gridDim.x;
+            unsigned spins = 0;
+            while (ld_acquire_gpu_u32(barrier) < target) {
+                if ((++spins & 1023u) == 0) {
+                    if (t0 == 0) t0 = clock64();
+                    if (clock64() - t0 > P.spin_limit || *(volatile int*)P.status != 0) {
+                        atomicCAS(P.status, 0, 102);
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int G, bool ICHOL>
+void launch_levels_g(bool exact, cudaStream_t s, FactorParams P, const int* lvl_ptr, int nlevels, unsigned* barrier,
+                     int sm_count) {
+    void* kern = exact ? (void*)k_factor_levels<G, ICHOL, true> : (void*)k_factor_levels<G, ICHOL, false>;
+    // few, fat CTAs: the barrier costs one atomic and one polling thread per CTA
+    const int block = 512;
+    int occ = 0;
+    ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, 0));
+    ILUB_REQUIRE(occ > 0, ILUB_ERR_CUDA, "level-loop factorisation kernel does not fit on an SM");
+    const int grid = std::min(occ, 2) * sm_count;
+    void* args[] = {(void*)&P, (void*)&lvl_ptr, (void*)&nlevels, (void*)&barrier};
+    ILUB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, 0, s));
+}
+
+template <bool ICHOL>
+void launch_levels(int G, bool exact, cudaStream_t s, const FactorParams& P, const int* lvl_ptr, int nlevels,
+                   unsigned* barrier, int sm_count) {
+    switch (G) {
+        case 4: launch_levels_g<4, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count); break;
+        case 8: launch_levels_g<8, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count); break;
+        case 16: launch_levels_g<16, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count); break;
+        default: launch_levels_g<32, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count); break;
+    }
+}
+
 template <int G, bool ICHOL, bool SYNCFREE>
 void launch_g(bool exact, int grid, int block, cudaStream_t s, const FactorParams& P) {
     if (exact)
@@ -206,6 +278,22 @@ void launch(int G, bool exact, int grid, int block, cudaStream_t s, const Factor
 }
 
 }  // namespace
+
+int factor_schedule(const ilub_handle* h) {
+    const TriSolve& T = h->solve[0];
+    const int algo = (int)options().factor_algo;
+    if (algo != 0) return algo;
+    return (T.nlevels <= 4096 && (int64_t)h->n >= (int64_t)T.nlevels * 256) ? 3 : 2;
+}
+
+// symbolic work the chosen schedule needs on top of the level numbers: the (level, row) listing, or the chunked
+// (part, level, row) order that the sync-free kernel walks
+void factor_prepare(ilub_handle* h, cudaStream_t s) {
+    if (factor_schedule(h) == 2)
+        analyse_generic(h, 0, s);
+    else
+        build_level_sets(h, 0, s);
+}
 
 void factor_numeric(ilub_handle* h, cudaStream_t s) {
     const Options& opt = options();
@@ -229,7 +317,23 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
         G = avg <= 10 ? 8 : (avg <= 24 ? 16 : 32);
     }
     const bool exact = opt.exact != 0;
-    if (opt.factor_algo == 0) {
+    // schedule: 1 = one launch per level, 2 = sync-free, 3 = level loop (one cooperative launch), 0 = level loop when
+    // the levels are few and wide (stencils, block-diagonal batches), sync-free otherwise
+    const int algo = factor_schedule(h);
+    factor_prepare(h, s);
+    if (algo == 3) {
+        if (h->fbarrier.n < 1) h->fbarrier.alloc(1);
+        ILUB_CUDA(cudaMemsetAsync(h->fbarrier.p, 0, sizeof(unsigned), s));
+        P.fflag = nullptr;
+        P.epoch = 0;
+        P.lvl_rows = T.lvl_rows.p;
+        P.lvl_begin = P.lvl_end = 0;
+        if (ichol)
+            launch_levels<true>(G, exact, s, P, T.lvl_ptr.p, T.nlevels, h->fbarrier.p, h->sm_count);
+        else
+            launch_levels<false>(G, exact, s, P, T.lvl_ptr.p, T.nlevels, h->fbarrier.p, h->sm_count);
+        h->launches++;
+    } else if (algo == 2) {
         if (h->fflag.n < (size_t)h->n) {
             h->fflag.alloc(h->n);
             ILUB_CUDA(cudaMemsetAsync(h->fflag.p, 0, h->n, s));
@@ -251,7 +355,6 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
             launch<false, true>(G, exact, T.nparts, block, s, P);
         h->launches++;
     } else {
-        build_level_sets(h, 0, s);
         std::vector<int> lptr(T.nlevels + 1);
         ILUB_CUDA(cudaMemcpyAsync(lptr.data(), T.lvl_ptr.p, sizeof(int) * (T.nlevels + 1), cudaMemcpyDeviceToHost, s));
         ILUB_CUDA(cudaStreamSynchronize(s));

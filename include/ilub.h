@@ -146,7 +146,8 @@ ILUB_API int ilub_create_ichol0_batched(const double* values, const int32_t* ind
 
 /* ---- options / instrumentation -------------------------------------------------------------- */
 /* global options, set before creating handles.  Known keys:
- *   "factor_algo"  0 = sync-free (default), 1 = level-scheduled
+ *   "factor_algo"  0 = auto (default: level loop when levels are few and wide, else sync-free), 1 = one launch per
+ *                  level, 2 = sync-free, 3 = level loop (one cooperative launch with grid barriers)
  *   "solve_algo"   0 = sync-free (default), 1 = level-scheduled
  *   "exact"        1 (default) = IEEE mul/sub/div in the reference's operation order (bit-for-bit
  *                  with a non-FMA build of the reference on lane-per-row chunks); 0 = FMA + reciprocal
