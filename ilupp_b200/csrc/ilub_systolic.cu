@@ -41,6 +41,11 @@ constexpr int kStageSteps = 8;                            // steps per coefficie
 constexpr int kStageBytes = kStageSteps * 4 * 32 * 8;
 constexpr int kMaxWarps = 6;                              // compute warps per CTA (each has a helper warp)
 constexpr int kMaxYChan = 8;
+// Mailbox fetchers poll global memory in blocking rounds (one L2 round trip each); a hand-off waits half a round on
+// average before the next poll is even issued.  Several fetcher warps running the same loop (forwarding is
+// idempotent) sample the mailbox proportionally more often.
+constexpr int kZFetchWarps = 3, kYFetchWarps = 2;
+inline int fetch_warps(int compute_warps) { return std::min(kZFetchWarps + kYFetchWarps, 14 - 2 * compute_warps); }
 
 inline int blocks_for(int64_t work, int threads) { return (int)((work + threads - 1) / threads); }
 
@@ -216,30 +221,31 @@ __device__ __forceinline__ void role_zfetch(const SysParams& P, const SysCtx& C,
     const ulonglong2* src = P.zmail + chan * P.nsteps_pad * 32 + lane;
     const uint32_t zin = smem_u32(C.smem + C.ring_off) + lane * 16;
     const int rzm = P.rz - 1;
+    // Sliding window: every round polls the next four entries this lane has not forwarded yet and forwards the
+    // valid prefix, so whatever has arrived since the last round moves on at once (a fixed group of four that must
+    // complete before the next one starts costs two L2 round trips per four steps -- slower than the producer).
     unsigned spins = 0;
-    for (int s0 = 0; s0 < P.nsteps_pad; s0 += 4) {
-        while (ld_prog(&C.progh[0]) < (s0 >> 2) - zlag) SYS_SPIN(spins, 201)
-        bool done[4] = {false, false, false, false};
-        while (true) {
-            unsigned long long xb[4], tg[4];
+    int e = 0;  // first step this lane has not forwarded
+    while (true) {
+        // entry s may overwrite ring slot s & (rz - 1) once the consumer has passed half-block (s >> 2) - rz / 4
+        const int limit = min(P.nsteps_pad, 4 * (ld_prog(&C.progh[0]) + zlag + 1));
+        unsigned long long xb[4], tg[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (!done[u]) ld_b128_gpu(src + (size_t)(s0 + u) * 32, xb[u], tg[u]);
-            bool pending = false;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (!done[u]) {
-                    if (tg[u] == (ehi | (unsigned long long)(s0 + u + 1))) {
-                        st_ring_s(zin + (((s0 + u) & rzm) << 9), __longlong_as_double((long long)xb[u]), tg[u]);
-                        done[u] = true;
-                    } else {
-                        pending = true;
-                    }
-                }
-            }
-            if (!__any_sync(FULL, pending)) break;
-            SYS_SPIN(spins, 202)
+        for (int u = 0; u < 4; ++u) {
+            tg[u] = 0ull;
+            if (e + u < limit) ld_b128_gpu(src + (size_t)(e + u) * 32, xb[u], tg[u]);
         }
+        int adv = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (adv == u && e + u < limit && tg[u] == (ehi | (unsigned long long)(e + u + 1))) {
+                st_ring_s(zin + (((e + u) & rzm) << 9), __longlong_as_double((long long)xb[u]), tg[u]);
+                adv = u + 1;
+            }
+        }
+        e += adv;
+        if (__all_sync(FULL, e >= P.nsteps_pad)) break;
+        SYS_SPIN(spins, 202)
     }
 }
 
@@ -250,13 +256,12 @@ __device__ __forceinline__ void role_yfetch(const SysParams& P, const SysCtx& C,
     const int jb = C.cy * P.pyb;
     if (C.cy == 0 || jb >= P.nyb) return;
     const unsigned long long ehi = (P.epoch & 0xffffffffull) << 32;
-    int i0[kMaxYChan];
-    bool done[kMaxYChan];
+    // lane l relays the entries of steps l, l + 32, l + 64, ... of every channel, each lane at its own pace
+    int sp[kMaxYChan];
     int nch = 0;
 #pragma unroll
     for (int c = 0; c < kMaxYChan; ++c) {
-        i0[c] = 0;
-        done[c] = false;
+        sp[c] = lane;
         if (c < P.pz && C.cz * P.pz + c < P.nplanes) nch = c + 1;
     }
     unsigned spins = 0;
@@ -267,33 +272,25 @@ __device__ __forceinline__ void role_yfetch(const SysParams& P, const SysCtx& C,
 #pragma unroll
         for (int c = 0; c < kMaxYChan; ++c) {
             can[c] = false;
-            if (c < nch && i0[c] < P.nsteps_pad) {
+            if (c < nch && sp[c] < P.nsteps_pad) {
                 active = true;
-                const int sp = i0[c] + lane;
                 const int cons = c * P.pyb;  // warp (wy = 0, wz = c)
                 // the slot's previous occupant (step sp - 64) is read by the consumer at its step sp - 96
-                can[c] = sp < P.nsteps_pad && !done[c] && sp < 4 * ld_prog(&C.progh[cons]) + 96;
+                can[c] = sp[c] < 4 * ld_prog(&C.progh[cons]) + 96;
                 if (can[c]) {
                     const size_t chan = (size_t)(C.cz * P.pz + c) * (P.gyb - 1) + (C.cy - 1);
-                    ld_b128_gpu(P.ymail + chan * P.nsteps_pad + sp, xb[c], tg[c]);
+                    ld_b128_gpu(P.ymail + chan * P.nsteps_pad + sp[c], xb[c], tg[c]);
                 }
             }
         }
-        if (!active) break;
+        if (!__any_sync(FULL, active)) break;
 #pragma unroll
         for (int c = 0; c < kMaxYChan; ++c) {
-            if (c < nch && i0[c] < P.nsteps_pad) {
-                const int sp = i0[c] + lane;
-                if (can[c] && tg[c] == (ehi | (unsigned long long)(sp + 1))) {
-                    const uint32_t yin =
-                        smem_u32(C.smem + (size_t)(c * P.pyb) * P.per_warp + C.ring_off + C.zbytes) + ((sp & (kRy - 1)) << 4);
-                    st_ring_s(yin, __longlong_as_double((long long)xb[c]), tg[c]);
-                    done[c] = true;
-                }
-                if (__all_sync(FULL, done[c] || sp >= P.nsteps_pad)) {
-                    i0[c] += 32;
-                    done[c] = false;
-                }
+            if (can[c] && tg[c] == (ehi | (unsigned long long)(sp[c] + 1))) {
+                const uint32_t yin =
+                    smem_u32(C.smem + (size_t)(c * P.pyb) * P.per_warp + C.ring_off + C.zbytes) + ((sp[c] & (kRy - 1)) << 4);
+                st_ring_s(yin, __longlong_as_double((long long)xb[c]), tg[c]);
+                sp[c] += 32;
             }
         }
         SYS_SPIN(spins, 203)
@@ -634,8 +631,12 @@ __global__ void __launch_bounds__(448, 1) k_trsv_systolic(const __grid_constant_
     if (C.cz < P.gz) {
         if (warp < W) role_compute<EXACT, ZC>(P, C, warp, lane);
         else if (warp < 2 * W) role_helper(P, C, warp - W, lane);
-        else if (warp == 2 * W) role_zfetch<ZC>(P, C, lane);
-        else role_yfetch(P, C, lane);
+        else {
+            // fetchers: z and y alternate (z first) so that a short budget still has one of each
+            const int f = warp - 2 * W;
+            if ((f & 1) == 0 && f / 2 < kZFetchWarps) role_zfetch<ZC>(P, C, lane);
+            else role_yfetch(P, C, lane);
+        }
     }
     // nobody leaves while a neighbour may still write into its shared memory
     cg::this_cluster().sync();
@@ -757,7 +758,7 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
             int nstc, rzc;
             fit_rings(pzc, nstc, rzc);
             const int gz = (nplanes + pzc - 1) / pzc;
-            const int block = (pzc * 2 + 2) * 32;
+            const int block = (pzc * 2 + fetch_warps(pzc)) * 32;
             const size_t sm = smem_of(pzc, nstc, rzc);
             for (int c = cmax; c >= 1; --c) {
                 const int gzpc = (gz + c - 1) / c * c;
@@ -895,7 +896,7 @@ void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cu
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(Y.gyb * Y.gzp, 1, 1);
-    cfg.blockDim = dim3((Y.pyb * Y.pz * 2 + 2) * 32, 1, 1);
+    cfg.blockDim = dim3((Y.pyb * Y.pz * 2 + fetch_warps(Y.pyb * Y.pz)) * 32, 1, 1);
     cfg.dynamicSmemBytes = Y.smem;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
