@@ -774,7 +774,12 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         sys_ok = opt.solve_algo != 2 && analyse_systolic(h, slot, s);
     }
     T.built = true;
-    if (!sys_ok) {  // (slot 0: the sync-free factorisation builds it on demand, factor_prepare)
+    if (!sys_ok && deep_wanted(h, slot)) {
+        DebugTimer t("  level-loop layout", s);
+        analyse_deep(h, slot, s);
+        T.part_mode = 5;
+        T.nparts = 1;
+    } else if (!sys_ok) {  // (slot 0: the sync-free factorisation builds it on demand, factor_prepare)
         DebugTimer t("  chunked layout", s);
         analyse_generic(h, slot, s);
     }
@@ -965,6 +970,7 @@ void pack_solve_values(ilub_handle* h, int slot, cudaStream_t s) {
     TriSolve& T = h->solve[slot];
     if (!T.built) return;
     if (T.sys.built) pack_systolic(h, slot, s);
+    if (T.deep.built) pack_deep(h, slot, s);
     if (!T.generic_built) return;
     const int64_t nent = T.nslabs * 32;
     const int64_t nlane = (int64_t)T.nchunks * 32;

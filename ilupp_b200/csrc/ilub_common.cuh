@@ -94,7 +94,7 @@ struct DebugTimer {
 
 struct Options {
     int64_t factor_algo = 0;    // 0 auto, 1 one launch per level, 2 sync-free, 3 level loop (one cooperative launch)
-    int64_t solve_algo = 0;     // 0 auto (line-systolic on structured grids, else sync-free), 1 level-scheduled, 2 sync-free
+    int64_t solve_algo = 0;     // 0 auto (line-systolic on structured grids, level loop on deep narrow DAGs, else sync-free), 1 level-scheduled, 2 sync-free, 3 level loop
     int64_t exact = 1;          // IEEE mul/sub/div in reference order
     int64_t ctas_per_sm = 1;
     int64_t warps_per_cta = 16;
@@ -155,6 +155,20 @@ struct SysSolve {
     unsigned long long epoch = 0;
 };
 
+// Level-loop layout of one triangular solve for deep, narrow DAGs (ilub_deep.cu): everything in solve order.
+struct DeepSolve {
+    bool built = false;
+    int nent = 0;
+    int packed_exact = -1;
+    DevBuf<int> eptr;       // [n + 1] first packed entry of every solve position
+    DevBuf<int4> meta;      // [n] {row, first entry, length, position of the diagonal in lu (-1: unit)}
+    DevBuf<int> dpos;       // [nent] solve position of the dependency
+    DevBuf<int> dsrc;       // [nent] position of the coefficient in lu
+    DevBuf<double> val;     // [nent] coefficient (pre-divided by the diagonal unless exact)
+    DevBuf<double> diag;    // [n] diagonal (exact) or its reciprocal
+    DevBuf<double> bs, xs;  // [n] right-hand side / solution in solve order
+};
+
 // One triangular solve packed in solve order (see DESIGN.md "data layout in HBM").
 struct TriSolve {
     bool built = false;
@@ -201,6 +215,7 @@ struct TriSolve {
     bool lvl_built = false;
     bool generic_built = false;   // the chunked sync-free layout above exists (always for slot 0: the factorisation uses it)
     SysSolve sys;                 // line-systolic layout (structured grids), preferred when built
+    DeepSolve deep;               // level-loop layout (deep narrow DAGs)
 };
 
 // Transposed pattern of the strict lower or strict upper triangle (for scatter-form solves).
@@ -302,6 +317,10 @@ void analyse_solve(ilub_handle* h, int which, cudaStream_t s);            // lev
 void analyse_generic(ilub_handle* h, int which, cudaStream_t s);          // partition + chunked sync-free layout
 void pack_solve_values(ilub_handle* h, int which, cudaStream_t s);        // (re)fill val/diag from lu
 void build_level_sets(ilub_handle* h, int which, cudaStream_t s);
+bool deep_wanted(const ilub_handle* h, int slot);
+void analyse_deep(ilub_handle* h, int slot, cudaStream_t s);
+void pack_deep(ilub_handle* h, int slot, cudaStream_t s);
+void run_deep(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s);
 int factor_schedule(const ilub_handle* h);
 void factor_prepare(ilub_handle* h, cudaStream_t s);
 int read_status(ilub_handle* h, cudaStream_t s);                          // syncs the stream

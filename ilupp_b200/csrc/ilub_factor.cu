@@ -310,7 +310,9 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
     P.part_chunk_ptr = T.part_chunk_ptr.p;
     P.rows = T.rows.p;
     P.status = h->status.p;
-    P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz * 4;
+    // a row of the sync-free schedule may wait for its whole upstream chain: the factorisation watchdog allows 40x the
+    // solve limit (one minute by default)
+    P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz * 40;
     int G = (int)opt.factor_group;
     if (G != 4 && G != 8 && G != 16 && G != 32) {
         const double avg = (double)h->nnz / (double)h->n;

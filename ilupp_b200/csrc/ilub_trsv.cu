@@ -574,8 +574,13 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
         return;
     }
 
-    if (opt.solve_algo != 2 && T.sys.built) {
+    if (opt.solve_algo != 2 && opt.solve_algo != 3 && T.sys.built) {
         run_systolic(h, slot, x, ldx, nrhs, s);
+        return;
+    }
+    if (deep_wanted(h, slot)) {
+        if (!T.deep.built) analyse_deep(h, slot, s);
+        run_deep(h, slot, x, ldx, nrhs, s);
         return;
     }
     if (!T.generic_built) {
