@@ -30,10 +30,8 @@
 namespace ilub {
 namespace {
 
-constexpr int kDeepThreads = 512;
 constexpr int kDeepG = 8;             // lanes per row
 constexpr int kDeepRing = 8192;       // solved values kept in shared memory (64 KB)
-constexpr int kDeepPf = 2;            // prefetched entries per lane of a group's first row of the next level
 
 inline int blocks_for(int64_t work, int threads) { return (int)((work + threads - 1) / threads); }
 
@@ -91,159 +89,253 @@ struct DeepParams {
     const int* dpos;
     const double* val;
     const double* diag;
+    const int* eptr;
     const double* bs;   // right-hand side in solve order
     double* xs;         // solution in solve order
     double* x;          // solution in row order (in/out vector of the solve)
     int unit_diag;
+    int* status;
 };
 
-__device__ __forceinline__ unsigned touch(const void* p) {
-    unsigned v;
-    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
-// value of the solved position p while positions [.., wend) are being written: the ring is safe for p >= wend - R
-__device__ __forceinline__ double deep_x(const DeepParams& P, const double* ring, int p, int wend) {
-    if (p >= wend - kDeepRing) return ring[p & (kDeepRing - 1)];
-    return __ldcg(P.xs + p);
-}
+// ---- decoupled access / execute.  STAGER warps run ahead of the level loop and do every global read: they copy
+// the packed rows into shared-memory rings (per position: first entry, length, row, right-hand side (times 1/d);
+// per entry: coefficient and either the VALUE of the dependency, gathered from xs through L2 because it was final
+// when the entry was staged, or -- for a dependency solved too recently for that -- its position).  The COMPUTE
+// warps walk the levels behind one named barrier per level and touch only shared memory: ring of staged rows, ring
+// of the most recent kDeepRing solved values.  A level therefore costs a barrier, three dependent shared-memory
+// reads, a few FMAs and a shuffle reduction -- no L2 round trip.
+constexpr int kStagers = 6;                                  // stager warps (interleaved blocks of 32 positions)
+constexpr int kComputeWarps = 8;                             // 32 groups of 8 lanes
+constexpr int kPosCap = 2048, kEntCap = 4096;                // staged rows / entries (powers of two)
+constexpr int kBigRow = 1024;                                // rows longer than this are not staged (read from global)
+constexpr int kOldMargin = 256;                              // positions this far behind the level loop are gathered by value
+struct DeepSmem {
+    double xring[kDeepRing];
+    double ev[kEntCap];      // coefficient
+    double ex[kEntCap];      // value of the dependency (if gathered at staging time)
+    int ep[kEntCap];         // position of the dependency, or -1: use ex
+    double pb[kPosCap];      // right-hand side (pre-scaled by 1/d unless exact)
+    double pd[kPosCap];      // diagonal (exact arithmetic only)
+    int4 pm[kPosCap];        // {first entry, length, row, big-row flag}
+    int staged;              // blocks of 32 positions completely staged (committed in block order)
+    int c_pos;               // positions below this are solved (start of the level being resolved)
+    int c_q;                 // entries below this are consumed
+    int abort;
+};
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kDeepThreads, 1) k_trsv_deep(const DeepParams P) {
-    extern __shared__ double ring[];
-    const int lane = threadIdx.x & 31;
-    const int gl = threadIdx.x % kDeepG;
-    const int g = threadIdx.x / kDeepG;
-    const int ng = (kDeepThreads - 32) / kDeepG;  // groups of the compute warps (the last warp only prefetches)
-    const unsigned gmask = 0xffu << ((lane / kDeepG) * kDeepG);
-
-    // finish one row whose first kDeepPf * 8 entries may already be (partly) accumulated
-    auto finish = [&](int pos, const int4 m, double acc, int jdone, int wend) {
-        if (EXACT) {
-            if (gl == 0) {
-                for (int j = 0; j < m.z; ++j)
-                    acc = __dsub_rn(acc, __dmul_rn(__ldg(P.val + m.y + j), deep_x(P, ring, __ldg(P.dpos + m.y + j), wend)));
-                if (!P.unit_diag) acc = __ddiv_rn(acc, __ldg(P.diag + pos));
-            }
-        } else {
-            for (int j = jdone + gl; j < m.z; j += kDeepG)
-                acc = fma(-__ldg(P.val + m.y + j), deep_x(P, ring, __ldg(P.dpos + m.y + j), wend), acc);
-            acc += __shfl_xor_sync(gmask, acc, 4, kDeepG);
-            acc += __shfl_xor_sync(gmask, acc, 2, kDeepG);
-            acc += __shfl_xor_sync(gmask, acc, 1, kDeepG);
-        }
-        if (gl == 0) {
-            ring[pos & (kDeepRing - 1)] = acc;
-            __stcg(P.xs + pos, acc);
-            P.x[m.x] = acc;
-        }
-    };
-
-    // ---- the last warp keeps the read-only streams of the coming levels in L1 by touching their lines ahead of the
-    //      level loop (plain loads: they allocate in L1, unlike prefetch hints): a level must never wait for a line
-    //      of metadata, entries or right-hand side from L2 / HBM.  It runs free of the per-level barrier.
-    __shared__ int prog[3];  // level loop position: end of the current level, its first entry, its number
-    if (threadIdx.x < 3) prog[threadIdx.x] = 0;
+__global__ void __launch_bounds__((kComputeWarps + kStagers) * 32, 1) k_trsv_deep(const DeepParams P) {
+    extern __shared__ __align__(16) unsigned char deep_smem_raw[];
+    DeepSmem& S = *reinterpret_cast<DeepSmem*>(deep_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) S.staged = 0, S.c_pos = 0, S.c_q = 0, S.abort = 0;
     __syncthreads();
-    if (threadIdx.x >= kDeepThreads - 32) {
-        int tpos = 0, tq = 0;
-        unsigned sink = 0;
-        while (true) {
-            const int cur = *(volatile int*)&prog[0], curq = *(volatile int*)&prog[1];
-            if (cur >= P.n) break;
-            const int wantp = min(P.n, cur + 1024), wantq = min(P.nent, curq + 6144);
-            if (tpos < wantp) {  // 256 positions per round: meta 16 B, bs / diag 8 B per position
-                sink += touch(P.meta + min(P.n - 1, tpos + lane * 8));
-                if (lane < 16) {
-                    sink += touch(P.bs + min(P.n - 1, tpos + lane * 16));
-                    sink += touch(P.diag + min(P.n - 1, tpos + lane * 16));
-                }
-                tpos += 256;
-            }
-            if (tq < wantq) {    // 512 entries per round: dpos 4 B, val 8 B per entry
-                if (lane < 16) sink += touch(P.dpos + min(P.nent - 1, tq + lane * 32));
-                sink += touch(P.val + min(P.nent - 1, tq + lane * 16));
-                tq += 512;
-            }
-            if (lane == 0) sink += touch(P.lvl_ptr + min(P.nlevels, *(volatile int*)&prog[2] + 64));
-            if (tpos >= wantp && tq >= wantq) __nanosleep(200);
-        }
-        if (sink == 0x9e3779b9u) prog[0] = (int)sink;  // keep the loads alive
-        return;
-    }
-    int lb = __ldg(P.lvl_ptr), le = __ldg(P.lvl_ptr + 1);
-    // prefetched state of this group's first row of the level about to be resolved
-    int4 pm = make_int4(-1, 0, 0, 0);
-    int ppos = -1;
-    double pacc = 0.0;
-    // per prefetched entry: coefficient, and either the dependency's value (requested before the barrier, consumed
-    // after it) or -- if the dependency lives in the level that was being resolved at that time -- its position
-    int dp[kDeepPf];
-    double dv[kDeepPf], dx[kDeepPf];
-#pragma unroll
-    for (int k = 0; k < kDeepPf; ++k) dp[k] = -1, dv[k] = 0.0, dx[k] = 0.0;
-    if (lb + g < le) {  // level 0 has no dependencies; prefetch trivially
-        ppos = lb + g;
-        pm = __ldg(P.meta + ppos);
-        pacc = gl == 0 ? (EXACT ? __ldg(P.bs + ppos) : __ldg(P.bs + ppos) * __ldg(P.diag + ppos)) : 0.0;
-    }
 
-    for (int l = 0; l < P.nlevels; ++l) {
-        const int lnb = le;                                                    // next level [lnb, lne)
-        const int lne = l + 1 < P.nlevels ? __ldg(P.lvl_ptr + l + 2) : le;
-        // ---- this group's first row of level l: only what could not be done before the barrier
-        if (ppos >= 0) {
-            double acc = pacc;
-            if (!EXACT) {
-#pragma unroll
-                for (int k = 0; k < kDeepPf; ++k) {
-                    if (dp[k] >= 0) dx[k] = deep_x(P, ring, dp[k], le);
-                    acc = fma(-dv[k], dx[k], acc);
-                }
+    if (warp >= kComputeWarps) {
+        // ------------------------------------------------------------------ stager: blocks of 32 positions, block b
+        // belongs to stager b % kStagers; one lane per position for the row record, then the block's entries
+        // (contiguous in the packed arrays) spread over the lanes
+        const int w = warp - kComputeWarps;
+        const int nblk = (P.n + 31) / 32;
+        int mine = 0;
+#ifdef ILUB_DEEP_PROFILE
+        long long s_load = 0, s_space = 0, s_ent = 0, s_pub = 0, sc = clock64();
+#define ST_TICK(var) { const long long tn = clock64(); var += tn - sc; sc = tn; }
+#else
+#define ST_TICK(var)
+#endif
+        for (int blk = w; blk < nblk; blk += kStagers, ++mine) {
+            const int p0 = blk * 32, pos = p0 + lane;
+            const int pend = min(P.n, p0 + 32);
+            int4 m = make_int4(0, 0, 0, 0);
+            double b = 0.0, d = 1.0;
+            if (pos < P.n) {
+                m = __ldg(P.meta + pos);
+                b = __ldg(P.bs + pos);
+                d = __ldg(P.diag + pos);
             }
-            finish(ppos, pm, acc, EXACT ? 0 : kDeepPf * kDeepG, le);
-        }
-        // ---- further rows of a wide level
-        for (int pos = lb + g + ng; pos < le; pos += ng) {
-            const int4 m = __ldg(P.meta + pos);
-            const double acc = gl == 0 ? (EXACT ? __ldg(P.bs + pos) : __ldg(P.bs + pos) * __ldg(P.diag + pos)) : 0.0;
-            finish(pos, m, acc, 0, le);
-        }
-        // ---- prefetch the first row of level l + 1 and gather what is already final (positions < lb ... < le are
-        //      being written right now: dependencies at positions >= lb wait for the barrier)
-        ppos = -1;
+            const int q0 = __shfl_sync(0xffffffffu, m.y, 0);
+            const int qe = __ldg(P.eptr + pend);
+            // space: position slots are free once the level loop has passed them; entry slots likewise
+            ST_TICK(s_load)
+            const bool blockbig = qe - q0 > kEntCap;  // (only with very long rows) nothing of this block is staged
+            while (true) {
+                const int cp = *(volatile int*)&S.c_pos, cq = *(volatile int*)&S.c_q;
+                if (pend - cp <= kPosCap && (blockbig || qe - cq <= kEntCap)) break;
+                if (*(volatile int*)&S.abort) return;
+                __nanosleep(100);
+            }
+            ST_TICK(s_space)
+            const int frontier = *(volatile int*)&S.c_pos - kOldMargin;  // positions below are final and visible in L2
+            __threadfence_block();
+            if (pos < P.n) {
+                const bool big = blockbig || m.z > kBigRow;
+                S.pm[pos & (kPosCap - 1)] = make_int4(m.y, m.z, m.x, big ? 1 : 0);
+                S.pb[pos & (kPosCap - 1)] = EXACT ? b : b * d;
+                if (EXACT) S.pd[pos & (kPosCap - 1)] = d;
+            }
+            // entries of the block (rows longer than kBigRow are skipped: the consumer reads them from global);
+            // a block whose entries exceed the ring (only possible with big rows) stages nothing
+            if (!blockbig) {
+                // eight entries per lane in flight: first every position / coefficient, then every gather
+                for (int qb = q0 + lane; qb < qe; qb += 32 * 8) {
+                    int dpv[8];
+                    double vv[8], xv[8];
 #pragma unroll
-        for (int k = 0; k < kDeepPf; ++k) dp[k] = -1, dv[k] = 0.0, dx[k] = 0.0;
-        if (lnb + g < lne) {
-            ppos = lnb + g;
-            pm = __ldg(P.meta + ppos);
-            pacc = gl == 0 ? (EXACT ? __ldg(P.bs + ppos) : __ldg(P.bs + ppos) * __ldg(P.diag + ppos)) : 0.0;
-            if (!EXACT) {
+                    for (int u = 0; u < 8; ++u) {
+                        const int q = qb + u * 32;
+                        dpv[u] = -2;
+                        if (q < qe) {
+                            dpv[u] = __ldg(P.dpos + q);
+                            vv[u] = __ldg(P.val + q);
+                        }
+                    }
 #pragma unroll
-                for (int k = 0; k < kDeepPf; ++k) {
-                    const int j = gl + k * kDeepG;
-                    if (j < pm.z) {
-                        const int p = __ldg(P.dpos + pm.y + j);
-                        const double v = __ldg(P.val + pm.y + j);
-                        dv[k] = v;
-                        if (p < lb)
-                            dx[k] = deep_x(P, ring, p, le);  // final already: requested now, used after the barrier
-                        else
-                            dp[k] = p;
+                    for (int u = 0; u < 8; ++u)
+                        if (dpv[u] >= 0 && dpv[u] < frontier) xv[u] = __ldcg(P.xs + dpv[u]);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (dpv[u] >= 0) {
+                            const int e = (qb + u * 32) & (kEntCap - 1);
+                            S.ev[e] = vv[u];
+                            if (dpv[u] < frontier) {
+                                S.ex[e] = xv[u];
+                                S.ep[e] = -1;
+                            } else {
+                                S.ep[e] = dpv[u];
+                            }
+                        }
                     }
                 }
             }
+            ST_TICK(s_ent)
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) {  // commit in block order: consumers test one counter
+                while (*(volatile int*)&S.staged != blk) {
+                    if (*(volatile int*)&S.abort) break;
+                }
+                *(volatile int*)&S.staged = blk + 1;
+            }
+            __syncwarp();
+            ST_TICK(s_pub)
         }
-        if (threadIdx.x == 0) {  // where the level loop is, for the toucher warp
-            *(volatile int*)&prog[0] = lne;
-            *(volatile int*)&prog[2] = l + 1;
-            *(volatile int*)&prog[1] = lne < P.n ? __ldg(P.meta + lne).y : P.nent;
+#ifdef ILUB_DEEP_PROFILE
+        if (lane == 0 && w < 2) printf("stager %d: blocks %d | cycles per block: row loads %.0f space wait %.0f entries %.0f publish %.0f\n", w, mine, (double)s_load / mine, (double)s_space / mine, (double)s_ent / mine, (double)s_pub / mine);
+#endif
+        return;
+    }
+
+    // ---------------------------------------------------------------------- compute warps
+    const int gl = threadIdx.x % kDeepG;
+    const int g = threadIdx.x / kDeepG;
+    const int ng = kComputeWarps * 32 / kDeepG;
+    const unsigned gmask = 0xffu << ((lane / kDeepG) * kDeepG);
+    int lb = __ldg(P.lvl_ptr), le = __ldg(P.lvl_ptr + 1);
+    int seen = 0;  // positions below this are known to be staged
+#ifdef ILUB_DEEP_PROFILE
+    long long t_wait = 0, t_row = 0, t_write = 0, t_bar = 0, t_pub = 0, tc = clock64();
+#define DEEP_TICK(var) { const long long tn = clock64(); var += tn - tc; tc = tn; }
+#else
+#define DEEP_TICK(var)
+#endif
+    for (int l = 0; l < P.nlevels; ++l) {
+        const int lne = l + 1 < P.nlevels ? __ldg(P.lvl_ptr + l + 2) : le;
+        for (int pos = lb + g; pos < le; pos += ng) {
+            // the block of this position has been staged
+            if (pos >= seen) {
+                unsigned spins = 0;
+                while (true) {
+                    seen = *(volatile int*)&S.staged * 32;
+                    if (pos < seen) break;
+                    if ((++spins & 0xffffu) == 0 && spins > (1u << 28)) {
+                        *(volatile int*)&S.abort = 1;
+                        break;
+                    }
+                }
+                __threadfence_block();
+            }
+            DEEP_TICK(t_wait)
+            const int4 m = S.pm[pos & (kPosCap - 1)];  // {first entry, length, row, big}
+            double acc = gl == 0 ? S.pb[pos & (kPosCap - 1)] : 0.0;
+            if (m.w == 0 && m.y <= kEntCap) {
+                if (EXACT) {
+                    if (gl == 0) {
+                        for (int j = 0; j < m.y; ++j) {
+                            const int e = (m.x + j) & (kEntCap - 1);
+                            const int dp = S.ep[e];
+                            const double xv = dp < 0 ? S.ex[e] : (dp >= le - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp));
+                            acc = __dsub_rn(acc, __dmul_rn(S.ev[e], xv));
+                        }
+                    }
+                } else {
+                    for (int j = gl; j < m.y; j += kDeepG) {
+                        const int e = (m.x + j) & (kEntCap - 1);
+                        const int dp = S.ep[e];
+                        // one shared-memory read either way (gathered value or ring); the global fall-back only
+                        // exists for levels wider than the ring
+                        const double* src = dp < 0 ? &S.ex[e] : &S.xring[dp & (kDeepRing - 1)];
+                        double xv = *src;
+                        if (dp >= 0 && dp < le - kDeepRing) xv = __ldcg(P.xs + dp);
+                        acc = fma(-S.ev[e], xv, acc);
+                    }
+                }
+            } else {
+                // long row: straight from the packed arrays in global memory
+                if (EXACT) {
+                    if (gl == 0)
+                        for (int j = 0; j < m.y; ++j) {
+                            const int dp = __ldg(P.dpos + m.x + j);
+                            const double xv = dp >= le - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp);
+                            acc = __dsub_rn(acc, __dmul_rn(__ldg(P.val + m.x + j), xv));
+                        }
+                } else {
+                    for (int j = gl; j < m.y; j += kDeepG) {
+                        const int dp = __ldg(P.dpos + m.x + j);
+                        const double xv = dp >= le - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp);
+                        acc = fma(-__ldg(P.val + m.x + j), xv, acc);
+                    }
+                }
+            }
+            DEEP_TICK(t_row)
+            if (EXACT) {
+                if (gl == 0 && !P.unit_diag) acc = __ddiv_rn(acc, S.pd[pos & (kPosCap - 1)]);
+            } else {
+                acc += __shfl_xor_sync(gmask, acc, 4, kDeepG);
+                acc += __shfl_xor_sync(gmask, acc, 2, kDeepG);
+                acc += __shfl_xor_sync(gmask, acc, 1, kDeepG);
+            }
+            if (gl == 0) {
+                S.xring[pos & (kDeepRing - 1)] = acc;
+                __stcg(P.xs + pos, acc);
+                P.x[m.z] = acc;
+            }
+            DEEP_TICK(t_write)
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kDeepThreads - 32) : "memory");  // the compute warps only
-        lb = lnb;
+        DEEP_TICK(t_wait)
+        asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
+        DEEP_TICK(t_bar)
+        if (threadIdx.x == kComputeWarps * 32 - 1) {
+            // every row below `le` is solved and behind the barrier; this thread's fence (cumulative over what the
+            // barrier ordered before it) makes the xs stores visible before the stagers see the new position.  It is
+            // the last compute thread: its group only has rows in wide levels, so the fence is off the critical path.
+            __threadfence_block();
+            *(volatile int*)&S.c_pos = le;
+            *(volatile int*)&S.c_q = le < P.n ? __ldg(P.eptr + le) : P.nent;
+        }
+        if (*(volatile int*)&S.abort) {
+            if (threadIdx.x == 0) atomicCAS(P.status, 0, 301);
+            return;
+        }
+        DEEP_TICK(t_pub)
+        lb = le;
         le = lne;
     }
+#ifdef ILUB_DEEP_PROFILE
+    if (threadIdx.x == 0 || threadIdx.x == 64 || threadIdx.x == 248)
+        printf("deep profile thread %3d: levels %d | cycles per level: wait %.0f row %.0f reduce+write %.0f barrier %.0f publish %.0f\n", threadIdx.x, P.nlevels,
+               (double)t_wait / P.nlevels, (double)t_row / P.nlevels, (double)t_write / P.nlevels, (double)t_bar / P.nlevels, (double)t_pub / P.nlevels);
+#endif
 }
 
 }  // namespace
@@ -311,7 +403,7 @@ void run_deep(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaSt
     DeepSolve& D = T.deep;
     const bool exact = options().exact != 0;
     if (D.packed_exact != (exact ? 1 : 0)) pack_deep(h, slot, s);
-    const size_t smem = (size_t)kDeepRing * sizeof(double);
+    const size_t smem = sizeof(DeepSmem);
     static thread_local bool attr_set[2] = {false, false};
     if (!attr_set[exact ? 1 : 0]) {
         if (exact)
@@ -326,19 +418,21 @@ void run_deep(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaSt
     P.nent = std::max(1, D.nent);
     P.lvl_ptr = T.lvl_ptr.p;
     P.meta = D.meta.p;
+    P.eptr = D.eptr.p;
     P.dpos = D.dpos.p;
     P.val = D.val.p;
     P.diag = D.diag.p;
     P.bs = D.bs.p;
     P.xs = D.xs.p;
     P.unit_diag = T.unit_diag ? 1 : 0;
+    P.status = h->status.p;
     for (int c = 0; c < nrhs; ++c) {
         P.x = x + (int64_t)c * ldx;
         k_deep_permute_in<<<blocks_for(h->n, 256), 256, 0, s>>>(h->n, D.meta.p, P.x, D.bs.p);
         if (exact)
-            k_trsv_deep<true><<<1, kDeepThreads, smem, s>>>(P);
+            k_trsv_deep<true><<<1, (kComputeWarps + kStagers) * 32, smem, s>>>(P);
         else
-            k_trsv_deep<false><<<1, kDeepThreads, smem, s>>>(P);
+            k_trsv_deep<false><<<1, (kComputeWarps + kStagers) * 32, smem, s>>>(P);
         h->launches += 2;
     }
     ILUB_CUDA(cudaGetLastError());
