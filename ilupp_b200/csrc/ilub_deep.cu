@@ -158,7 +158,9 @@ __global__ void __launch_bounds__((kComputeWarps + kStagers) * 32, 1) k_trsv_dee
             const int qe = __ldg(P.eptr + pend);
             // space: position slots are free once the level loop has passed them; entry slots likewise
             ST_TICK(s_load)
-            const bool blockbig = qe - q0 > kEntCap;  // (only with very long rows) nothing of this block is staged
+            // nothing of a block is staged if its entries, together with those of the 32 rows before it (a round of
+            // the level loop may start that far back), do not fit the entry ring: only with very long rows
+            const bool blockbig = qe - __ldg(P.eptr + max(0, p0 - 32)) > kEntCap;
             while (true) {
                 const int cp = *(volatile int*)&S.c_pos, cq = *(volatile int*)&S.c_q;
                 if (pend - cp <= kPosCap && (blockbig || qe - cq <= kEntCap)) break;
@@ -241,7 +243,12 @@ __global__ void __launch_bounds__((kComputeWarps + kStagers) * 32, 1) k_trsv_dee
 #endif
     for (int l = 0; l < P.nlevels; ++l) {
         const int lne = l + 1 < P.nlevels ? __ldg(P.lvl_ptr + l + 2) : le;
-        for (int pos = lb + g; pos < le; pos += ng) {
+        // rounds of `ng` rows: a level wider than that is resolved in several rounds, each behind its own barrier, so
+        // that the position the stagers measure their space against never lags more than one round
+        for (int base = lb; base < le; base += ng) {
+        const int pos = base + g;
+        const int rend = min(le, base + ng);
+        if (pos < le) {
             // the block of this position has been staged
             if (pos >= seen) {
                 unsigned spins = 0;
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__((kComputeWarps + kStagers) * 32, 1) k_trsv_dee
                         for (int j = 0; j < m.y; ++j) {
                             const int e = (m.x + j) & (kEntCap - 1);
                             const int dp = S.ep[e];
-                            const double xv = dp < 0 ? S.ex[e] : (dp >= le - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp));
+                            const double xv = dp < 0 ? S.ex[e] : (dp >= rend - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp));
                             acc = __dsub_rn(acc, __dmul_rn(S.ev[e], xv));
                         }
                     }
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__((kComputeWarps + kStagers) * 32, 1) k_trsv_dee
                         // exists for levels wider than the ring
                         const double* src = dp < 0 ? &S.ex[e] : &S.xring[dp & (kDeepRing - 1)];
                         double xv = *src;
-                        if (dp >= 0 && dp < le - kDeepRing) xv = __ldcg(P.xs + dp);
+                        if (dp >= 0 && dp < rend - kDeepRing) xv = __ldcg(P.xs + dp);
                         acc = fma(-S.ev[e], xv, acc);
                     }
                 }
@@ -286,13 +293,13 @@ __global__ void __launch_bounds__((kComputeWarps + kStagers) * 32, 1) k_trsv_dee
                     if (gl == 0)
                         for (int j = 0; j < m.y; ++j) {
                             const int dp = __ldg(P.dpos + m.x + j);
-                            const double xv = dp >= le - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp);
+                            const double xv = dp >= rend - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp);
                             acc = __dsub_rn(acc, __dmul_rn(__ldg(P.val + m.x + j), xv));
                         }
                 } else {
                     for (int j = gl; j < m.y; j += kDeepG) {
                         const int dp = __ldg(P.dpos + m.x + j);
-                        const double xv = dp >= le - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp);
+                        const double xv = dp >= rend - kDeepRing ? S.xring[dp & (kDeepRing - 1)] : __ldcg(P.xs + dp);
                         acc = fma(-__ldg(P.val + m.x + j), xv, acc);
                     }
                 }
@@ -316,18 +323,19 @@ __global__ void __launch_bounds__((kComputeWarps + kStagers) * 32, 1) k_trsv_dee
         asm volatile("bar.sync 1, %0;" ::"n"(kComputeWarps * 32) : "memory");
         DEEP_TICK(t_bar)
         if (threadIdx.x == kComputeWarps * 32 - 1) {
-            // every row below `le` is solved and behind the barrier; this thread's fence (cumulative over what the
+            // every row below `rend` is solved and behind the barrier; this thread's fence (cumulative over what the
             // barrier ordered before it) makes the xs stores visible before the stagers see the new position.  It is
             // the last compute thread: its group only has rows in wide levels, so the fence is off the critical path.
             __threadfence_block();
-            *(volatile int*)&S.c_pos = le;
-            *(volatile int*)&S.c_q = le < P.n ? __ldg(P.eptr + le) : P.nent;
+            *(volatile int*)&S.c_pos = rend;
+            *(volatile int*)&S.c_q = rend < P.n ? __ldg(P.eptr + rend) : P.nent;
         }
         if (*(volatile int*)&S.abort) {
             if (threadIdx.x == 0) atomicCAS(P.status, 0, 301);
             return;
         }
         DEEP_TICK(t_pub)
+        }
         lb = le;
         le = lne;
     }
