@@ -151,8 +151,173 @@ __device__ __forceinline__ bool ichol0_row(const FactorParams& P, int i, int gl,
     return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Short rows (the common case: at most 4 * G entries) are factorised in SHARED memory.  The row routines above
+// spend their time in chains of dependent global loads (per strictly-lower entry: column -> diagonal position ->
+// pivot, then a binary search through row k in L2: ~8 round trips, ~25 per stencil row).  Here a row costs
+//   1 round trip  to stage row i (indices, values),
+//   3 round trips to fetch {diagonal position, row end, pivot} of ALL its strictly-lower columns in parallel,
+//   1 round trip  per strictly-lower entry for row k's upper part (coalesced), matched against row i by a binary
+//                 search in shared memory.
+// The arithmetic and its order are those of the routines above (ascending k; IChol0 dot products accumulated in
+// ascending column order), so `exact` results stay bit-for-bit the reference's.
+template <int G>
+struct RowSmem {
+    static constexpr int L = 4 * G;        // longest row handled here
+    static constexpr int kBytes = 28 * L;  // per group
+    double* val;   // [L] row i values (become the factor's)
+    double* piv;   // [L] per strictly-lower entry: pivot u_kk (ILU0) / l_jj (IChol0)
+    int* idx;      // [L] row i columns
+    int* ra;       // [L] ILU0: first upper entry of row k / IChol0: first entry of row j
+    int* rb;       // [L] ILU0: end of row k / IChol0: diagonal position of row j
+    __device__ RowSmem(unsigned char* base) {
+        val = reinterpret_cast<double*>(base);
+        piv = val + L;
+        idx = reinterpret_cast<int*>(piv + L);
+        ra = idx + L;
+        rb = ra + L;
+    }
+};
+
+__device__ __forceinline__ int lower_bound_s(const int* s, int b, int e, int c) {
+    while (b < e) {
+        const int m = (b + e) >> 1;
+        if (s[m] < c)
+            b = m + 1;
+        else
+            e = m;
+    }
+    return b;
+}
+
+template <int G, bool SYNCFREE, bool EXACT>
+__device__ __forceinline__ bool ilu0_row_fast(const FactorParams& P, int i, int gl, unsigned gmask, const RowSmem<G>& R) {
+    const int p0 = P.ptr[i], p1 = P.ptr[i + 1], dp = P.dpos[i];
+    const int len = p1 - p0, nl = dp - p0;
+    for (int t = gl; t < len; t += G) {  // ILU0.hpp:37
+        R.idx[t] = __ldg(P.idx + p0 + t);
+        R.val[t] = P.a[p0 + t];
+    }
+    __syncwarp(gmask);
+    long long t0 = 0;
+    bool ok = true;
+    for (int t = gl; t < nl; t += G) {
+        const int k = R.idx[t];
+        if (!wait_row<SYNCFREE>(P, k, t0)) ok = false;
+        const int dk = P.dpos[k];
+        R.ra[t] = dk + 1;
+        R.rb[t] = P.ptr[k + 1];
+        R.piv[t] = __ldcg(P.lu + dk);
+    }
+    if (SYNCFREE && !__all_sync(gmask, ok)) return false;
+    __syncwarp(gmask);
+    for (int kk = 0; kk < nl; ++kk) {  // ILU0.hpp:47-62, ascending k
+        const double wkk = R.val[kk], ukk = R.piv[kk];
+        const double lik = EXACT ? __ddiv_rn(wkk, ukk) : wkk / ukk;  // ILU0.hpp:52
+        const int qb = R.ra[kk], qe = R.rb[kk];
+        // U[i, k+1:] -= L_ik * U[k, k+1:]   (ILU0.hpp:55-59): row k's upper part against my entries right of kk
+        for (int q = qb + gl; q < qe; q += G) {
+            const int c = __ldg(P.idx + q);
+            const double u = __ldcg(P.lu + q);
+            const int pos = lower_bound_s(R.idx, kk + 1, len, c);
+            if (pos < len && R.idx[pos] == c) R.val[pos] = sub_mul<EXACT>(R.val[pos], lik, u);
+        }
+        __syncwarp(gmask);
+        if (gl == 0) R.val[kk] = lik;  // ILU0.hpp:61
+    }
+    __syncwarp(gmask);
+    for (int t = gl; t < len; t += G) P.lu[p0 + t] = R.val[t];
+    return true;
+}
+
+template <int G, bool SYNCFREE, bool EXACT>
+__device__ __forceinline__ bool ichol0_row_fast(const FactorParams& P, int i, int gl, unsigned gmask, int gshift,
+                                                const RowSmem<G>& R) {
+    const int p0 = P.ptr[i], dp = P.dpos[i];
+    const int len = dp - p0 + 1;  // row i of tril(A), diagonal last
+    for (int t = gl; t < len; t += G) {
+        R.idx[t] = __ldg(P.idx + p0 + t);
+        R.val[t] = P.a[p0 + t];
+    }
+    __syncwarp(gmask);
+    long long t0 = 0;
+    bool ok = true;
+    for (int t = gl; t < len - 1; t += G) {
+        const int j = R.idx[t];
+        if (!wait_row<SYNCFREE>(P, j, t0)) ok = false;
+        const int je = P.dpos[j];
+        R.ra[t] = P.ptr[j];
+        R.rb[t] = je;
+        R.piv[t] = __ldcg(P.lu + je);  // diagonal is the last entry of row j of L (IChol.hpp:50)
+    }
+    if (SYNCFREE && !__all_sync(gmask, ok)) return false;
+    __syncwarp(gmask);
+    for (int t = 0; t < len; ++t) {  // IChol.hpp:39-57
+        const bool diag = t == len - 1;
+        const int qb = diag ? 0 : R.ra[t], qe = diag ? t : R.rb[t];
+        // sum over the common columns of (row i left of t) and (row j without its diagonal), ascending column
+        double sum = 0.0;
+        for (int q0 = qb; q0 < qe; q0 += G) {
+            const int q = q0 + gl;
+            double prod = 0.0;
+            bool hit = false;
+            if (q < qe) {
+                if (diag) {
+                    const double v = R.val[q];
+                    prod = EXACT ? __dmul_rn(v, v) : v * v;
+                    hit = true;
+                } else {
+                    const int c = __ldg(P.idx + q);
+                    const int pos = lower_bound_s(R.idx, 0, t, c);
+                    if (pos < t && R.idx[pos] == c) {
+                        const double v = R.val[pos], u = __ldcg(P.lu + q);
+                        prod = EXACT ? __dmul_rn(v, u) : v * u;
+                        hit = true;
+                    }
+                }
+            }
+            unsigned m = (__ballot_sync(gmask, hit) & gmask) >> gshift;
+            while (m) {  // ordered accumulation, IChol.hpp:18-27
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const double tt = __shfl_sync(gmask, prod, src, G);
+                sum = EXACT ? __dadd_rn(sum, tt) : sum + tt;
+            }
+        }
+        const double aij = R.val[t];
+        double v;
+        if (!diag) {
+            const double ljj = R.piv[t];
+            v = EXACT ? __ddiv_rn(__dsub_rn(aij, sum), ljj) : (aij - sum) / ljj;  // IChol.hpp:49-51
+        } else {
+            v = EXACT ? __dsqrt_rn(__dsub_rn(aij, sum)) : sqrt(aij - sum);        // IChol.hpp:52-53
+        }
+        __syncwarp(gmask);
+        if (gl == 0) R.val[t] = v;
+        __syncwarp(gmask);
+    }
+    for (int t = gl; t < len; t += G) P.lu[p0 + t] = R.val[t];
+    return true;
+}
+
+// one row, short or long
+template <int G, bool ICHOL, bool SYNCFREE, bool EXACT>
+__device__ __forceinline__ bool factor_row(const FactorParams& P, int i, int gl, unsigned gmask, int gshift,
+                                           const RowSmem<G>& R) {
+    if (ICHOL) {
+        if (P.dpos[i] - P.ptr[i] + 1 <= RowSmem<G>::L) return ichol0_row_fast<G, SYNCFREE, EXACT>(P, i, gl, gmask, gshift, R);
+        return ichol0_row<G, SYNCFREE, EXACT>(P, i, gl, gmask, gshift);
+    } else {
+        if (P.ptr[i + 1] - P.ptr[i] <= RowSmem<G>::L) return ilu0_row_fast<G, SYNCFREE, EXACT>(P, i, gl, gmask, R);
+        return ilu0_row<G, SYNCFREE, EXACT>(P, i, gl, gmask);
+    }
+}
+
 template <int G, bool ICHOL, bool SYNCFREE, bool EXACT>
 __global__ void __launch_bounds__(512) k_factor(FactorParams P) {
+    extern __shared__ __align__(16) unsigned char factor_smem[];
+    const RowSmem<G> R(factor_smem + (size_t)(threadIdx.x / G) * RowSmem<G>::kBytes);
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int gshift = (lane / G) * G;
@@ -165,12 +330,7 @@ __global__ void __launch_bounds__(512) k_factor(FactorParams P) {
         for (int64_t s = s0 + gidx; s < s1; s += ng) {
             const int i = P.rows[s];
             if (i < 0) continue;
-            bool ok;
-            if (ICHOL)
-                ok = ichol0_row<G, true, EXACT>(P, i, gl, gmask, gshift);
-            else
-                ok = ilu0_row<G, true, EXACT>(P, i, gl, gmask);
-            if (!ok) return;
+            if (!factor_row<G, ICHOL, true, EXACT>(P, i, gl, gmask, gshift, R)) return;
             __syncwarp(gmask);
             if (gl == 0) {
                 __threadfence();
@@ -181,10 +341,7 @@ __global__ void __launch_bounds__(512) k_factor(FactorParams P) {
         const int64_t s = (int64_t)P.lvl_begin + (int64_t)blockIdx.x * ng + gidx;
         if (s < P.lvl_end) {
             const int i = P.lvl_rows[s];
-            if (ICHOL)
-                ichol0_row<G, false, EXACT>(P, i, gl, gmask, gshift);
-            else
-                ilu0_row<G, false, EXACT>(P, i, gl, gmask);
+            factor_row<G, ICHOL, false, EXACT>(P, i, gl, gmask, gshift, R);
         }
     }
 }
@@ -195,6 +352,8 @@ __global__ void __launch_bounds__(512) k_factor(FactorParams P) {
 template <int G, bool ICHOL, bool EXACT>
 __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int* __restrict__ lvl_ptr, int nlevels,
                                                        unsigned* barrier) {
+    extern __shared__ __align__(16) unsigned char factor_smem[];
+    const RowSmem<G> R(factor_smem + (size_t)(threadIdx.x / G) * RowSmem<G>::kBytes);
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int gshift = (lane / G) * G;
@@ -207,10 +366,7 @@ __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int
         const int b = __ldg(lvl_ptr + l), e = __ldg(lvl_ptr + l + 1);
         for (int64_t s = b + g; s < e; s += gstride) {
             const int i = P.lvl_rows[s];
-            if (ICHOL)
-                ichol0_row<G, false, EXACT>(P, i, gl, gmask, gshift);
-            else
-                ilu0_row<G, false, EXACT>(P, i, gl, gmask);
+            factor_row<G, ICHOL, false, EXACT>(P, i, gl, gmask, gshift, R);
         }
         if (l + 1 == nlevels) break;
         // grid barrier: the rows of level l are visible (lu is read through L2) before anyone starts level l + 1
@@ -220,7 +376,7 @@ __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int
             atomicAdd(barrier, 1u);
             const unsigned target = (unsigned)(l + 1) * gridDim.x;
             unsigned spins = 0;
-            while (ld_acquire_gpu_u32(barrier) < target) {
+            while (ld_relaxed_gpu_u32(barrier) < target) {
                 if ((++spins & 1023u) == 0) {
                     if (t0 == 0) t0 = clock64();
                     if (clock64() - t0 > P.spin_limit || *(volatile int*)P.status != 0) {
@@ -229,6 +385,7 @@ __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int
                     }
                 }
             }
+            __threadfence();  // acquire side of the barrier (the polls above are relaxed: no fence per poll)
         }
         __syncthreads();
     }
@@ -240,12 +397,14 @@ void launch_levels_g(bool exact, cudaStream_t s, FactorParams P, const int* lvl_
     void* kern = exact ? (void*)k_factor_levels<G, ICHOL, true> : (void*)k_factor_levels<G, ICHOL, false>;
     // few, fat CTAs: the barrier costs one atomic and one polling thread per CTA
     const int block = 512;
+    const size_t smem = (size_t)(block / G) * RowSmem<G>::kBytes;
+    ILUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, 0));
+    ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
     ILUB_REQUIRE(occ > 0, ILUB_ERR_CUDA, "level-loop factorisation kernel does not fit on an SM");
-    const int grid = std::min(occ, 2) * sm_count;
+    const int grid = std::min(occ, 2) * sm_count;  // (measured: two CTAs per SM beat one; the level time is row latency, not the barrier)
     void* args[] = {(void*)&P, (void*)&lvl_ptr, (void*)&nlevels, (void*)&barrier};
-    ILUB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, 0, s));
+    ILUB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));
 }
 
 template <bool ICHOL>
@@ -261,10 +420,14 @@ void launch_levels(int G, bool exact, cudaStream_t s, const FactorParams& P, con
 
 template <int G, bool ICHOL, bool SYNCFREE>
 void launch_g(bool exact, int grid, int block, cudaStream_t s, const FactorParams& P) {
-    if (exact)
-        k_factor<G, ICHOL, SYNCFREE, true><<<grid, block, 0, s>>>(P);
-    else
-        k_factor<G, ICHOL, SYNCFREE, false><<<grid, block, 0, s>>>(P);
+    const size_t smem = (size_t)(block / G) * RowSmem<G>::kBytes;  // 112 bytes per thread
+    if (exact) {
+        if (smem > 48 * 1024) ILUB_CUDA(cudaFuncSetAttribute(k_factor<G, ICHOL, SYNCFREE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_factor<G, ICHOL, SYNCFREE, true><<<grid, block, smem, s>>>(P);
+    } else {
+        if (smem > 48 * 1024) ILUB_CUDA(cudaFuncSetAttribute(k_factor<G, ICHOL, SYNCFREE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_factor<G, ICHOL, SYNCFREE, false><<<grid, block, smem, s>>>(P);
+    }
 }
 
 template <bool ICHOL, bool SYNCFREE>
@@ -283,7 +446,10 @@ int factor_schedule(const ilub_handle* h) {
     const TriSolve& T = h->solve[0];
     const int algo = (int)options().factor_algo;
     if (algo != 0) return algo;
-    return (T.nlevels <= 4096 && (int64_t)h->n >= (int64_t)T.nlevels * 256) ? 3 : 2;
+    if (T.nlevels <= 4096 && (int64_t)h->n >= (int64_t)T.nlevels * 256) return 3;  // few wide levels: level loop
+    if ((int64_t)T.nlevels * 64 > (int64_t)h->n) return 1;  // deep narrow DAG: row latency rules; one launch per level
+                                                             // measured fastest (config 4: 5.5 s vs 9.3 s sync-free)
+    return 2;
 }
 
 // symbolic work the chosen schedule needs on top of the level numbers: the (level, row) listing, or the chunked
