@@ -74,7 +74,7 @@ def precond_config(name, A, kind, use_ref, ref_applies=5):
     by = apply_bytes(B.total_nnz, n, ichol)
     st = B.stats
     out = {"config": name, "kind": kind, "n": n, "nnz": int(A.nnz), "total_nnz": int(B.total_nnz),
-           "levels": list(st["levels"][:2]), "kernel": "line-systolic" if st["part_mode"] == 4 else "chunked sync-free",
+           "levels": list(st["levels"][:2]), "kernel": {4: "line-systolic", 5: "level loop (deep DAG)"}.get(st["part_mode"], "chunked sync-free"),
            "apply_us": ms * 1e3, "apply_GBs": by / ms / 1e6, "pct_hbm_measured": 100 * by / ms / 1e6 / PEAK,
            "bytes_per_apply": by,
            "factor_ms": {"symbolic": sym, "numeric": num, "pack": pack, "total": tot, "refactor_numeric": refac,
