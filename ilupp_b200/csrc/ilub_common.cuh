@@ -116,6 +116,7 @@ struct Options {
     int64_t factor_group = 0;   // lanes per row in the factorisation kernels (0 = auto)
     int64_t sys_pz = 0;         // line-systolic: planes per CTA (0 = auto)
     int64_t sys_stages = 0;     // line-systolic: coefficient stages per warp (0 = auto)
+    int64_t sys_pdl = 1;        // line-systolic: programmatic dependent launch (prologue of the next solve overlaps this one)
     int64_t sys_cluster = 0;    // line-systolic: largest thread-block cluster to try (0 = auto: 8, 1 = no clusters)
 };
 Options& options();

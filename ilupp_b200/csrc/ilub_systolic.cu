@@ -146,6 +146,7 @@ struct SysParams {
     int order_xyz, unit_diag;
     int nst, rz;
     int per_warp;  // shared-memory bytes per compute warp
+    int pdl;  // launched with programmatic stream serialisation
     int* status;
     unsigned spin_iters;  // failed polls before a wait gives up (watchdog)
     long long* trace;     // debug (option trace): %globaltimer at every block start of every task, and at its end
@@ -356,6 +357,9 @@ __device__ __forceinline__ void role_helper(const SysParams& P, const SysCtx& C,
 
     if (lane == 0)
         for (int b = 0; b < nst && b < nblocks; ++b) issue_stage(b);
+    // the vector belongs to the previous kernel of the stream until that grid has completed (everything else this
+    // kernel reads -- coefficients, its own mailboxes -- does not): nothing of this solve moves before rectangle 0
+    if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     // rectangles 0 and 1 before the compute warp may start; 2 stays in registers until iteration 0
     rect_load(0);
     rect_deposit(0);
@@ -627,6 +631,10 @@ __global__ void __launch_bounds__(448, 1) k_trsv_systolic(const __grid_constant_
     fence_mbar_init();
     __syncthreads();
     cg::this_cluster().sync();  // every CTA of the cluster has initialised its rings before anyone writes into them
+    // programmatic dependent launch: the next kernel of the stream (the second solve of an apply) may start its own
+    // prologue -- shared-memory set-up, cluster sync, first coefficient stages -- on idle SMs while this one runs;
+    // it touches the vector only behind griddepcontrol.wait (role_helper), i.e. after this grid has completed
+    if (P.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (C.cz < P.gz) {
         if (warp < W) role_compute<EXACT, ZC>(P, C, warp, lane);
@@ -899,13 +907,16 @@ void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cu
     cfg.blockDim = dim3((Y.pyb * Y.pz * 2 + fetch_warps(Y.pyb * Y.pz)) * 32, 1, 1);
     cfg.dynamicSmemBytes = Y.smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = Y.csize;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    P.pdl = opt.sys_pdl != 0 ? 1 : 0;
+    cfg.numAttrs = P.pdl ? 2 : 1;
     for (int c = 0; c < nrhs; ++c) {
         P.epoch = ++Y.epoch;
         P.x = x + (int64_t)c * ldx;
