@@ -174,6 +174,14 @@ def run_ours(args):
     n = A.shape[0]
     t0 = time.perf_counter()
     B = ilupp.IChol0Preconditioner(A, device=local)
+    first_create_wall_ms = (time.perf_counter() - t0) * 1e3
+    first_sym_ms = B.timings_ms[0]
+    # second creation: the library's caching allocator is warm (the first one pays every cudaMalloc and module load)
+    del B
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    B = ilupp.IChol0Preconditioner(A, device=local)
+    torch.cuda.synchronize()
     create_wall_ms = (time.perf_counter() - t0) * 1e3
     sym_ms, num_ms, pack_ms, tot_ms = B.timings_ms
     # numeric-only re-factorisation (unchanged pattern), device-resident values
@@ -299,8 +307,10 @@ def run_ours(args):
                        "parallelism": "replicated factors, one RHS per GPU" if world > 1 else "single GPU"},
             "pct_hbm_peak": 100.0 * value / world / peak,
             "factor_ms": {"symbolic": sym_ms, "numeric": num_ms, "pack": pack_ms, "total": tot_ms,
-                          "refactor_numeric_plus_pack": refactor_ms, "create_wall_incl_h2d": create_wall_ms},
-            "roofline": {"bound": "hbm", "kernel": "k_trsv_systolic" if B.stats["part_mode"] == 4 else "k_trsv_syncfree", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                          "refactor_numeric_plus_pack": refactor_ms, "create_wall_incl_h2d": create_wall_ms,
+                          "first_creation": {"symbolic": first_sym_ms, "create_wall_incl_h2d": first_create_wall_ms},
+                          "numeric_schedule": "level loop (one cooperative launch, grid barrier per level), rows staged in shared memory"},
+            "roofline": {"bound": "hbm", "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep"}.get(B.stats["part_mode"], "k_trsv_syncfree"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": by / 2.0, "avg_launch_ms": kernel_ms,
                          "second_bound": "dependency critical path: %d levels per solve" % B.stats["levels"][0]},
