@@ -410,6 +410,70 @@ def test_baseline_config4_irregular(ilupp):
     assert nlev == nlo and np.array_equal(lev, lo)
 
 
+def _level_loop_stress_matrix(n=30000, hub=3000, seed=5):
+    """One level wider than the level loop's shared-memory rings, then a deep chain, then hub rows longer than the
+    staging limit: exercises the global fall-backs of k_trsv_deep (ilub_deep.cu)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    wide = n - 2000                      # rows [0, wide) have no dependencies at all: one level of `wide` rows
+    for i in range(wide, n):             # a chain with a few random far dependencies
+        deps = {i - 1} | set(rng.integers(0, i, size=3).tolist())
+        if (i - wide) % 400 == 7:        # hub rows: `hub` dependencies
+            deps |= set(rng.integers(0, i, size=hub).tolist())
+        for j in deps:
+            rows.append(i), cols.append(int(j)), vals.append(-rng.random())
+    L = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+    A = L + L.T
+    A = A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)
+    A = A.tocsr()
+    A.sort_indices()
+    A.indices = A.indices.astype(np.int32)
+    A.indptr = A.indptr.astype(np.int32)
+    return A
+
+
+@pytest.mark.parametrize("hub", [3000, 5000], ids=["long-rows", "unstaged-blocks"])
+@pytest.mark.parametrize("exact", [1, 0])
+def test_level_loop_solve_fallbacks(ilupp, exact, hub):
+    """wide level (> ring), hub rows (> staging limit, > entry ring) and the deep chain through the level-loop solve"""
+    A = _level_loop_stress_matrix(hub=hub)
+    b = P.rhs(A.shape[0], 3)
+    saved = {k: ilupp.get_option(k) for k in ("solve_algo", "exact")}
+    try:
+        ilupp.set_option("solve_algo", 3)
+        ilupp.set_option("exact", exact)
+        B = ilupp.ILU0Preconditioner(A)
+        assert B.stats["levels"][0] > 1500
+        Lo, Uo = oracle.port.ilu0(A)
+        for tr in (False, True):
+            y = b.copy()
+            (B.apply_trans if tr else B.apply)(y)
+            yo = oracle.port.apply_lu(Lo, Uo, b, tr)
+            assert relerr(y, yo) <= TOL
+            if exact:
+                assert np.array_equal(y, yo)
+    finally:
+        for k, v in saved.items():
+            ilupp.set_option(k, v)
+
+
+def test_handles_reuse_cached_device_memory(ilupp):
+    """creating and destroying handles through the caching allocator never changes results"""
+    A = P.poisson3d(20)
+    b = P.rhs(A.shape[0], 1)
+    ref = None
+    for _ in range(6):
+        B = ilupp.IChol0Preconditioner(A)
+        C = ilupp.ILU0Preconditioner(P.convdiff3d(14))
+        y = b.copy()
+        B.apply(y)
+        if ref is None:
+            ref = y
+        assert np.array_equal(y, ref)
+        del B, C
+
+
 def test_baseline_config5_batched(ilupp):
     nsys, N = 24, 128
     pat, vals = P.batched_poisson2d(nsys, N)
