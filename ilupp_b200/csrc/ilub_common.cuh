@@ -93,7 +93,7 @@ struct DebugTimer {
 };
 
 struct Options {
-    int64_t factor_algo = 0;    // 0 auto, 1 one launch per level, 2 sync-free, 3 level loop (one cooperative launch)
+    int64_t factor_algo = 0;    // 0 auto, 1 one launch per level, 2 sync-free, 3 level loop (one cooperative launch), 4 stencil (line-systolic; needs exact = 0)
     int64_t solve_algo = 0;     // 0 auto (line-systolic on structured grids, level loop on deep narrow DAGs, else sync-free), 1 level-scheduled, 2 sync-free, 3 level loop
     int64_t exact = 1;          // IEEE mul/sub/div in reference order
     int64_t ctas_per_sm = 1;
@@ -153,6 +153,10 @@ struct SysSolve {
     DevBuf<int> srcpos;                         // [ntasks1][nsteps_pad][4][32] position in lu (-1: absent / unit)
     DevBuf<double> coef;                        // [ntasks][nsteps_pad][4][32] {z, y, x, diagonal} per lane and step
     DevBuf<ulonglong2> zmail, ymail;            // cross-CTA hand-off {x, epoch}
+    // stencil factorisation on the same kernel (slot 0 only): value / partner positions and the product stream
+    bool ftried = false, fbuilt = false;
+    DevBuf<int> fsrc, fpart;
+    DevBuf<double> fcoef;
     unsigned long long epoch = 0;
 };
 
@@ -299,6 +303,7 @@ struct ilub_handle {
     ilub::TriSolve solve[4];
     ilub::DevBuf<unsigned char> fflag;  // factorisation row flags
     ilub::DevBuf<unsigned> fbarrier;    // grid barrier of the level-loop factorisation
+    ilub::DevBuf<double> fpivot;        // pivots of the stencil factorisation
     unsigned fepoch = 0;
     ilub::DevBuf<int> status;           // device status word(s) written by kernels (watchdog / structure errors)
     ilub::DevBuf<double> work;          // vector workspace (host-side apply, bicgstab)
@@ -322,6 +327,8 @@ bool deep_wanted(const ilub_handle* h, int slot);
 void analyse_deep(ilub_handle* h, int slot, cudaStream_t s);
 void pack_deep(ilub_handle* h, int slot, cudaStream_t s);
 void run_deep(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s);
+bool stencil_factor_possible(ilub_handle* h, cudaStream_t s);
+void factor_stencil(ilub_handle* h, cudaStream_t s);
 int factor_schedule(const ilub_handle* h);
 void factor_prepare(ilub_handle* h, cudaStream_t s);
 int read_status(ilub_handle* h, cudaStream_t s);                          // syncs the stream

@@ -445,6 +445,9 @@ void launch(int G, bool exact, int grid, int block, cudaStream_t s, const Factor
 int factor_schedule(const ilub_handle* h) {
     const TriSolve& T = h->solve[0];
     const int algo = (int)options().factor_algo;
+    // stencil matrices, fast arithmetic: the pivot recurrence on the line-systolic kernel (ilub_systolic.cu)
+    if ((algo == 0 || algo == 4) && options().exact == 0 && T.sys.fbuilt) return 4;
+    if (algo == 4) return 3;
     if (algo != 0) return algo;
     if (T.nlevels <= 4096 && (int64_t)h->n >= (int64_t)T.nlevels * 256) return 3;  // few wide levels: level loop
     if ((int64_t)T.nlevels * 64 > (int64_t)h->n) return 1;  // deep narrow DAG: row latency rules; one launch per level
@@ -455,6 +458,8 @@ int factor_schedule(const ilub_handle* h) {
 // symbolic work the chosen schedule needs on top of the level numbers: the (level, row) listing, or the chunked
 // (part, level, row) order that the sync-free kernel walks
 void factor_prepare(ilub_handle* h, cudaStream_t s) {
+    if ((options().factor_algo == 0 || options().factor_algo == 4) && options().exact == 0) stencil_factor_possible(h, s);
+    if (factor_schedule(h) == 4) return;
     if (factor_schedule(h) == 2)
         analyse_generic(h, 0, s);
     else
@@ -487,8 +492,12 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
     const bool exact = opt.exact != 0;
     // schedule: 1 = one launch per level, 2 = sync-free, 3 = level loop (one cooperative launch), 0 = level loop when
     // the levels are few and wide (stencils, block-diagonal batches), sync-free otherwise
-    const int algo = factor_schedule(h);
     factor_prepare(h, s);
+    const int algo = factor_schedule(h);
+    if (algo == 4) {
+        factor_stencil(h, s);
+        return;
+    }
     if (algo == 3) {
         if (h->fbarrier.n < 1) h->fbarrier.alloc(1);
         ILUB_CUDA(cudaMemsetAsync(h->fbarrier.p, 0, sizeof(unsigned), s));

@@ -132,6 +132,101 @@ __global__ void k_sys_pack(int64_t total, int per_task, int nyb, int nz1, int ns
     coef[e] = v;
 }
 
+// ---- stencil factorisation (factor_stencil below): placement of the rows of ONE system in the (task, step, lane)
+// layout of the forward solve, with the positions the factorisation needs: roles z / y / x = the strictly-lower
+// entry and its PARTNER (the entry (k, r) of row k's strict upper part, -1 if absent), role 3 = the diagonal
+__global__ void k_sys_map_factor(SysGeom G, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                 const int* __restrict__ dpos, int* __restrict__ fsrc, int* __restrict__ fpart, int* fail) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= G.n1) return;
+    const int i = r % G.nx;
+    const int j = (r / G.nx) % G.ny;
+    const int k = r / (G.nx * G.ny);
+    const int task = k * G.nyb + (j >> 5);
+    const int lane = j & 31;
+    const int step = i + lane;
+    const size_t base = ((size_t)task * G.nsteps_pad + step) * 128 + lane * 2;
+    bool bad = false;
+    for (int q = ptr[r]; q < dpos[r]; ++q) {
+        const int dep = idx[q];
+        const int off = r - dep;
+        int role = -1;
+        if (off == 1 && i > 0) role = 2;
+        else if (off == G.sy && j > 0) role = 1;
+        else if (G.sz > 0 && off == G.sz && k > 0) role = 0;
+        if (role < 0) {
+            bad = true;
+            break;
+        }
+        // partner: column r in the strict upper part of row dep
+        int b = dpos[dep] + 1, e = ptr[dep + 1];
+        while (b < e) {
+            const int m = (b + e) >> 1;
+            if (idx[m] < r) b = m + 1;
+            else e = m;
+        }
+        const size_t slot = base + (role >> 1) * 64 + (role & 1);
+        fsrc[slot] = q;
+        fpart[slot] = (b < ptr[dep + 1] && idx[b] == r) ? b : -1;
+    }
+    fsrc[base + 64 + 1] = dpos[r];
+    if (bad) *fail = 1;
+}
+// ILU(0) only: every strict-upper entry sits at offset 1, sy or sz too (then no update can hit anything but a diagonal)
+__global__ void k_sys_check_upper(int n1, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                  const int* __restrict__ dpos, int sy, int sz, int* fail) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n1) return;
+    for (int q = dpos[r] + 1; q < ptr[r + 1]; ++q) {
+        const int off = idx[q] - r;
+        if (off != 1 && off != sy && !(sz > 0 && off == sz)) *fail = 1;
+    }
+}
+// coefficient stream of the factorisation: products a_ik * a_ki (IChol(0): a_ik^2) and the diagonal a_ii
+__global__ void k_sys_pack_factor(int64_t total, int per_task, int nyb, int nz1, int64_t nnz1, int ichol,
+                                  const int* __restrict__ fsrc, const int* __restrict__ fpart,
+                                  const double* __restrict__ a, double* __restrict__ coef) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int task = (int)(e / per_task);
+    const int rem = (int)(e - (int64_t)task * per_task);
+    const int p = task / nyb, jb = task - p * nyb;
+    const int sys = p / nz1, k = p - sys * nz1;
+    const size_t tbase = (size_t)(k * nyb + jb) * per_task;
+    const int pos = fsrc[tbase + rem];
+    const int role = ((rem >> 6) & 1) * 2 + (rem & 1);
+    const int64_t soff = (int64_t)sys * nnz1;
+    double v;
+    if (role == 3) {
+        v = pos >= 0 ? a[(int64_t)pos + soff] : 1.0;  // (padding: pivot 1, nothing depends on it)
+    } else if (pos < 0) {
+        v = 0.0;
+    } else if (ichol) {
+        const double t = a[(int64_t)pos + soff];
+        v = t * t;
+    } else {
+        const int pp = fpart[tbase + rem];
+        v = pp >= 0 ? a[(int64_t)pos + soff] * a[(int64_t)pp + soff] : 0.0;
+    }
+    coef[e] = v;
+}
+// from the pivots to the factor on A's pattern: ILU(0): L_ik = a_ik / d_k, U = a with the pivot on the diagonal;
+// IChol(0): L_ik = a_ik / sqrt(d_k), L_ii = sqrt(d_i)
+__global__ void k_stencil_finish(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                 const int* __restrict__ dpos, const double* __restrict__ a,
+                                 const double* __restrict__ d, double* __restrict__ lu, int ichol) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(t >> 3), gl = (int)(t & 7);
+    if (i >= n) return;
+    const int p0 = ptr[i], p1 = ichol ? dpos[i] + 1 : ptr[i + 1], dp = dpos[i];
+    for (int p = p0 + gl; p < p1; p += 8) {
+        double v = a[p];
+        if (p < dp) v = ichol ? v / sqrt(d[idx[p]]) : v / d[idx[p]];
+        else if (p == dp) v = ichol ? sqrt(d[i]) : d[i];
+        lu[p] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 struct SysParams {
     const double* coef;
@@ -355,11 +450,11 @@ __device__ __forceinline__ void role_helper(const SysParams& P, const SysCtx& C,
         bulk_g2s(mine + (size_t)slot * kStageBytes, coef_task + (size_t)b * (kStageBytes / 8), (unsigned)kStageBytes, &bar[slot]);
     };
 
+    // the vector -- and, right after a (re)factorisation, the coefficient stream -- belong to the previous kernels of
+    // the stream until those grids have completed: nothing of this solve reads global memory before this point
+    if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (lane == 0)
         for (int b = 0; b < nst && b < nblocks; ++b) issue_stage(b);
-    // the vector belongs to the previous kernel of the stream until that grid has completed (everything else this
-    // kernel reads -- coefficients, its own mailboxes -- does not): nothing of this solve moves before rectangle 0
-    if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     // rectangles 0 and 1 before the compute warp may start; 2 stays in registers until iteration 0
     rect_load(0);
     rect_deposit(0);
@@ -390,7 +485,7 @@ __device__ __forceinline__ void role_helper(const SysParams& P, const SysCtx& C,
 }
 
 // ---------------------------------------------------------------- compute warp: one task, one wavefront level per step
-template <bool EXACT, bool ZC>
+template <bool EXACT, bool ZC, bool FACTOR>
 __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C, int warp, int lane) {
     namespace cg = cooperative_groups;
     const int W = C.W;
@@ -552,7 +647,10 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
                 // coefficients are pre-divided by the diagonal (dvu = 1/d); absent entries carry 0.0 and every operand
                 // that can reach them is finite.  Only ONE fused multiply-add waits for the other warp's value, and it
                 // is issued speculatively: the vote on the tags resolves beside it.
-                double acc = bbu * dvu;
+                // FACTOR (stencil ILU(0) / IChol(0), see factor_stencil below): the same recurrence on the pivots --
+                // d = a_ii - sum p_k / d_k with p_k = a_ik * a_ki packed in the coefficient slots and a_ii in the
+                // diagonal slot; what travels between rows is r = 1 / d, what is stored is d
+                double acc = FACTOR ? dvu : bbu * dvu;
                 acc = fma(-cxu, xprev, acc);
                 acc = fma(-cyu, xy, acc);
                 while (true) {
@@ -564,9 +662,14 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
                 }
             }
             ynext = __longlong_as_double((long long)vy);
+            if (FACTOR) {
+                sts_f64(wb + u * 8, xnew);  // the pivot
+                xnew = 1.0 / xnew;          // its reciprocal goes to the rows that depend on it
+            } else {
+                sts_f64(wb + u * 8, xnew);
+            }
             xprev = xnew;
             ycur = ynext;
-            sts_f64(wb + u * 8, xnew);
             // ---- hand-offs: {x, {epoch, step + 1}}
             const unsigned long long tag64 = ehi | (unsigned long long)(unsigned)tag;
             if (has_zout) st_gen128(zdst + u * 512, xnew, tag64);
@@ -589,7 +692,7 @@ __device__ __forceinline__ void role_compute(const SysParams& P, const SysCtx& C
     }
 }
 
-template <bool EXACT, bool ZC>
+template <bool EXACT, bool ZC, bool FACTOR = false>
 __global__ void __launch_bounds__(448, 1) k_trsv_systolic(const __grid_constant__ SysParams P) {
     namespace cg = cooperative_groups;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -637,7 +740,7 @@ __global__ void __launch_bounds__(448, 1) k_trsv_systolic(const __grid_constant_
     if (P.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (C.cz < P.gz) {
-        if (warp < W) role_compute<EXACT, ZC>(P, C, warp, lane);
+        if (warp < W) role_compute<EXACT, ZC, FACTOR>(P, C, warp, lane);
         else if (warp < 2 * W) role_helper(P, C, warp - W, lane);
         else {
             // fetchers: z and y alternate (z first) so that a short budget still has one of each
@@ -654,6 +757,12 @@ __global__ void __launch_bounds__(448, 1) k_trsv_systolic(const __grid_constant_
 
 // ================================================================================================== host
 typedef void (*sys_kern_t)(const SysParams);
+static sys_kern_t sys_factor_kernel(bool zc) {
+    const sys_kern_t k = zc ? (sys_kern_t)k_trsv_systolic<false, true, true> : (sys_kern_t)k_trsv_systolic<false, false, true>;
+    ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    return k;
+}
 static sys_kern_t sys_kernel(bool exact, bool zc) {
     const sys_kern_t k = exact ? (zc ? (sys_kern_t)k_trsv_systolic<true, true> : (sys_kern_t)k_trsv_systolic<true, false>)
                                : (zc ? (sys_kern_t)k_trsv_systolic<false, true> : (sys_kern_t)k_trsv_systolic<false, false>);
@@ -865,14 +974,14 @@ void pack_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     Y.packed_exact = exact;
 }
 
-void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
+static void launch_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s, const double* fcoef) {
     TriSolve& T = h->solve[slot];
     SysSolve& Y = T.sys;
     const Options& opt = options();
-    const bool exact = opt.exact != 0;
-    if (Y.packed_exact != (exact ? 1 : 0)) pack_systolic(h, slot, s);
+    const bool exact = fcoef ? false : opt.exact != 0;
+    if (!fcoef && Y.packed_exact != (exact ? 1 : 0)) pack_systolic(h, slot, s);
     SysParams P;
-    P.coef = Y.coef.p;
+    P.coef = fcoef ? fcoef : Y.coef.p;
     P.nx = Y.nx;
     P.ny = Y.ny;
     P.nyb = Y.nyb;
@@ -894,7 +1003,7 @@ void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cu
     P.status = h->status.p;
     // watchdog in failed polls (a poll round is >= ~40 cycles)
     P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 16, (long long)opt.spin_limit_ms * h->clock_khz / 64));
-    const sys_kern_t kern = sys_kernel(exact, Y.zcoupled != 0);
+    const sys_kern_t kern = fcoef ? sys_factor_kernel(Y.zcoupled != 0) : sys_kernel(exact, Y.zcoupled != 0);
     if (opt.trace && T.trace.n < (size_t)Y.ntasks * 3 * (Y.nsteps_pad / kStageSteps + 1))
         T.trace.alloc((size_t)Y.ntasks * 3 * (Y.nsteps_pad / kStageSteps + 1));
     P.trace = opt.trace ? T.trace.p : nullptr;
@@ -923,6 +1032,77 @@ void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cu
         ILUB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
         h->launches++;
     }
+    ILUB_CUDA(cudaGetLastError());
+}
+
+void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
+    launch_systolic(h, slot, x, ldx, nrhs, s, nullptr);
+}
+
+// ================================================================================================== stencil factorisation
+// ILU(0) / IChol(0) of a 5- / 7-point stencil matrix change nothing but the pivots: for the lower neighbours k of
+// row i (offsets 1, nx, nx*ny) no entry (k, j), j != i, of row k's upper part meets an entry of row i once nx >= 3
+// and ny >= 3, so the only update is  d_i = a_ii - sum_k a_ik a_ki / d_k  (IChol(0): d_i = l_ii^2, a_ik^2 / d_k).
+// That is the wavefront recurrence of the forward solve with a reciprocal in it, and it runs on the same
+// line-systolic kernel (template parameter FACTOR): the coefficient stream carries the products, the vector carries
+// the pivots.  Replaces compute_ilu0 / compute_ichol0 (ILU0.hpp:8-66, IChol.hpp:15-59) for such matrices when `exact`
+// is off: the result differs from the reference's operation order by the rounding of (a_ik a_ki) / d_k against
+// (a_ik / d_k) a_ki -- a few 1e-16 relative (tests hold it to 1e-12); `exact` keeps the general kernels.
+bool stencil_factor_possible(ilub_handle* h, cudaStream_t s) {
+    SysSolve& Y = h->solve[0].sys;
+    if (Y.ftried) return Y.fbuilt;
+    Y.ftried = true;
+    if (!Y.built || Y.nx < 3 || (Y.zcoupled && Y.ny < 3)) return false;
+    const int n1 = h->n / h->nsys;
+    DevBuf<int> fail;
+    fail.alloc(1);
+    ILUB_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), s));
+    SysGeom G;
+    G.n1 = n1;
+    G.nx = Y.nx;
+    G.ny = Y.ny;
+    G.nz1 = Y.nz1;
+    G.nyb = Y.nyb;
+    G.nsteps_pad = Y.nsteps_pad;
+    G.sy = Y.nx;
+    G.sz = Y.zcoupled ? Y.nx * Y.ny : 0;
+    G.backward = 0;
+    G.unit_diag = 0;
+    const size_t per_task = (size_t)Y.nsteps_pad * 128;
+    Y.fsrc.alloc((size_t)Y.ntasks1 * per_task);
+    Y.fpart.alloc((size_t)Y.ntasks1 * per_task);
+    ILUB_CUDA(cudaMemsetAsync(Y.fsrc.p, 0xff, sizeof(int) * (size_t)Y.ntasks1 * per_task, s));
+    ILUB_CUDA(cudaMemsetAsync(Y.fpart.p, 0xff, sizeof(int) * (size_t)Y.ntasks1 * per_task, s));
+    // (the pattern of a batch is that of its first system repeated: rows [0, n1) of the expanded arrays)
+    k_sys_map_factor<<<blocks_for(n1, 256), 256, 0, s>>>(G, h->ptr.p, h->idx.p, h->dpos.p, Y.fsrc.p, Y.fpart.p, fail.p);
+    if (h->kind != KIND_ICHOL0)
+        k_sys_check_upper<<<blocks_for(n1, 256), 256, 0, s>>>(n1, h->ptr.p, h->idx.p, h->dpos.p, G.sy, G.sz, fail.p);
+    h->launches += 2;
+    int hf = 0;
+    ILUB_CUDA(cudaMemcpyAsync(&hf, fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    if (hf) {
+        Y.fsrc.release();
+        Y.fpart.release();
+        return false;
+    }
+    Y.fcoef.alloc((size_t)Y.ntasks * per_task);
+    h->fpivot.alloc(h->n);
+    Y.fbuilt = true;
+    return true;
+}
+
+void factor_stencil(ilub_handle* h, cudaStream_t s) {
+    SysSolve& Y = h->solve[0].sys;
+    const int ichol = h->kind == KIND_ICHOL0 ? 1 : 0;
+    const int per_task = Y.nsteps_pad * 128;
+    const int64_t total = (int64_t)Y.ntasks * per_task;
+    k_sys_pack_factor<<<blocks_for(total, 256), 256, 0, s>>>(total, per_task, Y.nyb, Y.nz1, h->nnz / h->nsys, ichol, Y.fsrc.p,
+                                                             Y.fpart.p, h->a.p, Y.fcoef.p);
+    launch_systolic(h, 0, h->fpivot.p, h->n, 1, s, Y.fcoef.p);
+    k_stencil_finish<<<blocks_for((int64_t)h->n * 8, 256), 256, 0, s>>>(h->n, h->ptr.p, h->idx.p, h->dpos.p, h->a.p, h->fpivot.p,
+                                                                       h->lu.p, ichol);
+    h->launches += 2;
     ILUB_CUDA(cudaGetLastError());
 }
 

@@ -147,7 +147,8 @@ ILUB_API int ilub_create_ichol0_batched(const double* values, const int32_t* ind
 /* ---- options / instrumentation -------------------------------------------------------------- */
 /* global options, set before creating handles.  Known keys:
  *   "factor_algo"  0 = auto (default: level loop when levels are few and wide, else sync-free), 1 = one launch per
- *                  level, 2 = sync-free, 3 = level loop (one cooperative launch with grid barriers)
+ *                  level, 2 = sync-free, 3 = level loop (one cooperative launch with grid barriers), 4 = stencil path
+ *                  (pivot recurrence on the line-systolic kernel; stencil matrices with "exact" = 0 only, else 3)
  *   "solve_algo"   0 = auto (default: line-systolic on structured grids, level loop on deep narrow DAGs, else chunked
  *                  sync-free), 1 = one launch per level, 2 = chunked sync-free, 3 = level loop (one CTA, one barrier per level)
  *   "exact"        1 (default) = IEEE mul/sub/div in the reference's operation order (bit-for-bit

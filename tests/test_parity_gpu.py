@@ -474,6 +474,48 @@ def test_handles_reuse_cached_device_memory(ilupp):
         del B, C
 
 
+STENCILS = [("poisson2d_33", lambda: P.poisson2d(33), True), ("poisson3d_20", lambda: P.poisson3d(20), True),
+            ("convdiff3d_13", lambda: P.convdiff3d(13), False), ("poisson2d_128", lambda: P.poisson2d(128), True)]
+
+
+@pytest.mark.parametrize("name,gen,sym", STENCILS, ids=[p[0] for p in STENCILS])
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_stencil_factorisation(ilupp, name, gen, sym, fmt):
+    """fast arithmetic on a stencil matrix: the pivot recurrence on the line-systolic kernel (factor_stencil)"""
+    A = gen().asformat(fmt)
+    b = P.rhs(A.shape[0], 2)
+    saved = ilupp.get_option("exact")
+    try:
+        ilupp.set_option("exact", 0)
+        B = ilupp.ILU0Preconditioner(A)
+        Lo, Uo = oracle.port.ilu0(A)
+        L, U = B.factors()
+        assert same_pattern(L, Lo) and same_pattern(U, Uo)
+        assert relerr(L.data, Lo.data) <= TOL and relerr(U.data, Uo.data) <= TOL
+        y = b.copy()
+        B.apply(y)
+        assert relerr(y, oracle.port.apply_lu(Lo, Uo, b)) <= TOL
+        A2 = A.copy()
+        A2.data = A.data * (1.0 + 0.1 * np.cos(np.arange(A.nnz)))   # numeric re-factorisation on the same pattern
+        if sym:
+            A2 = ((A2 + A2.T) * 0.5).asformat(fmt)
+            A2.sort_indices()
+        B.refactor(A2)
+        Lo2, Uo2 = oracle.port.ilu0(A2)
+        L2, U2 = B.factors()
+        assert relerr(L2.data, Lo2.data) <= TOL and relerr(U2.data, Uo2.data) <= TOL
+        if sym:
+            C = ilupp.IChol0Preconditioner(A)
+            (Lc,) = C.factors()
+            Lco = oracle.port.ichol0(A)
+            assert same_pattern(Lc, Lco) and relerr(Lc.data, Lco.data) <= TOL
+            y = b.copy()
+            C.apply(y)
+            assert relerr(y, oracle.port.apply_llt(Lco, b)) <= TOL
+    finally:
+        ilupp.set_option("exact", saved)
+
+
 def test_baseline_config5_batched(ilupp):
     nsys, N = 24, 128
     pat, vals = P.batched_poisson2d(nsys, N)
