@@ -309,7 +309,8 @@ def run_ours(args):
             "factor_ms": {"symbolic": sym_ms, "numeric": num_ms, "pack": pack_ms, "total": tot_ms,
                           "refactor_numeric_plus_pack": refactor_ms, "create_wall_incl_h2d": create_wall_ms,
                           "first_creation": {"symbolic": first_sym_ms, "create_wall_incl_h2d": first_create_wall_ms},
-                          "numeric_schedule": "level loop (one cooperative launch, grid barrier per level), rows staged in shared memory"},
+                          "numeric_schedule": ("stencil path: pivot recurrence on the line-systolic kernel" if not args.exact else
+                                               "level loop (one cooperative launch, grid barrier per level), rows staged in shared memory")},
             "roofline": {"bound": "hbm", "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep"}.get(B.stats["part_mode"], "k_trsv_syncfree"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": by / 2.0, "avg_launch_ms": kernel_ms,
