@@ -92,6 +92,16 @@ struct DebugTimer {
     }
 };
 
+// per-thread, per-device "done once" flags for function attributes (cudaFuncSetAttribute is per device)
+inline bool first_use_on_this_device(unsigned* masks /* one word per kernel variant */, int variant) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned bit = 1u << (dev & 31);
+    if (masks[variant] & bit) return false;
+    masks[variant] |= bit;
+    return true;
+}
+
 struct Options {
     int64_t factor_algo = 0;    // 0 auto, 1 one launch per level, 2 sync-free, 3 level loop (one cooperative launch), 4 stencil (line-systolic; needs exact = 0)
     int64_t solve_algo = 0;     // 0 auto (line-systolic on structured grids, level loop on deep narrow DAGs, else sync-free), 1 level-scheduled, 2 sync-free, 3 level loop

@@ -412,13 +412,12 @@ void run_deep(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaSt
     const bool exact = options().exact != 0;
     if (D.packed_exact != (exact ? 1 : 0)) pack_deep(h, slot, s);
     const size_t smem = sizeof(DeepSmem);
-    static thread_local bool attr_set[2] = {false, false};
-    if (!attr_set[exact ? 1 : 0]) {
+    static thread_local unsigned attr_set[2] = {0, 0};
+    if (first_use_on_this_device(attr_set, exact ? 1 : 0)) {
         if (exact)
             ILUB_CUDA(cudaFuncSetAttribute(k_trsv_deep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else
             ILUB_CUDA(cudaFuncSetAttribute(k_trsv_deep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[exact ? 1 : 0] = true;
     }
     DeepParams P;
     P.n = h->n;

@@ -759,18 +759,21 @@ __global__ void __launch_bounds__(448, 1) k_trsv_systolic(const __grid_constant_
 typedef void (*sys_kern_t)(const SysParams);
 static sys_kern_t sys_factor_kernel(bool zc) {
     const sys_kern_t k = zc ? (sys_kern_t)k_trsv_systolic<false, true, true> : (sys_kern_t)k_trsv_systolic<false, false, true>;
-    ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    static thread_local unsigned attr_set[2] = {0, 0};
+    if (first_use_on_this_device(attr_set, zc ? 1 : 0)) {
+        ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
     return k;
 }
 static sys_kern_t sys_kernel(bool exact, bool zc) {
     const sys_kern_t k = exact ? (zc ? (sys_kern_t)k_trsv_systolic<true, true> : (sys_kern_t)k_trsv_systolic<true, false>)
                                : (zc ? (sys_kern_t)k_trsv_systolic<false, true> : (sys_kern_t)k_trsv_systolic<false, false>);
-    static thread_local bool attr_set[4] = {false, false, false, false};
+    static thread_local unsigned attr_set[4] = {0, 0, 0, 0};
     const int ki = (exact ? 2 : 0) + (zc ? 1 : 0);
-    if (!attr_set[ki]) {
+    if (first_use_on_this_device(attr_set, ki)) {
         ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[ki] = true;
+        ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
     return k;
 }

@@ -617,15 +617,14 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz;
     if (opt.trace && T.trace.n < (size_t)T.nchunks * 4) T.trace.alloc((size_t)T.nchunks * 4);
     P.trace = opt.trace ? T.trace.p : nullptr;
-    static thread_local bool attr_set[2] = {false, false};
-    if (!attr_set[exact ? 1 : 0]) {
+    static thread_local unsigned attr_set[2] = {0, 0};
+    if (first_use_on_this_device(attr_set, exact ? 1 : 0)) {
         if (exact)
             ILUB_CUDA(cudaFuncSetAttribute(k_trsv_syncfree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            227 * 1024));
         else
             ILUB_CUDA(cudaFuncSetAttribute(k_trsv_syncfree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            227 * 1024));
-        attr_set[exact ? 1 : 0] = true;
     }
     for (int c = 0; c < nrhs; ++c) {
         P.epoch = ++T.epoch;  // 64-bit tag: never wraps, the mailbox is never reset
