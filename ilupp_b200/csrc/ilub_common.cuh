@@ -314,6 +314,7 @@ struct ilub_handle {
     ilub::DevBuf<unsigned char> fflag;  // factorisation row flags
     ilub::DevBuf<unsigned> fbarrier;    // grid barrier of the level-loop factorisation
     ilub::DevBuf<double> fpivot;        // pivots of the stencil factorisation
+    int max_row_len = -1;               // longest row of the CSR-read arrays (computed once, factor_prepare)
     unsigned fepoch = 0;
     ilub::DevBuf<int> status;           // device status word(s) written by kernels (watchdog / structure errors)
     ilub::DevBuf<double> work;          // vector workspace (host-side apply, bicgstab)

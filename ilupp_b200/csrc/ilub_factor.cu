@@ -36,6 +36,10 @@ struct FactorParams {
     int lvl_begin, lvl_end;
     int* status;
     long long spin_limit;
+    // level-scheduled kernels: one big row buffer per CTA (28 bytes x big_cap, behind the groups' buffers, then a lock
+    // word) for the rare rows longer than 4 * G entries -- hub rows of irregular matrices, which the slow row routines
+    // would otherwise turn into milliseconds on the critical path
+    int big_cap;
 };
 
 // first position in [b, e) with idx >= c
@@ -171,12 +175,12 @@ struct RowSmem {
     int* idx;      // [L] row i columns
     int* ra;       // [L] ILU0: first upper entry of row k / IChol0: first entry of row j
     int* rb;       // [L] ILU0: end of row k / IChol0: diagonal position of row j
-    __device__ RowSmem(unsigned char* base) {
+    __device__ RowSmem(unsigned char* base, int cap = L) {
         val = reinterpret_cast<double*>(base);
-        piv = val + L;
-        idx = reinterpret_cast<int*>(piv + L);
-        ra = idx + L;
-        rb = ra + L;
+        piv = val + cap;
+        idx = reinterpret_cast<int*>(piv + cap);
+        ra = idx + cap;
+        rb = ra + cap;
     }
 };
 
@@ -212,19 +216,47 @@ __device__ __forceinline__ bool ilu0_row_fast(const FactorParams& P, int i, int 
     }
     if (SYNCFREE && !__all_sync(gmask, ok)) return false;
     __syncwarp(gmask);
-    for (int kk = 0; kk < nl; ++kk) {  // ILU0.hpp:47-62, ascending k
-        const double wkk = R.val[kk], ukk = R.piv[kk];
-        const double lik = EXACT ? __ddiv_rn(wkk, ukk) : wkk / ukk;  // ILU0.hpp:52
-        const int qb = R.ra[kk], qe = R.rb[kk];
-        // U[i, k+1:] -= L_ik * U[k, k+1:]   (ILU0.hpp:55-59): row k's upper part against my entries right of kk
-        for (int q = qb + gl; q < qe; q += G) {
-            const int c = __ldg(P.idx + q);
-            const double u = __ldcg(P.lu + q);
-            const int pos = lower_bound_s(R.idx, kk + 1, len, c);
-            if (pos < len && R.idx[pos] == c) R.val[pos] = sub_mul<EXACT>(R.val[pos], lik, u);
+    // row k's upper parts are final and independent of the updates below: the first G entries of the next four rows
+    // are requested ahead, so the loop runs at the pace of the shared-memory work, not of one L2 round trip per k
+    constexpr int PF = 4;
+    int pc[PF];
+    double pu[PF];
+    auto fetch = [&](int kk, int& c, double& u) {
+        c = -1;
+        if (kk < nl) {
+            const int q = R.ra[kk] + gl;
+            if (q < R.rb[kk]) {
+                c = __ldg(P.idx + q);
+                u = __ldcg(P.lu + q);
+            }
         }
-        __syncwarp(gmask);
-        if (gl == 0) R.val[kk] = lik;  // ILU0.hpp:61
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u) fetch(u, pc[u], pu[u]);
+    for (int kk0 = 0; kk0 < nl; kk0 += PF) {  // ILU0.hpp:47-62, ascending k
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int kk = kk0 + u;
+            if (kk < nl) {
+                const double wkk = R.val[kk], ukk = R.piv[kk];
+                const double lik = EXACT ? __ddiv_rn(wkk, ukk) : wkk / ukk;  // ILU0.hpp:52
+                const int qb = R.ra[kk], qe = R.rb[kk];
+                // U[i, k+1:] -= L_ik * U[k, k+1:]   (ILU0.hpp:55-59): row k's upper part against my entries right of kk
+                if (pc[u] >= 0) {
+                    const int pos = lower_bound_s(R.idx, kk + 1, len, pc[u]);
+                    if (pos < len && R.idx[pos] == pc[u]) R.val[pos] = sub_mul<EXACT>(R.val[pos], lik, pu[u]);
+                }
+                for (int q = qb + gl + G; q < qe; q += G) {
+                    const int c = __ldg(P.idx + q);
+                    const double uu = __ldcg(P.lu + q);
+                    const int pos = lower_bound_s(R.idx, kk + 1, len, c);
+                    if (pos < len && R.idx[pos] == c) R.val[pos] = sub_mul<EXACT>(R.val[pos], lik, uu);
+                }
+                fetch(kk + PF, pc[u], pu[u]);
+                __syncwarp(gmask);
+                if (gl == 0) R.val[kk] = lik;  // ILU0.hpp:61
+            }
+        }
     }
     __syncwarp(gmask);
     for (int t = gl; t < len; t += G) P.lu[p0 + t] = R.val[t];
@@ -301,23 +333,44 @@ __device__ __forceinline__ bool ichol0_row_fast(const FactorParams& P, int i, in
     return true;
 }
 
-// one row, short or long
+// one row: short (the group's own buffer), long (the CTA's big buffer, one long row at a time), or longer still
 template <int G, bool ICHOL, bool SYNCFREE, bool EXACT>
 __device__ __forceinline__ bool factor_row(const FactorParams& P, int i, int gl, unsigned gmask, int gshift,
-                                           const RowSmem<G>& R) {
-    if (ICHOL) {
-        if (P.dpos[i] - P.ptr[i] + 1 <= RowSmem<G>::L) return ichol0_row_fast<G, SYNCFREE, EXACT>(P, i, gl, gmask, gshift, R);
-        return ichol0_row<G, SYNCFREE, EXACT>(P, i, gl, gmask, gshift);
-    } else {
-        if (P.ptr[i + 1] - P.ptr[i] <= RowSmem<G>::L) return ilu0_row_fast<G, SYNCFREE, EXACT>(P, i, gl, gmask, R);
-        return ilu0_row<G, SYNCFREE, EXACT>(P, i, gl, gmask);
+                                           const RowSmem<G>& R, unsigned char* big) {
+    const int len = ICHOL ? P.dpos[i] - P.ptr[i] + 1 : P.ptr[i + 1] - P.ptr[i];
+    if (len <= RowSmem<G>::L) {
+        if (ICHOL) return ichol0_row_fast<G, SYNCFREE, EXACT>(P, i, gl, gmask, gshift, R);
+        return ilu0_row_fast<G, SYNCFREE, EXACT>(P, i, gl, gmask, R);
     }
+    if (!SYNCFREE && len <= P.big_cap) {  // (never while rows wait on each other: the lock holder could wait forever)
+        int* lock = reinterpret_cast<int*>(big + (size_t)28 * P.big_cap);
+        if (gl == 0)
+            while (atomicCAS(lock, 0, 1) != 0) __nanosleep(64);
+        __syncwarp(gmask);
+        const RowSmem<G> RB(big, P.big_cap);
+        bool ok;
+        if (ICHOL) ok = ichol0_row_fast<G, SYNCFREE, EXACT>(P, i, gl, gmask, gshift, RB);
+        else ok = ilu0_row_fast<G, SYNCFREE, EXACT>(P, i, gl, gmask, RB);
+        __syncwarp(gmask);
+        if (gl == 0) {
+            __threadfence_block();
+            atomicExch(lock, 0);
+        }
+        return ok;
+    }
+    if (ICHOL) return ichol0_row<G, SYNCFREE, EXACT>(P, i, gl, gmask, gshift);
+    return ilu0_row<G, SYNCFREE, EXACT>(P, i, gl, gmask);
 }
 
 template <int G, bool ICHOL, bool SYNCFREE, bool EXACT>
 __global__ void __launch_bounds__(512) k_factor(FactorParams P) {
     extern __shared__ __align__(16) unsigned char factor_smem[];
     const RowSmem<G> R(factor_smem + (size_t)(threadIdx.x / G) * RowSmem<G>::kBytes);
+    unsigned char* big = factor_smem + (size_t)(blockDim.x / G) * RowSmem<G>::kBytes;
+    if (!SYNCFREE && P.big_cap > 0) {
+        if (threadIdx.x == 0) *reinterpret_cast<int*>(big + (size_t)28 * P.big_cap) = 0;
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int gshift = (lane / G) * G;
@@ -330,7 +383,7 @@ __global__ void __launch_bounds__(512) k_factor(FactorParams P) {
         for (int64_t s = s0 + gidx; s < s1; s += ng) {
             const int i = P.rows[s];
             if (i < 0) continue;
-            if (!factor_row<G, ICHOL, true, EXACT>(P, i, gl, gmask, gshift, R)) return;
+            if (!factor_row<G, ICHOL, true, EXACT>(P, i, gl, gmask, gshift, R, big)) return;
             __syncwarp(gmask);
             if (gl == 0) {
                 __threadfence();
@@ -341,7 +394,7 @@ __global__ void __launch_bounds__(512) k_factor(FactorParams P) {
         const int64_t s = (int64_t)P.lvl_begin + (int64_t)blockIdx.x * ng + gidx;
         if (s < P.lvl_end) {
             const int i = P.lvl_rows[s];
-            factor_row<G, ICHOL, false, EXACT>(P, i, gl, gmask, gshift, R);
+            factor_row<G, ICHOL, false, EXACT>(P, i, gl, gmask, gshift, R, big);
         }
     }
 }
@@ -354,6 +407,11 @@ __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int
                                                        unsigned* barrier) {
     extern __shared__ __align__(16) unsigned char factor_smem[];
     const RowSmem<G> R(factor_smem + (size_t)(threadIdx.x / G) * RowSmem<G>::kBytes);
+    unsigned char* big = factor_smem + (size_t)(blockDim.x / G) * RowSmem<G>::kBytes;
+    if (P.big_cap > 0) {
+        if (threadIdx.x == 0) *reinterpret_cast<int*>(big + (size_t)28 * P.big_cap) = 0;
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int gshift = (lane / G) * G;
@@ -366,7 +424,7 @@ __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int
         const int b = __ldg(lvl_ptr + l), e = __ldg(lvl_ptr + l + 1);
         for (int64_t s = b + g; s < e; s += gstride) {
             const int i = P.lvl_rows[s];
-            factor_row<G, ICHOL, false, EXACT>(P, i, gl, gmask, gshift, R);
+            factor_row<G, ICHOL, false, EXACT>(P, i, gl, gmask, gshift, R, big);
         }
         if (l + 1 == nlevels) break;
         // grid barrier: the rows of level l are visible (lu is read through L2) before anyone starts level l + 1
@@ -397,7 +455,7 @@ void launch_levels_g(bool exact, cudaStream_t s, FactorParams P, const int* lvl_
     void* kern = exact ? (void*)k_factor_levels<G, ICHOL, true> : (void*)k_factor_levels<G, ICHOL, false>;
     // few, fat CTAs: the barrier costs one atomic and one polling thread per CTA
     const int block = 512;
-    const size_t smem = (size_t)(block / G) * RowSmem<G>::kBytes;
+    const size_t smem = (size_t)(block / G) * RowSmem<G>::kBytes + (P.big_cap > 0 ? (size_t)28 * P.big_cap + 16 : 0);
     ILUB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
@@ -420,14 +478,19 @@ void launch_levels(int G, bool exact, cudaStream_t s, const FactorParams& P, con
 
 template <int G, bool ICHOL, bool SYNCFREE>
 void launch_g(bool exact, int grid, int block, cudaStream_t s, const FactorParams& P) {
-    const size_t smem = (size_t)(block / G) * RowSmem<G>::kBytes;  // 112 bytes per thread
-    if (exact) {
-        if (smem > 48 * 1024) ILUB_CUDA(cudaFuncSetAttribute(k_factor<G, ICHOL, SYNCFREE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_factor<G, ICHOL, SYNCFREE, true><<<grid, block, smem, s>>>(P);
-    } else {
-        if (smem > 48 * 1024) ILUB_CUDA(cudaFuncSetAttribute(k_factor<G, ICHOL, SYNCFREE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_factor<G, ICHOL, SYNCFREE, false><<<grid, block, smem, s>>>(P);
+    const size_t smem = (size_t)(block / G) * RowSmem<G>::kBytes  // 112 bytes per thread
+                        + (!SYNCFREE && P.big_cap > 0 ? (size_t)28 * P.big_cap + 16 : 0);
+    static thread_local unsigned attr_set[2] = {0, 0};  // (per template instantiation)
+    if (smem > 48 * 1024 && first_use_on_this_device(attr_set, exact ? 1 : 0)) {
+        if (exact)
+            ILUB_CUDA(cudaFuncSetAttribute(k_factor<G, ICHOL, SYNCFREE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        else
+            ILUB_CUDA(cudaFuncSetAttribute(k_factor<G, ICHOL, SYNCFREE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
+    if (exact)
+        k_factor<G, ICHOL, SYNCFREE, true><<<grid, block, smem, s>>>(P);
+    else
+        k_factor<G, ICHOL, SYNCFREE, false><<<grid, block, smem, s>>>(P);
 }
 
 template <bool ICHOL, bool SYNCFREE>
@@ -442,6 +505,13 @@ void launch(int G, bool exact, int grid, int block, cudaStream_t s, const Factor
 
 }  // namespace
 
+__global__ void k_max_row_len(int n, const int* __restrict__ ptr, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = i < n ? ptr[i + 1] - ptr[i] : 0;
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
 int factor_schedule(const ilub_handle* h) {
     const TriSolve& T = h->solve[0];
     const int algo = (int)options().factor_algo;
@@ -450,14 +520,26 @@ int factor_schedule(const ilub_handle* h) {
     if (algo == 4) return 3;
     if (algo != 0) return algo;
     if (T.nlevels <= 4096 && (int64_t)h->n >= (int64_t)T.nlevels * 256) return 3;  // few wide levels: level loop
-    if ((int64_t)T.nlevels * 64 > (int64_t)h->n) return 1;  // deep narrow DAG: row latency rules; one launch per level
-                                                             // measured fastest (config 4: 5.5 s vs 9.3 s sync-free)
+    if ((int64_t)T.nlevels * 64 > (int64_t)h->n) return 3;  // deep narrow DAG: row latency rules; the level loop and one
+                                                             // launch per level measure alike (config 4: 2.9 / 3.2 s),
+                                                             // sync-free is 3x slower there
     return 2;
 }
 
 // symbolic work the chosen schedule needs on top of the level numbers: the (level, row) listing, or the chunked
 // (part, level, row) order that the sync-free kernel walks
 void factor_prepare(ilub_handle* h, cudaStream_t s) {
+    if (h->max_row_len < 0) {
+        DevBuf<int> m;
+        m.alloc(1);
+        ILUB_CUDA(cudaMemsetAsync(m.p, 0, sizeof(int), s));
+        k_max_row_len<<<(h->n + 255) / 256, 256, 0, s>>>(h->n, h->ptr.p, m.p);
+        int v = 0;
+        ILUB_CUDA(cudaMemcpyAsync(&v, m.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        ILUB_CUDA(cudaStreamSynchronize(s));
+        h->max_row_len = v;
+        h->launches++;
+    }
     if ((options().factor_algo == 0 || options().factor_algo == 4) && options().exact == 0) stencil_factor_possible(h, s);
     if (factor_schedule(h) == 4) return;
     if (factor_schedule(h) == 2)
@@ -484,11 +566,13 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
     // a row of the sync-free schedule may wait for its whole upstream chain: the factorisation watchdog allows 40x the
     // solve limit (one minute by default)
     P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz * 40;
+    P.big_cap = 0;  // (set below, once the lanes per row are known)
     int G = (int)opt.factor_group;
     if (G != 4 && G != 8 && G != 16 && G != 32) {
         const double avg = (double)h->nnz / (double)h->n;
         G = avg <= 10 ? 8 : (avg <= 24 ? 16 : 32);
     }
+    P.big_cap = h->max_row_len > 4 * G ? std::min(4096, (h->max_row_len + 63) / 64 * 64) : 0;
     const bool exact = opt.exact != 0;
     // schedule: 1 = one launch per level, 2 = sync-free, 3 = level loop (one cooperative launch), 0 = level loop when
     // the levels are few and wide (stencils, block-diagonal batches), sync-free otherwise
