@@ -471,6 +471,9 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "sys_pz") o.sys_pz = value;
         else if (k == "sys_stages") o.sys_stages = value;
         else if (k == "sys_cluster") o.sys_cluster = value;
+        else if (k == "sys_plane") o.sys_plane = value;
+        else if (k == "plane_r") o.plane_r = value;
+        else if (k == "plane_wpc") o.plane_wpc = value;
         else if (k == "sys_pdl") o.sys_pdl = value;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
     });
@@ -498,6 +501,9 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "sys_pz") *value = o.sys_pz;
         else if (k == "sys_stages") *value = o.sys_stages;
         else if (k == "sys_cluster") *value = o.sys_cluster;
+        else if (k == "sys_plane") *value = o.sys_plane;
+        else if (k == "plane_r") *value = o.plane_r;
+        else if (k == "plane_wpc") *value = o.plane_wpc;
         else if (k == "sys_pdl") *value = o.sys_pdl;
         else if (k == "fetch_warps") *value = o.fetch_warps;
         else if (k == "halo_entries") *value = o.halo_entries;

@@ -128,6 +128,9 @@ struct Options {
     int64_t sys_stages = 0;     // line-systolic: coefficient stages per warp (0 = auto)
     int64_t sys_pdl = 1;        // line-systolic: programmatic dependent launch (prologue of the next solve overlaps this one)
     int64_t sys_cluster = 0;    // line-systolic: largest thread-block cluster to try (0 = auto: 8, 1 = no clusters)
+    int64_t sys_plane = 1;      // plane-per-warp kernel for grids without a plane-to-plane dependency: 0 off, 1 auto, 2 whenever applicable
+    int64_t plane_r = 1;        // plane-per-warp: right-hand sides per warp (1 or 2)
+    int64_t plane_wpc = 0;      // plane-per-warp: consumer warps per CTA (0 = as many as shared memory holds, at most 8)
 };
 Options& options();
 
@@ -145,6 +148,8 @@ constexpr unsigned kHaloBit = 0x40000000u;
 
 // Line-systolic layout of one triangular solve (ilub_systolic.cu): chosen at analysis when every dependency of
 // the solve sits at grid offset 1, nx or nx*ny of a lexicographically numbered nx x ny x nplanes grid.
+constexpr int kSysStageSteps = 8;                            // steps per coefficient stage (8 KB per task)
+constexpr long long kSysAbsentBits = 0x7ff8dead00000001ll;  // absent stencil entry (exact mode): a quiet NaN arithmetic never produces
 struct SysSolve {
     bool built = false;
     bool tried = false;
@@ -353,6 +358,8 @@ void factor_numeric(ilub_handle* h, cudaStream_t s);
 bool analyse_systolic(ilub_handle* h, int which, cudaStream_t s);         // false: structure not eligible
 void pack_systolic(ilub_handle* h, int which, cudaStream_t s);
 void run_systolic(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);
+// ---- plane-per-warp variant for 2-D grids / batches and many right-hand sides (ilub_plane.cu); false: not applicable
+bool run_plane(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);
 
 // ---- triangular solves (ilub_trsv.cu)
 void run_solve(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);

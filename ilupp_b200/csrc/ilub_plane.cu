@@ -1,0 +1,387 @@
+// Plane-per-warp triangular solves for 2-D grids and block-diagonal batches of them (BASELINE config 5: 4096
+// independent 2-D Poisson systems x 16 right-hand sides; config 1: one 256 x 256 grid) -- the multi-right-hand-side
+// path behind apply() / `B @ X` (replaces the column loop over matrix_sparse::triangular_solve,
+// sparse_implementation.h:4040-4087, ilupp/__init__.py:122-150 `_matmat`).
+//
+// Same (task, step, lane) coefficient stream as the line-systolic kernel (ilub_systolic.cu): one lane per grid line,
+// lanes skewed by one step, the offset-1 chain in a register, the offset-nx dependency one shuffle.  What differs is
+// how the work is spread.  Planes of a 2-D problem are independent, so there is nothing to hand over between warps:
+//   * ONE warp owns a whole plane for one right-hand side.  Its line blocks (32 lines each) run in the same warp as
+//     independent instruction streams, line block jb delayed by 32 steps, so the value lane 0 of block jb needs from
+//     lane 31 of block jb - 1 is what that lane produced one warp step earlier: the shuffle simply wraps around.
+//     No rings, no polling, no flags -- and NB-fold instruction-level parallelism in a warp that used to issue one
+//     dependent chain.
+//   * The consumer warps of a CTA solve the SAME plane for different right-hand sides and share one copy of the
+//     coefficient stages (1-D bulk copies issued by a producer warp, full/empty mbarrier pipeline): the factor is
+//     read from HBM once per CTA instead of once per right-hand side; CTAs of the same plane are adjacent in the
+//     grid, so the remaining re-reads are L2 hits.
+//   * Right-hand side in / solution out: every warp moves its own data with 8-byte cp.async copies in skewed
+//     4-line x 8-column rectangles (line group q is shifted by -4q columns, so a rectangle is consumed within 11
+//     steps of its arrival): the window is 32 slots per line instead of 64, 8.25 KB per (line block, rhs).
+// Arithmetic and rounding are those of the line-systolic kernel (`exact` = the reference's operation order, bit for
+// bit; otherwise coefficients pre-divided by the diagonal and FMAs).
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+
+#include "ilub_common.cuh"
+#include "ilub_ptx.cuh"
+
+namespace ilub {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kSteps = kSysStageSteps;            // steps per coefficient stage
+constexpr int kStageLB = kSteps * 4 * 32 * 8;     // bytes of one stage of one line block (8 KB)
+constexpr int kWin = 32;                          // window slots per line
+constexpr int kWinStride = kWin + 1;              // odd stride: a warp's column accesses are conflict-free
+constexpr int kWinBytes = 32 * kWinStride * 8;    // one (line block, rhs) window
+constexpr int kSkew = 4;                          // warp blocks between the starts of consecutive line blocks (32 steps)
+constexpr int kMaxConsumers = 8;
+
+struct PlaneParams {
+    const double* coef;
+    double* x;
+    long long ldx;
+    long long n;
+    int nrhs;
+    int nx, ny, nyb, nplanes, nsteps_pad;
+    int backward, order_xyz, unit_diag;
+    int wpc;     // consumer warps per CTA
+    int nst;     // coefficient stages
+    int groups;  // CTAs per plane (groups of wpc * R right-hand sides)
+    int* status;
+    unsigned spin_iters;
+};
+
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds_2f64(uint32_t a, double& v0, double& v1) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a));
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+// 8-byte asynchronous copy global -> shared; src_bytes = 0 writes zeros (padding rows and columns)
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, unsigned src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void give_up(int* status, int code) { atomicCAS(status, 0, code); }
+
+#define PLANE_SPIN(spins, code)                                        \
+    if ((++(spins) & 0xfffu) == 0) {                                   \
+        if ((spins) >= P.spin_iters || *(volatile int*)P.status != 0) { \
+            give_up(P.status, code);                                   \
+            return;                                                    \
+        }                                                              \
+    }
+
+template <bool EXACT, int NB, int R>
+__global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(const __grid_constant__ PlaneParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x % P.groups, p = blockIdx.x / P.groups;
+    const int rhs_cta = g * P.wpc * R;
+    const int nactive = min(P.wpc, (P.nrhs - rhs_cta + R - 1) / R);  // consumer warps with at least one right-hand side
+    // shared memory: [nst][NB] coefficient stages | [wpc][NB][R] windows | full[nst], empty[nst]
+    unsigned char* const win0 = smem + (size_t)P.nst * NB * kStageLB;
+    uint64_t* const full = reinterpret_cast<uint64_t*>(win0 + (size_t)P.wpc * NB * R * kWinBytes);
+    uint64_t* const empty = full + P.nst;
+    if ((int)threadIdx.x < P.nst) {
+        mbar_init(&full[threadIdx.x], 1);
+        mbar_init(&empty[threadIdx.x], (unsigned)nactive);
+    }
+    fence_mbar_init();
+    __syncthreads();
+
+    const int nyb = P.nyb, nst = P.nst;
+    const int nbl = P.nsteps_pad / kSteps;  // coefficient blocks of a line block
+    const int KL = nbl + 2;                 // ... plus the blocks that only drain
+    const int K = kSkew * (nyb - 1) + KL;
+    unsigned spins = 0;
+
+    if (warp == P.wpc) {
+        // ------------------------------------------------------------ producer: coefficient stages for everyone
+        if (lane != 0) return;
+        int use = 0;
+        for (int k = 0; k < K; ++k) {
+            int cnt = 0;
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
+                const int kl = k - kSkew * jb;
+                if (jb < nyb && kl >= 0 && kl < nbl) ++cnt;
+            }
+            if (cnt == 0) continue;
+            const int slot = use % nst;
+            if (use >= nst) {
+                const unsigned parity = (unsigned)(use / nst - 1) & 1u;
+                while (!mbar_try_wait(&empty[slot], parity)) PLANE_SPIN(spins, 221)
+            }
+            mbar_arrive_expect_tx(&full[slot], (unsigned)(cnt * kStageLB));
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
+                const int kl = k - kSkew * jb;
+                if (jb < nyb && kl >= 0 && kl < nbl)
+                    bulk_g2s(smem + (size_t)(slot * NB + jb) * kStageLB,
+                             P.coef + ((size_t)(p * nyb + jb) * P.nsteps_pad + (size_t)kl * kSteps) * 128, (unsigned)kStageLB, &full[slot]);
+            }
+            ++use;
+        }
+        return;
+    }
+    if (warp >= nactive) return;
+
+    // ---------------------------------------------------------------- consumer: plane p, right-hand sides rhs0 ...
+    const int rhs0 = rhs_cta + warp * R;
+    const int nr = min(R, P.nrhs - rhs0);
+    const int nx = P.nx, ny = P.ny;
+    const uint32_t win_s = smem_u32(win0 + (size_t)warp * NB * R * kWinBytes);
+    const uint32_t win_lane = win_s + lane * (kWinStride * 8);
+    const uint32_t stage_lane = smem_u32(smem) + lane * 16;
+    // rectangle roles: lane = (line rl of a 4-line group, column rc of 8)
+    const int rl = lane >> 3, rc = lane & 7;
+    const long long dir = P.backward ? -1 : 1;
+    const long long e0 = ((long long)p * ny + rl) * nx + rc;  // element (line rl, column rc) of this plane, solve numbering
+    double* const g0 = P.x + (P.backward ? P.n - 1 - e0 : e0) + (long long)rhs0 * P.ldx;
+    const long long qstride = dir * (4 * (long long)nx - 4);  // next line group: 4 lines down, 4 columns back
+    const uint32_t rect_s = win_s + rl * (kWinStride * 8);
+
+    // element (line block jb, group q, rectangle m): line 32 jb + 4 q + rl, column 8 m - 4 q + rc, consumed at local
+    // step 8 m + rc + rl (any q) -> window slot (8 m + rc + rl) & 31 of its line
+    auto rect_issue = [&](int jb, int r, int m) {
+        double* const b = g0 + dir * ((long long)jb * 32 * nx + 8 * m) + (long long)r * P.ldx;
+        const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * m + rc + rl) & (kWin - 1)) << 3);
+        const bool interior = 8 * m - 28 >= 0 && 8 * m + 8 <= nx && 32 * jb + 32 <= ny;
+        if (interior) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cp_async8(d + q * (4 * kWinStride * 8), b + q * qstride, 8u);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = 8 * m - 4 * q + rc;
+                const bool ok = col >= 0 && col < nx && 32 * jb + 4 * q + rl < ny;
+                cp_async8(d + q * (4 * kWinStride * 8), ok ? (const void*)(b + q * qstride) : (const void*)P.x, ok ? 8u : 0u);
+            }
+        }
+    };
+    auto rect_drain = [&](int jb, int r, int m) {
+        double* const b = g0 + dir * ((long long)jb * 32 * nx + 8 * m) + (long long)r * P.ldx;
+        const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * m + rc + rl) & (kWin - 1)) << 3);
+        const bool interior = 8 * m - 28 >= 0 && 8 * m + 8 <= nx && 32 * jb + 32 <= ny;
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = lds_f64(d + q * (4 * kWinStride * 8));
+        if (interior) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) __stcs(b + q * qstride, v[q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = 8 * m - 4 * q + rc;
+                if (col >= 0 && col < nx && 32 * jb + 4 * q + rl < ny) __stcs(b + q * qstride, v[q]);
+            }
+        }
+    };
+
+    // slots of local steps 0..2 hold columns < 0 for lines 4q + 1..3 that no rectangle covers: zero them (a stale NaN
+    // would travel down the line through the zero coefficients of the fast arithmetic)
+#pragma unroll
+    for (int c = 0; c < NB * R; ++c)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) sts_f64(win_lane + c * kWinBytes + t * 8, 0.0);
+    __syncwarp();
+
+    double xprev[NB][R];
+#pragma unroll
+    for (int jb = 0; jb < NB; ++jb)
+#pragma unroll
+        for (int r = 0; r < R; ++r) xprev[jb][r] = 0.0;
+    const int order_xyz = P.order_xyz, unit_diag = P.unit_diag;
+    const int src_lane = (lane + 31) & 31;
+    int use = 0;
+
+    for (int k = -2; k < K; ++k) {
+        __syncwarp();  // the previous block's solution values are in the window
+        // ---- solution out: rectangles consumed two blocks ago
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            const int m = k - kSkew * jb - 2;
+            if (jb < nyb && m >= 0 && m < nbl) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r < nr) rect_drain(jb, r, m);
+            }
+        }
+        __syncwarp();  // ... before their slots are handed to the copies below
+        // ---- right-hand side in: rectangles needed two blocks from now (they reuse the slots just drained)
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            const int m = k - kSkew * jb + 2;
+            if (jb < nyb && m >= 0 && m < nbl) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r < nr) rect_issue(jb, r, m);
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<2>();  // the group committed two iterations ago (this block's rectangles) has landed
+        __syncwarp();
+        if (k < 0) continue;
+
+        bool act[NB];
+        bool any = false;
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            const int kl = k - kSkew * jb;
+            act[jb] = jb < nyb && kl >= 0 && kl < nbl;
+            any = any || act[jb];
+        }
+        if (!any) continue;
+        const int slot = use % nst;
+        const unsigned phase = (unsigned)(use / nst) & 1u;
+        while (!mbar_try_wait(&full[slot], phase)) PLANE_SPIN(spins, 222)
+        const uint32_t st = stage_lane + (uint32_t)(slot * NB) * kStageLB;
+#pragma unroll
+        for (int u = 0; u < kSteps; ++u) {
+            // what the neighbouring line produced one step ago; lane 0 takes lane 31 of the previous line block
+            double rot[NB][R];
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb)
+#pragma unroll
+                for (int r = 0; r < R; ++r) rot[jb][r] = __shfl_sync(FULL, xprev[jb][r], src_lane);
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
+                if (!act[jb]) continue;
+                const int kl = k - kSkew * jb;
+                double cz_, cy_, cx_, dv;
+                lds_2f64(st + jb * kStageLB + u * 1024, cz_, cy_);
+                lds_2f64(st + jb * kStageLB + u * 1024 + 512, cx_, dv);
+                (void)cz_;
+                const uint32_t wslot = (uint32_t)((((kl & 3) << 3) + u) << 3);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (r >= nr) continue;
+                    const uint32_t wa = win_lane + (jb * R + r) * kWinBytes + wslot;
+                    const double bb = lds_f64(wa);
+                    double xy = rot[jb][r];
+                    if (lane == 0) xy = jb > 0 ? rot[jb > 0 ? jb - 1 : 0][r] : 0.0;
+                    double xnew;
+                    if (EXACT) {
+                        const bool ay = __double_as_longlong(cy_) == kSysAbsentBits;
+                        const bool ax = __double_as_longlong(cx_) == kSysAbsentBits;
+                        double acc = bb;
+                        if (order_xyz) {
+                            if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_, xprev[jb][r]));
+                            if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_, xy));
+                        } else {
+                            if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_, xy));
+                            if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_, xprev[jb][r]));
+                        }
+                        xnew = unit_diag ? acc : __ddiv_rn(acc, dv);
+                    } else {
+                        double acc = bb * dv;
+                        acc = fma(-cx_, xprev[jb][r], acc);
+                        xnew = fma(-cy_, xy, acc);
+                    }
+                    sts_f64(wa, xnew);
+                    xprev[jb][r] = xnew;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        ++use;
+    }
+    cp_async_wait<0>();
+}
+
+typedef void (*plane_kern_t)(const PlaneParams);
+
+template <bool EXACT, int R>
+plane_kern_t plane_kernel_nb(int nb) {
+    switch (nb) {
+        case 1: return (plane_kern_t)k_trsv_plane<EXACT, 1, R>;
+        case 2: return (plane_kern_t)k_trsv_plane<EXACT, 2, R>;
+        case 4: return (plane_kern_t)k_trsv_plane<EXACT, 4, R>;
+        default: return (plane_kern_t)k_trsv_plane<EXACT, 8, R>;
+    }
+}
+int nb_index(int nb) { return nb == 1 ? 0 : nb == 2 ? 1 : nb == 4 ? 2 : 3; }
+
+plane_kern_t plane_kernel(bool exact, int nb, int r) {
+    const plane_kern_t k = exact ? (r == 2 ? plane_kernel_nb<true, 2>(nb) : plane_kernel_nb<true, 1>(nb))
+                                 : (r == 2 ? plane_kernel_nb<false, 2>(nb) : plane_kernel_nb<false, 1>(nb));
+    static thread_local unsigned attr_set[16] = {0};
+    const int ki = (exact ? 8 : 0) + (r == 2 ? 4 : 0) + nb_index(nb);
+    if (first_use_on_this_device(attr_set, ki))
+        ILUB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return k;
+}
+
+}  // namespace
+
+// Plane-per-warp variant of run_systolic for grids without a plane-to-plane dependency; false: not applicable
+// (3-D coupling, more than 8 line blocks per plane, or switched off), the caller keeps the line-systolic kernel.
+bool run_plane(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    SysSolve& Y = T.sys;
+    const Options& opt = options();
+    if (!Y.built || Y.zcoupled || Y.nyb > 8 || opt.sys_plane == 0 || opt.trace) return false;
+    // one plane on one warp only pays when there are planes (or right-hand sides) to fill the machine, or when the
+    // plane is so small that the line-systolic kernel is all hand-offs
+    if (opt.sys_plane == 1 && (int64_t)Y.nplanes * nrhs < 2 && Y.nyb > 4) return false;
+    const bool exact = opt.exact != 0;
+    if (Y.packed_exact != (exact ? 1 : 0)) pack_systolic(h, slot, s);
+    const int nb = Y.nyb <= 1 ? 1 : Y.nyb <= 2 ? 2 : Y.nyb <= 4 ? 4 : 8;
+    int r = opt.plane_r == 2 ? 2 : 1;
+    const int nst = 2;
+    const size_t budget = (size_t)227 * 1024 - 256;
+    const size_t coef_bytes = (size_t)nst * nb * kStageLB;
+    if (coef_bytes + (size_t)nb * r * kWinBytes + 64 > budget) r = 1;
+    if (coef_bytes + (size_t)nb * r * kWinBytes + 64 > budget) return false;
+    int wpc = (int)std::min<size_t>(kMaxConsumers, (budget - coef_bytes - 64) / ((size_t)nb * r * kWinBytes));
+    if (opt.plane_wpc > 0) wpc = std::min<int>(wpc, (int)opt.plane_wpc);
+    wpc = std::max(1, std::min(wpc, (nrhs + r - 1) / r));
+    PlaneParams P;
+    P.coef = Y.coef.p;
+    P.x = x;
+    P.ldx = ldx;
+    P.n = h->n;
+    P.nrhs = nrhs;
+    P.nx = Y.nx;
+    P.ny = Y.ny;
+    P.nyb = Y.nyb;
+    P.nplanes = Y.nplanes;
+    P.nsteps_pad = Y.nsteps_pad;
+    P.backward = T.backward ? 1 : 0;
+    P.order_xyz = Y.order_xyz;
+    P.unit_diag = T.unit_diag ? 1 : 0;
+    P.wpc = wpc;
+    P.nst = nst;
+    P.groups = (nrhs + wpc * r - 1) / (wpc * r);
+    P.status = h->status.p;
+    P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 16, (long long)opt.spin_limit_ms * h->clock_khz / 64));
+    const size_t smem = coef_bytes + (size_t)wpc * nb * r * kWinBytes + 2 * nst * sizeof(uint64_t) + 16;
+    const plane_kern_t kern = plane_kernel(exact, nb, r);
+    const int64_t ctas = (int64_t)Y.nplanes * P.groups;
+    ILUB_REQUIRE(ctas < ((int64_t)1 << 31), ILUB_ERR_SIZE, "plane solve: too many CTAs");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas, 1, 1);
+    cfg.blockDim = dim3((wpc + 1) * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    ILUB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
+    h->launches++;
+    ILUB_CUDA(cudaGetLastError());
+    return true;
+}
+
+}  // namespace ilub

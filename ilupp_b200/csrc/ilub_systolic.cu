@@ -36,8 +36,8 @@ namespace ilub {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr long long kAbsentBits = 0x7ff8dead00000001ll;  // quiet NaN with a payload arithmetic never produces
-constexpr int kStageSteps = 8;                            // steps per coefficient stage (8 KB)
+constexpr long long kAbsentBits = kSysAbsentBits;        // quiet NaN with a payload arithmetic never produces
+constexpr int kStageSteps = kSysStageSteps;               // steps per coefficient stage (8 KB)
 constexpr int kStageBytes = kStageSteps * 4 * 32 * 8;
 constexpr int kMaxWarps = 6;                              // compute warps per CTA (each has a helper warp)
 constexpr int kMaxYChan = 8;
@@ -1039,6 +1039,7 @@ static void launch_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, in
 }
 
 void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
+    if (run_plane(h, slot, x, ldx, nrhs, s)) return;
     launch_systolic(h, slot, x, ldx, nrhs, s, nullptr);
 }
 

@@ -530,3 +530,106 @@ def test_baseline_config5_batched(ilupp):
         Lo, Uo = oracle.port.ilu0(As)
         for c in (0, 15):
             assert relerr(Y[s * n1:(s + 1) * n1, c], oracle.port.apply_lu(Lo, Uo, X[s * n1:(s + 1) * n1, c])) <= TOL
+
+
+# ---- plane-per-warp solve (ilub_plane.cu): 2-D grids / batches, many right-hand sides ------------------------
+def _grid2d(nx, ny, seed):
+    """nonsymmetric 5-point stencil on an nx x ny grid (x fastest), random coefficients, diagonally dominant"""
+    rng = np.random.default_rng(seed)
+    n = nx * ny
+    i = np.arange(n)
+    rows, cols = [], []
+    for off, ok in ((-1, i % nx > 0), (1, i % nx < nx - 1), (-nx, i >= nx), (nx, i < n - nx)):
+        rows.append(i[ok])
+        cols.append(i[ok] + off)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    A = scipy.sparse.csr_matrix((-rng.uniform(0.5, 1.5, rows.size), (rows, cols)), shape=(n, n))
+    A = (A + scipy.sparse.diags(1.0 + np.asarray(abs(A).sum(axis=1)).ravel())).tocsr()
+    A.sort_indices()
+    A.indices = A.indices.astype(np.int32)
+    A.indptr = A.indptr.astype(np.int32)
+    return A
+
+
+PLANE_GRIDS = [("1-block", 20, 20), ("2-blocks-ragged", 37, 50), ("4-blocks-ragged", 70, 100), ("4-blocks", 128, 128),
+               ("8-blocks", 256, 256), ("wide", 300, 9)]
+
+
+@pytest.mark.parametrize("name,nx,ny", PLANE_GRIDS, ids=[g[0] for g in PLANE_GRIDS])
+@pytest.mark.parametrize("exact", [1, 0])
+def test_plane_solve_matches_line_systolic_and_oracle(ilupp, name, nx, ny, exact):
+    """the plane-per-warp kernel runs the same recurrence in the same order as the line-systolic kernel: results are
+    bit-for-bit equal in both arithmetic modes, for every solve form, any number of right-hand sides per warp / CTA"""
+    A = _grid2d(nx, ny, 3)
+    n = A.shape[0]
+    X = np.asfortranarray(P.rhs(n, 5, k=5))
+    keys = ("exact", "sys_plane", "plane_r", "plane_wpc")
+    defaults = {k: ilupp.get_option(k) for k in keys}
+    try:
+        ilupp.set_option("exact", exact)
+        B = ilupp.ILU0Preconditioner(A)
+        assert B.stats["part_mode"] == 4                              # line-systolic layout
+        Lo, Uo = oracle.port.ilu0(A)
+        ilupp.set_option("sys_plane", 0)
+        ref = [B._matmat(X), B._rmatmat(X)]
+        launches0 = B.stats["launches"]
+        for r, wpc in ((1, 0), (2, 0), (1, 2), (2, 1)):
+            ilupp.set_option("sys_plane", 2)
+            ilupp.set_option("plane_r", r)
+            ilupp.set_option("plane_wpc", wpc)
+            got = [B._matmat(X), B._rmatmat(X)]
+            for tr in (0, 1):
+                assert np.array_equal(got[tr], ref[tr]), (r, wpc, tr)
+            y = X[:, 0].copy()
+            B.apply(y)                                                # single right-hand side through apply()
+            assert np.array_equal(y, ref[0][:, 0])
+        assert B.stats["launches"] - launches0 == 4 * 6               # one launch per triangular solve, all columns
+        for tr in (False, True):
+            for c in (0, 4):
+                yo = oracle.port.apply_lu(Lo, Uo, np.ascontiguousarray(X[:, c]), tr)
+                assert relerr(ref[int(tr)][:, c], yo) <= TOL
+                if exact:
+                    assert np.array_equal(ref[int(tr)][:, c], yo)
+    finally:
+        for k, v in defaults.items():
+            ilupp.set_option(k, v)
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+@pytest.mark.parametrize("kind", ["ilu0", "ichol0"])
+def test_plane_solve_batched(ilupp, kind, exact):
+    nsys, N, k = 7, 40, 19
+    pat, vals = P.batched_poisson2d(nsys, N)
+    n1 = pat.shape[0]
+    keys = ("exact", "sys_plane", "plane_r")
+    defaults = {k_: ilupp.get_option(k_) for k_ in keys}
+    try:
+        ilupp.set_option("exact", exact)
+        Bb = (ilupp.ILU0PreconditionerBatched if kind == "ilu0" else ilupp.IChol0PreconditionerBatched)(pat, vals)
+        X = np.asfortranarray(P.rhs(nsys * n1, 11, k=k))
+        ilupp.set_option("sys_plane", 0)
+        ref = [Bb._matmat(X), Bb._rmatmat(X)]
+        for r in (1, 2):
+            ilupp.set_option("sys_plane", 1)                          # auto: batches take the plane kernel
+            ilupp.set_option("plane_r", r)
+            l0 = Bb.stats["launches"]
+            got = [Bb._matmat(X), Bb._rmatmat(X)]
+            assert Bb.stats["launches"] - l0 == 4
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+        for s in (0, 3, nsys - 1):
+            As = pat.copy()
+            As.data = vals[s].copy()
+            sl = slice(s * n1, (s + 1) * n1)
+            for c in (0, k - 1):
+                b = np.ascontiguousarray(X[sl, c])
+                if kind == "ilu0":
+                    Lo, Uo = oracle.port.ilu0(As)
+                    yo = oracle.port.apply_lu(Lo, Uo, b)
+                else:
+                    yo = oracle.port.apply_llt(oracle.port.ichol0(As), b)
+                assert relerr(ref[0][sl, c], yo) <= TOL
+                if exact:
+                    assert np.array_equal(ref[0][sl, c], yo)
+    finally:
+        for k_, v in defaults.items():
+            ilupp.set_option(k_, v)
