@@ -68,6 +68,16 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, unsigned src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async8_if(uint32_t dst, const void* src, unsigned pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}" ::"r"(dst), "l"(src), "r"(pred)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_cs_if(double* dst, double v, unsigned pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.cs.f64 [%0], %1;\n\t}" ::"l"(dst), "d"(v), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void sts_f64_if(uint32_t a, double v, unsigned pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(a), "d"(v), "r"(pred) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -110,7 +120,8 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
     if (warp == P.wpc) {
         // ------------------------------------------------------------ producer: coefficient stages for everyone
         if (lane != 0) return;
-        int use = 0;
+        int use = 0, slot = 0;
+        unsigned parity = 1;  // phase parity of the PREVIOUS use of the slot
         for (int k = 0; k < K; ++k) {
             int cnt = 0;
 #pragma unroll
@@ -119,10 +130,11 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
                 if (jb < nyb && kl >= 0 && kl < nbl) ++cnt;
             }
             if (cnt == 0) continue;
-            const int slot = use % nst;
             if (use >= nst) {
-                const unsigned parity = (unsigned)(use / nst - 1) & 1u;
-                while (!mbar_try_wait(&empty[slot], parity)) PLANE_SPIN(spins, 221)
+                while (!mbar_try_wait(&empty[slot], parity)) {
+                    __nanosleep(40);
+                    PLANE_SPIN(spins, 221)
+                }
             }
             mbar_arrive_expect_tx(&full[slot], (unsigned)(cnt * kStageLB));
 #pragma unroll
@@ -133,6 +145,10 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
                              P.coef + ((size_t)(p * nyb + jb) * P.nsteps_pad + (size_t)kl * kSteps) * 128, (unsigned)kStageLB, &full[slot]);
             }
             ++use;
+            if (++slot == nst) {
+                slot = 0;
+                parity ^= 1u;
+            }
         }
         return;
     }
@@ -152,50 +168,43 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
     double* const g0 = P.x + (P.backward ? P.n - 1 - e0 : e0) + (long long)rhs0 * P.ldx;
     const long long qstride = dir * (4 * (long long)nx - 4);  // next line group: 4 lines down, 4 columns back
     const uint32_t rect_s = win_s + rl * (kWinStride * 8);
+    // line groups of the (ragged) last line block that exist for this lane
+    unsigned lm_last = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (32 * (nyb - 1) + 4 * q + rl < ny) lm_last |= 1u << q;
 
     // element (line block jb, group q, rectangle m): line 32 jb + 4 q + rl, column 8 m - 4 q + rc, consumed at local
-    // step 8 m + rc + rl (any q) -> window slot (8 m + rc + rl) & 31 of its line
-    auto rect_issue = [&](int jb, int r, int m) {
-        double* const b = g0 + dir * ((long long)jb * 32 * nx + 8 * m) + (long long)r * P.ldx;
-        const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * m + rc + rl) & (kWin - 1)) << 3);
-        const bool interior = 8 * m - 28 >= 0 && 8 * m + 8 <= nx && 32 * jb + 32 <= ny;
-        if (interior) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) cp_async8(d + q * (4 * kWinStride * 8), b + q * qstride, 8u);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int col = 8 * m - 4 * q + rc;
-                const bool ok = col >= 0 && col < nx && 32 * jb + 4 * q + rl < ny;
-                cp_async8(d + q * (4 * kWinStride * 8), ok ? (const void*)(b + q * qstride) : (const void*)P.x, ok ? 8u : 0u);
-            }
-        }
+    // step 8 m + rc + rl (any q) -> window slot (8 m + rc + rl) & 31 of its line.  Mask of the groups q whose element
+    // exists (0 <= column < nx, line < ny):
+    auto rect_mask = [&](int jb, int m) -> unsigned {
+        const int a = 8 * m + rc;  // column of group 0; group q sits 4 q columns to the left
+        const int qhi = a >> 2, qlo = (a - nx + 4) >> 2;
+        const unsigned hi = qhi >= 7 ? 0xffu : ((2u << qhi) - 1u);
+        const unsigned lo = qlo <= 0 ? 0xffu : (qlo >= 8 ? 0u : (0xffu << qlo) & 0xffu);
+        return hi & lo & (jb == nyb - 1 ? lm_last : 0xffu);
     };
-    auto rect_drain = [&](int jb, int r, int m) {
+    auto rect_issue = [&](int jb, int r, int m, unsigned mask) {
+        const double* const b = g0 + dir * ((long long)jb * 32 * nx + 8 * m) + (long long)r * P.ldx;
+        const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * m + rc + rl) & (kWin - 1)) << 3);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cp_async8_if(d + q * (4 * kWinStride * 8), b + q * qstride, mask & (1u << q));
+    };
+    auto rect_drain = [&](int jb, int r, int m, unsigned mask) {
         double* const b = g0 + dir * ((long long)jb * 32 * nx + 8 * m) + (long long)r * P.ldx;
         const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * m + rc + rl) & (kWin - 1)) << 3);
-        const bool interior = 8 * m - 28 >= 0 && 8 * m + 8 <= nx && 32 * jb + 32 <= ny;
         double v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = lds_f64(d + q * (4 * kWinStride * 8));
-        if (interior) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) __stcs(b + q * qstride, v[q]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int col = 8 * m - 4 * q + rc;
-                if (col >= 0 && col < nx && 32 * jb + 4 * q + rl < ny) __stcs(b + q * qstride, v[q]);
-            }
-        }
+        for (int q = 0; q < 8; ++q) stg_cs_if(b + q * qstride, v[q], mask & (1u << q));
     };
 
-    // slots of local steps 0..2 hold columns < 0 for lines 4q + 1..3 that no rectangle covers: zero them (a stale NaN
-    // would travel down the line through the zero coefficients of the fast arithmetic)
-#pragma unroll
-    for (int c = 0; c < NB * R; ++c)
-#pragma unroll
-        for (int t = 0; t < 3; ++t) sts_f64(win_lane + c * kWinBytes + t * 8, 0.0);
+    // windows start as zeros: elements that do not exist (columns < 0 at the head of a line, lines >= ny) are never
+    // copied in and must read as finite values -- a stale NaN would travel down the line through the zero coefficients
+    // of the fast arithmetic.  (Columns >= nx keep whatever the slot held: nothing that exists depends on them.)
+    for (int t = lane; t < NB * R * kWinBytes / 16; t += 32)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(win_s + t * 16), "d"(0.0) : "memory");
     __syncwarp();
 
     double xprev[NB][R];
@@ -205,7 +214,8 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
         for (int r = 0; r < R; ++r) xprev[jb][r] = 0.0;
     const int order_xyz = P.order_xyz, unit_diag = P.unit_diag;
     const int src_lane = (lane + 31) & 31;
-    int use = 0;
+    int slot = 0;
+    unsigned phase = 0;
 
     for (int k = -2; k < K; ++k) {
         __syncwarp();  // the previous block's solution values are in the window
@@ -214,9 +224,10 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
         for (int jb = 0; jb < NB; ++jb) {
             const int m = k - kSkew * jb - 2;
             if (jb < nyb && m >= 0 && m < nbl) {
+                const unsigned mask = rect_mask(jb, m);
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    if (r < nr) rect_drain(jb, r, m);
+                    if (R == 1 || r < nr) rect_drain(jb, r, m, mask);
             }
         }
         __syncwarp();  // ... before their slots are handed to the copies below
@@ -225,9 +236,10 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
         for (int jb = 0; jb < NB; ++jb) {
             const int m = k - kSkew * jb + 2;
             if (jb < nyb && m >= 0 && m < nbl) {
+                const unsigned mask = rect_mask(jb, m);
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    if (r < nr) rect_issue(jb, r, m);
+                    if (R == 1 || r < nr) rect_issue(jb, r, m, mask);
             }
         }
         cp_async_commit();
@@ -235,69 +247,80 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
         __syncwarp();
         if (k < 0) continue;
 
-        bool act[NB];
+        // a line block outside its own step range (not started yet / finished) runs along on whatever its addresses
+        // hold; its results are dropped (no store, xprev unchanged) -- the step body stays free of branches, so the
+        // chains of a step overlap
+        unsigned act[NB][R];
         bool any = false;
+        uint32_t wa[NB][R];
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
             const int kl = k - kSkew * jb;
-            act[jb] = jb < nyb && kl >= 0 && kl < nbl;
-            any = any || act[jb];
+            const bool a = jb < nyb && kl >= 0 && kl < nbl;
+            any = any || a;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                act[jb][r] = (a && (R == 1 || r < nr)) ? 1u : 0u;
+                wa[jb][r] = win_lane + (jb * R + r) * kWinBytes + (uint32_t)((kl & 3) << 6);
+            }
         }
         if (!any) continue;
-        const int slot = use % nst;
-        const unsigned phase = (unsigned)(use / nst) & 1u;
         while (!mbar_try_wait(&full[slot], phase)) PLANE_SPIN(spins, 222)
         const uint32_t st = stage_lane + (uint32_t)(slot * NB) * kStageLB;
 #pragma unroll
         for (int u = 0; u < kSteps; ++u) {
             // what the neighbouring line produced one step ago; lane 0 takes lane 31 of the previous line block
-            double rot[NB][R];
+            double rot[NB][R], cy_[NB], cx_[NB], dv[NB], bb[NB][R], xnew[NB][R];
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb)
 #pragma unroll
                 for (int r = 0; r < R; ++r) rot[jb][r] = __shfl_sync(FULL, xprev[jb][r], src_lane);
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb) {
-                if (!act[jb]) continue;
-                const int kl = k - kSkew * jb;
-                double cz_, cy_, cx_, dv;
-                lds_2f64(st + jb * kStageLB + u * 1024, cz_, cy_);
-                lds_2f64(st + jb * kStageLB + u * 1024 + 512, cx_, dv);
-                (void)cz_;
-                const uint32_t wslot = (uint32_t)((((kl & 3) << 3) + u) << 3);
+                cy_[jb] = lds_f64(st + jb * kStageLB + u * 1024 + 8);
+                lds_2f64(st + jb * kStageLB + u * 1024 + 512, cx_[jb], dv[jb]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) bb[jb][r] = lds_f64(wa[jb][r] + u * 8);
+            }
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (r >= nr) continue;
-                    const uint32_t wa = win_lane + (jb * R + r) * kWinBytes + wslot;
-                    const double bb = lds_f64(wa);
                     double xy = rot[jb][r];
                     if (lane == 0) xy = jb > 0 ? rot[jb > 0 ? jb - 1 : 0][r] : 0.0;
-                    double xnew;
                     if (EXACT) {
-                        const bool ay = __double_as_longlong(cy_) == kSysAbsentBits;
-                        const bool ax = __double_as_longlong(cx_) == kSysAbsentBits;
-                        double acc = bb;
+                        const bool ay = __double_as_longlong(cy_[jb]) == kSysAbsentBits;
+                        const bool ax = __double_as_longlong(cx_[jb]) == kSysAbsentBits;
+                        double acc = bb[jb][r];
                         if (order_xyz) {
-                            if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_, xprev[jb][r]));
-                            if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_, xy));
+                            if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_[jb], xprev[jb][r]));
+                            if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_[jb], xy));
                         } else {
-                            if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_, xy));
-                            if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_, xprev[jb][r]));
+                            if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_[jb], xy));
+                            if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_[jb], xprev[jb][r]));
                         }
-                        xnew = unit_diag ? acc : __ddiv_rn(acc, dv);
+                        xnew[jb][r] = unit_diag ? acc : __ddiv_rn(acc, dv[jb]);
                     } else {
-                        double acc = bb * dv;
-                        acc = fma(-cx_, xprev[jb][r], acc);
-                        xnew = fma(-cy_, xy, acc);
+                        double acc = bb[jb][r] * dv[jb];
+                        acc = fma(-cx_[jb], xprev[jb][r], acc);
+                        xnew[jb][r] = fma(-cy_[jb], xy, acc);
                     }
-                    sts_f64(wa, xnew);
-                    xprev[jb][r] = xnew;
                 }
             }
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    sts_f64_if(wa[jb][r] + u * 8, xnew[jb][r], act[jb][r]);
+                    xprev[jb][r] = act[jb][r] ? xnew[jb][r] : xprev[jb][r];
+                }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);
-        ++use;
+        if (++slot == nst) {
+            slot = 0;
+            phase ^= 1u;
+        }
     }
     cp_async_wait<0>();
 }
