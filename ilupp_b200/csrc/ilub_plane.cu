@@ -51,6 +51,7 @@ struct PlaneParams {
     int wpc;     // consumer warps per CTA
     int nst;     // coefficient stages
     int groups;  // CTAs per plane (groups of wpc * R right-hand sides)
+    int npc;     // consecutive planes per CTA
     int* status;
     unsigned spin_iters;
 };
@@ -93,11 +94,26 @@ __device__ __forceinline__ void give_up(int* status, int code) { atomicCAS(statu
         }                                                              \
     }
 
+// position of a line block in the sequence of (plane, 8-step block) pairs a CTA walks through: g counts blocks from
+// the line block's own start (negative: not started), (pl, m) = (plane of this CTA, block inside the plane)
+struct BlockPos {
+    int g, pl, m;
+    __device__ __forceinline__ void init(int g0) { g = g0; pl = 0; m = 0; }
+    __device__ __forceinline__ void advance(int nbl) {
+        if (++g > 0 && ++m == nbl) {
+            m = 0;
+            ++pl;
+        }
+    }
+};
+
 template <bool EXACT, int NB, int R>
 __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(const __grid_constant__ PlaneParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x % P.groups, p = blockIdx.x / P.groups;
+    const int g = blockIdx.x % P.groups;
+    const int p0 = (blockIdx.x / P.groups) * P.npc;     // first plane of this CTA
+    const int np = min(P.npc, P.nplanes - p0);          // ... and how many it solves, one after the other
     const int rhs_cta = g * P.wpc * R;
     const int nactive = min(P.wpc, (P.nrhs - rhs_cta + R - 1) / R);  // consumer warps with at least one right-hand side
     // shared memory: [nst][NB] coefficient stages | [wpc][NB][R] windows | full[nst], empty[nst]
@@ -112,9 +128,11 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
     __syncthreads();
 
     const int nyb = P.nyb, nst = P.nst;
-    const int nbl = P.nsteps_pad / kSteps;  // coefficient blocks of a line block
-    const int KL = nbl + 2;                 // ... plus the blocks that only drain
-    const int K = kSkew * (nyb - 1) + KL;
+    const int nbl = P.nsteps_pad / kSteps;  // 8-step blocks of a line block in one plane
+    // Line block jb runs kSkew blocks behind jb - 1, and it moves on to the next plane of the CTA as soon as it has
+    // finished the previous one: apart from the ramps at the two ends every line block is busy in every warp block.
+    const int TL = np * nbl;
+    const int K = kSkew * (nyb - 1) + TL + 2;  // ... plus the blocks that only drain
     unsigned spins = 0;
 
     if (warp == P.wpc) {
@@ -126,8 +144,8 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
             int cnt = 0;
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb) {
-                const int kl = k - kSkew * jb;
-                if (jb < nyb && kl >= 0 && kl < nbl) ++cnt;
+                const int gl = k - kSkew * jb;
+                if (jb < nyb && gl >= 0 && gl < TL) ++cnt;
             }
             if (cnt == 0) continue;
             if (use >= nst) {
@@ -139,10 +157,13 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
             mbar_arrive_expect_tx(&full[slot], (unsigned)(cnt * kStageLB));
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb) {
-                const int kl = k - kSkew * jb;
-                if (jb < nyb && kl >= 0 && kl < nbl)
+                const int gl = k - kSkew * jb;
+                if (jb < nyb && gl >= 0 && gl < TL) {
+                    const int pl = gl / nbl, kl = gl - pl * nbl;
                     bulk_g2s(smem + (size_t)(slot * NB + jb) * kStageLB,
-                             P.coef + ((size_t)(p * nyb + jb) * P.nsteps_pad + (size_t)kl * kSteps) * 128, (unsigned)kStageLB, &full[slot]);
+                             P.coef + ((size_t)((p0 + pl) * nyb + jb) * P.nsteps_pad + (size_t)kl * kSteps) * 128, (unsigned)kStageLB,
+                             &full[slot]);
+                }
             }
             ++use;
             if (++slot == nst) {
@@ -154,29 +175,35 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
     }
     if (warp >= nactive) return;
 
-    // ---------------------------------------------------------------- consumer: plane p, right-hand sides rhs0 ...
+    // ---------------------------------------------------------------- consumer: planes p0 ..., right-hand sides rhs0 ...
     const int rhs0 = rhs_cta + warp * R;
     const int nr = min(R, P.nrhs - rhs0);
     const int nx = P.nx, ny = P.ny;
+    const long long ldx = P.ldx;
     const uint32_t win_s = smem_u32(win0 + (size_t)warp * NB * R * kWinBytes);
     const uint32_t win_lane = win_s + lane * (kWinStride * 8);
     const uint32_t stage_lane = smem_u32(smem) + lane * 16;
     // rectangle roles: lane = (line rl of a 4-line group, column rc of 8)
     const int rl = lane >> 3, rc = lane & 7;
     const long long dir = P.backward ? -1 : 1;
-    const long long e0 = ((long long)p * ny + rl) * nx + rc;  // element (line rl, column rc) of this plane, solve numbering
-    double* const g0 = P.x + (P.backward ? P.n - 1 - e0 : e0) + (long long)rhs0 * P.ldx;
+    const long long e0 = ((long long)p0 * ny + rl) * nx + rc;  // element (line rl, column rc) of plane p0, solve numbering
+    double* const g0 = P.x + (P.backward ? P.n - 1 - e0 : e0) + (long long)rhs0 * ldx;
     const long long qstride = dir * (4 * (long long)nx - 4);  // next line group: 4 lines down, 4 columns back
+    const long long pstride = dir * (long long)ny * nx;       // next plane
     const uint32_t rect_s = win_s + rl * (kWinStride * 8);
     // line groups of the (ragged) last line block that exist for this lane
     unsigned lm_last = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
         if (32 * (nyb - 1) + 4 * q + rl < ny) lm_last |= 1u << q;
+    // columns [0, nxe) of this lane's line exist (0: the line itself does not)
+    unsigned nxe[NB];
+#pragma unroll
+    for (int jb = 0; jb < NB; ++jb) nxe[jb] = 32 * jb + lane < ny ? (unsigned)nx : 0u;
 
-    // element (line block jb, group q, rectangle m): line 32 jb + 4 q + rl, column 8 m - 4 q + rc, consumed at local
-    // step 8 m + rc + rl (any q) -> window slot (8 m + rc + rl) & 31 of its line.  Mask of the groups q whose element
-    // exists (0 <= column < nx, line < ny):
+    // element (line block jb, group q, block m of a plane): line 32 jb + 4 q + rl, column 8 m - 4 q + rc, consumed at the
+    // line block's step 8 g + rc + rl (any q; g = blocks since the line block started) -> window slot (that step) & 31.
+    // Mask of the groups q whose element exists (0 <= column < nx, line < ny):
     auto rect_mask = [&](int jb, int m) -> unsigned {
         const int a = 8 * m + rc;  // column of group 0; group q sits 4 q columns to the left
         const int qhi = a >> 2, qlo = (a - nx + 4) >> 2;
@@ -184,28 +211,21 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
         const unsigned lo = qlo <= 0 ? 0xffu : (qlo >= 8 ? 0u : (0xffu << qlo) & 0xffu);
         return hi & lo & (jb == nyb - 1 ? lm_last : 0xffu);
     };
-    auto rect_issue = [&](int jb, int r, int m, unsigned mask) {
-        const double* const b = g0 + dir * ((long long)jb * 32 * nx + 8 * m) + (long long)r * P.ldx;
-        const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * m + rc + rl) & (kWin - 1)) << 3);
+    auto rect_issue = [&](int jb, int r, const BlockPos& bp, unsigned mask) {
+        const double* const b = g0 + bp.pl * pstride + dir * ((long long)jb * 32 * nx + 8 * bp.m) + (long long)r * ldx;
+        const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * bp.g + rc + rl) & (kWin - 1)) << 3);
 #pragma unroll
         for (int q = 0; q < 8; ++q) cp_async8_if(d + q * (4 * kWinStride * 8), b + q * qstride, mask & (1u << q));
     };
-    auto rect_drain = [&](int jb, int r, int m, unsigned mask) {
-        double* const b = g0 + dir * ((long long)jb * 32 * nx + 8 * m) + (long long)r * P.ldx;
-        const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * m + rc + rl) & (kWin - 1)) << 3);
+    auto rect_drain = [&](int jb, int r, const BlockPos& bp, unsigned mask) {
+        double* const b = g0 + bp.pl * pstride + dir * ((long long)jb * 32 * nx + 8 * bp.m) + (long long)r * ldx;
+        const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * bp.g + rc + rl) & (kWin - 1)) << 3);
         double v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = lds_f64(d + q * (4 * kWinStride * 8));
 #pragma unroll
         for (int q = 0; q < 8; ++q) stg_cs_if(b + q * qstride, v[q], mask & (1u << q));
     };
-
-    // windows start as zeros: elements that do not exist (columns < 0 at the head of a line, lines >= ny) are never
-    // copied in and must read as finite values -- a stale NaN would travel down the line through the zero coefficients
-    // of the fast arithmetic.  (Columns >= nx keep whatever the slot held: nothing that exists depends on them.)
-    for (int t = lane; t < NB * R * kWinBytes / 16; t += 32)
-        asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(win_s + t * 16), "d"(0.0) : "memory");
-    __syncwarp();
 
     double xprev[NB][R];
 #pragma unroll
@@ -216,78 +236,113 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
     const int src_lane = (lane + 31) & 31;
     int slot = 0;
     unsigned phase = 0;
+    BlockPos pin[NB], pcur[NB], pout[NB];  // rectangle copied in / block computed / rectangle written back
+#pragma unroll
+    for (int jb = 0; jb < NB; ++jb) {
+        pin[jb].init(-kSkew * jb);
+        pcur[jb].init(-2 - kSkew * jb);
+        pout[jb].init(-4 - kSkew * jb);
+    }
 
     for (int k = -2; k < K; ++k) {
         __syncwarp();  // the previous block's solution values are in the window
         // ---- solution out: rectangles consumed two blocks ago
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
-            const int m = k - kSkew * jb - 2;
-            if (jb < nyb && m >= 0 && m < nbl) {
-                const unsigned mask = rect_mask(jb, m);
+            if (jb < nyb && pout[jb].g >= 0 && pout[jb].g < TL) {
+                const unsigned mask = rect_mask(jb, pout[jb].m);
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    if (R == 1 || r < nr) rect_drain(jb, r, m, mask);
+                    if (R == 1 || r < nr) rect_drain(jb, r, pout[jb], mask);
             }
         }
         __syncwarp();  // ... before their slots are handed to the copies below
         // ---- right-hand side in: rectangles needed two blocks from now (they reuse the slots just drained)
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
-            const int m = k - kSkew * jb + 2;
-            if (jb < nyb && m >= 0 && m < nbl) {
-                const unsigned mask = rect_mask(jb, m);
+            if (jb < nyb && pin[jb].g >= 0 && pin[jb].g < TL) {
+                const unsigned mask = rect_mask(jb, pin[jb].m);
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    if (R == 1 || r < nr) rect_issue(jb, r, m, mask);
+                    if (R == 1 || r < nr) rect_issue(jb, r, pin[jb], mask);
             }
         }
         cp_async_commit();
         cp_async_wait<2>();  // the group committed two iterations ago (this block's rectangles) has landed
         __syncwarp();
-        if (k < 0) continue;
 
-        // a line block outside its own step range (not started yet / finished) runs along on whatever its addresses
-        // hold; its results are dropped (no store, xprev unchanged) -- the step body stays free of branches, so the
-        // chains of a step overlap
+        // A line block outside its own range (not started yet / finished: only in the ramps at the two ends) runs along
+        // on whatever its addresses hold and its results are dropped; steps of a lane that fall outside its line
+        // (column < 0 or >= nx, line >= ny) produce 0.0, so nothing stale -- no NaN of a neighbouring plane -- ever
+        // reaches an element that exists.  The step body has no branches: the chains of a step overlap.
         unsigned act[NB][R];
         bool any = false;
         uint32_t wa[NB][R];
+        int col0[NB];
+        unsigned nxb[NB];
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
-            const int kl = k - kSkew * jb;
-            const bool a = jb < nyb && kl >= 0 && kl < nbl;
+            const bool a = jb < nyb && pcur[jb].g >= 0 && pcur[jb].g < TL;
             any = any || a;
+            col0[jb] = 8 * pcur[jb].m - lane;
+            nxb[jb] = a ? nxe[jb] : 0u;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 act[jb][r] = (a && (R == 1 || r < nr)) ? 1u : 0u;
-                wa[jb][r] = win_lane + (jb * R + r) * kWinBytes + (uint32_t)((kl & 3) << 6);
+                wa[jb][r] = win_lane + (jb * R + r) * kWinBytes + (uint32_t)((pcur[jb].g & 3) << 6);
             }
         }
-        if (!any) continue;
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            pin[jb].advance(nbl);
+            pcur[jb].advance(nbl);
+            pout[jb].advance(nbl);
+        }
+        if (k < 0 || !any) continue;
         while (!mbar_try_wait(&full[slot], phase)) PLANE_SPIN(spins, 222)
         const uint32_t st = stage_lane + (uint32_t)(slot * NB) * kStageLB;
+        // operands of a step are loaded one step ahead
+        double cyn[NB], cxn[NB], dvn[NB], bbn[NB][R];
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            cyn[jb] = lds_f64(st + jb * kStageLB + 8);
+            lds_2f64(st + jb * kStageLB + 512, cxn[jb], dvn[jb]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) bbn[jb][r] = lds_f64(wa[jb][r]);
+        }
 #pragma unroll
         for (int u = 0; u < kSteps; ++u) {
-            // what the neighbouring line produced one step ago; lane 0 takes lane 31 of the previous line block
             double rot[NB][R], cy_[NB], cx_[NB], dv[NB], bb[NB][R], xnew[NB][R];
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
+                cy_[jb] = cyn[jb];
+                cx_[jb] = cxn[jb];
+                dv[jb] = dvn[jb];
+#pragma unroll
+                for (int r = 0; r < R; ++r) bb[jb][r] = bbn[jb][r];
+            }
+            // what the neighbouring line produced one step ago; lane 0 takes lane 31 of the previous line block
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb)
 #pragma unroll
                 for (int r = 0; r < R; ++r) rot[jb][r] = __shfl_sync(FULL, xprev[jb][r], src_lane);
+            if (u + 1 < kSteps) {
 #pragma unroll
-            for (int jb = 0; jb < NB; ++jb) {
-                cy_[jb] = lds_f64(st + jb * kStageLB + u * 1024 + 8);
-                lds_2f64(st + jb * kStageLB + u * 1024 + 512, cx_[jb], dv[jb]);
+                for (int jb = 0; jb < NB; ++jb) {
+                    cyn[jb] = lds_f64(st + jb * kStageLB + (u + 1) * 1024 + 8);
+                    lds_2f64(st + jb * kStageLB + (u + 1) * 1024 + 512, cxn[jb], dvn[jb]);
 #pragma unroll
-                for (int r = 0; r < R; ++r) bb[jb][r] = lds_f64(wa[jb][r] + u * 8);
+                    for (int r = 0; r < R; ++r) bbn[jb][r] = lds_f64(wa[jb][r] + (u + 1) * 8);
+                }
             }
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb) {
+                const bool inside = (unsigned)(col0[jb] + u) < nxb[jb];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     double xy = rot[jb][r];
                     if (lane == 0) xy = jb > 0 ? rot[jb > 0 ? jb - 1 : 0][r] : 0.0;
+                    double xn;
                     if (EXACT) {
                         const bool ay = __double_as_longlong(cy_[jb]) == kSysAbsentBits;
                         const bool ax = __double_as_longlong(cx_[jb]) == kSysAbsentBits;
@@ -299,12 +354,13 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
                             if (!ay) acc = __dsub_rn(acc, __dmul_rn(cy_[jb], xy));
                             if (!ax) acc = __dsub_rn(acc, __dmul_rn(cx_[jb], xprev[jb][r]));
                         }
-                        xnew[jb][r] = unit_diag ? acc : __ddiv_rn(acc, dv[jb]);
+                        xn = unit_diag ? acc : __ddiv_rn(acc, dv[jb]);
                     } else {
                         double acc = bb[jb][r] * dv[jb];
                         acc = fma(-cx_[jb], xprev[jb][r], acc);
-                        xnew[jb][r] = fma(-cy_[jb], xy, acc);
+                        xn = fma(-cy_[jb], xy, acc);
                     }
+                    xnew[jb][r] = inside ? xn : 0.0;
                 }
             }
 #pragma unroll
@@ -312,7 +368,7 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     sts_f64_if(wa[jb][r] + u * 8, xnew[jb][r], act[jb][r]);
-                    xprev[jb][r] = act[jb][r] ? xnew[jb][r] : xprev[jb][r];
+                    xprev[jb][r] = xnew[jb][r];
                 }
         }
         __syncwarp();
@@ -389,11 +445,28 @@ bool run_plane(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.wpc = wpc;
     P.nst = nst;
     P.groups = (nrhs + wpc * r - 1) / (wpc * r);
+    {   // planes per CTA: a CTA that walks several planes pays the ramp of the line-block skew once; fewest estimated
+        // warp blocks on the busiest SM (CTAs of this size: one per SM at a time when wpc is at its maximum)
+        const int nbl = Y.nsteps_pad / kSteps;
+        const int64_t per_sm = std::max<int64_t>(1, ((int64_t)budget + 1024) / (int64_t)(coef_bytes + (size_t)wpc * nb * r * kWinBytes + 64));
+        int64_t best = INT64_MAX;
+        int best_np = 1;
+        for (int npc = 1; npc <= 64 && npc <= Y.nplanes; ++npc) {
+            const int64_t ctas_ = (int64_t)((Y.nplanes + npc - 1) / npc) * P.groups;
+            const int64_t waves = (ctas_ + h->sm_count * per_sm - 1) / (h->sm_count * per_sm);
+            const int64_t cost = waves * ((int64_t)npc * nbl + kSkew * (Y.nyb - 1) + 2 + 3);  // + start-up latency of a CTA
+            if (cost < best) {
+                best = cost;
+                best_np = npc;
+            }
+        }
+        P.npc = opt.plane_npc > 0 ? (int)std::min<int64_t>(opt.plane_npc, Y.nplanes) : best_np;
+    }
     P.status = h->status.p;
     P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 16, (long long)opt.spin_limit_ms * h->clock_khz / 64));
     const size_t smem = coef_bytes + (size_t)wpc * nb * r * kWinBytes + 2 * nst * sizeof(uint64_t) + 16;
     const plane_kern_t kern = plane_kernel(exact, nb, r);
-    const int64_t ctas = (int64_t)Y.nplanes * P.groups;
+    const int64_t ctas = (int64_t)((Y.nplanes + P.npc - 1) / P.npc) * P.groups;
     ILUB_REQUIRE(ctas < ((int64_t)1 << 31), ILUB_ERR_SIZE, "plane solve: too many CTAs");
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
