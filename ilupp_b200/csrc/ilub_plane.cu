@@ -38,7 +38,7 @@ constexpr int kWin = 32;                          // window slots per line
 constexpr int kWinStride = kWin + 1;              // odd stride: a warp's column accesses are conflict-free
 constexpr int kWinBytes = 32 * kWinStride * 8;    // one (line block, rhs) window
 constexpr int kSkew = 4;                          // warp blocks between the starts of consecutive line blocks (32 steps)
-constexpr int kMaxConsumers = 8;
+constexpr int kMaxConsumers = 7;                    // + the producer warp = 256 threads: the register file allows 255 per thread
 
 struct PlaneParams {
     const double* coef;
@@ -95,14 +95,19 @@ __device__ __forceinline__ void give_up(int* status, int code) { atomicCAS(statu
     }
 
 // position of a line block in the sequence of (plane, 8-step block) pairs a CTA walks through: g counts blocks from
-// the line block's own start (negative: not started), (pl, m) = (plane of this CTA, block inside the plane)
+// the line block's own start (negative: not started), m = block inside the current plane, off = element offset of
+// (that plane, column 8 m) from the CTA's first plane
 struct BlockPos {
-    int g, pl, m;
-    __device__ __forceinline__ void init(int g0) { g = g0; pl = 0; m = 0; }
-    __device__ __forceinline__ void advance(int nbl) {
-        if (++g > 0 && ++m == nbl) {
-            m = 0;
-            ++pl;
+    int g, m;
+    long long off;
+    __device__ __forceinline__ void init(int g0, long long off0) { g = g0; m = 0; off = off0; }
+    __device__ __forceinline__ void advance(int nbl, long long step, long long wrap) {
+        if (++g > 0) {
+            off += step;
+            if (++m == nbl) {
+                m = 0;
+                off += wrap;
+            }
         }
     }
 };
@@ -189,7 +194,8 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
     const long long e0 = ((long long)p0 * ny + rl) * nx + rc;  // element (line rl, column rc) of plane p0, solve numbering
     double* const g0 = P.x + (P.backward ? P.n - 1 - e0 : e0) + (long long)rhs0 * ldx;
     const long long qstride = dir * (4 * (long long)nx - 4);  // next line group: 4 lines down, 4 columns back
-    const long long pstride = dir * (long long)ny * nx;       // next plane
+    const long long step8 = dir * 8;                                        // next block of a plane: 8 columns on
+    const long long wrap8 = dir * ((long long)ny * nx - 8 * (long long)nbl);  // ... and from its last block to the next plane
     const uint32_t rect_s = win_s + rl * (kWinStride * 8);
     // line groups of the (ragged) last line block that exist for this lane
     unsigned lm_last = 0;
@@ -211,20 +217,34 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
         const unsigned lo = qlo <= 0 ? 0xffu : (qlo >= 8 ? 0u : (0xffu << qlo) & 0xffu);
         return hi & lo & (jb == nyb - 1 ? lm_last : 0xffu);
     };
-    auto rect_issue = [&](int jb, int r, const BlockPos& bp, unsigned mask) {
-        const double* const b = g0 + bp.pl * pstride + dir * ((long long)jb * 32 * nx + 8 * bp.m) + (long long)r * ldx;
+    const int qs = (int)qstride;
+    const bool full_last = (ny & 31) == 0;
+    auto rect_issue = [&](int jb, int r, const BlockPos& bp) {
+        const double* const b = g0 + bp.off + (long long)r * ldx;
         const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * bp.g + rc + rl) & (kWin - 1)) << 3);
+        if (8 * bp.m >= 28 && 8 * bp.m + 8 <= nx && (jb < nyb - 1 || full_last)) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) cp_async8_if(d + q * (4 * kWinStride * 8), b + q * qstride, mask & (1u << q));
+            for (int q = 0; q < 8; ++q) cp_async8(d + q * (4 * kWinStride * 8), b + q * qs, 8u);
+        } else {
+            const unsigned mask = rect_mask(jb, bp.m);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cp_async8_if(d + q * (4 * kWinStride * 8), b + q * qs, mask & (1u << q));
+        }
     };
-    auto rect_drain = [&](int jb, int r, const BlockPos& bp, unsigned mask) {
-        double* const b = g0 + bp.pl * pstride + dir * ((long long)jb * 32 * nx + 8 * bp.m) + (long long)r * ldx;
+    auto rect_drain = [&](int jb, int r, const BlockPos& bp) {
+        double* const b = g0 + bp.off + (long long)r * ldx;
         const uint32_t d = rect_s + (uint32_t)((jb * R + r) * kWinBytes) + (((8 * bp.g + rc + rl) & (kWin - 1)) << 3);
         double v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = lds_f64(d + q * (4 * kWinStride * 8));
+        if (8 * bp.m >= 28 && 8 * bp.m + 8 <= nx && (jb < nyb - 1 || full_last)) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) stg_cs_if(b + q * qstride, v[q], mask & (1u << q));
+            for (int q = 0; q < 8; ++q) __stcs(b + q * qs, v[q]);
+        } else {
+            const unsigned mask = rect_mask(jb, bp.m);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) stg_cs_if(b + q * qs, v[q], mask & (1u << q));
+        }
     };
 
     double xprev[NB][R];
@@ -239,9 +259,9 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
     BlockPos pin[NB], pcur[NB], pout[NB];  // rectangle copied in / block computed / rectangle written back
 #pragma unroll
     for (int jb = 0; jb < NB; ++jb) {
-        pin[jb].init(-kSkew * jb);
-        pcur[jb].init(-2 - kSkew * jb);
-        pout[jb].init(-4 - kSkew * jb);
+        pin[jb].init(-kSkew * jb, dir * ((long long)jb * 32 * nx));
+        pcur[jb].init(-2 - kSkew * jb, 0);
+        pout[jb].init(-4 - kSkew * jb, dir * ((long long)jb * 32 * nx));
     }
 
     for (int k = -2; k < K; ++k) {
@@ -250,10 +270,9 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
             if (jb < nyb && pout[jb].g >= 0 && pout[jb].g < TL) {
-                const unsigned mask = rect_mask(jb, pout[jb].m);
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    if (R == 1 || r < nr) rect_drain(jb, r, pout[jb], mask);
+                    if (R == 1 || r < nr) rect_drain(jb, r, pout[jb]);
             }
         }
         __syncwarp();  // ... before their slots are handed to the copies below
@@ -261,10 +280,9 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
             if (jb < nyb && pin[jb].g >= 0 && pin[jb].g < TL) {
-                const unsigned mask = rect_mask(jb, pin[jb].m);
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    if (R == 1 || r < nr) rect_issue(jb, r, pin[jb], mask);
+                    if (R == 1 || r < nr) rect_issue(jb, r, pin[jb]);
             }
         }
         cp_async_commit();
@@ -294,9 +312,9 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 1) k_trsv_plane(cons
         }
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
-            pin[jb].advance(nbl);
-            pcur[jb].advance(nbl);
-            pout[jb].advance(nbl);
+            pin[jb].advance(nbl, step8, wrap8);
+            pcur[jb].advance(nbl, 0, 0);
+            pout[jb].advance(nbl, step8, wrap8);
         }
         if (k < 0 || !any) continue;
         while (!mbar_try_wait(&full[slot], phase)) PLANE_SPIN(spins, 222)
