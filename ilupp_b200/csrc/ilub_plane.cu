@@ -35,7 +35,8 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int kSteps = kSysStageSteps;            // steps per coefficient stage
 constexpr int kStageLB = kSteps * 4 * 32 * 8;     // bytes of one stage of one line block (8 KB)
 constexpr int kWin = 32;                          // window slots per line
-constexpr int kWinStride = kWin + 1;              // odd stride: a warp's column accesses are conflict-free
+constexpr int kWinStride = kWin + 1;              // odd stride: a warp's column accesses are conflict-free (stride 39 would also free the
+                                                  // rectangle accesses of their 2-way conflicts: measured, no gain)
 constexpr int kWinBytes = 32 * kWinStride * 8;    // one (line block, rhs) window
 constexpr int kSkew = 4;                          // warp blocks between the starts of consecutive line blocks (32 steps)
 constexpr int kMaxConsumers = 7;                    // + the producer warp = 256 threads: the register file allows 255 per thread
@@ -431,9 +432,11 @@ bool run_plane(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     SysSolve& Y = T.sys;
     const Options& opt = options();
     if (!Y.built || Y.zcoupled || Y.nyb > 8 || opt.sys_plane == 0 || opt.trace) return false;
-    // one plane on one warp only pays when there are planes (or right-hand sides) to fill the machine, or when the
-    // plane is so small that the line-systolic kernel is all hand-offs
-    if (opt.sys_plane == 1 && (int64_t)Y.nplanes * nrhs < 2 && Y.nyb > 4) return false;
+    // One warp per (plane, right-hand side) walks a plane 2-4x slower than the line-systolic kernel's team of warps
+    // (measured: 256^2, one right-hand side: 623 us against 155 us), so it pays when there is other work to overlap:
+    // several right-hand sides (the line-systolic kernel takes them one launch after the other) or more planes than
+    // two waves of CTAs
+    if (opt.sys_plane == 1 && nrhs < 3 && Y.nplanes < 2 * h->sm_count) return false;
     const bool exact = opt.exact != 0;
     if (Y.packed_exact != (exact ? 1 : 0)) pack_systolic(h, slot, s);
     const int nb = Y.nyb <= 1 ? 1 : Y.nyb <= 2 ? 2 : Y.nyb <= 4 ? 4 : 8;

@@ -18,6 +18,8 @@ def grid2d(nx, ny):
 name = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 ilupp.set_option("exact", 0)
+if os.environ.get("ILUB_SYS_PLANE"):
+    ilupp.set_option("sys_plane", int(os.environ["ILUB_SYS_PLANE"]))
 A = {"strip": lambda: grid2d(4096, 32), "strip2": lambda: grid2d(2048, 64), "p2d256": lambda: P.poisson2d(256),
      "p3d128": lambda: P.poisson3d(128), "cd3d160": lambda: P.convdiff3d(160)}[name]()
 n = A.shape[0]
