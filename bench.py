@@ -281,8 +281,13 @@ def run_ours(args):
         apply_ms = max_over_ranks(e0.elapsed_time(e1), dev)
         fac_ms = max_over_ranks(Bb.timings_ms[1], dev)
         sym_b = max_over_ranks(Bb.timings_ms[0], dev)
+        # matrix + pointer terms once, vector term per right-hand side
+        by_b = nsys_total * (12.0 * (Bb.total_nnz / (hi - lo)) + 8.0 * (n1 + 1)) + 32.0 * nsys_total * n1 * 16
         batched = {"systems": nsys_total, "rhs_per_system": 16, "n_per_system": n1,
+                   "kernel": "k_trsv_plane (one launch per triangular solve, all right-hand sides)" if Bb.stats["launches"] else None,
                    "factor_numeric_ms": fac_ms, "symbolic_ms": sym_b, "apply16_ms": apply_ms,
+                   "apply16_algorithmic_GBs": by_b / (apply_ms * 1e-3) / 1e9,
+                   "apply16_pct_hbm_peak": 100.0 * by_b / (apply_ms * 1e-3) / 1e9 / peak / world,
                    "solves_per_s": nsys_total * 16 / (apply_ms * 1e-3),
                    "systems_per_s": nsys_total / ((fac_ms + apply_ms) * 1e-3), "scaling": "strong"}
         del Bb, X
