@@ -267,6 +267,52 @@ class IChol0Preconditioner(_BaseWrapper):
         scipy.sparse.linalg.LinearOperator.__init__(self, shape=A.shape, dtype=A.dtype)
 
 
+class FactorsPreconditioner(_BaseWrapper):
+    """GPU `apply` for triangular factors computed elsewhere: `x = U^-1 L^-1 b` for a lower
+    triangular `L` and an upper triangular `U` (one of the two with a unit diagonal), or `x = L^-T L^-1 b` when only `L` (lower triangular, with its
+    diagonal) is given.  This is how the factors of the reference's other triangular preconditioners --
+    `ICholTPreconditioner`, `ILUTPreconditioner`, `ILUCPreconditioner` (`.factors()`), whose threshold factorisations
+    stay on the CPU -- run through the same triangular-solve kernels as ILU(0) / IChol(0).
+
+    Args:
+        L: sparse lower triangular factor (any scipy format)
+        U: sparse upper triangular factor, or None for `L L^T`
+    """
+    def __init__(self, L, U=None, device=0):
+        L = scipy.sparse.csr_matrix(L)
+        if L.shape[0] != L.shape[1]:
+            raise ValueError('Input matrix must be square!')
+        if U is None:
+            if scipy.sparse.triu(L, 1).nnz:
+                raise ValueError('L must be lower triangular!')
+            F = L.copy()
+        else:
+            U = scipy.sparse.csr_matrix(U)
+            if U.shape != L.shape:
+                raise ValueError('L and U must have the same shape!')
+            if scipy.sparse.triu(L, 1).nnz or scipy.sparse.tril(U, -1).nnz:
+                raise ValueError('L must be lower and U upper triangular!')
+            ones = np.ones(L.shape[0])
+            if np.array_equal(L.diagonal(), ones):
+                F = (scipy.sparse.tril(L, -1) + U).tocsr()
+            elif np.array_equal(U.diagonal(), ones):
+                # pivots on L, unit diagonal on U (what the reference's ILU0 returns for CSC input): the CSC arrays of
+                # the pair are the CSR arrays of its transpose U^T L^T = (unit lower)(upper)
+                F = (L + scipy.sparse.triu(U, 1)).tocsc()
+            else:
+                raise ValueError('L or U must have a unit diagonal!')
+        F.sum_duplicates()
+        F.sort_indices()
+        if F.nnz >= 2**31 - 64:
+            raise ValueError('factors exceed 32-bit indexing')
+        F.indices = F.indices.astype(_index_dtype)
+        F.indptr = F.indptr.astype(_index_dtype)
+        Fd, Fi, Fp, Fo = _matrix_fields(F)
+        make = _ilupp.LLTFactorsPreconditioner if U is None else _ilupp.LUFactorsPreconditioner
+        self.pr = make(Fd, Fi, Fp, Fo, device)
+        scipy.sparse.linalg.LinearOperator.__init__(self, shape=L.shape, dtype=np.dtype(np.float64))
+
+
 class _BatchedWrapper(_BaseWrapper):
     def _init(self, factory, A, values, device):
         _, Ai, Ap, Ao = _matrix_fields(A)

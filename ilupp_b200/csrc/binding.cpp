@@ -129,6 +129,21 @@ P create(bool ichol, py::buffer A_data, py::buffer A_indices, py::buffer A_indpt
     return P(h);
 }
 
+// factors computed elsewhere (the reference's ICholT / ILUT / ILUC, binding.cpp:388-397,432-470)
+template <class P>
+P create_from_factors(int kind, py::buffer F_data, py::buffer F_indices, py::buffer F_indptr, bool is_csr, int device) {
+    MatrixView M = make_matrix(F_data, F_indices, F_indptr);
+    ilub_handle* h = nullptr;
+    int st;
+    {
+        py::gil_scoped_release release;
+        st = ilub_create_from_factors(kind, (const double*)M.data.ptr, (const Integer*)M.indices.ptr,
+                                      (const Integer*)M.indptr.ptr, M.n, M.nnz, is_csr ? 1 : 0, ILUB_HOST, device, nullptr, &h);
+    }
+    check(st);
+    return P(h);
+}
+
 template <class P>
 P create_batched(bool ichol, py::array_t<double, py::array::c_style | py::array::forcecast> values,
                  py::buffer A_indices, py::buffer A_indptr, bool is_csr, int device) {
@@ -413,6 +428,16 @@ PYBIND11_MODULE(_ilupp, m) {
               return create<LLTPrecond>(true, d, i, p, is_csr, device);
           },
           py::arg("A_data"), py::arg("A_indices"), py::arg("A_indptr"), py::arg("is_csr"), py::arg("device") = 0);
+    m.def("LUFactorsPreconditioner",
+          [](py::buffer d, py::buffer i, py::buffer p, bool is_csr, int device) {
+              return create_from_factors<LUPrecond>(0, d, i, p, is_csr, device);
+          },
+          py::arg("F_data"), py::arg("F_indices"), py::arg("F_indptr"), py::arg("is_csr"), py::arg("device") = 0);
+    m.def("LLTFactorsPreconditioner",
+          [](py::buffer d, py::buffer i, py::buffer p, bool is_csr, int device) {
+              return create_from_factors<LLTPrecond>(1, d, i, p, is_csr, device);
+          },
+          py::arg("F_data"), py::arg("F_indices"), py::arg("F_indptr"), py::arg("is_csr"), py::arg("device") = 0);
     m.def("ILU0PreconditionerBatched",
           [](py::array_t<double, py::array::c_style | py::array::forcecast> v, py::buffer i, py::buffer p, bool is_csr,
              int device) { return create_batched<LUPrecond>(false, v, i, p, is_csr, device); },

@@ -74,7 +74,8 @@ int slot_of(const ilub_handle* h, int which_solve) {
 }
 
 void create_common(int kind, const double* data, const int32_t* indices, const int32_t* indptr, int32_t n1,
-                   int64_t nnz1, int32_t nsys, int is_csr, int where, int device, void* stream, ilub_handle** out) {
+                   int64_t nnz1, int32_t nsys, int is_csr, int where, int device, void* stream, ilub_handle** out,
+                   bool prefactored = false) {
     ILUB_REQUIRE(out != nullptr, ILUB_ERR_INVALID, "out is null");
     *out = nullptr;
     ILUB_REQUIRE(data && indices && indptr, ILUB_ERR_INVALID, "null matrix array");
@@ -99,6 +100,7 @@ void create_common(int kind, const double* data, const int32_t* indices, const i
     h->n = (int32_t)n64;
     h->nnz = nnz64;
     h->nsys = nsys;
+    h->prefactored = prefactored ? 1 : 0;
     cudaDeviceProp prop;
     ILUB_CUDA(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
@@ -152,12 +154,15 @@ void create_common(int kind, const double* data, const int32_t* indices, const i
         DebugTimer t("analyse second solve", s);
         analyse_solve(h.get(), second, s);
     }
-    {
+    if (!prefactored) {
         DebugTimer t("factorisation schedule", s);
         factor_prepare(h.get(), s);
     }
     ILUB_CUDA(cudaEventRecord(h->ev[1], s));
-    {
+    if (prefactored) {
+        // the values ARE the factors (computed elsewhere): nothing to factorise
+        ILUB_CUDA(cudaMemcpyAsync(h->lu.p, h->a.p, sizeof(double) * nnz64, cudaMemcpyDeviceToDevice, s));
+    } else {
         DebugTimer t("numeric factorisation", s);
         factor_numeric(h.get(), s);
     }
@@ -221,6 +226,14 @@ int ilub_create_ichol0_batched(const double* values, const int32_t* indices, con
     });
 }
 
+int ilub_create_from_factors(int kind, const double* data, const int32_t* indices, const int32_t* indptr, int32_t n,
+                             int64_t nnz, int is_csr, int where, int device, void* stream, ilub_handle** out) {
+    return guarded([&] {
+        ILUB_REQUIRE(kind == KIND_ILU0 || kind == KIND_ICHOL0, ILUB_ERR_INVALID, "kind must be 0 (L U) or 1 (L L^T)");
+        create_common(kind, data, indices, indptr, n, nnz, 1, is_csr, where, device, stream, out, true);
+    });
+}
+
 int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream) {
     return guarded([&] {
         ILUB_REQUIRE(h && data, ILUB_ERR_INVALID, "null argument");
@@ -229,7 +242,10 @@ int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream) {
         set_alloc_stream(s);
         ILUB_CUDA(cudaEventRecord(h->ev[1], s));
         ILUB_CUDA(cudaMemcpyAsync(h->a.p, data, sizeof(double) * h->nnz, to_dev(where), s));
-        factor_numeric(h, s);
+        if (h->prefactored)
+            ILUB_CUDA(cudaMemcpyAsync(h->lu.p, h->a.p, sizeof(double) * h->nnz, cudaMemcpyDeviceToDevice, s));
+        else
+            factor_numeric(h, s);
         ILUB_CUDA(cudaEventRecord(h->ev[2], s));
         for (int k = 0; k < 4; ++k) pack_solve_values(h, k, s);
         ILUB_CUDA(cudaEventRecord(h->ev[3], s));
@@ -398,6 +414,7 @@ int ilub_get_level_sets(ilub_handle* h, int which_solve, int32_t* level_ptr, int
 int ilub_spmv(ilub_handle* h, const double* x, double* y, int where, void* stream) {
     return guarded([&] {
         ILUB_REQUIRE(h && x && y, ILUB_ERR_INVALID, "null argument");
+        ILUB_REQUIRE(!h->prefactored, ILUB_ERR_INVALID, "handle was created from factors: it holds no matrix");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -419,6 +436,7 @@ int ilub_bicgstab(ilub_handle* h, const double* b, double* x, double rtol, doubl
                   int32_t* iters, double* rel_achieved, double* abs_achieved, int where, void* stream) {
     return guarded([&] {
         ILUB_REQUIRE(h && b && x && iters && rel_achieved && abs_achieved, ILUB_ERR_INVALID, "null argument");
+        ILUB_REQUIRE(!h->prefactored, ILUB_ERR_INVALID, "handle was created from factors: it holds no matrix");
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);

@@ -306,6 +306,7 @@ struct ilub_handle {
     int32_t n = 0;       // dimension (nsys * n_one for batches)
     int64_t nnz = 0;
     int32_t nsys = 1;
+    int prefactored = 0;  // created from factors computed elsewhere (ilub_create_from_factors): `a` holds the factors, not a matrix
     // the matrix as given (CSR-read arrays), kept for spmv / bicgstab / refactor
     ilub::DevBuf<int> ptr, idx;
     ilub::DevBuf<double> a;

@@ -408,7 +408,7 @@ plane_kern_t plane_kernel_nb(int nb) {
         case 1: return (plane_kern_t)k_trsv_plane<EXACT, 1, R>;
         case 2: return (plane_kern_t)k_trsv_plane<EXACT, 2, R>;
         case 4: return (plane_kern_t)k_trsv_plane<EXACT, 4, R>;
-        default: return (plane_kern_t)k_trsv_plane<EXACT, 8, R>;
+        default: return (plane_kern_t)k_trsv_plane<EXACT, 8, 1>;  // (8 line blocks leave shared memory for one right-hand side per warp)
     }
 }
 int nb_index(int nb) { return nb == 1 ? 0 : nb == 2 ? 1 : nb == 4 ? 2 : 3; }
@@ -440,7 +440,7 @@ bool run_plane(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     const bool exact = opt.exact != 0;
     if (Y.packed_exact != (exact ? 1 : 0)) pack_systolic(h, slot, s);
     const int nb = Y.nyb <= 1 ? 1 : Y.nyb <= 2 ? 2 : Y.nyb <= 4 ? 4 : 8;
-    int r = opt.plane_r == 2 ? 2 : 1;
+    int r = opt.plane_r == 2 && nb < 8 ? 2 : 1;
     const int nst = 2;
     const size_t budget = (size_t)227 * 1024 - 256;
     const size_t coef_bytes = (size_t)nst * nb * kStageLB;

@@ -85,6 +85,21 @@ ILUB_API int ilub_create_ilu0(const double* data, const int32_t* indices, const 
  * compute_ichol0 (IChol.hpp:32-59).  The factor is always CSR lower, diagonal last. */
 ILUB_API int ilub_create_ichol0(const double* data, const int32_t* indices, const int32_t* indptr, int32_t n,
                                 int64_t nnz, int is_csr, int where, int device, void* stream, ilub_handle** out);
+/* SURVEY.md 8(f)1 -- apply() for triangular factors computed elsewhere: the reference's ICholTPreconditioner
+ * (binding.cpp:388-397, IChol.hpp:77-164), ILUT / ILUC (binding.cpp:432-470,
+ * indirect_split_triangular_preconditioner, preconditioner_implementation.h:939-1011) keep their CPU
+ * factorisations; their factors run through the same triangular-solve kernels as ILU(0) / IChol(0), i.e. this
+ * replaces split_preconditioner::apply_preconditioner_only (preconditioner_implementation.h:91-111) and
+ * matrix_sparse::triangular_solve (sparse_implementation.h:4040-4093) for them.
+ * kind 0 (L U): `data` holds, on ONE square CSR pattern with sorted unique columns and a full diagonal, L strictly
+ * below the diagonal (its unit diagonal is implied) and U on and above it; kind 1 (L L^T): L on the lower triangle,
+ * diagonal included (entries above it are ignored).  is_csr = 0: the arrays are the CSC arrays of the factor pair
+ * (= CSR of its transpose, exactly how ILU0.hpp:100-105 treats CSC input), i.e. the pair has the unit diagonal on
+ * U and the pivots on L -- what the reference's ILU0 returns for CSC matrices.  ilub_refactor on such a handle
+ * replaces the factor values; ilub_spmv / ilub_bicgstab are refused (the handle holds no matrix). */
+ILUB_API int ilub_create_from_factors(int kind, const double* data, const int32_t* indices, const int32_t* indptr,
+                                      int32_t n, int64_t nnz, int is_csr, int where, int device, void* stream,
+                                      ilub_handle** out);
 /* numeric re-factorisation with new values on the unchanged pattern; reuses the
  * symbolic analysis (levels, partition, packed layout). */
 ILUB_API int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream);

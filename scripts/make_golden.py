@@ -87,6 +87,28 @@ def main():
                        ichol0_apply=yc, ichol0_apply_trans=yct, ichol0_total_nnz=np.array(C.total_nnz))
             np.savez_compressed(os.path.join(out, "%s_%s.npz" % (name, fmt)), **rec)
             print("wrote", name, fmt, "n", n, "nnz", A.nnz)
+    # factors + apply of the reference's other triangular preconditioners (their threshold
+    # factorisations stay on the CPU; FactorsPreconditioner applies such factors on the GPU)
+    for name, gen, sym in (("laplace2d", laplace2d_matrix, True), ("random", random_matrix, False)):
+        A = gen(144 if name == "laplace2d" else 120, "csr")
+        data, idx, ptr = fields(A)
+        n = A.shape[0]
+        b = np.random.default_rng(12).standard_normal(n)
+        rec = {"A_data": data, "A_indices": idx, "A_indptr": ptr, "is_csr": np.array(True), "b": b}
+        kinds = [("ilut", ref.ILUTPreconditioner, (4, 1e-3)), ("iluc", ref.ILUCPreconditioner, (4, 1e-3))]
+        if sym:
+            kinds.append(("icholt", ref.ICholTPreconditioner, (3, 1e-3)))
+        for key, cls, args in kinds:
+            Pq = cls(data, idx, ptr, True, *args)
+            fi = Pq.factors_info()
+            for fname, (Fd, Fi, Fp, Fc, _, _) in zip(("L", "U"), fi):
+                rec.update({"%s_%s_data" % (key, fname): Fd, "%s_%s_indices" % (key, fname): Fi,
+                            "%s_%s_indptr" % (key, fname): Fp, "%s_%s_is_csr" % (key, fname): np.array(Fc)})
+            y = b.copy(); Pq.apply(y)
+            yt = b.copy(); Pq.apply_trans(yt)
+            rec.update({key + "_apply": y, key + "_apply_trans": yt, key + "_total_nnz": np.array(Pq.total_nnz)})
+        np.savez_compressed(os.path.join(out, "factors_%s.npz" % name), **rec)
+        print("wrote factors", name, "n", n, [k for k, _, _ in kinds])
     # BiCGStab with ILU0 through the reference templates (harness)
     from ilupp_b200 import problems
     A = problems.convdiff3d(12)

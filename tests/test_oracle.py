@@ -164,3 +164,20 @@ def test_generators_match_survey_sizes():
     assert (A != A.T).nnz > 0 and np.all(A.diagonal() > 0)
     pat, vals = P.batched_poisson2d(3, 8)
     assert vals.shape == (3, pat.nnz) and not np.array_equal(vals[0], vals[1])
+
+
+# ---- the triangular solves on the factors of the reference's other preconditioners ----------
+@pytest.mark.parametrize("name,key", [("laplace2d", "ilut"), ("laplace2d", "iluc"), ("laplace2d", "icholt"),
+                                      ("random", "ilut"), ("random", "iluc")])
+def test_port_apply_on_reference_threshold_factors(name, key):
+    """golden fixtures: factors and apply / apply_trans outputs of the reference's ILUT / ILUC / ICholT"""
+    from helpers import golden_factor, load_golden, relerr
+    g = load_golden("factors_" + name)
+    L = golden_factor(g, key + "_L").tocsr()
+    if key == "icholt":
+        assert relerr(oracle.port.apply_llt(L, g["b"]), g[key + "_apply"]) <= 1e-12
+        assert relerr(oracle.port.apply_llt(L, g["b"]), g[key + "_apply_trans"]) <= 1e-12
+    else:
+        U = golden_factor(g, key + "_U").tocsr()
+        assert relerr(oracle.port.apply_lu(L, U, g["b"]), g[key + "_apply"]) <= 1e-12
+        assert relerr(oracle.port.apply_lu(L, U, g["b"], True), g[key + "_apply_trans"]) <= 1e-12

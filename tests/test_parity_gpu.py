@@ -633,3 +633,64 @@ def test_plane_solve_batched(ilupp, kind, exact):
     finally:
         for k_, v in defaults.items():
             ilupp.set_option(k_, v)
+
+
+# ---- GPU apply for factors computed elsewhere (reference ILUT / ILUC / ICholT) --------------------
+@pytest.mark.parametrize("name,key", [("laplace2d", "ilut"), ("laplace2d", "iluc"), ("laplace2d", "icholt"),
+                                      ("random", "ilut"), ("random", "iluc")])
+def test_factors_preconditioner_golden(ilupp, name, key):
+    g = load_golden("factors_" + name)
+    L = golden_factor(g, key + "_L")
+    U = None if key == "icholt" else golden_factor(g, key + "_U")
+    B = ilupp.FactorsPreconditioner(L, U)
+    b = g["b"]
+    y = b.copy()
+    B.apply(y)
+    assert relerr(y, g[key + "_apply"]) <= TOL
+    yt = b.copy()
+    B.apply_trans(yt)
+    assert relerr(yt, g[key + "_apply_trans"]) <= TOL
+    X = np.asfortranarray(P.rhs(b.size, 2, k=3))
+    Y = B @ X
+    Lc = L.tocsr()
+    for c in range(3):
+        yo = oracle.port.apply_llt(Lc, X[:, c]) if U is None else oracle.port.apply_lu(Lc, U.tocsr(), X[:, c])
+        assert relerr(Y[:, c], yo) <= TOL
+    # the handle hands the factors back in the reference's layout
+    F = B.factors()
+    assert abs(F[0] - L).max() == 0
+    if U is not None:
+        assert abs(F[1] - U).max() == 0
+        assert B.total_nnz == Lc.nnz + U.nnz
+
+
+def test_factors_preconditioner_runs_the_same_kernels(ilupp):
+    """zero-fill factors handed back in: same kernels, same values -> bit-for-bit the same apply (line-systolic,
+    level-loop and chunked sync-free paths)"""
+    for A in (P.poisson3d(14), P.poisson2d(40), P.irregular_powerlaw(4000, 9, seed=3), P.convdiff3d(9).tocsc()):
+        A.indices = A.indices.astype(np.int32)
+        A.indptr = A.indptr.astype(np.int32)
+        b = P.rhs(A.shape[0], 6)
+        B0 = ilupp.ILU0Preconditioner(A)
+        L, U = B0.factors()
+        B1 = ilupp.FactorsPreconditioner(L, U)
+        for tr in (False, True):
+            y0, y1 = b.copy(), b.copy()
+            (B0.apply_trans if tr else B0.apply)(y0)
+            (B1.apply_trans if tr else B1.apply)(y1)
+            if A.format == "csr":
+                assert np.array_equal(y0, y1)
+            assert relerr(y1, oracle.port.apply_lu(L, U, b, tr)) <= TOL
+    A = P.poisson3d(12)
+    C0 = ilupp.IChol0Preconditioner(A)
+    (Lc,) = C0.factors()
+    C1 = ilupp.FactorsPreconditioner(Lc)
+    b = P.rhs(A.shape[0], 6)
+    y0, y1 = b.copy(), b.copy()
+    C0.apply(y0)
+    C1.apply(y1)
+    assert np.array_equal(y0, y1)
+    with pytest.raises(ValueError):
+        ilupp.FactorsPreconditioner(U, U)                             # not lower / no unit diagonal
+    with pytest.raises(ValueError):
+        ilupp.FactorsPreconditioner(scipy.sparse.tril(A, -1) + 2 * scipy.sparse.eye(A.shape[0]), scipy.sparse.triu(A))
