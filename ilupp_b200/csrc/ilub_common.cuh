@@ -104,7 +104,7 @@ inline bool first_use_on_this_device(unsigned* masks /* one word per kernel vari
 
 struct Options {
     int64_t factor_algo = 0;    // 0 auto, 1 one launch per level, 2 sync-free, 3 level loop (one cooperative launch), 4 stencil (line-systolic; needs exact = 0)
-    int64_t solve_algo = 0;     // 0 auto (line-systolic on structured grids, level loop on deep narrow DAGs, else sync-free), 1 level-scheduled, 2 sync-free, 3 level loop
+    int64_t solve_algo = 0;     // 0 auto (line-systolic on structured grids, level loop on deep narrow DAGs, else sync-free), 1 level-scheduled, 2 sync-free, 3 level loop (one CTA), 4 cooperative level loop (grid barrier)
     int64_t exact = 1;          // IEEE mul/sub/div in reference order
     int64_t ctas_per_sm = 1;
     int64_t warps_per_cta = 16;

@@ -15,6 +15,7 @@ import sys
 import time
 
 import numpy as np
+import scipy.sparse as sp
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
@@ -136,6 +137,96 @@ def bicgstab_config(N, use_ref, ref_iters=3):
     return out
 
 
+def batched_config(nsys, N, nrhs, use_ref):
+    """BASELINE config 5: nsys independent 2-D Poisson N x N systems, ILU0 factor + nrhs-column apply"""
+    pat, vals = P.batched_poisson2d(nsys, N)
+    n1 = pat.shape[0]
+    B = ilupp.ILU0PreconditionerBatched(pat, vals)
+    del B
+    torch.cuda.synchronize()
+    B = ilupp.ILU0PreconditionerBatched(pat, vals)
+    sym, num, pack, tot = B.timings_ms
+    X = torch.randn((nrhs, nsys * n1), dtype=torch.float64, device="cuda").t()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for i in range(8):
+        torch.cuda.synchronize()
+        e0.record()
+        B.apply(X)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    by = nsys * (12.0 * B.total_nnz / nsys + 8.0 * (n1 + 1)) + 32.0 * nsys * n1 * nrhs
+    out = {"config": "5: %d x poisson2d(%d) ILU0, %d-RHS apply" % (nsys, N, nrhs), "n_per_system": n1, "systems": nsys,
+           "kernel": "plane-per-warp (one launch per triangular solve)", "apply_ms": ms, "solves_per_s": nsys * nrhs / ms * 1e3,
+           "apply_GBs": by / ms / 1e6, "pct_hbm_measured": 100 * by / ms / 1e6 / PEAK, "bytes_per_apply": by,
+           "factor_ms": {"symbolic": sym, "numeric": num, "pack": pack, "total": tot},
+           "systems_per_s": nsys / (num + pack + ms) * 1e3}
+    if use_ref and oracle.ref is not None:
+        As = pat.copy()
+        As.data = vals[0].copy()
+        t = time.perf_counter()
+        R = oracle.ref.ILU0(As)
+        rf = time.perf_counter() - t
+        b = P.rhs(n1, 1)
+        ts = []
+        for _ in range(nrhs):
+            yy = b.copy()
+            t = time.perf_counter()
+            R.apply_inplace(yy)
+            ts.append(time.perf_counter() - t)
+        ra = float(np.median(ts))
+        out["reference_cpu"] = {"cores": 1, "sample": "one system: factorisation + %d applies, scaled to %d systems" % (nrhs, nsys),
+                                "factor_ms_per_system": rf * 1e3, "apply_ms_per_solve": ra * 1e3,
+                                "solves_per_s": 1.0 / ra, "systems_per_s": 1.0 / (rf + nrhs * ra)}
+    print(json.dumps(out), flush=True)
+    return out
+
+
+def factors_config(N, use_ref):
+    """SURVEY.md 8(f)1: the reference's threshold factorisations stay on the CPU (compiled reference, oracle/_ref);
+    their factors are applied on the GPU through FactorsPreconditioner"""
+    m = oracle.ref_module()
+    if m is None:
+        return []
+    A = P.poisson3d(N)
+    A.indices = A.indices.astype(np.int32)
+    A.indptr = A.indptr.astype(np.int32)
+    n = A.shape[0]
+    res = []
+    for name, make in (("ILUT(fill 10, 1e-3)", lambda: m.ILUTPreconditioner(A.data, A.indices, A.indptr, True, 10, 1e-3)),
+                       ("ICholT(fill 5, 1e-3)", lambda: m.ICholTPreconditioner(A.data, A.indices, A.indptr, True, 5, 1e-3))):
+        t = time.perf_counter()
+        R = make()
+        rf = (time.perf_counter() - t) * 1e3
+        fs = [(sp.csr_matrix if f[3] else sp.csc_matrix)((f[0], f[1], f[2]), shape=(n, n)) for f in R.factors_info()]
+        t = time.perf_counter()
+        B = ilupp.FactorsPreconditioner(fs[0], fs[1] if len(fs) > 1 else None)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t) * 1e3
+        ms, b, y = time_apply(B, n)
+        ts = []
+        for _ in range(3):
+            yy = b.copy()
+            t = time.perf_counter()
+            R.apply(yy)
+            ts.append(time.perf_counter() - t)
+        st = B.stats
+        by = apply_bytes(B.total_nnz, n, len(fs) == 1)
+        out = {"config": "f1: poisson3d(%d) %s factors from the reference, GPU apply" % (N, name), "n": n,
+               "total_nnz": int(B.total_nnz), "levels": list(st["levels"][:2]),
+               "kernel": {4: "line-systolic", 5: "level loop (deep DAG)"}.get(st["part_mode"], "chunked sync-free"),
+               "apply_us": ms * 1e3, "apply_GBs": by / ms / 1e6, "pct_hbm_measured": 100 * by / ms / 1e6 / PEAK,
+               "create_wall_ms_incl_host_assembly": wall, "symbolic_ms": B.timings_ms[0],
+               "reference_cpu": {"cores": 1, "factor_ms": rf, "apply_ms": float(np.median(ts)) * 1e3},
+               "apply_relerr_vs_reference": relerr(y, yy)}
+        print(json.dumps(out), flush=True)
+        res.append(out)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/all_configs.json")
@@ -157,6 +248,9 @@ def main():
     o = precond_config("4: irregular power-law n=1M", A, "ilu0", use_ref, ref_applies=3)
     o["row_length"] = {"max": int(rl.max()), "mean": float(rl.mean())}
     res.append(o)
+    res.append(batched_config(64 if args.small else 4096, 128, 16, use_ref))
+    if use_ref:
+        res += factors_config(16 if args.small else 96, use_ref)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(res, f, indent=1)
