@@ -316,7 +316,7 @@ def run_ours(args):
                           "first_creation": {"symbolic": first_sym_ms, "create_wall_incl_h2d": first_create_wall_ms},
                           "numeric_schedule": ("stencil path: pivot recurrence on the line-systolic kernel" if not args.exact else
                                                "level loop (one cooperative launch, grid barrier per level), rows staged in shared memory")},
-            "roofline": {"bound": "hbm", "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep"}.get(B.stats["part_mode"], "k_trsv_syncfree"), "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels"}.get(B.stats["part_mode"], "k_trsv_syncfree"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": by / 2.0, "avg_launch_ms": kernel_ms,
                          "second_bound": "dependency critical path: %d levels per solve" % B.stats["levels"][0]},

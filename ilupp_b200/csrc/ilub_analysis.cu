@@ -779,6 +779,11 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         analyse_deep(h, slot, s);
         T.part_mode = 5;
         T.nparts = 1;
+    } else if (!sys_ok && levels_wanted(h, slot)) {
+        DebugTimer t("  level sets", s);
+        build_level_sets(h, slot, s);  // the cooperative level loop walks the CSR-read arrays: no packed layout
+        T.part_mode = 6;
+        T.nparts = 0;
     } else if (!sys_ok) {  // (slot 0: the sync-free factorisation builds it on demand, factor_prepare)
         DebugTimer t("  chunked layout", s);
         analyse_generic(h, slot, s);

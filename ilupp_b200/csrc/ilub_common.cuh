@@ -224,7 +224,7 @@ struct TriSolve {
     DevBuf<ulonglong2> mail;      // [n] {x bits, epoch tag}: the global dependency path (one 16-B atomic access)
     unsigned long long epoch = 0;
     int level_aligned = 0;
-    int part_mode = 0;            // 0 contiguous ranges, 2 / 3: strips / pencils from detected strides
+    int part_mode = 0;            // 0 contiguous ranges, 2 / 3: strips / pencils from detected strides, 4 line-systolic, 5 level loop (one CTA), 6 cooperative level loop
     int stride_y = 0, stride_z = 0, grid_y = 1, grid_z = 1;
     // launch configuration of the sync-free kernel, fixed at analysis (near is baked into idx)
     int cfg_warps = 16, cfg_fetch = 2, cfg_ring_chunks = 128, cfg_near = 56, cfg_halo = 2048, cfg_stages = 2,
@@ -342,6 +342,7 @@ void analyse_generic(ilub_handle* h, int which, cudaStream_t s);          // par
 void pack_solve_values(ilub_handle* h, int which, cudaStream_t s);        // (re)fill val/diag from lu
 void build_level_sets(ilub_handle* h, int which, cudaStream_t s);
 bool deep_wanted(const ilub_handle* h, int slot);
+bool levels_wanted(const ilub_handle* h, int slot);   // cooperative level loop (ilub_trsv.cu)
 void analyse_deep(ilub_handle* h, int slot, cudaStream_t s);
 void pack_deep(ilub_handle* h, int slot, cudaStream_t s);
 void run_deep(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s);

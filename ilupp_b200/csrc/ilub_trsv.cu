@@ -662,6 +662,16 @@ inline int blocks_for(int64_t work, int threads) { return (int)((work + threads 
 
 }  // namespace
 
+// many levels of moderate width: the cooperative level loop (the chunked kernel's contiguous row ranges serialise on
+// such DAGs: measured 92 ms against 5 ms on ILUT factors of a 64^3 Poisson matrix)
+bool levels_wanted(const ilub_handle* h, int slot) {
+    const TriSolve& T = h->solve[slot];
+    const int64_t algo = options().solve_algo;
+    if (algo == 4) return true;
+    if (algo != 0 || T.sys.built || deep_wanted(h, slot)) return false;
+    return T.nlevels > 32 && (int64_t)h->n < (int64_t)T.nlevels * 16384;
+}
+
 void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
     TriSolve& T = h->solve[slot];
     ILUB_REQUIRE(T.built, ILUB_ERR_INVALID, "solve not analysed");
@@ -701,9 +711,7 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
         run_deep(h, slot, x, ldx, nrhs, s);
         return;
     }
-    // many levels of moderate width: the cooperative level loop (the chunked kernel's contiguous row ranges serialise on
-    // such DAGs: measured 92 ms against 5 ms on ILUT factors of a 64^3 Poisson matrix)
-    if (opt.solve_algo == 4 || (opt.solve_algo == 0 && T.nlevels > 32 && (int64_t)h->n < (int64_t)T.nlevels * 16384)) {
+    if (levels_wanted(h, slot)) {
         build_level_sets(h, slot, s);
         const SolveSource src = solve_source(h, slot);
         const SrcDev S = to_dev(src);

@@ -77,7 +77,7 @@ def precond_config(name, A, kind, use_ref, ref_applies=5):
     by = apply_bytes(B.total_nnz, n, ichol)
     st = B.stats
     out = {"config": name, "kind": kind, "n": n, "nnz": int(A.nnz), "total_nnz": int(B.total_nnz),
-           "levels": list(st["levels"][:2]), "kernel": {4: "line-systolic", 5: "level loop (deep DAG)"}.get(st["part_mode"], "chunked sync-free"),
+           "levels": list(st["levels"][:2]), "kernel": {4: "line-systolic", 5: "level loop (deep DAG)", 6: "cooperative level loop"}.get(st["part_mode"], "chunked sync-free"),
            "apply_us": ms * 1e3, "apply_GBs": by / ms / 1e6, "pct_hbm_measured": 100 * by / ms / 1e6 / PEAK,
            "bytes_per_apply": by,
            "factor_ms": {"symbolic": sym, "numeric": num, "pack": pack, "total": tot, "refactor_numeric": refac,
@@ -217,7 +217,7 @@ def factors_config(N, use_ref):
         by = apply_bytes(B.total_nnz, n, len(fs) == 1)
         out = {"config": "f1: poisson3d(%d) %s factors from the reference, GPU apply" % (N, name), "n": n,
                "total_nnz": int(B.total_nnz), "levels": list(st["levels"][:2]),
-               "kernel": {4: "line-systolic", 5: "level loop (deep DAG)"}.get(st["part_mode"], "chunked sync-free"),
+               "kernel": {4: "line-systolic", 5: "level loop (deep DAG)", 6: "cooperative level loop"}.get(st["part_mode"], "chunked sync-free"),
                "apply_us": ms * 1e3, "apply_GBs": by / ms / 1e6, "pct_hbm_measured": 100 * by / ms / 1e6 / PEAK,
                "create_wall_ms_incl_host_assembly": wall, "symbolic_ms": B.timings_ms[0],
                "reference_cpu": {"cores": 1, "factor_ms": rf, "apply_ms": float(np.median(ts)) * 1e3},
