@@ -554,7 +554,7 @@ def _grid2d(nx, ny, seed):
 
 
 PLANE_GRIDS = [("1-block", 20, 20), ("2-blocks-ragged", 37, 50), ("4-blocks-ragged", 70, 100), ("4-blocks", 128, 128),
-               ("8-blocks", 256, 256), ("wide", 300, 9)]
+               ("8-blocks", 256, 256), ("wide", 300, 9), ("tiny", 3, 5), ("two-columns", 2, 70), ("ragged-8", 9, 230)]
 
 
 @pytest.mark.parametrize("name,nx,ny", PLANE_GRIDS, ids=[g[0] for g in PLANE_GRIDS])
