@@ -114,6 +114,10 @@ __global__ void k_tri_unpack(int64_t nt, const unsigned long long* __restrict__ 
 // sync-free level analysis: one thread per row, rows handed out in dependency-safe order by a
 // ticket counter (a warp only ever waits for rows whose ticket was drawn before its own, and those
 // warps are running), levels published with volatile stores -- the value itself is the flag.
+// Dependencies on rows of the SAME warp (the offset-1 chain of a lexicographic grid: 32 dependent hops through L2
+// per warp if they went through memory) never touch memory: they are collected in a lane mask and resolved by one
+// pass of 31 shuffles in lane order -- lane k is final when the pass reaches it, because its own in-warp
+// dependencies are lanes below k.
 __global__ void __launch_bounds__(256) k_levels(SrcDev S, int n, int* level, int* ticket, int* nlev,
                                                 long long spin_limit, int* status) {
     const int lane = threadIdx.x & 31;
@@ -130,30 +134,36 @@ __global__ void __launch_bounds__(256) k_levels(SrcDev S, int n, int* level, int
         int p = valid ? src_beg(S, row) : 0;
         const int e = valid ? src_end(S, row) : 0;
         int lv = 0;
-        bool fin = !valid;
+        unsigned inmask = 0;
+        bool dead = false;
         const long long t0 = clock64();
         unsigned spins = 0;
-        while (true) {
-            if (!fin) {
-                while (p < e) {
-                    const int l = vlevel[S.dep_idx[p]];
-                    if (l < 0) break;
-                    lv = max(lv, l + 1);
-                    ++p;
-                }
-                if (p >= e) {
-                    vlevel[row] = lv;
-                    fin = true;
+        for (; p < e && !dead; ++p) {
+            const int dep = S.dep_idx[p];
+            const int64_t pd = S.backward ? (int64_t)n - 1 - dep : (int64_t)dep;  // solve position of the dependency
+            if (pd >= base && pd < r) {
+                inmask |= 1u << (int)(pd - base);
+                continue;
+            }
+            int l;
+            while ((l = vlevel[dep]) < 0) {
+                if ((++spins & 255u) == 0 && (clock64() - t0 > spin_limit || *(volatile int*)status != 0)) {
+                    dead = true;
+                    break;
                 }
             }
-            if (__all_sync(0xffffffffu, fin)) break;
-            if ((++spins & 255u) == 0) {
-                if (clock64() - t0 > spin_limit || *(volatile int*)status != 0) {
-                    if (lane == 0) atomicCAS(status, 0, 100);
-                    return;
-                }
-            }
+            if (!dead) lv = max(lv, l + 1);
         }
+        if (__any_sync(0xffffffffu, dead)) {
+            if (lane == 0) atomicCAS(status, 0, 100);
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < 31; ++k) {
+            const int v = __shfl_sync(0xffffffffu, lv, k);
+            if ((inmask >> k) & 1u) lv = max(lv, v + 1);
+        }
+        if (valid) vlevel[row] = lv;
         const int m = __reduce_max_sync(0xffffffffu, valid ? lv + 1 : 0);
         if (lane == 0) atomicMax(nlev, m);
     }
