@@ -11,6 +11,8 @@
 #include <cstring>
 #include <cub/cub.cuh>
 
+#include <climits>
+
 #include "ilub_common.cuh"
 
 namespace ilub {
@@ -138,13 +140,37 @@ __global__ void __launch_bounds__(256) k_levels(SrcDev S, int n, int* level, int
         bool dead = false;
         const long long t0 = clock64();
         unsigned spins = 0;
-        for (; p < e && !dead; ++p) {
-            const int dep = S.dep_idx[p];
-            const int64_t pd = S.backward ? (int64_t)n - 1 - dep : (int64_t)dep;  // solve position of the dependency
-            if (pd >= base && pd < r) {
-                inmask |= 1u << (int)(pd - base);
-                continue;
+        // first sweep: the levels of eight dependencies are requested together (independent loads: one L2 round trip
+        // per eight entries, not one per entry); what was not ready yet -- in a deep DAG the few entries nearest to
+        // the row -- is polled afterwards
+        int lo = e, hi = -1;
+        for (int q0 = p; q0 < e; q0 += 8) {
+            int l8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                l8[u] = INT_MAX;
+                if (q0 + u < e) {
+                    const int dep = S.dep_idx[q0 + u];
+                    const int64_t pd = S.backward ? (int64_t)n - 1 - dep : (int64_t)dep;  // solve position of the dependency
+                    if (pd >= base && pd < r) inmask |= 1u << (int)(pd - base);
+                    else l8[u] = vlevel[dep];
+                }
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (l8[u] == INT_MAX) continue;
+                if (l8[u] >= 0) {
+                    lv = max(lv, l8[u] + 1);
+                } else {
+                    lo = min(lo, q0 + u);
+                    hi = max(hi, q0 + u);
+                }
+            }
+        }
+        for (int q = lo; q <= hi && !dead; ++q) {
+            const int dep = S.dep_idx[q];
+            const int64_t pd = S.backward ? (int64_t)n - 1 - dep : (int64_t)dep;
+            if (pd >= base && pd < r) continue;
             int l;
             while ((l = vlevel[dep]) < 0) {
                 if ((++spins & 255u) == 0 && (clock64() - t0 > spin_limit || *(volatile int*)status != 0)) {
