@@ -164,8 +164,13 @@ ILUB_API int ilub_create_ichol0_batched(const double* values, const int32_t* ind
  *   "factor_algo"  0 = auto (default: level loop when levels are few and wide, else sync-free), 1 = one launch per
  *                  level, 2 = sync-free, 3 = level loop (one cooperative launch with grid barriers), 4 = stencil path
  *                  (pivot recurrence on the line-systolic kernel; stencil matrices with "exact" = 0 only, else 3)
- *   "solve_algo"   0 = auto (default: line-systolic on structured grids, level loop on deep narrow DAGs, else chunked
- *                  sync-free), 1 = one launch per level, 2 = chunked sync-free, 3 = level loop (one CTA, one barrier per level)
+ *   "solve_algo"   0 = auto (default: line-systolic / plane-per-warp on structured grids, level loop on deep narrow
+ *                  DAGs, cooperative level loop for many moderately wide levels, else chunked sync-free), 1 = one
+ *                  launch per level, 2 = chunked sync-free, 3 = level loop (one CTA, one barrier per level),
+ *                  4 = cooperative level loop (one launch, grid barrier per level)
+ *   "sys_plane"    plane-per-warp kernel for 2-D grids / batches: 0 = off, 1 = auto (default: at least 3 right-hand
+ *                  sides or more planes than two waves of CTAs), 2 = whenever applicable; "plane_r", "plane_wpc",
+ *                  "plane_npc": right-hand sides per warp (1 | 2), consumer warps per CTA, planes per CTA (0 = auto)
  *   "exact"        1 (default) = IEEE mul/sub/div in the reference's operation order (bit-for-bit
  *                  with a non-FMA build of the reference on lane-per-row chunks); 0 = FMA + reciprocal
  *   "ctas_per_sm", "warps_per_cta", "near_window", "spin_limit_ms" : tuning / watchdog */
