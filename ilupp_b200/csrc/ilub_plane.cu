@@ -1,6 +1,5 @@
 // Plane-per-warp triangular solves for 2-D grids and block-diagonal batches of them (BASELINE config 5: 4096
-// independent 2-D Poisson systems x 16 right-hand sides; config 1: one 256 x 256 grid) -- the multi-right-hand-side
-// path behind apply() / `B @ X` (replaces the column loop over matrix_sparse::triangular_solve,
+// independent 2-D Poisson systems x 16 right-hand sides) -- the multi-right-hand-side path behind apply() / `B @ X` (replaces the column loop over matrix_sparse::triangular_solve,
 // sparse_implementation.h:4040-4087, ilupp/__init__.py:122-150 `_matmat`).
 //
 // Same (task, step, lane) coefficient stream as the line-systolic kernel (ilub_systolic.cu): one lane per grid line,
@@ -18,6 +17,8 @@
 //   * Right-hand side in / solution out: every warp moves its own data with 8-byte cp.async copies in skewed
 //     4-line x 8-column rectangles (line group q is shifted by -4q columns, so a rectangle is consumed within 11
 //     steps of its arrival): the window is 32 slots per line instead of 64, 8.25 KB per (line block, rhs).
+//   * A CTA walks several consecutive planes: a line block starts the next plane as soon as it has finished the
+//     previous one, so the ramps of the line-block skew are paid once per CTA, not once per plane.
 // Arithmetic and rounding are those of the line-systolic kernel (`exact` = the reference's operation order, bit for
 // bit; otherwise coefficients pre-divided by the diagonal and FMAs).
 #include <algorithm>
@@ -65,7 +66,6 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 __device__ __forceinline__ void lds_2f64(uint32_t a, double& v0, double& v1) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a));
 }
-__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 // 8-byte asynchronous copy global -> shared; src_bytes = 0 writes zeros (padding rows and columns)
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, unsigned src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
