@@ -581,11 +581,24 @@ __global__ void __launch_bounds__(256) k_trsv_levels(SrcDev S, const double* __r
             const int row = lvl_rows[sidx];
             const int b = src_beg(S, row), e = src_end(S, row);
             if (EXACT) {
+                // the reference's accumulation order, one lane per row; the operands of eight entries are requested
+                // together (independent loads), then consumed in order: same bits, an eighth of the round trips
                 double acc = __ldcg(x + row);
-                for (int j = 0; j < e - b; ++j) {
-                    const int q = S.reverse ? e - 1 - j : b + j;
-                    const int vp = S.val_pos ? S.val_pos[q] : q;
-                    acc = sub_mul<true>(acc, lu[vp], __ldcg(x + S.dep_idx[q]));
+                for (int j0 = 0; j0 < e - b; j0 += 8) {
+                    double v8[8], x8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v8[u] = 0.0;
+                        x8[u] = 0.0;
+                        if (j0 + u < e - b) {
+                            const int q = S.reverse ? e - 1 - (j0 + u) : b + j0 + u;
+                            v8[u] = lu[S.val_pos ? S.val_pos[q] : q];
+                            x8[u] = __ldcg(x + S.dep_idx[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (j0 + u < e - b) acc = sub_mul<true>(acc, v8[u], x8[u]);
                 }
                 if (!unit_diag) acc = __ddiv_rn(acc, lu[S.diag_pos[row]]);
                 x[row] = acc;
