@@ -493,6 +493,7 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "plane_r") o.plane_r = value;
         else if (k == "plane_wpc") o.plane_wpc = value;
         else if (k == "plane_npc") o.plane_npc = value;
+        else if (k == "levels_cluster") o.levels_cluster = value;
         else if (k == "sys_pdl") o.sys_pdl = value;
         else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
     });
@@ -524,6 +525,7 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "plane_r") *value = o.plane_r;
         else if (k == "plane_wpc") *value = o.plane_wpc;
         else if (k == "plane_npc") *value = o.plane_npc;
+        else if (k == "levels_cluster") *value = o.levels_cluster;
         else if (k == "sys_pdl") *value = o.sys_pdl;
         else if (k == "fetch_warps") *value = o.fetch_warps;
         else if (k == "halo_entries") *value = o.halo_entries;

@@ -130,6 +130,7 @@ struct Options {
     int64_t sys_cluster = 0;    // line-systolic: largest thread-block cluster to try (0 = auto: 8, 1 = no clusters)
     int64_t sys_plane = 1;      // plane-per-warp kernel for grids without a plane-to-plane dependency: 0 off, 1 auto, 2 whenever applicable
     int64_t plane_r = 1;        // plane-per-warp: right-hand sides per warp (1 or 2)
+    int64_t levels_cluster = 1; // cooperative level loop: one thread-block cluster with the hardware barrier when the levels fit (0: always the grid barrier)
     int64_t plane_npc = 0;      // plane-per-warp: consecutive planes per CTA (0 = auto)
     int64_t plane_wpc = 0;      // plane-per-warp: consumer warps per CTA (0 = as many as shared memory holds, at most 8)
 };

@@ -23,6 +23,10 @@
 #include <climits>
 #include <cub/cub.cuh>
 
+#include <cooperative_groups.h>
+
+#include <cstring>
+
 #include "ilub_common.cuh"
 #include "ilub_ptx.cuh"
 
@@ -516,8 +520,8 @@ __global__ void k_trsv_level(SrcDev S, const double* __restrict__ lu, int unit_d
 // straight from the CSR-read arrays, G lanes per row (EXACT: one lane per row, the reference's accumulation order),
 // and every CTA passes a grid-wide barrier (monotone arrival counter, relaxed polls) between two levels.  The grid is
 // sized to the average level -- the barrier costs one atomic and one polling thread per CTA.
-template <bool EXACT, int G>
-__global__ void __launch_bounds__(256) k_trsv_levels(SrcDev S, const double* __restrict__ lu, int unit_diag,
+template <bool EXACT, int G, bool CLUSTER>
+__global__ void __launch_bounds__(512) k_trsv_levels(SrcDev S, const double* __restrict__ lu, int unit_diag,
                                                      const int* __restrict__ lvl_ptr, const int* __restrict__ lvl_rows,
                                                      int nlevels, double* x, unsigned* barrier, long long spin_limit,
                                                      int* status) {
@@ -620,7 +624,13 @@ __global__ void __launch_bounds__(256) k_trsv_levels(SrcDev S, const double* __r
         }
         prefetch(l + 1);
         if (l + 1 == nlevels) break;
-        // grid barrier: the values of level l are visible (x is read through L2) before anyone starts level l + 1
+        // barrier: the values of level l are visible (x is read through L2) before anyone starts level l + 1
+        if (CLUSTER) {
+            // the whole grid is ONE thread-block cluster: the hardware cluster barrier (arrive.release / wait.acquire at
+            // cluster scope) replaces the atomic counter in global memory -- a fraction of its latency
+            cooperative_groups::this_cluster().sync();
+            continue;
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -730,13 +740,7 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
         const SrcDev S = to_dev(src);
         const int unit = src.unit_diag ? 1 : 0;
         const int G = exact ? 1 : 8;
-        void* kern = exact ? (void*)k_trsv_levels<true, 1> : (void*)k_trsv_levels<false, 8>;
-        const int block = 256;
-        int occ = 0;
-        ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, 0));
-        ILUB_REQUIRE(occ > 0, ILUB_ERR_CUDA, "level-loop solve kernel does not fit on an SM");
         const int64_t avg = ((int64_t)h->n + T.nlevels - 1) / T.nlevels;  // rows of an average level
-        int grid = (int)std::min<int64_t>((int64_t)occ * h->sm_count, std::max<int64_t>(4, (2 * avg * G + block - 1) / block));
         if (h->fbarrier.n < 1) h->fbarrier.alloc(1);
         const int* lvl_ptr = T.lvl_ptr.p;
         const int* lvl_rows = T.lvl_rows.p;
@@ -747,13 +751,44 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
         int* status = h->status.p;
         int unit_arg = unit;
         SrcDev Sarg = S;
-        for (int c = 0; c < nrhs; ++c) {
-            double* xc = x + (int64_t)c * ldx;
-            ILUB_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), s));
-            void* args[] = {(void*)&Sarg, (void*)&lu, (void*)&unit_arg, (void*)&lvl_ptr, (void*)&lvl_rows, (void*)&nlevels,
-                            (void*)&xc,   (void*)&barrier, (void*)&spin_limit, (void*)&status};
-            ILUB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, 0, s));
-            h->launches++;
+        // levels that fit a thread-block cluster of 8 CTAs (512 lane groups at G = 8) a few times over: one cluster, hardware
+        // barrier; wider ones: a cooperative grid sized to the average level, atomic-counter barrier
+        const bool cluster = opt.levels_cluster != 0 && avg * G <= 4 * 8 * 512;
+        if (cluster) {
+            typedef void (*kern_t)(SrcDev, const double*, int, const int*, const int*, int, double*, unsigned*, long long, int*);
+            const kern_t kern = exact ? (kern_t)k_trsv_levels<true, 1, true> : (kern_t)k_trsv_levels<false, 8, true>;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(8, 1, 1);
+            cfg.blockDim = dim3(512, 1, 1);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 8;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            for (int c = 0; c < nrhs; ++c) {
+                double* xc = x + (int64_t)c * ldx;
+                ILUB_CUDA(cudaLaunchKernelEx(&cfg, kern, Sarg, lu, unit_arg, lvl_ptr, lvl_rows, nlevels, xc, barrier, spin_limit, status));
+                h->launches++;
+            }
+        } else {
+            void* kern = exact ? (void*)k_trsv_levels<true, 1, false> : (void*)k_trsv_levels<false, 8, false>;
+            const int block = 256;
+            int occ = 0;
+            ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, 0));
+            ILUB_REQUIRE(occ > 0, ILUB_ERR_CUDA, "level-loop solve kernel does not fit on an SM");
+            int grid = (int)std::min<int64_t>((int64_t)occ * h->sm_count, std::max<int64_t>(4, (2 * avg * G + block - 1) / block));
+            for (int c = 0; c < nrhs; ++c) {
+                double* xc = x + (int64_t)c * ldx;
+                ILUB_CUDA(cudaMemsetAsync(barrier, 0, sizeof(unsigned), s));
+                void* args[] = {(void*)&Sarg, (void*)&lu, (void*)&unit_arg, (void*)&lvl_ptr, (void*)&lvl_rows, (void*)&nlevels,
+                                (void*)&xc,   (void*)&barrier, (void*)&spin_limit, (void*)&status};
+                ILUB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, 0, s));
+                h->launches++;
+            }
         }
         ILUB_CUDA(cudaGetLastError());
         return;

@@ -200,11 +200,13 @@ def test_oracle_parity(ilupp, name, gen, sym, fmt):
                                   {"solve_algo": 2, "ring_chunks": 64, "near_window": 8}, {"sys_pz": 3},
                                   {"sys_stages": 2, "sys_pz": 2}, {"factor_algo": 2}, {"factor_algo": 3},
                                   {"factor_algo": 3, "exact": 0}, {"solve_algo": 3}, {"solve_algo": 3, "exact": 0},
-                                  {"solve_algo": 4}, {"solve_algo": 4, "exact": 0}],
+                                  {"solve_algo": 4}, {"solve_algo": 4, "exact": 0},
+                                  {"solve_algo": 4, "levels_cluster": 0}, {"solve_algo": 4, "levels_cluster": 0, "exact": 0}],
                          ids=["level-scheduled", "fma", "syncfree", "syncfree-fma", "few-warps", "contiguous",
                               "one-stage-narrow", "small-ring", "systolic-pz3", "systolic-2stage", "factor-syncfree",
                               "factor-level-loop", "factor-level-loop-fma", "solve-level-loop", "solve-level-loop-fma",
-                              "solve-coop-level-loop", "solve-coop-level-loop-fma"])
+                              "solve-coop-level-loop", "solve-coop-level-loop-fma", "solve-grid-barrier-level-loop",
+                              "solve-grid-barrier-level-loop-fma"])
 def test_kernel_variants(ilupp, opts):
     """every schedule / arithmetic variant meets the same parity bar"""
     defaults = {k: ilupp.get_option(k) for k in opts}
