@@ -751,9 +751,11 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
         int* status = h->status.p;
         int unit_arg = unit;
         SrcDev Sarg = S;
-        // levels that fit a thread-block cluster of 8 CTAs (512 lane groups at G = 8) a few times over: one cluster, hardware
-        // barrier; wider ones: a cooperative grid sized to the average level, atomic-counter barrier
-        const bool cluster = opt.levels_cluster != 0 && avg * G <= 4 * 8 * 512;
+        // an average level that fits ONE pass of a thread-block cluster of 8 CTAs (4096 lanes) with room to spare: one
+        // cluster, hardware barrier (64^3 ILUT factors, 297 rows per level: 3.9 ms against 4.9 ms); wider levels: a
+        // cooperative grid sized to the average level, atomic-counter barrier (96^3, 664 rows per level: 8.5 ms against
+        // 12.5 ms on the eight SMs of a cluster)
+        const bool cluster = opt.levels_cluster != 0 && avg * G <= 2400;
         if (cluster) {
             typedef void (*kern_t)(SrcDev, const double*, int, const int*, const int*, int, double*, unsigned*, long long, int*);
             const kern_t kern = exact ? (kern_t)k_trsv_levels<true, 1, true> : (kern_t)k_trsv_levels<false, 8, true>;
