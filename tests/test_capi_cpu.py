@@ -52,7 +52,20 @@ def test_argument_errors_do_not_need_a_gpu():
     v = C.c_int64()
     assert lib.ilub_set_option(b"exact", C.c_int64(1)) == 0 and lib.ilub_get_option(b"exact", C.byref(v)) == 0
     assert v.value == 1
+    # every documented option key round-trips (include/ilub.h "options"), defaults restored
+    for key, probe in ((b"solve_algo", 4), (b"factor_algo", 3), (b"sys_plane", 2), (b"plane_r", 2), (b"plane_wpc", 3),
+                       (b"plane_npc", 5), (b"levels_cluster", 0), (b"sys_pdl", 0), (b"spin_limit_ms", 77)):
+        old = C.c_int64()
+        assert lib.ilub_get_option(key, C.byref(old)) == 0, key
+        assert lib.ilub_set_option(key, C.c_int64(probe)) == 0 and lib.ilub_get_option(key, C.byref(v)) == 0
+        assert v.value == probe
+        assert lib.ilub_set_option(key, old) == 0
     assert lib.ilub_apply(None, 0, None, C.c_int64(1), C.c_int32(1), 0, None) == 1
+    # factors handed in from elsewhere: same argument checks, no device needed to be refused
+    rc = lib.ilub_create_from_factors(0, None, None, None, C.c_int32(4), C.c_int64(4), 1, 0, 0, None, C.byref(h))
+    assert rc == 1 and b"null" in lib.ilub_last_error()
+    rc = lib.ilub_create_from_factors(7, d, i, p, C.c_int32(1), C.c_int64(1), 1, 0, 0, None, C.byref(h))
+    assert rc == 1 and b"kind" in lib.ilub_last_error()
 
 
 def test_python_layer_errors_match_reference():
