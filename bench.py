@@ -252,10 +252,10 @@ def run_ours(args):
                   "factor_relerr": float(np.abs(L.data - Lo.data).max() / np.abs(Lo.data).max()),
                   "pattern_equal": bool(np.array_equal(L.indices, Lo.indices) and np.array_equal(L.indptr, Lo.indptr)),
                   "bit_exact": bool(np.array_equal(y, yo))}
-        if world == 1 or True:
-            c = cpu_reference_apply(steps=40 if not args.quick else 5, warmup=2)
-            cpu = {"value": c["gbs"], "unit": UNIT, "cores": 1, "kind": c["kind"], "sample": c["sample"],
-                   "apply_ms": c["apply_ms"], "factor_ms": c["factor_ms"]}
+        # the reference's CPU path on this box's host cores, bounded sample (rank 0; reported at every N)
+        c = cpu_reference_apply(steps=40 if not args.quick else 5, warmup=2)
+        cpu = {"value": c["gbs"], "unit": UNIT, "cores": 1, "kind": c["kind"], "sample": c["sample"],
+               "apply_ms": c["apply_ms"], "factor_ms": c["factor_ms"]}
 
     # ---- BASELINE config 5: 4096 independent 2-D Poisson 128^2 systems, ILU0 factor + 16-RHS apply, sharded
     batched = None
