@@ -125,3 +125,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "ilub_oracle" not in text and "oracle/" not in text, f
+
+
+def test_factors_preconditioner_argument_checks():
+    """SURVEY.md 8(f)1 entry point: shape / triangularity / unit-diagonal checks happen on the host, and without a device
+    the call fails loudly instead of falling back"""
+    import ilupp_b200 as ilupp
+    n = 6
+    L = scipy.sparse.tril(scipy.sparse.random(n, n, density=0.5, random_state=1), -1) + scipy.sparse.identity(n)
+    U = scipy.sparse.triu(scipy.sparse.random(n, n, density=0.5, random_state=2), 1) + 3.0 * scipy.sparse.identity(n)
+    with pytest.raises(ValueError, match="square"):
+        ilupp.FactorsPreconditioner(scipy.sparse.csr_matrix(np.ones((3, 4))))
+    with pytest.raises(ValueError, match="same shape"):
+        ilupp.FactorsPreconditioner(L, scipy.sparse.identity(n + 1, format="csr"))
+    with pytest.raises(ValueError, match="lower and U upper"):
+        ilupp.FactorsPreconditioner(U, U)
+    with pytest.raises(ValueError, match="lower triangular"):
+        ilupp.FactorsPreconditioner(U)
+    with pytest.raises(ValueError, match="unit diagonal"):
+        ilupp.FactorsPreconditioner(L + scipy.sparse.identity(n), U)
+    if ilupp._ilupp.device_count() == 0:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            ilupp.FactorsPreconditioner(L, U)
