@@ -102,13 +102,45 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
+def load_problems():
+    """ilupp_b200/problems.py loaded by path: the CPU reference arm must not import the package (that would map
+    libilub.so / _ilupp into a process that is supposed to run the reference only)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench_problems", os.path.join(ROOT, "ilupp_b200", "problems.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def pin_to_one_core():
+    """the single-threaded CPU baseline runs pinned to one core."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, {cores[len(cores) // 2]})
+        return cores
+    except Exception:
+        return None
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_reference_apply(steps, warmup):
     """The reference's own C++ ILU0/IChol0 path on the host (oracle/_ref when built, else the C port)."""
     import oracle
-    from ilupp_b200 import problems as P
+    P = load_problems()
     A = P.poisson3d(GRID)
     n = A.shape[0]
     kind = "reference" if oracle.ref is not None else "port"
+    prev_affinity = pin_to_one_core()
     t0 = time.perf_counter()
     if oracle.ref is not None:
         R = oracle.ref.IChol0(A)
@@ -134,10 +166,15 @@ def cpu_reference_apply(steps, warmup):
         apply_inplace(y)
         ts.append(time.perf_counter() - t)
     by = apply_bytes(total_nnz, n)
+    if prev_affinity:
+        try:
+            os.sched_setaffinity(0, set(prev_affinity))
+        except Exception:
+            pass
     return {"kind": kind, "cores": 1, "factor_ms": factor_s * 1e3, "apply_ms": float(np.mean(ts)) * 1e3,
-            "gbs": by / float(np.mean(ts)) / 1e9, "steps": steps,
-            "sample": "1 IChol0 factorisation + %d applies of the full 128^3 workload, single thread "
-                      "(the reference has no threading), %d host cores present" % (steps, os.cpu_count())}
+            "gbs": by / float(np.mean(ts)) / 1e9, "steps": steps, "cpu_model": cpu_model(),
+            "sample": "1 IChol0 factorisation + %d applies of the full 128^3 workload, single thread pinned to one core "
+                      "(the reference has no threading), %d host cores present, CPU: %s" % (steps, os.cpu_count(), cpu_model())}
 
 
 def run_reference(args):

@@ -115,17 +115,26 @@ def _device_args(x, n):
     elif x.dim() == 2:
         if x.shape[0] != n:
             raise RuntimeError("vector has wrong size for preconditioner!")
-        if x.stride(0) != 1 and x.shape[1] != 1:
-            raise RuntimeError("Expected column-major (n, k) tensor for multi-RHS apply!")
+        if x.stride(0) != 1 and n > 1:
+            # also for (n, 1) views such as X[:, :1] of a C-ordered (n, k) tensor: the kernels read n contiguous doubles
+            raise RuntimeError("Expected contiguous array for b!" if x.shape[1] == 1 else
+                               "Expected column-major (n, k) tensor for multi-RHS apply!")
         nrhs = x.shape[1]
         ldx = x.stride(1) if nrhs > 1 else n
+        if nrhs > 1 and ldx < n:
+            raise RuntimeError("Expected column-major (n, k) tensor for multi-RHS apply!")
     else:
         raise RuntimeError("Expected 1D array for b!")
     return x.data_ptr(), nrhs, ldx, torch.cuda.current_stream(x.device).cuda_stream
 
 
+def trim_cache():
+    """Return the device memory cached by libilub's allocator (freed blocks kept for reuse) to the driver."""
+    _ilupp.trim_cache()
+
+
 def solve(A, b, rtol=1e-4, atol=1e-4, max_iter=500, threshold=0.1, fill_in=None, params=None, info=False,
-          precond="ilu0"):
+          precond="ilu0", device=0):
     """Solve Ax=b with preconditioned BiCGStab (reference ilupp/__init__.py:85-119).
 
     Same signature and return convention as the reference.  The reference always builds its
@@ -138,11 +147,11 @@ def solve(A, b, rtol=1e-4, atol=1e-4, max_iter=500, threshold=0.1, fill_in=None,
     Ad, Ai, Ap, Ao = _matrix_fields(A)
     b = np.ascontiguousarray(b, dtype=np.float64)
     if precond == "ilu0":
-        sol, it, rtol_out, atol_out = _ilupp.solve(Ad, Ai, Ap, Ao, b, rtol, atol, max_iter, params)
+        sol, it, rtol_out, atol_out = _ilupp.solve(Ad, Ai, Ap, Ao, b, rtol, atol, max_iter, params, device)
     elif precond == "ichol0":
         if b.shape[0] != A.shape[0]:
             raise RuntimeError("right-hand side has wrong size!")
-        pr = _ilupp.IChol0Preconditioner(Ad, Ai, Ap, Ao)
+        pr = _ilupp.IChol0Preconditioner(Ad, Ai, Ap, Ao, device)
         sol, it, rtol_out, atol_out = pr.solve(b, rtol, atol, max_iter)
     else:
         raise ValueError("precond must be 'ilu0' or 'ichol0'")
@@ -231,6 +240,11 @@ class _BaseWrapper(scipy.sparse.linalg.LinearOperator):
         """BiCGStab for the matrix this preconditioner was built from, with self as split preconditioner."""
         sol, it, r, a = self.pr.solve(np.ascontiguousarray(b, dtype=np.float64), rtol, atol, max_iter)
         return (sol, (it, r, a)) if info else sol
+
+    def check_status(self, stream=0):
+        """Synchronise `stream` and raise if a kernel of an asynchronous (torch-tensor) call on this object was aborted
+        by the watchdog.  (Such a failure is otherwise raised by the next call on the object.)"""
+        self.pr.check_status(stream)
 
     @property
     def timings_ms(self):
@@ -339,11 +353,11 @@ class IChol0PreconditionerBatched(_BatchedWrapper):
 
 ########################################
 
-def ichol0(A):
+def ichol0(A, device=0):
     """Compute the L factor of an incomplete Cholesky decomposition without fill-in for the symmetric matrix A."""
-    return _matrix_from_info(*_ilupp.ichol0(*_matrix_fields(A)))
+    return _matrix_from_info(*_ilupp.ichol0(*_matrix_fields(A), device))
 
 
-def ilu0(A):
+def ilu0(A, device=0):
     """Compute the (L,U) factors of an incomplete LU decomposition without fill-in."""
-    return tuple(_matrix_from_info(*mtx) for mtx in _ilupp.ilu0(*_matrix_fields(A)))
+    return tuple(_matrix_from_info(*mtx) for mtx in _ilupp.ilu0(*_matrix_fields(A), device))

@@ -201,7 +201,7 @@ void apply_buffer(const Precond& pr, py::buffer x, int transpose) {
     if (info.shape[0] != pr.dim()) throw std::runtime_error("vector has wrong size for preconditioner!");
     int st;
     {
-        py::gil_scoped_release release;  // (the reference holds the GIL here; releasing it is a superset)
+        py::gil_scoped_release release;  // safe: libilub serialises calls on one handle (per-handle lock)
         st = ilub_apply(pr.h, transpose, (double*)info.ptr, info.shape[0], 1, ILUB_HOST, nullptr);
     }
     check(st);
@@ -257,6 +257,9 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
              },
              py::arg("ptr"), py::arg("n"), py::arg("nrhs") = 1, py::arg("ldx") = 0, py::arg("stream") = 0,
              py::arg("transpose") = false)
+        .def("check_status",
+             [](const P& pr, uintptr_t stream) { check(ilub_check_status(pr.h, reinterpret_cast<void*>(stream))); },
+             py::arg("stream") = 0)
         .def("levels",
              [](const P& pr, int which) {
                  py::array_t<Integer> lev(pr.dim());
@@ -447,25 +450,26 @@ PYBIND11_MODULE(_ilupp, m) {
              int device) { return create_batched<LLTPrecond>(true, v, i, p, is_csr, device); },
           py::arg("values"), py::arg("A_indices"), py::arg("A_indptr"), py::arg("is_csr"), py::arg("device") = 0);
 
-    m.def("ichol0", [](py::buffer d, py::buffer i, py::buffer p, bool is_csr) {  // binding.cpp:399-408
-        LLTPrecond pr = create<LLTPrecond>(true, d, i, p, is_csr, 0);
+    m.def("trim_cache", []() { check(ilub_trim_cache()); });
+    m.def("ichol0", [](py::buffer d, py::buffer i, py::buffer p, bool is_csr, int device) {  // binding.cpp:399-408
+        LLTPrecond pr = create<LLTPrecond>(true, d, i, p, is_csr, device);
         return factor_tuple(pr, 0);
-    });
-    m.def("ilu0", [](py::buffer d, py::buffer i, py::buffer p, bool is_csr) {  // binding.cpp:421-430
-        LUPrecond pr = create<LUPrecond>(false, d, i, p, is_csr, 0);
+    }, py::arg("A_data"), py::arg("A_indices"), py::arg("A_indptr"), py::arg("is_csr"), py::arg("device") = 0);
+    m.def("ilu0", [](py::buffer d, py::buffer i, py::buffer p, bool is_csr, int device) {  // binding.cpp:421-430
+        LUPrecond pr = create<LUPrecond>(false, d, i, p, is_csr, device);
         return py::make_tuple(factor_tuple(pr, 0), factor_tuple(pr, 1));
-    });
+    }, py::arg("A_data"), py::arg("A_indices"), py::arg("A_indptr"), py::arg("is_csr"), py::arg("device") = 0);
 
     // binding.cpp:200-230.  `param` is accepted for signature compatibility and ignored: the
     // preconditioner is ILU(0) (SURVEY.md 3.3 "gap the build must own").
     m.def("solve",
           [](py::buffer A_data, py::buffer A_indices, py::buffer A_indptr, bool is_csr, py::buffer rhs, double rtol,
-             double atol, Integer max_iter, py::object /*param*/) {
+             double atol, Integer max_iter, py::object /*param*/, int device) {
               MatrixView M = make_matrix(A_data, A_indices, A_indptr);
               py::buffer_info b = rhs.request();
               check_is_real_array(b, "b");
               if (M.n != b.shape[0]) throw std::runtime_error("right-hand side has wrong size!");
-              LUPrecond pr = create<LUPrecond>(false, A_data, A_indices, A_indptr, is_csr, 0);
+              LUPrecond pr = create<LUPrecond>(false, A_data, A_indices, A_indptr, is_csr, device);
               py::array_t<Real> x(M.n);
               int32_t iters = 0;
               double rel = 0, ab = 0;
@@ -480,5 +484,5 @@ PYBIND11_MODULE(_ilupp, m) {
               return py::make_tuple(x, iters, rel, ab);
           },
           py::arg("A_data"), py::arg("A_indices"), py::arg("A_indptr"), py::arg("is_csr"), py::arg("rhs"),
-          py::arg("rtol"), py::arg("atol"), py::arg("max_iter"), py::arg("param") = py::none());
+          py::arg("rtol"), py::arg("atol"), py::arg("max_iter"), py::arg("param") = py::none(), py::arg("device") = 0);
 }

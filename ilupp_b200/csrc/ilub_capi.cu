@@ -67,6 +67,21 @@ void ensure_solve(ilub_handle* h, int slot, cudaStream_t s) {
     pack_solve_values(h, slot, s);
 }
 
+typedef std::lock_guard<std::recursive_mutex> HandleLock;
+
+// a kernel of an earlier asynchronous (device-path) call gave up: raise it now instead of returning garbage silently
+void raise_deferred(ilub_handle* h, cudaStream_t s) {
+    if (!h->host_status || *(volatile int*)h->host_status == 0) return;
+    const int code = *(volatile int*)h->host_status;
+    *(volatile int*)h->host_status = 0;
+    ILUB_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(int) * 4, s));
+    throw Error{ILUB_ERR_WATCHDOG, "an earlier asynchronous call on this handle was aborted by the watchdog (code " +
+                                       std::to_string(code) + "): its results are invalid"};
+}
+void post_deferred(ilub_handle* h, cudaStream_t s) {
+    if (h->host_status) ILUB_CUDA(cudaMemcpyAsync(h->host_status, h->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+}
+
 int slot_of(const ilub_handle* h, int which_solve) {
     int a, b;
     apply_slots(h, which_solve >= 2 ? 1 : 0, a, b);
@@ -106,6 +121,8 @@ void create_common(int kind, const double* data, const int32_t* indices, const i
     h->sm_count = prop.multiProcessorCount;
     h->clock_khz = prop.clockRate > 0 ? prop.clockRate : 1965000;
     for (int i = 0; i < 4; ++i) ILUB_CUDA(cudaEventCreate(&h->ev[i]));
+    ILUB_CUDA(cudaHostAlloc((void**)&h->host_status, sizeof(int), cudaHostAllocDefault));
+    *h->host_status = 0;
     h->ptr.alloc(n64 + 1);
     h->idx.alloc(nnz64);
     h->a.alloc(nnz64);
@@ -237,6 +254,7 @@ int ilub_create_from_factors(int kind, const double* data, const int32_t* indice
 int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream) {
     return guarded([&] {
         ILUB_REQUIRE(h && data, ILUB_ERR_INVALID, "null argument");
+        HandleLock lock(h->mu);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -263,10 +281,8 @@ int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream) {
 int ilub_destroy(ilub_handle* h) {
     return guarded([&] {
         if (!h) return;
-        cudaSetDevice(h->device);
+        DeviceGuard guard(h->device);  // the caller's current device is left as it was
         cudaDeviceSynchronize();
-        for (int i = 0; i < 4; ++i)
-            if (h->ev[i]) cudaEventDestroy(h->ev[i]);
         set_alloc_stream(kIdleStream);  // the device is idle: the handle's blocks can be reused on any stream
         delete h;
         set_alloc_stream(nullptr);
@@ -285,9 +301,11 @@ int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nr
         ILUB_REQUIRE(h && x, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(nrhs >= 1, ILUB_ERR_INVALID, "nrhs must be >= 1");
         ILUB_REQUIRE(ldx >= h->n, ILUB_ERR_SIZE, "vector has wrong size for preconditioner!");
+        HandleLock lock(h->mu);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
+        raise_deferred(h, s);
         int first, second;
         apply_slots(h, transpose, first, second);
         ensure_solve(h, first, s);
@@ -295,6 +313,7 @@ int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nr
         if (where == ILUB_DEVICE) {
             run_solve(h, first, x, ldx, nrhs, s);
             run_solve(h, second, x, ldx, nrhs, s);
+            post_deferred(h, s);
         } else {
             const size_t cnt = (size_t)h->n * nrhs;
             h->work.ensure(cnt);
@@ -309,6 +328,19 @@ int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nr
             read_status(h, s);
         }
     });
+}
+
+int ilub_check_status(ilub_handle* h, void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h, ILUB_ERR_INVALID, "null handle");
+        HandleLock lock(h->mu);
+        DeviceGuard guard(h->device);
+        read_status(h, static_cast<cudaStream_t>(stream));  // synchronises the stream; throws ILUB_ERR_WATCHDOG
+        if (h->host_status) *(volatile int*)h->host_status = 0;
+    });
+}
+int ilub_trim_cache(void) {
+    return guarded([&] { pool_trim(); });
 }
 
 int ilub_total_nnz(const ilub_handle* h, int64_t* out) {
@@ -353,6 +385,7 @@ int ilub_get_factor(ilub_handle* h, int which, double* data, int32_t* indices, i
     return guarded([&] {
         ILUB_REQUIRE(h && data && indices && indptr, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(which == 0 || (which == 1 && h->kind == KIND_ILU0), ILUB_ERR_INVALID, "no such factor");
+        HandleLock lock(h->mu);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -380,6 +413,7 @@ int ilub_get_levels(ilub_handle* h, int which_solve, int32_t* nlevels, int32_t* 
     return guarded([&] {
         ILUB_REQUIRE(h, ILUB_ERR_INVALID, "null handle");
         ILUB_REQUIRE(which_solve >= 0 && which_solve < 4, ILUB_ERR_INVALID, "bad which_solve");
+        HandleLock lock(h->mu);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -398,6 +432,7 @@ int ilub_get_level_sets(ilub_handle* h, int which_solve, int32_t* level_ptr, int
     return guarded([&] {
         ILUB_REQUIRE(h && level_ptr && level_rows, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(which_solve >= 0 && which_solve < 4, ILUB_ERR_INVALID, "bad which_solve");
+        HandleLock lock(h->mu);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -415,6 +450,7 @@ int ilub_spmv(ilub_handle* h, const double* x, double* y, int where, void* strea
     return guarded([&] {
         ILUB_REQUIRE(h && x && y, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(!h->prefactored, ILUB_ERR_INVALID, "handle was created from factors: it holds no matrix");
+        HandleLock lock(h->mu);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -437,6 +473,7 @@ int ilub_bicgstab(ilub_handle* h, const double* b, double* x, double rtol, doubl
     return guarded([&] {
         ILUB_REQUIRE(h && b && x && iters && rel_achieved && abs_achieved, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(!h->prefactored, ILUB_ERR_INVALID, "handle was created from factors: it holds no matrix");
+        HandleLock lock(h->mu);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);

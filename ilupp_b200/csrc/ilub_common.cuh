@@ -7,6 +7,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -330,6 +331,18 @@ struct ilub_handle {
     double timings[4] = {0, 0, 0, 0};
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // The handle is not re-entrant (shared workspace, mailbox epochs, lazily built solves): every entry point of the
+    // C ABI that touches it holds this lock, so threads sharing one preconditioner are serialised like the
+    // reference's GIL-holding apply (binding.cpp:237-245) serialises them.
+    std::recursive_mutex mu;
+    // Device-path calls (where = ILUB_DEVICE) are asynchronous: a watchdog abort of one of their kernels is copied
+    // here behind the kernels (pinned host word) and raised by the NEXT call on the handle / ilub_check_status.
+    int* host_status = nullptr;
+    ~ilub_handle() {
+        for (int i = 0; i < 4; ++i)
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        if (host_status) cudaFreeHost(host_status);
+    }
 };
 
 namespace ilub {

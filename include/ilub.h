@@ -114,6 +114,16 @@ ILUB_API int ilub_destroy(ilub_handle* h);
  * exact equivalent. */
 ILUB_API int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nrhs, int where,
                         void* stream);
+/* Threads: every entry point that takes a handle serialises on a per-handle lock, so one preconditioner may be
+ * shared between threads like the reference's (its apply holds the GIL, binding.cpp:237-245).
+ * Errors of asynchronous calls: with where = ILUB_DEVICE the kernels run asynchronously on `stream`.  Their
+ * watchdog (spin_limit_ms: the persistent sync-free / systolic kernels need all their CTAs co-resident and give up
+ * instead of hanging when the GPU is shared and they are not) cannot be reported by the call that launched them:
+ * the NEXT call on the handle returns ILUB_ERR_WATCHDOG, or ask explicitly -- ilub_check_status synchronises
+ * `stream` and returns ILUB_OK / ILUB_ERR_WATCHDOG (and clears the condition). */
+ILUB_API int ilub_check_status(ilub_handle* h, void* stream);
+/* give the device memory cached by the library's allocator (freed blocks kept for reuse) back to the driver */
+ILUB_API int ilub_trim_cache(void);
 /* size check of binding.cpp:241-242 for FFI callers that hold a length: ILUB_ERR_SIZE if len != n */
 ILUB_API int ilub_check_vector(const ilub_handle* h, int64_t len);
 

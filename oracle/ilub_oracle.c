@@ -7,7 +7,7 @@
  *
  * Parity status: PINNED.  tests/test_oracle.py checks every function below against
  *   (1) the reference's own golden / known-answer tests for this path (test/tests.py:26-31,
- *       197-207,229-259,286-306,324-338 restated in tests/test_reference_cases.py),
+ *       197-207,229-259,286-306,324-338 restated in tests/test_oracle.py and tests/test_parity_gpu.py),
  *   (2) the unmodified reference compiled from /root/reference/src (oracle/_ref, bit-for-bit on
  *       factors and apply outputs), and
  *   (3) fixtures generated from that compiled reference (tests/golden/, scripts/make_golden.py).
