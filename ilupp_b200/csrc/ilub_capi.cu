@@ -527,6 +527,9 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "sys_stages") o.sys_stages = value;
         else if (k == "sys_cluster") o.sys_cluster = value;
         else if (k == "sys_plane") o.sys_plane = value;
+        else if (k == "sys_tile") o.sys_tile = value;
+        else if (k == "tile_fetch") o.tile_fetch = value;
+        else if (k == "tile_warps") o.tile_warps = value;
         else if (k == "plane_r") o.plane_r = value;
         else if (k == "plane_wpc") o.plane_wpc = value;
         else if (k == "plane_npc") o.plane_npc = value;
@@ -559,6 +562,9 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "sys_stages") *value = o.sys_stages;
         else if (k == "sys_cluster") *value = o.sys_cluster;
         else if (k == "sys_plane") *value = o.sys_plane;
+        else if (k == "sys_tile") *value = o.sys_tile;
+        else if (k == "tile_fetch") *value = o.tile_fetch;
+        else if (k == "tile_warps") *value = o.tile_warps;
         else if (k == "plane_r") *value = o.plane_r;
         else if (k == "plane_wpc") *value = o.plane_wpc;
         else if (k == "plane_npc") *value = o.plane_npc;
@@ -647,6 +653,13 @@ int ilub_get_stats(const ilub_handle* h, int64_t out[16]) {
             out[13] = Y.nsteps_pad;
             out[14] = Y.pyb * Y.pz + 2;
             out[15] = (int64_t)Y.smem;
+            if (Y.tile) {  // tile-systolic: CTA grid of twy x twz tiles each
+                out[8] = (int64_t)Y.tgy * Y.tgz;
+                out[9] = 7;
+                out[10] = Y.tgy;
+                out[11] = Y.tgz;
+                out[14] = Y.twy * Y.twz;
+            }
         }
     });
 }

@@ -129,6 +129,9 @@ struct Options {
     int64_t sys_stages = 0;     // line-systolic: coefficient stages per warp (0 = auto)
     int64_t sys_pdl = 1;        // line-systolic: programmatic dependent launch (prologue of the next solve overlaps this one)
     int64_t sys_cluster = 0;    // line-systolic: largest thread-block cluster to try (0 = auto: 8, 1 = no clusters)
+    int64_t sys_tile = 1;       // tile-systolic kernel (8 x 4 lines per warp) for plane-coupled 3-D grids: 0 off, 1 auto
+    int64_t tile_fetch = 2;     // tile-systolic: mailbox fetcher warps per CTA
+    int64_t tile_warps = 0;     // tile-systolic: compute warps per CTA (0 = auto: 4, or 6 when the grid needs them)
     int64_t sys_plane = 1;      // plane-per-warp kernel for grids without a plane-to-plane dependency: 0 off, 1 auto, 2 whenever applicable
     int64_t plane_r = 1;        // plane-per-warp: right-hand sides per warp (1 or 2)
     int64_t levels_cluster = 1; // cooperative level loop: one thread-block cluster with the hardware barrier when the levels fit (0: always the grid barrier)
@@ -165,6 +168,12 @@ struct SysSolve {
     int order_xyz = 0;                          // exact arithmetic: accumulate x, y, z (bwd-gather) instead of z, y, x
     int ntasks = 0, ntasks1 = 0;                // tasks = (line block, plane); ntasks1: tasks of one system
     int nstages = 3, rz = 8, ry = 64;
+    // tile-systolic variant (ilub_tile.cu): a warp owns ty x tz adjacent lines (lane = a + ty * b, skew a + b), so the
+    // y AND the z dependency of most rows is a shuffle.  The line-systolic layout above is the case ty = 32, tz = 1.
+    int tile = 0, ty = 32, tz = 1;
+    int nty = 0, ntz = 0, ntz1 = 0;             // tiles along y, along z (all systems), along z per system
+    int twy = 2, twz = 2, tgy = 1, tgz = 1;     // tiles per CTA and CTA grid
+    int tnst = 3, tnwin = 6, tring = 64;        // coefficient stages, window blocks, hand-off ring depth (steps) per warp
     size_t smem = 0;
     int nzchan = 0, nychan = 0;
     int packed_exact = -1;                      // arithmetic mode the coefficients were packed for
@@ -327,6 +336,7 @@ struct ilub_handle {
     unsigned fepoch = 0;
     ilub::DevBuf<int> status;           // device status word(s) written by kernels (watchdog / structure errors)
     ilub::DevBuf<double> work;          // vector workspace (host-side apply, bicgstab)
+    ilub::DevBuf<double> xalign;        // 16-byte aligned stand-in for an odd-aligned vector (tile-systolic tensor maps)
     ilub::DevBuf<double> scal;          // device scalars for bicgstab
     double timings[4] = {0, 0, 0, 0};
     int64_t launches = 0;
@@ -375,6 +385,9 @@ void factor_numeric(ilub_handle* h, cudaStream_t s);
 bool analyse_systolic(ilub_handle* h, int which, cudaStream_t s);         // false: structure not eligible
 void pack_systolic(ilub_handle* h, int which, cudaStream_t s);
 void run_systolic(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);
+// ---- tile-systolic variant for plane-coupled 3-D grids (ilub_tile.cu)
+bool tile_configure(ilub_handle* h, SysSolve& Y, int nsys);               // false: this grid does not fit the tile kernel
+void launch_tile(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s, const double* fcoef);
 // ---- plane-per-warp variant for 2-D grids / batches and many right-hand sides (ilub_plane.cu); false: not applicable
 bool run_plane(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);
 

@@ -72,7 +72,18 @@ struct SysGeom {
     int sy, sz;  // offsets of the y and z dependencies (sz = 0: 2-D)
     int n1;
     int backward, unit_diag;
+    int ty, tz;  // lines per task along y and z (line-systolic: 32 x 1; tile-systolic: 8 x 4); nyb = tasks along y
+    // tile-systolic backward solves: the mirrored grid is shifted so that the padding of ragged extents comes FIRST
+    // in solve order (TMA boxes then never start at a negative coordinate of the original vector)
+    int xoff, yoff, zoff;
 };
+// task / lane / step of grid point (i, j, k) of one system: lane = a + ty * b runs its line skewed by a + b steps
+__device__ __forceinline__ void sys_place(const SysGeom& G, int i, int j, int k, int& task, int& lane, int& step) {
+    const int jt = j / G.ty, a = j - jt * G.ty, kt = k / G.tz, b = k - kt * G.tz;
+    task = kt * G.nyb + jt;
+    lane = a + G.ty * b;
+    step = i + a + b;
+}
 
 // every row of ONE system: where do its coefficients go in the (task, step, lane) layout?
 __global__ void k_sys_map(SysGeom G, SrcDev S, int* __restrict__ srcpos, int* fail) {
@@ -82,9 +93,8 @@ __global__ void k_sys_map(SysGeom G, SrcDev S, int* __restrict__ srcpos, int* fa
     const int i = rm % G.nx;
     const int j = (rm / G.nx) % G.ny;
     const int k = rm / (G.nx * G.ny);
-    const int task = k * G.nyb + (j >> 5);
-    const int lane = j & 31;
-    const int step = i + lane;
+    int task, lane, step;
+    sys_place(G, i + G.xoff, j + G.yoff, k + G.zoff, task, lane, step);
     // per step: [lane]{z, y} (64 values) then [lane]{x, diagonal}: role r sits at (r >> 1) * 64 + lane * 2 + (r & 1)
     const size_t base = ((size_t)task * G.nsteps_pad + step) * 128 + lane * 2;
     bool bad = false;
@@ -142,9 +152,8 @@ __global__ void k_sys_map_factor(SysGeom G, const int* __restrict__ ptr, const i
     const int i = r % G.nx;
     const int j = (r / G.nx) % G.ny;
     const int k = r / (G.nx * G.ny);
-    const int task = k * G.nyb + (j >> 5);
-    const int lane = j & 31;
-    const int step = i + lane;
+    int task, lane, step;
+    sys_place(G, i, j, k, task, lane, step);
     const size_t base = ((size_t)task * G.nsteps_pad + step) * 128 + lane * 2;
     bool bad = false;
     for (int q = ptr[r]; q < dpos[r]; ++q) {
@@ -842,10 +851,35 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
         G.nz1 = 1;
     }
     if (G.nx < 2 || G.ny < 2) return false;
+    G.ty = 32;
+    G.tz = 1;
+    G.xoff = G.yoff = G.zoff = 0;
     G.nyb = (G.ny + 31) / 32;
     G.nsteps_pad = (G.nx + 31 + kStageSteps - 1) / kStageSteps * kStageSteps;
     G.backward = src.backward ? 1 : 0;
     G.unit_diag = src.unit_diag ? 1 : 0;
+    Y.nx = G.nx;
+    Y.ny = G.ny;
+    Y.nz1 = G.nz1;
+    Y.nplanes = G.nz1 * nsys;
+    Y.zcoupled = G.sz > 0 ? 1 : 0;
+    Y.tile = 0;
+    Y.ty = 32;
+    Y.tz = 1;
+    Y.ntz1 = G.nz1;
+    // plane-coupled 3-D grids: the tile-systolic kernel (ilub_tile.cu) when the grid fits it
+    if (Y.zcoupled && opt.sys_tile != 0 && tile_configure(h, Y, nsys)) {
+        G.ty = Y.ty;
+        G.tz = Y.tz;
+        G.nyb = Y.nty;
+        const int nxp = (G.nx + kStageSteps - 1) / kStageSteps * kStageSteps;
+        G.nsteps_pad = nxp + 2 * kStageSteps;  // >= nxp + ty + tz - 2
+        if (G.backward) {
+            G.xoff = nxp - G.nx;
+            G.yoff = Y.nty * Y.ty - G.ny;
+            G.zoff = Y.ntz1 * Y.tz - G.nz1;
+        }
+    }
 
     // ---- tiling of tasks onto CTAs, shared-memory budget
     const int zc = G.sz > 0 ? 1 : 0;
@@ -854,6 +888,7 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     auto per_warp = [&](int nst, int rz) { return (size_t)nst * kStageBytes + kWinBytes + (zc ? rz * 512 : 0) + kRy * 16; };
     auto max_warps = [&](int nst, int rz) { return (int)std::min<size_t>(kMaxWarps, budget / (per_warp(nst, rz) + 64)); };
     int pyb = 1, pz = 1, nst = 3, rz = 16, csize = 1, gzp = 1;
+    const bool tile = Y.tile != 0;
     auto fit_rings = [&](int warps, int& nst_, int& rz_) {  // three stages and the 16-step z ring if they fit
         if (warps <= max_warps(3, 16)) { nst_ = 3; rz_ = 16; }
         else if (warps <= max_warps(3, 8)) { nst_ = 3; rz_ = 8; }
@@ -861,7 +896,9 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
         else { nst_ = 2; rz_ = 8; }
     };
     auto smem_of = [&](int warps, int nst_, int rz_) { return (size_t)warps * per_warp(nst_, rz_) + (size_t)warps * nst_ * 8 + kCtlInts * 4 + 64; };
-    if (zc) {
+    if (tile) {
+        // (CTA tiling chosen by tile_configure)
+    } else if (zc) {
         // planes per CTA: the fewest that keep the whole grid co-resident, then up to two more if that lets a
         // larger thread-block cluster (fewer global-memory hand-offs on the z chain) stay co-resident
         int pz0 = 1;
@@ -915,7 +952,7 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
 
     // ---- (task, step, lane) map of one system; fails on anything that is not the grid stencil
     const size_t per_task = (size_t)G.nsteps_pad * 128;
-    const int ntasks1 = G.nyb * G.nz1;
+    const int ntasks1 = G.nyb * (tile ? Y.ntz1 : G.nz1);
     ILUB_REQUIRE((int64_t)ntasks1 * nsys * (int64_t)per_task < ((int64_t)1 << 40), ILUB_ERR_SIZE, "systolic layout too large");
     Y.srcpos.alloc((size_t)ntasks1 * per_task);
     ILUB_CUDA(cudaMemsetAsync(Y.srcpos.p, 0xff, sizeof(int) * (size_t)ntasks1 * per_task, s));
@@ -928,33 +965,37 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
         Y.srcpos.release();
         return false;
     }
-    Y.nx = G.nx;
-    Y.ny = G.ny;
-    Y.nz1 = G.nz1;
-    Y.nplanes = nplanes;
     Y.nyb = G.nyb;
     Y.nsteps_pad = G.nsteps_pad;
     Y.pyb = pyb;
     Y.pz = pz;
     Y.gyb = (G.nyb + pyb - 1) / pyb;
     Y.gz = (nplanes + pz - 1) / pz;
-    Y.zcoupled = zc;
     Y.order_xyz = slot == 1 ? 1 : 0;  // bwd-gather accumulates i+1, i+nx, i+nx*ny in stored order
     Y.ntasks1 = ntasks1;
     Y.ntasks = ntasks1 * nsys;
     Y.nstages = nst;
     Y.rz = rz;
     Y.ry = kRy;
-    Y.smem = smem_of(pyb * pz, nst, rz);
+    if (!tile) Y.smem = smem_of(pyb * pz, nst, rz);
     // thread-block cluster along z (chosen with the tiling above): hand-offs between consecutive CTAs of a cluster
     // go through distributed shared memory instead of a global mailbox
     Y.csize = zc ? csize : 1;
     Y.gzp = zc ? gzp : Y.gz;
     Y.coef.alloc((size_t)Y.ntasks * per_task);
-    Y.nzchan = zc ? G.nyb * std::max(0, Y.gz - 1) : 0;
-    Y.nychan = nplanes * std::max(0, Y.gyb - 1);
-    Y.zmail.alloc((size_t)Y.nzchan * G.nsteps_pad * 32);
-    Y.ymail.alloc((size_t)Y.nychan * G.nsteps_pad);
+    if (tile) {
+        // global mailboxes for hand-offs between CTAs: one line of nsteps_pad entries per (tile-row boundary, plane) /
+        // (tile-column boundary, grid line), indexed by the producer's step
+        Y.nychan = std::max(0, Y.nty - 1) * Y.ntz * Y.tz;
+        Y.nzchan = std::max(0, Y.ntz - 1) * Y.nty * Y.ty;
+        Y.ymail.alloc((size_t)Y.nychan * G.nsteps_pad);
+        Y.zmail.alloc((size_t)Y.nzchan * G.nsteps_pad);
+    } else {
+        Y.nzchan = zc ? G.nyb * std::max(0, Y.gz - 1) : 0;
+        Y.nychan = nplanes * std::max(0, Y.gyb - 1);
+        Y.zmail.alloc((size_t)Y.nzchan * G.nsteps_pad * 32);
+        Y.ymail.alloc((size_t)Y.nychan * G.nsteps_pad);
+    }
     ILUB_CUDA(cudaMemsetAsync(Y.zmail.p, 0, Y.zmail.bytes(), s));
     ILUB_CUDA(cudaMemsetAsync(Y.ymail.p, 0, Y.ymail.bytes(), s));
     Y.epoch = 0;
@@ -971,7 +1012,7 @@ void pack_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     const int exact = options().exact != 0 ? 1 : 0;
     const int per_task = Y.nsteps_pad * 128;
     const int64_t total = (int64_t)Y.ntasks * per_task;
-    k_sys_pack<<<blocks_for(total, 256), 256, 0, s>>>(total, per_task, Y.nyb, Y.nz1, h->nsys, src.backward ? 1 : 0,
+    k_sys_pack<<<blocks_for(total, 256), 256, 0, s>>>(total, per_task, Y.nyb, Y.ntz1, h->nsys, src.backward ? 1 : 0,
                                                       h->nnz / h->nsys, exact ? 0 : 1, Y.srcpos.p, h->lu.p, Y.coef.p);
     h->launches++;
     Y.packed_exact = exact;
@@ -1040,7 +1081,12 @@ static void launch_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, in
 
 void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
     if (run_plane(h, slot, x, ldx, nrhs, s)) return;
-    launch_systolic(h, slot, x, ldx, nrhs, s, nullptr);
+    if (h->solve[slot].sys.tile) {
+        if (h->solve[slot].sys.packed_exact != (options().exact != 0 ? 1 : 0)) pack_systolic(h, slot, s);
+        launch_tile(h, slot, x, ldx, nrhs, s, nullptr);
+    } else {
+        launch_systolic(h, slot, x, ldx, nrhs, s, nullptr);
+    }
 }
 
 // ================================================================================================== stencil factorisation
@@ -1072,6 +1118,9 @@ bool stencil_factor_possible(ilub_handle* h, cudaStream_t s) {
     G.sz = Y.zcoupled ? Y.nx * Y.ny : 0;
     G.backward = 0;
     G.unit_diag = 0;
+    G.ty = Y.ty;
+    G.tz = Y.tz;
+    G.xoff = G.yoff = G.zoff = 0;
     const size_t per_task = (size_t)Y.nsteps_pad * 128;
     Y.fsrc.alloc((size_t)Y.ntasks1 * per_task);
     Y.fpart.alloc((size_t)Y.ntasks1 * per_task);
@@ -1101,9 +1150,10 @@ void factor_stencil(ilub_handle* h, cudaStream_t s) {
     const int ichol = h->kind == KIND_ICHOL0 ? 1 : 0;
     const int per_task = Y.nsteps_pad * 128;
     const int64_t total = (int64_t)Y.ntasks * per_task;
-    k_sys_pack_factor<<<blocks_for(total, 256), 256, 0, s>>>(total, per_task, Y.nyb, Y.nz1, h->nnz / h->nsys, ichol, Y.fsrc.p,
+    k_sys_pack_factor<<<blocks_for(total, 256), 256, 0, s>>>(total, per_task, Y.nyb, Y.ntz1, h->nnz / h->nsys, ichol, Y.fsrc.p,
                                                              Y.fpart.p, h->a.p, Y.fcoef.p);
-    launch_systolic(h, 0, h->fpivot.p, h->n, 1, s, Y.fcoef.p);
+    if (Y.tile) launch_tile(h, 0, h->fpivot.p, h->n, 1, s, Y.fcoef.p);
+    else launch_systolic(h, 0, h->fpivot.p, h->n, 1, s, Y.fcoef.p);
     k_stencil_finish<<<blocks_for((int64_t)h->n * 8, 256), 256, 0, s>>>(h->n, h->ptr.p, h->idx.p, h->dpos.p, h->a.p, h->fpivot.p,
                                                                        h->lu.p, ichol);
     h->launches += 2;
