@@ -530,6 +530,12 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "sys_tile") o.sys_tile = value;
         else if (k == "tile_fetch") o.tile_fetch = value;
         else if (k == "tile_warps") o.tile_warps = value;
+        else if (k == "tile_debug") o.tile_debug = value;
+        else if (k == "tile_nst") o.tile_nst = value;
+        else if (k == "tile_ring") o.tile_ring = value;
+        else if (k == "tile_nap_fwd") o.tile_nap_fwd = value;
+        else if (k == "tile_nap_fetch") o.tile_nap_fetch = value;
+        else if (k == "tile_nap_tma") o.tile_nap_tma = value;
         else if (k == "plane_r") o.plane_r = value;
         else if (k == "plane_wpc") o.plane_wpc = value;
         else if (k == "plane_npc") o.plane_npc = value;
@@ -565,6 +571,12 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "sys_tile") *value = o.sys_tile;
         else if (k == "tile_fetch") *value = o.tile_fetch;
         else if (k == "tile_warps") *value = o.tile_warps;
+        else if (k == "tile_debug") *value = o.tile_debug;
+        else if (k == "tile_nst") *value = o.tile_nst;
+        else if (k == "tile_ring") *value = o.tile_ring;
+        else if (k == "tile_nap_fwd") *value = o.tile_nap_fwd;
+        else if (k == "tile_nap_fetch") *value = o.tile_nap_fetch;
+        else if (k == "tile_nap_tma") *value = o.tile_nap_tma;
         else if (k == "plane_r") *value = o.plane_r;
         else if (k == "plane_wpc") *value = o.plane_wpc;
         else if (k == "plane_npc") *value = o.plane_npc;
@@ -588,6 +600,20 @@ ILUB_API int ilub_debug_sys_trace(ilub_handle* h, int which_solve, int32_t* dims
         TriSolve& T = h->solve[slot_of(h, which_solve)];
         ILUB_REQUIRE(T.built && T.sys.built, ILUB_ERR_INVALID, "no line-systolic solve");
         const SysSolve& Y = T.sys;
+        if (Y.tile) {  // tile-systolic: per task the start time of every stage, then the end time
+            dims[0] = Y.ntasks;
+            dims[1] = 3 * (Y.nsteps_pad / 8 + 1);  // per task: stage start times + end time, data-wait cycles, gate-wait cycles
+            dims[2] = Y.nty;
+            dims[3] = Y.ntz;
+            dims[4] = Y.twy;
+            dims[5] = Y.twz;
+            dims[6] = 0;
+            dims[7] = Y.tnst * 100 + Y.tring;
+            ILUB_CUDA(cudaDeviceSynchronize());
+            const size_t cnt = (size_t)dims[0] * dims[1];
+            if (trace && T.trace.n >= cnt) ILUB_CUDA(cudaMemcpy(trace, T.trace.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost));
+            return;
+        }
         dims[0] = Y.ntasks;
         dims[1] = 3 * (Y.nsteps_pad / 8 + 1);  // per task: time, failed polls, helper/stage wait cycles
         dims[2] = Y.nyb;

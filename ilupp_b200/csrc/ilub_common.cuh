@@ -129,8 +129,11 @@ struct Options {
     int64_t sys_stages = 0;     // line-systolic: coefficient stages per warp (0 = auto)
     int64_t sys_pdl = 1;        // line-systolic: programmatic dependent launch (prologue of the next solve overlaps this one)
     int64_t sys_cluster = 0;    // line-systolic: largest thread-block cluster to try (0 = auto: 8, 1 = no clusters)
-    int64_t sys_tile = 1;       // tile-systolic kernel (8 x 4 lines per warp) for plane-coupled 3-D grids: 0 off, 1 auto
+    int64_t sys_tile = 0;       // tile-systolic kernel (8 x 4 lines per warp) for plane-coupled 3-D grids: 0 off, 1 auto
     int64_t tile_fetch = 2;     // tile-systolic: mailbox fetcher warps per CTA
+    int64_t tile_nap_fwd = 20, tile_nap_fetch = 20, tile_nap_tma = 20;  // tile-systolic: idle helper warps sleep this many ns between polls
+    int64_t tile_nst = 0, tile_ring = 0;  // tile-systolic: coefficient stages / ring depth per warp (0 = auto)
+    int64_t tile_debug = 0;     // tile-systolic: debug switches (timing experiments only)
     int64_t tile_warps = 0;     // tile-systolic: compute warps per CTA (0 = auto: 4, or 6 when the grid needs them)
     int64_t sys_plane = 1;      // plane-per-warp kernel for grids without a plane-to-plane dependency: 0 off, 1 auto, 2 whenever applicable
     int64_t plane_r = 1;        // plane-per-warp: right-hand sides per warp (1 or 2)
@@ -173,6 +176,7 @@ struct SysSolve {
     int tile = 0, ty = 32, tz = 1;
     int nty = 0, ntz = 0, ntz1 = 0;             // tiles along y, along z (all systems), along z per system
     int twy = 2, twz = 2, tgy = 1, tgz = 1;     // tiles per CTA and CTA grid
+    int tccy = 0, tccz = 0;                     // thread-block cluster shape in CTAs (0: not chosen yet)
     int tnst = 3, tnwin = 6, tring = 64;        // coefficient stages, window blocks, hand-off ring depth (steps) per warp
     size_t smem = 0;
     int nzchan = 0, nychan = 0;

@@ -873,7 +873,7 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
         G.tz = Y.tz;
         G.nyb = Y.nty;
         const int nxp = (G.nx + kStageSteps - 1) / kStageSteps * kStageSteps;
-        G.nsteps_pad = nxp + 2 * kStageSteps;  // >= nxp + ty + tz - 2
+        G.nsteps_pad = (nxp + 2 * kStageSteps + 2 * kStageSteps - 1) / (2 * kStageSteps) * (2 * kStageSteps);  // >= nxp + ty + tz - 2, whole 16-step iterations
         if (G.backward) {
             G.xoff = nxp - G.nx;
             G.yoff = Y.nty * Y.ty - G.ny;
