@@ -1,4 +1,4 @@
 cd /root/repo
-timeout 200 python scripts/dev_tile.py parity 2>&1 | tail -1
-timeout 300 python scripts/trace_tile.py p3d128 2>&1 | grep -E "apply|solve 0|tile duration|per tile|y lags|z lags" | head -8
-timeout 300 python scripts/trace_tile.py p3d128 tile_warps=6 2>&1 | grep -E "apply|solve 0|tile duration|per tile|y lags|z lags" | head -8
+timeout 200 python scripts/dev_tile_time.py "2048 8 4" "2048 16 8" "128 128 128" sys_tile=1 2>&1 | tail -3
+timeout 200 python scripts/dev_tile_time.py "128 128 128" sys_tile=1 tile_nap_fwd=0 tile_nap_fetch=0 tile_nap_tma=0 2>&1 | tail -1
+timeout 200 python scripts/dev_tile_time.py "128 128 128" sys_tile=0 2>&1 | tail -1

@@ -881,3 +881,67 @@ def test_shared_handle_across_threads(ilupp):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs
+
+
+# ---- tile-systolic kernel (ilub_tile.cu; option sys_tile): 8 x 4 lines per warp, TMA in / out, forwarder warps ------
+def _grid3d(nx, ny, nz, seed, sym=False):
+    """7-point stencil on an nx x ny x nz grid (x fastest), random coefficients, diagonally dominant"""
+    rng = np.random.default_rng(seed)
+    n = nx * ny * nz
+    i = np.arange(n)
+    ix, iy, iz = i % nx, (i // nx) % ny, i // (nx * ny)
+    rows, cols = [], []
+    for off, ok in ((-1, ix > 0), (1, ix < nx - 1), (-nx, iy > 0), (nx, iy < ny - 1), (-nx * ny, iz > 0), (nx * ny, iz < nz - 1)):
+        rows.append(i[ok])
+        cols.append(i[ok] + off)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    A = scipy.sparse.csr_matrix((-rng.uniform(0.5, 1.5, rows.size), (rows, cols)), shape=(n, n))
+    if sym:
+        A = (A + A.T) * 0.5
+    A = (A + scipy.sparse.diags(1.0 + np.asarray(abs(A).sum(axis=1)).ravel())).tocsr()
+    A.sort_indices()
+    A.indices = A.indices.astype(np.int32)
+    A.indptr = A.indptr.astype(np.int32)
+    return A
+
+
+TILE_GRIDS = [("one-tile", 16, 8, 4), ("ragged", 10, 9, 5), ("ragged-4-ctas", 30, 21, 13), ("short-lines", 6, 40, 37),
+              ("clusters", 64, 50, 30)]
+
+
+@pytest.mark.parametrize("name,nx,ny,nz", TILE_GRIDS, ids=[g[0] for g in TILE_GRIDS])
+@pytest.mark.parametrize("exact", [1, 0])
+def test_tile_systolic_kernel(ilupp, exact, name, nx, ny, nz):
+    """all four solve forms (apply / apply_trans, csr / csc) through k_trsv_tile; exact mode bit-for-bit, and the stencil
+    factorisation on the same kernel in fast arithmetic"""
+    saved = {k: ilupp.get_option(k) for k in ("exact", "sys_tile")}
+    try:
+        ilupp.set_option("exact", exact)
+        ilupp.set_option("sys_tile", 1)
+        A0 = _grid3d(nx, ny, nz, 7)
+        b = P.rhs(A0.shape[0], 1)
+        for fmt in ("csr", "csc"):
+            A = A0.asformat(fmt)
+            B = ilupp.ILU0Preconditioner(A)
+            assert B.stats["part_mode"] == 7                          # the tile kernel took it
+            Lo, Uo = oracle.port.ilu0(A)
+            L, U = B.factors()
+            assert relerr(L.data, Lo.data) <= TOL and relerr(U.data, Uo.data) <= TOL
+            for tr in (False, True):
+                y = b.copy()
+                (B.apply_trans if tr else B.apply)(y)
+                yo = oracle.port.apply_lu(Lo, Uo, b, tr)
+                assert relerr(y, yo) <= TOL
+                if exact:
+                    assert np.array_equal(y, yo)
+        S = _grid3d(nx, ny, nz, 8, sym=True)
+        C = ilupp.IChol0Preconditioner(S)
+        Lco = oracle.port.ichol0(S)
+        (Lc,) = C.factors()
+        assert relerr(Lc.data, Lco.data) <= TOL
+        y = b.copy()
+        C.apply(y)
+        assert relerr(y, oracle.port.apply_llt(Lco, b)) <= TOL
+    finally:
+        for k, v in saved.items():
+            ilupp.set_option(k, v)
