@@ -205,6 +205,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ilupp.set_option("exact", args.exact)
+    if args.zero_copy is not None:
+        ilupp.set_option("zero_copy", args.zero_copy)
     peak, peak_src = measured_peaks()
 
     A = P.poisson3d(GRID)
@@ -386,6 +388,7 @@ def main():
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--batched-systems", type=int, default=4096)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--zero-copy", type=int, default=None, help="override the library's zero_copy option (experiments)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -82,6 +82,17 @@ void post_deferred(ilub_handle* h, cudaStream_t s) {
     if (h->host_status) ILUB_CUDA(cudaMemcpyAsync(h->host_status, h->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
 }
 
+// device-side address of a HOST pointer if it is pinned (page-locked) memory the current device can access, else null
+double* device_view_of_host(const double* x) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, x) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+    return static_cast<double*>(at.devicePointer);
+}
+
 int slot_of(const ilub_handle* h, int which_solve) {
     int a, b;
     apply_slots(h, which_solve >= 2 ? 1 : 0, a, b);
@@ -314,6 +325,19 @@ int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nr
             run_solve(h, first, x, ldx, nrhs, s);
             run_solve(h, second, x, ldx, nrhs, s);
             post_deferred(h, s);
+        } else if (nrhs == 1 && options().zero_copy != 0 && systolic_out_of_place_ok(h, first) && systolic_out_of_place_ok(h, second) &&
+                   device_view_of_host(x) != nullptr) {
+            // Zero copy: x is pinned host memory the device can address.  The first solve reads the right-hand side
+            // straight from it (PCIe reads trail the wavefront: no H2D copy ahead of the kernel), the second writes
+            // the solution straight into it (posted PCIe writes behind the wavefront: no D2H copy after the kernel).
+            double* xd = device_view_of_host(x);
+            h->work.ensure((size_t)h->n);
+            const int64_t zc = options().zero_copy;   // 1: both directions, 2: solution out only, 3: right-hand side in only
+            if (zc == 2) ILUB_CUDA(cudaMemcpyAsync(h->work.p, x, sizeof(double) * h->n, cudaMemcpyHostToDevice, s));
+            run_systolic_io(h, first, zc == 2 ? h->work.p : xd, h->work.p, s);
+            run_systolic_io(h, second, h->work.p, zc == 3 ? h->work.p : xd, s);
+            if (zc == 3) ILUB_CUDA(cudaMemcpyAsync(x, h->work.p, sizeof(double) * h->n, cudaMemcpyDeviceToHost, s));
+            read_status(h, s);
         } else {
             const size_t cnt = (size_t)h->n * nrhs;
             h->work.ensure(cnt);
@@ -527,6 +551,7 @@ int ilub_set_option(const char* key, int64_t value) {
         else if (k == "sys_stages") o.sys_stages = value;
         else if (k == "sys_cluster") o.sys_cluster = value;
         else if (k == "sys_plane") o.sys_plane = value;
+        else if (k == "zero_copy") o.zero_copy = value;
         else if (k == "sys_tile") o.sys_tile = value;
         else if (k == "tile_fetch") o.tile_fetch = value;
         else if (k == "tile_warps") o.tile_warps = value;
@@ -568,6 +593,7 @@ int ilub_get_option(const char* key, int64_t* value) {
         else if (k == "sys_stages") *value = o.sys_stages;
         else if (k == "sys_cluster") *value = o.sys_cluster;
         else if (k == "sys_plane") *value = o.sys_plane;
+        else if (k == "zero_copy") *value = o.zero_copy;
         else if (k == "sys_tile") *value = o.sys_tile;
         else if (k == "tile_fetch") *value = o.tile_fetch;
         else if (k == "tile_warps") *value = o.tile_warps;

@@ -135,6 +135,7 @@ struct Options {
     int64_t tile_nst = 0, tile_ring = 0;  // tile-systolic: coefficient stages / ring depth per warp (0 = auto)
     int64_t tile_debug = 0;     // tile-systolic: debug switches (timing experiments only)
     int64_t tile_warps = 0;     // tile-systolic: compute warps per CTA (0 = auto: 4, or 6 when the grid needs them)
+    int64_t zero_copy = 0;      // apply() on a pinned host vector: the solve kernels read / write it directly over PCIe (1: both ways, 2: out only, 3: in only). Measured SLOWER than staged copies (64-byte PCIe requests): 0.91-1.06 ms against 0.79 ms at 128^3, so off
     int64_t sys_plane = 1;      // plane-per-warp kernel for grids without a plane-to-plane dependency: 0 off, 1 auto, 2 whenever applicable
     int64_t plane_r = 1;        // plane-per-warp: right-hand sides per warp (1 or 2)
     int64_t levels_cluster = 1; // cooperative level loop: one thread-block cluster with the hardware barrier when the levels fit (0: always the grid barrier)
@@ -389,6 +390,8 @@ void factor_numeric(ilub_handle* h, cudaStream_t s);
 bool analyse_systolic(ilub_handle* h, int which, cudaStream_t s);         // false: structure not eligible
 void pack_systolic(ilub_handle* h, int which, cudaStream_t s);
 void run_systolic(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);
+bool systolic_out_of_place_ok(const ilub_handle* h, int which);
+void run_systolic_io(ilub_handle* h, int which, const double* xin, double* xout, cudaStream_t s);
 // ---- tile-systolic variant for plane-coupled 3-D grids (ilub_tile.cu)
 bool tile_configure(ilub_handle* h, SysSolve& Y, int nsys);               // false: this grid does not fit the tile kernel
 void launch_tile(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s, const double* fcoef);

@@ -239,7 +239,8 @@ __global__ void k_stencil_finish(int n, const int* __restrict__ ptr, const int* 
 // ------------------------------------------------------------------------------------------------ kernel
 struct SysParams {
     const double* coef;
-    double* x;
+    double* x;          // solution out (and right-hand side in, unless xin differs)
+    const double* xin;  // right-hand side in: x itself, or another buffer -- e.g. the caller's pinned host vector (zero copy)
     int nx, ny, nyb, nplanes, nz1, nsteps_pad;
     int pyb, pz, gyb, gz, gzp, csize;  // gzp: gz padded to the cluster size; CTA = blockIdx.x = cy * gzp + cz
     int backward;
@@ -424,12 +425,13 @@ __device__ __forceinline__ void role_helper(const SysParams& P, const SysCtx& C,
     const long long dir = P.backward ? -1 : 1;
     const long long g0 = P.backward ? P.n - 1 - (tile_base + (long long)rl * nx + rc) : tile_base + (long long)rl * nx + rc;
     double* const gp = P.x + g0;
+    const double* const gin = P.xin + g0;
     const long long qstride = dir * 4 * nx;
     const uint32_t xw_rl = xw_s + rl * (kWinStride * 8);
     const bool full_lines = nlines == 32;
     double pre[8];
     auto rect_load = [&](int m) {
-        double* b = gp + dir * 8 * m;
+        const double* b = gin + dir * 8 * m;
         if (full_lines && 8 * m + 8 <= nx) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) pre[q] = __ldcs(b + q * qstride);
@@ -1018,7 +1020,8 @@ void pack_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     Y.packed_exact = exact;
 }
 
-static void launch_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s, const double* fcoef) {
+static void launch_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s, const double* fcoef,
+                            const double* xin = nullptr) {
     TriSolve& T = h->solve[slot];
     SysSolve& Y = T.sys;
     const Options& opt = options();
@@ -1073,10 +1076,21 @@ static void launch_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, in
     for (int c = 0; c < nrhs; ++c) {
         P.epoch = ++Y.epoch;
         P.x = x + (int64_t)c * ldx;
+        P.xin = xin ? xin + (int64_t)c * ldx : P.x;
         ILUB_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
         h->launches++;
     }
     ILUB_CUDA(cudaGetLastError());
+}
+
+// out-of-place solve of one right-hand side on the line-systolic kernel: xin -> xout, either of which may be the caller's
+// pinned host vector (the kernel then streams it over PCIe while the wavefront advances: no staging copy)
+bool systolic_out_of_place_ok(const ilub_handle* h, int slot) {
+    const SysSolve& Y = h->solve[slot].sys;
+    return h->solve[slot].built && Y.built && !Y.tile && options().solve_algo == 0;
+}
+void run_systolic_io(ilub_handle* h, int slot, const double* xin, double* xout, cudaStream_t s) {
+    launch_systolic(h, slot, xout, h->n, 1, s, nullptr, xin);
 }
 
 void run_systolic(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {

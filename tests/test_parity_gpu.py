@@ -945,3 +945,26 @@ def test_tile_systolic_kernel(ilupp, exact, name, nx, ny, nz):
     finally:
         for k, v in saved.items():
             ilupp.set_option(k, v)
+
+
+def test_zero_copy_apply_on_pinned_host_vector(ilupp):
+    """apply() on a pinned host vector: the solve kernels read / write it over PCIe (no staging copies); same bits as
+    the staged path, for all four solve forms"""
+    import torch
+    for A, cls in ((P.poisson3d(40), ilupp.IChol0Preconditioner), (P.convdiff3d(33), ilupp.ILU0Preconditioner),
+                   (P.poisson2d(96), ilupp.ILU0Preconditioner)):
+        n = A.shape[0]
+        for fmt in ("csr", "csc"):
+            B = cls(A.asformat(fmt))
+            b = P.rhs(n, 2)
+            for tr in (False, True):
+                want = b.copy()
+                ilupp.set_option("zero_copy", 0)
+                (B.apply_trans if tr else B.apply)(want)
+                ilupp.set_option("zero_copy", 1)
+                hx = torch.from_numpy(b.copy()).pin_memory()
+                launches0 = B.stats["launches"]
+                (B.apply_trans if tr else B.apply)(hx.numpy())
+                ilupp.set_option("zero_copy", 0)
+                assert B.stats["launches"] - launches0 == 2
+                assert np.array_equal(hx.numpy(), want)
