@@ -140,8 +140,10 @@ def solve(A, b, rtol=1e-4, atol=1e-4, max_iter=500, threshold=0.1, fill_in=None,
     Same signature and return convention as the reference.  The reference always builds its
     multilevel ILU++ preconditioner here (out of scope); this build runs the same
     BiCGStab loop (SPLIT preconditioning, zero start, tolerances on the preconditioned residual,
-    both rtol and atol required) with ``precond`` = "ilu0" (default) or "ichol0", entirely on the
-    GPU.  ``threshold``/``fill_in``/``params`` are accepted and ignored.
+    both rtol and atol required) with ``precond`` = "ilu0" (default), entirely on the GPU.  With
+    ``precond`` = "ichol0" (symmetric positive definite A) the Krylov method is the reference's preconditioned
+    conjugate gradients (cg, iterative_solvers_implementation.h:133-216) with the IChol(0) factor as split
+    preconditioner.  ``threshold``/``fill_in``/``params`` are accepted and ignored.
     Raises RuntimeError("did not converge") like the reference.
     """
     Ad, Ai, Ap, Ao = _matrix_fields(A)
@@ -152,7 +154,7 @@ def solve(A, b, rtol=1e-4, atol=1e-4, max_iter=500, threshold=0.1, fill_in=None,
         if b.shape[0] != A.shape[0]:
             raise RuntimeError("right-hand side has wrong size!")
         pr = _ilupp.IChol0Preconditioner(Ad, Ai, Ap, Ao, device)
-        sol, it, rtol_out, atol_out = pr.solve(b, rtol, atol, max_iter)
+        sol, it, rtol_out, atol_out = pr.solve(b, rtol, atol, max_iter, True)
     else:
         raise ValueError("precond must be 'ilu0' or 'ichol0'")
     if info:
@@ -236,9 +238,14 @@ class _BaseWrapper(scipy.sparse.linalg.LinearOperator):
         """(level_ptr, level_rows): rows sorted by (level, row)."""
         return self.pr.level_sets(which)
 
-    def solve(self, b, rtol=1e-4, atol=1e-4, max_iter=500, info=False):
-        """BiCGStab for the matrix this preconditioner was built from, with self as split preconditioner."""
-        sol, it, r, a = self.pr.solve(np.ascontiguousarray(b, dtype=np.float64), rtol, atol, max_iter)
+    def solve(self, b, rtol=1e-4, atol=1e-4, max_iter=500, info=False, method=None):
+        """Krylov solve for the matrix this preconditioner was built from, with self as split preconditioner:
+        method = "bicgstab" or "cg" (default: cg for IChol0Preconditioner, BiCGStab otherwise)."""
+        if method is None:
+            method = "cg" if isinstance(self, (IChol0Preconditioner, IChol0PreconditionerBatched)) else "bicgstab"
+        if method not in ("cg", "bicgstab"):
+            raise ValueError("method must be 'cg' or 'bicgstab'")
+        sol, it, r, a = self.pr.solve(np.ascontiguousarray(b, dtype=np.float64), rtol, atol, max_iter, method == "cg")
         return (sol, (it, r, a)) if info else sol
 
     def check_status(self, stream=0):
@@ -288,14 +295,32 @@ class FactorsPreconditioner(_BaseWrapper):
     `ICholTPreconditioner`, `ILUTPreconditioner`, `ILUCPreconditioner` (`.factors()`), whose threshold factorisations
     stay on the CPU -- run through the same triangular-solve kernels as ILU(0) / IChol(0).
 
+    Pivoted factors (the reference's `ILUTPPreconditioner` / `ILUCPPreconditioner`, whose `.permutations()` returns
+    `(perm_left, perm_right)`; `triangular_solve_perm`, sparse_implementation.h:4166-4258): pass the factors as the
+    reference returns them together with `perm_left` (then `L[perm_left, :]` is lower triangular) and / or
+    `perm_right` (then `U[:, perm_right]` is upper triangular).
+
     Args:
         L: sparse lower triangular factor (any scipy format)
         U: sparse upper triangular factor, or None for `L L^T`
+        perm_left, perm_right: pivoting permutations (None: identity)
     """
-    def __init__(self, L, U=None, device=0):
+    def __init__(self, L, U=None, device=0, perm_left=None, perm_right=None):
         L = scipy.sparse.csr_matrix(L)
         if L.shape[0] != L.shape[1]:
             raise ValueError('Input matrix must be square!')
+        for perm in (perm_left, perm_right):
+            if perm is not None and (np.asarray(perm).shape != (L.shape[0],) or
+                                     not np.array_equal(np.sort(np.asarray(perm)), np.arange(L.shape[0]))):
+                raise ValueError('perm_left / perm_right must be permutations of range(n)!')
+        if perm_left is not None and U is None:
+            raise ValueError('permutations need both factors!')
+        if perm_left is not None:
+            L = L[np.asarray(perm_left), :].tocsr()      # the truly triangular factor; apply gathers b[perm_left] first
+        if perm_right is not None:
+            if U is None:
+                raise ValueError('permutations need both factors!')
+            U = scipy.sparse.csc_matrix(U)[:, np.asarray(perm_right)].tocsr()   # apply scatters x[perm_right[k]] = z[k] last
         if U is None:
             if scipy.sparse.triu(L, 1).nnz:
                 raise ValueError('L must be lower triangular!')
@@ -324,6 +349,9 @@ class FactorsPreconditioner(_BaseWrapper):
         Fd, Fi, Fp, Fo = _matrix_fields(F)
         make = _ilupp.LLTFactorsPreconditioner if U is None else _ilupp.LUFactorsPreconditioner
         self.pr = make(Fd, Fi, Fp, Fo, device)
+        if perm_left is not None or perm_right is not None:
+            self.pr.set_permutations(None if perm_left is None else np.asarray(perm_left, dtype=_index_dtype),
+                                     None if perm_right is None else np.asarray(perm_right, dtype=_index_dtype))
         scipy.sparse.linalg.LinearOperator.__init__(self, shape=L.shape, dtype=np.dtype(np.float64))
 
 

@@ -257,6 +257,24 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
              },
              py::arg("ptr"), py::arg("n"), py::arg("nrhs") = 1, py::arg("ldx") = 0, py::arg("stream") = 0,
              py::arg("transpose") = false)
+        .def("set_permutations",
+             [](const P& pr, py::object gather_in, py::object scatter_out) {
+                 py::array_t<Integer, py::array::c_style | py::array::forcecast> gi, so;
+                 const Integer* g = nullptr;
+                 const Integer* s = nullptr;
+                 if (!gather_in.is_none()) {
+                     gi = gather_in.cast<py::array_t<Integer, py::array::c_style | py::array::forcecast>>();
+                     if (gi.ndim() != 1 || gi.shape(0) != pr.dim()) throw std::runtime_error("permutation has wrong size!");
+                     g = gi.data();
+                 }
+                 if (!scatter_out.is_none()) {
+                     so = scatter_out.cast<py::array_t<Integer, py::array::c_style | py::array::forcecast>>();
+                     if (so.ndim() != 1 || so.shape(0) != pr.dim()) throw std::runtime_error("permutation has wrong size!");
+                     s = so.data();
+                 }
+                 check(ilub_set_permutations(pr.h, g, s, ILUB_HOST, nullptr));
+             },
+             py::arg("gather_in") = py::none(), py::arg("scatter_out") = py::none())
         .def("check_status",
              [](const P& pr, uintptr_t stream) { check(ilub_check_status(pr.h, reinterpret_cast<void*>(stream))); },
              py::arg("stream") = 0)
@@ -311,7 +329,7 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
         // BiCGStab with this object as split preconditioner; returns the reference's result tuple
         .def("solve",
              [](const P& pr, py::array_t<double, py::array::c_style | py::array::forcecast> b, double rtol, double atol,
-                Integer max_iter) {
+                Integer max_iter, bool cg) {
                  if (b.ndim() != 1 || b.shape(0) != pr.dim()) throw std::runtime_error("right-hand side has wrong size!");
                  py::array_t<Real> x(pr.dim());
                  int32_t iters = 0;
@@ -319,29 +337,30 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
                  int st;
                  {
                      py::gil_scoped_release release;
-                     st = ilub_bicgstab(pr.h, b.data(), x.mutable_data(), rtol, atol, max_iter, &iters, &rel, &ab,
-                                        ILUB_HOST, nullptr);
+                     st = (cg ? ilub_pcg : ilub_bicgstab)(pr.h, b.data(), x.mutable_data(), rtol, atol, max_iter, &iters, &rel,
+                                                          &ab, ILUB_HOST, nullptr);
                  }
                  if (st == ILUB_ERR_NOT_CONVERGED) throw std::runtime_error("did not converge");  // binding.cpp:228
                  check(st);
                  return py::make_tuple(x, iters, rel, ab);
              },
-             py::arg("b"), py::arg("rtol") = 1e-4, py::arg("atol") = 1e-4, py::arg("max_iter") = 500)
+             py::arg("b"), py::arg("rtol") = 1e-4, py::arg("atol") = 1e-4, py::arg("max_iter") = 500, py::arg("cg") = false)
         .def("solve_device",
-             [](const P& pr, uintptr_t b, uintptr_t x, double rtol, double atol, Integer max_iter, uintptr_t stream) {
+             [](const P& pr, uintptr_t b, uintptr_t x, double rtol, double atol, Integer max_iter, uintptr_t stream, bool cg) {
                  int32_t iters = 0;
                  double rel = 0, ab = 0;
                  int st;
                  {
                      py::gil_scoped_release release;
-                     st = ilub_bicgstab(pr.h, reinterpret_cast<const double*>(b), reinterpret_cast<double*>(x), rtol,
-                                        atol, max_iter, &iters, &rel, &ab, ILUB_DEVICE, reinterpret_cast<void*>(stream));
+                     st = (cg ? ilub_pcg : ilub_bicgstab)(pr.h, reinterpret_cast<const double*>(b), reinterpret_cast<double*>(x),
+                                                          rtol, atol, max_iter, &iters, &rel, &ab, ILUB_DEVICE,
+                                                          reinterpret_cast<void*>(stream));
                  }
                  if (st != ILUB_OK && st != ILUB_ERR_NOT_CONVERGED) raise_status(st);
                  return py::make_tuple(iters, rel, ab, st == ILUB_OK);
              },
              py::arg("b"), py::arg("x"), py::arg("rtol") = 1e-4, py::arg("atol") = 1e-4, py::arg("max_iter") = 500,
-             py::arg("stream") = 0)
+             py::arg("stream") = 0, py::arg("cg") = false)
         .def("debug_sys_trace",
              [](const P& pr, int which) {
                  int32_t dims[8];

@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <vector>
 
 #include "ilub_common.cuh"
 
@@ -262,6 +263,33 @@ int ilub_create_from_factors(int kind, const double* data, const int32_t* indice
     });
 }
 
+int ilub_set_permutations(ilub_handle* h, const int32_t* gather_in, const int32_t* scatter_out, int where, void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h, ILUB_ERR_INVALID, "null handle");
+        ILUB_REQUIRE(h->prefactored, ILUB_ERR_INVALID, "permutations belong to factors computed elsewhere (ilub_create_from_factors)");
+        HandleLock lock(h->mu);
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
+        auto load = [&](DevBuf<int>& buf, const int32_t* p) {
+            buf.release();
+            if (!p) return;
+            if (where == ILUB_HOST) {  // a permutation: every index in range, none twice
+                std::vector<char> seen((size_t)h->n, 0);
+                for (int32_t k = 0; k < h->n; ++k) {
+                    ILUB_REQUIRE(p[k] >= 0 && p[k] < h->n && !seen[p[k]], ILUB_ERR_INVALID, "not a permutation");
+                    seen[p[k]] = 1;
+                }
+            }
+            buf.alloc((size_t)h->n);
+            ILUB_CUDA(cudaMemcpyAsync(buf.p, p, sizeof(int) * (size_t)h->n, to_dev(where), s));
+        };
+        load(h->perm_in, gather_in);
+        load(h->perm_out, scatter_out);
+        ILUB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream) {
     return guarded([&] {
         ILUB_REQUIRE(h && data, ILUB_ERR_INVALID, "null argument");
@@ -321,10 +349,29 @@ int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nr
         apply_slots(h, transpose, first, second);
         ensure_solve(h, first, s);
         ensure_solve(h, second, s);
+        // pivoted factors (ilub_set_permutations): apply = scatter_out . T^-1 . gather_in, apply_trans = its transpose
+        const int* pre = transpose ? (h->perm_out.n ? h->perm_out.p : nullptr) : (h->perm_in.n ? h->perm_in.p : nullptr);
+        const int* post = transpose ? (h->perm_in.n ? h->perm_in.p : nullptr) : (h->perm_out.n ? h->perm_out.p : nullptr);
         if (where == ILUB_DEVICE) {
+            if (pre) permute_gather(h, pre, x, ldx, nrhs, s);
             run_solve(h, first, x, ldx, nrhs, s);
             run_solve(h, second, x, ldx, nrhs, s);
+            if (post) permute_scatter(h, post, x, ldx, nrhs, s);
             post_deferred(h, s);
+        } else if (pre || post) {
+            const size_t cnt = (size_t)h->n * nrhs;
+            h->work.ensure(cnt);
+            for (int c = 0; c < nrhs; ++c)
+                ILUB_CUDA(cudaMemcpyAsync(h->work.p + (size_t)c * h->n, x + (size_t)c * ldx, sizeof(double) * h->n,
+                                          cudaMemcpyHostToDevice, s));
+            if (pre) permute_gather(h, pre, h->work.p, h->n, nrhs, s);
+            run_solve(h, first, h->work.p, h->n, nrhs, s);
+            run_solve(h, second, h->work.p, h->n, nrhs, s);
+            if (post) permute_scatter(h, post, h->work.p, h->n, nrhs, s);
+            for (int c = 0; c < nrhs; ++c)
+                ILUB_CUDA(cudaMemcpyAsync(x + (size_t)c * ldx, h->work.p + (size_t)c * h->n, sizeof(double) * h->n,
+                                          cudaMemcpyDeviceToHost, s));
+            read_status(h, s);
         } else if (nrhs == 1 && options().zero_copy != 0 && systolic_out_of_place_ok(h, first) && systolic_out_of_place_ok(h, second) &&
                    device_view_of_host(x) != nullptr) {
             // Zero copy: x is pinned host memory the device can address.  The first solve reads the right-hand side
@@ -514,6 +561,35 @@ int ilub_bicgstab(ilub_handle* h, const double* b, double* x, double rtol, doubl
             dx.alloc(h->n);
             ILUB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * h->n, cudaMemcpyHostToDevice, s));
             ok = bicgstab(h, db.p, dx.p, rtol, atol, max_iter, iters, rel_achieved, abs_achieved, s);
+            ILUB_CUDA(cudaMemcpyAsync(x, dx.p, sizeof(double) * h->n, cudaMemcpyDeviceToHost, s));
+        }
+        read_status(h, s);
+        if (!ok) throw Error{ILUB_ERR_NOT_CONVERGED, "did not converge"};
+    });
+}
+
+int ilub_pcg(ilub_handle* h, const double* b, double* x, double rtol, double atol, int32_t max_iter,
+                  int32_t* iters, double* rel_achieved, double* abs_achieved, int where, void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && b && x && iters && rel_achieved && abs_achieved, ILUB_ERR_INVALID, "null argument");
+        ILUB_REQUIRE(!h->prefactored, ILUB_ERR_INVALID, "handle was created from factors: it holds no matrix");
+        HandleLock lock(h->mu);
+        DeviceGuard guard(h->device);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        set_alloc_stream(s);
+        int first, second;
+        apply_slots(h, 0, first, second);
+        ensure_solve(h, first, s);
+        ensure_solve(h, second, s);
+        int ok;
+        if (where == ILUB_DEVICE) {
+            ok = pcg(h, b, x, rtol, atol, max_iter, iters, rel_achieved, abs_achieved, s);
+        } else {
+            DevBuf<double> db, dx;
+            db.alloc(h->n);
+            dx.alloc(h->n);
+            ILUB_CUDA(cudaMemcpyAsync(db.p, b, sizeof(double) * h->n, cudaMemcpyHostToDevice, s));
+            ok = pcg(h, db.p, dx.p, rtol, atol, max_iter, iters, rel_achieved, abs_achieved, s);
             ILUB_CUDA(cudaMemcpyAsync(x, dx.p, sizeof(double) * h->n, cudaMemcpyDeviceToHost, s));
         }
         read_status(h, s);

@@ -341,6 +341,9 @@ struct ilub_handle {
     unsigned fepoch = 0;
     ilub::DevBuf<int> status;           // device status word(s) written by kernels (watchdog / structure errors)
     ilub::DevBuf<double> work;          // vector workspace (host-side apply, bicgstab)
+    // pivoting permutations of factors computed elsewhere (ilub_set_permutations): apply = scatter_out . T^-1 . gather_in
+    ilub::DevBuf<int> perm_in, perm_out;
+    ilub::DevBuf<double> permbuf;
     ilub::DevBuf<double> xalign;        // 16-byte aligned stand-in for an odd-aligned vector (tile-systolic tensor maps)
     ilub::DevBuf<double> scal;          // device scalars for bicgstab
     double timings[4] = {0, 0, 0, 0};
@@ -402,9 +405,15 @@ bool run_plane(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cuda
 void run_solve(ilub_handle* h, int which, double* x, int64_t ldx, int nrhs, cudaStream_t s);
 void extract_factor(ilub_handle* h, int which, double* data, int* indices, int* indptr, cudaStream_t s);
 
+// ---- permutations around the solves of pivoted factors (ilub_krylov.cu)
+void permute_gather(ilub_handle* h, const int* perm, double* x, int64_t ldx, int nrhs, cudaStream_t s);   // x[k] <- x[perm[k]]
+void permute_scatter(ilub_handle* h, const int* perm, double* x, int64_t ldx, int nrhs, cudaStream_t s);  // x[perm[k]] <- x[k]
+
 // ---- Krylov (ilub_krylov.cu)
 void spmv(ilub_handle* h, const double* x, double* y, cudaStream_t s);
 int bicgstab(ilub_handle* h, const double* b, double* x, double rtol, double atol, int max_iter, int* iters,
              double* rel, double* abs_, cudaStream_t s);
+int pcg(ilub_handle* h, const double* b, double* x, double rtol, double atol, int max_iter, int* iters, double* rel,
+        double* abs_, cudaStream_t s);
 
 }  // namespace ilub

@@ -235,7 +235,94 @@ __global__ void k_bicg_check(State* st) {
     if (!go) st->done = 1;
 }
 
+// ---- permutations of pivoted factors (triangular_solve_perm, sparse_implementation.h:4166-4258)
+__global__ void k_perm_gather(int n, const int* __restrict__ perm, const double* __restrict__ x, double* __restrict__ y) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) y[k] = x[perm[k]];
+}
+__global__ void k_perm_scatter(int n, const int* __restrict__ perm, const double* __restrict__ x, double* __restrict__ y) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) y[perm[k]] = x[k];
+}
+
+// ---- preconditioned CG (SPLIT), iterative_solvers_implementation.h:133-216: two reductions per iteration
+// initial: p = r; tmp = p; y = 0; gamma_old = r.r; initial_res = res = ||r||   (:173-177)
+__global__ void __launch_bounds__(RB) k_cg_init(int n, const double* __restrict__ r, double* __restrict__ p,
+                                                double* __restrict__ tmp, double* __restrict__ y, State* st, double* partial) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)gridDim.x * RB) {
+        const double v = r[i];
+        p[i] = v;
+        tmp[i] = v;
+        y[i] = 0.0;
+        acc += v * v;
+    }
+    finish_reduction(st, partial, acc, 0.0, [](State* s, double d0, double) {
+        s->rho = d0;  // gamma_old
+        s->initial_res = s->res = sqrt(d0);
+        s->iter = 0;
+        s->done = 0;
+    });
+}
+// alpha = gamma_old / (Ap.p)                 (:182)
+__global__ void __launch_bounds__(RB) k_cg_alpha(int n, const double* __restrict__ Ap, const double* __restrict__ p, State* st,
+                                                 double* partial) {
+    if (*(volatile int*)&st->done) return;
+    double a0 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)gridDim.x * RB) a0 += Ap[i] * p[i];
+    finish_reduction(st, partial, a0, 0.0, [](State* s, double d0, double) { s->alpha = s->rho / d0; });
+}
+// y += alpha p ; r -= alpha Ap ; gamma_new = r.r ; beta = gamma_new / gamma_old ; res = ||r||   (:183-189)
+__global__ void __launch_bounds__(RB) k_cg_update(int n, const double* __restrict__ p, const double* __restrict__ Ap,
+                                                  double* __restrict__ y, double* __restrict__ r, State* st, double* partial) {
+    if (*(volatile int*)&st->done) return;
+    const double alpha = st->alpha;
+    double a0 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)gridDim.x * RB) {
+        y[i] += alpha * p[i];
+        const double rv = r[i] + (-alpha) * Ap[i];
+        r[i] = rv;
+        a0 += rv * rv;
+    }
+    finish_reduction(st, partial, a0, 0.0, [](State* s, double d0, double) {
+        s->beta = d0 / s->rho;
+        s->rho = d0;
+        s->res = sqrt(d0);
+        s->iter += 1;
+    });
+}
+// p = beta p + r ; tmp = p                    (:188)
+__global__ void __launch_bounds__(RB) k_cg_p(int n, double* __restrict__ p, const double* __restrict__ r, double* __restrict__ tmp,
+                                             const State* st) {
+    if (*(volatile const int*)&st->done) return;
+    const double beta = st->beta;
+    for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)gridDim.x * RB) {
+        const double pv = beta * p[i] + r[i];
+        p[i] = pv;
+        tmp[i] = pv;
+    }
+}
+
 }  // namespace
+
+void permute_gather(ilub_handle* h, const int* perm, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
+    h->permbuf.ensure((size_t)h->n);
+    for (int c = 0; c < nrhs; ++c) {
+        double* xc = x + (int64_t)c * ldx;
+        k_perm_gather<<<blocks_for(h->n, 256), 256, 0, s>>>(h->n, perm, xc, h->permbuf.p);
+        ILUB_CUDA(cudaMemcpyAsync(xc, h->permbuf.p, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, s));
+        h->launches++;
+    }
+}
+void permute_scatter(ilub_handle* h, const int* perm, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
+    h->permbuf.ensure((size_t)h->n);
+    for (int c = 0; c < nrhs; ++c) {
+        double* xc = x + (int64_t)c * ldx;
+        k_perm_scatter<<<blocks_for(h->n, 256), 256, 0, s>>>(h->n, perm, xc, h->permbuf.p);
+        ILUB_CUDA(cudaMemcpyAsync(xc, h->permbuf.p, sizeof(double) * h->n, cudaMemcpyDeviceToDevice, s));
+        h->launches++;
+    }
+}
 
 void spmv(ilub_handle* h, const double* x, double* y, cudaStream_t s) {
     const Options& opt = options();
@@ -350,6 +437,63 @@ int bicgstab(ilub_handle* h, const double* b, double* x, double rtol, double ato
     *iters = out.iter;
     const bool ok = (out.res / out.initial_res < hs.rel_tol) && (out.res < hs.abs_tol);  // :498
     *rel = pow(10.0, log10(out.res / out.initial_res));                                  // :499 + binding.cpp:226
+    *abs_ = pow(10.0, log10(out.res));
+    return ok ? 1 : 0;
+}
+
+// Preconditioned conjugate gradients with the handle's factors as SPLIT preconditioner (the natural Krylov method for
+// IChol(0): L^-1 A L^-T is symmetric positive definite); replaces cg (iterative_solvers_implementation.h:133-216).
+int pcg(ilub_handle* h, const double* b, double* x, double rtol, double atol, int max_iter, int* iters, double* rel,
+        double* abs_, cudaStream_t s) {
+    const int n = h->n;
+    int sl_left, sl_right;
+    apply_slots(h, sl_left, sl_right);
+    h->work.ensure((size_t)5 * n);  // r, p, Ap, y, tmp
+    h->scal.ensure(2 * MAXBLK + 64);
+    double* r = h->work.p;
+    double* p = r + n;
+    double* Ap = p + n;
+    double* y = Ap + n;
+    double* tmp = y + n;
+    double* partial = h->scal.p;
+    State* st = reinterpret_cast<State*>(h->scal.p + 2 * MAXBLK);
+    State hs;
+    memset(&hs, 0, sizeof(hs));
+    hs.rel_tol = exp(-(-log10(rtol)) * log(10.0));  // :150-151
+    hs.abs_tol = exp(-(-log10(atol)) * log(10.0));
+    hs.max_iter = max_iter;
+    hs.min_iter = 1;
+    ILUB_CUDA(cudaMemcpyAsync(st, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
+    const int grid = std::min(MAXBLK, std::max(1, blocks_for(n, RB)));
+    ILUB_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    run_solve(h, sl_left, r, n, 1, s);  // r = L^-1 b
+    k_cg_init<<<grid, RB, 0, s>>>(n, r, p, tmp, y, st, partial);
+    h->launches++;
+    const int poll = 4;
+    State out;
+    int launched = 0;
+    while (true) {
+        for (int k = 0; k < poll; ++k) {
+            run_solve(h, sl_right, tmp, n, 1, s);  // Ap = L^-1 A U^-1 p
+            spmv(h, tmp, Ap, s);
+            run_solve(h, sl_left, Ap, n, 1, s);
+            k_cg_alpha<<<grid, RB, 0, s>>>(n, Ap, p, st, partial);
+            k_cg_update<<<grid, RB, 0, s>>>(n, p, Ap, y, r, st, partial);
+            k_cg_p<<<grid, RB, 0, s>>>(n, p, r, tmp, st);
+            k_bicg_check<<<1, 1, 0, s>>>(st);
+            h->launches += 4;
+            ++launched;
+        }
+        ILUB_CUDA(cudaMemcpyAsync(&out, st, sizeof(State), cudaMemcpyDeviceToHost, s));
+        ILUB_CUDA(cudaStreamSynchronize(s));
+        if (out.done || launched > max_iter + poll) break;
+    }
+    ILUB_CUDA(cudaMemcpyAsync(x, y, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    run_solve(h, sl_right, x, n, 1, s);  // x = U^-1 y
+    ILUB_CUDA(cudaGetLastError());
+    *iters = out.iter;
+    const bool ok = (out.res / out.initial_res < hs.rel_tol) && (out.res < hs.abs_tol);
+    *rel = pow(10.0, log10(out.res / out.initial_res));
     *abs_ = pow(10.0, log10(out.res));
     return ok ? 1 : 0;
 }

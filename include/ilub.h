@@ -100,6 +100,15 @@ ILUB_API int ilub_create_ichol0(const double* data, const int32_t* indices, cons
 ILUB_API int ilub_create_from_factors(int kind, const double* data, const int32_t* indices, const int32_t* indptr,
                                       int32_t n, int64_t nnz, int is_csr, int where, int device, void* stream,
                                       ilub_handle** out);
+/* Pivoting permutations of factors computed elsewhere: replaces matrix_sparse::triangular_solve_perm
+ * (sparse_implementation.h:4166-4258) as used by the reference's ILUTP / ILUCP classes
+ * (indirect_split_pseudo_triangular_preconditioner, preconditioner_implementation.h:655-757).  With the factors handed
+ * to ilub_create_from_factors made truly triangular by the caller (L[perm_left, :] resp. U[:, perm_right]),
+ * apply computes  x <- scatter_out(U^-1 L^-1 gather_in(x)),  gather_in(x)[k] = x[gather_in[k]] (the reference's left
+ * permutation), scatter_out(z)[scatter_out[k]] = z[k] (its right permutation); apply_trans the transposed operator.
+ * Either array may be NULL (identity). */
+ILUB_API int ilub_set_permutations(ilub_handle* h, const int32_t* gather_in, const int32_t* scatter_out, int where,
+                                   void* stream);
 /* numeric re-factorisation with new values on the unchanged pattern; reuses the
  * symbolic analysis (levels, partition, packed layout). */
 ILUB_API int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream);
@@ -156,6 +165,12 @@ ILUB_API int ilub_spmv(ilub_handle* h, const double* x, double* y, int where, vo
  * *abs_achieved are as in the reference's result tuple; ILUB_ERR_NOT_CONVERGED mirrors
  * RuntimeError("did not converge") (x is still written). */
 ILUB_API int ilub_bicgstab(ilub_handle* h, const double* b, double* x, double rtol, double atol, int32_t max_iter,
+                           int32_t* iters, double* rel_achieved, double* abs_achieved, int where, void* stream);
+/* preconditioned conjugate gradients (SPLIT preconditioning with the handle's factors, zero start): replaces cg
+ * (iterative_solvers_implementation.h:133-216), the natural Krylov method behind an IChol(0) preconditioner
+ * (SURVEY.md 8(f)2).  Same arguments and result convention as ilub_bicgstab; ILUB_ERR_NOT_CONVERGED when the
+ * tolerances are not both met (the criterion of iterative_solvers_implementation.h:498). */
+ILUB_API int ilub_pcg(ilub_handle* h, const double* b, double* x, double rtol, double atol, int32_t max_iter,
                            int32_t* iters, double* rel_achieved, double* abs_achieved, int where, void* stream);
 
 /* ---- batched independent systems (BASELINE config 5) ---------------------------------------- */

@@ -82,6 +82,8 @@ class _Port:
                                       _i32p, _f64p, _f64p, _f64p, f64, f64, i32, C.POINTER(i32), C.POINTER(f64),
                                       C.POINTER(f64)]
         L.oracle_bicgstab.restype = C.c_int
+        L.oracle_cg.argtypes = L.oracle_bicgstab.argtypes
+        L.oracle_cg.restype = C.c_int
 
     # -- factorisations, returning scipy matrices laid out exactly like ilupp.ilu0 / ilupp.ichol0
     def ilu0(self, A):
@@ -148,7 +150,11 @@ class _Port:
         self.lib.oracle_spmv(A.shape[0], int(is_csr), ptr, idx, val, np.ascontiguousarray(x, np.float64), y)
         return y
 
-    def bicgstab(self, A, b, factors, rtol=1e-8, atol=1e-8, max_iter=2000):
+    def cg(self, A, b, factors, rtol=1e-8, atol=1e-8, max_iter=2000):
+        """reference cg (SPLIT preconditioning); same arguments and result as bicgstab"""
+        return self.bicgstab(A, b, factors, rtol, atol, max_iter, fn="oracle_cg")
+
+    def bicgstab(self, A, b, factors, rtol=1e-8, atol=1e-8, max_iter=2000, fn="oracle_bicgstab"):
         """factors = (L, U) from ilu0 or (L,) from ichol0.  Returns (x, iters, rel, abs, ok)."""
         ptr, idx, val, a_csr = _csr_arrays(A)
         n = A.shape[0]
@@ -160,9 +166,9 @@ class _Port:
             Up, Ui, Ux, kind = Lp, Li, Lx, 1
         x = np.empty(n)
         it, rel, ab = C.c_int32(), C.c_double(), C.c_double()
-        ok = self.lib.oracle_bicgstab(kind, int(lcsr), n, Lp, Li, Lx, Up, Ui, Ux, int(a_csr), ptr, idx, val,
-                                      np.ascontiguousarray(b, np.float64), x, rtol, atol, max_iter, C.byref(it),
-                                      C.byref(rel), C.byref(ab))
+        ok = getattr(self.lib, fn)(kind, int(lcsr), n, Lp, Li, Lx, Up, Ui, Ux, int(a_csr), ptr, idx, val,
+                                   np.ascontiguousarray(b, np.float64), x, rtol, atol, max_iter, C.byref(it),
+                                   C.byref(rel), C.byref(ab))
         return x, it.value, rel.value, ab.value, bool(ok)
 
 
@@ -198,11 +204,14 @@ class _RefPrecond:
             out.append(_mk(p, i, d, bool(is_csr.value), self.n))
         return out
 
-    def bicgstab(self, A, b, rtol=1e-8, atol=1e-8, max_iter=2000):
+    def cg(self, A, b, rtol=1e-8, atol=1e-8, max_iter=2000):
+        return self.bicgstab(A, b, rtol, atol, max_iter, fn="ref_cg")
+
+    def bicgstab(self, A, b, rtol=1e-8, atol=1e-8, max_iter=2000, fn="ref_bicgstab"):
         ptr, idx, val, is_csr = _csr_arrays(A)
         x = np.zeros(self.n)
         it, rel, ab = C.c_int32(), C.c_double(), C.c_double()
-        ok = self._ref.lib.ref_bicgstab(self._h, val, idx, ptr, self.n, int(is_csr), np.ascontiguousarray(b, np.float64),
+        ok = getattr(self._ref.lib, fn)(self._h, val, idx, ptr, self.n, int(is_csr), np.ascontiguousarray(b, np.float64),
                                         x, rtol, atol, max_iter, C.byref(it), C.byref(rel), C.byref(ab))
         return x, it.value, rel.value, ab.value, bool(ok)
 
@@ -227,6 +236,9 @@ class _Ref:
         L.ref_bicgstab.argtypes = [C.c_void_p, _f64p, _i32p, _i32p, i32, C.c_int, _f64p, _f64p, f64, f64, i32,
                                    C.POINTER(i32), C.POINTER(f64), C.POINTER(f64)]
         L.ref_bicgstab.restype = C.c_int
+        if hasattr(L, "ref_cg"):
+            L.ref_cg.argtypes = L.ref_bicgstab.argtypes
+            L.ref_cg.restype = C.c_int
 
     def _create(self, fn, A):
         ptr, idx, val, is_csr = _csr_arrays(A)

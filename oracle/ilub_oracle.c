@@ -379,3 +379,48 @@ API int oracle_bicgstab(int kind, int factors_csr, int32_t n, const int32_t* Lp,
     free(r); free(y); free(p); free(s); free(Apv); free(As); free(r0); free(t);
     return ok;
 }
+
+/* cg (SPLIT preconditioning, zero start, min_iter = 1): iterative_solvers_implementation.h:133-216.
+ * The reference returns true whatever the residual (:208); the convergence flag returned here is the one its
+ * bicgstab applies (:498), which is what the drop-in solve() reports. */
+API int oracle_cg(int kind, int factors_csr, int32_t n, const int32_t* Lp, const int32_t* Li, const double* Lx,
+                  const int32_t* Up, const int32_t* Ui, const double* Ux, int a_is_csr, const int32_t* Ap,
+                  const int32_t* Ai, const double* Ax, const double* b, double* x, double rtol, double atol,
+                  int32_t max_iter, int32_t* iters, double* rel_achieved, double* abs_achieved) {
+    pre_t P = {kind, factors_csr, n, Lp, Li, Up, Ui, Lx, Ux};
+    double rel_tol = -log10(rtol), abs_tol = -log10(atol);
+    rel_tol = exp(-rel_tol * log(10.0)); /* :150-151 */
+    abs_tol = exp(-abs_tol * log(10.0));
+    const size_t nb = sizeof(double) * (size_t)n;
+    double *r = malloc(nb), *y = calloc((size_t)n, sizeof(double)), *p = malloc(nb), *Apv = malloc(nb), *t = malloc(nb);
+    memcpy(r, b, nb); /* p = b; r = L^-1 p  (:165,171) */
+    pre_left(&P, r);
+    memcpy(p, r, nb); /* :173 */
+    double initial_res = sqrt(dot(n, r, r)), res = initial_res; /* :174-175 */
+    int32_t iter = 0;
+    const int32_t min_iter = 1;
+    double gamma_old = dot(n, r, r); /* :177 */
+    while ((((res / initial_res > rel_tol) || res > abs_tol) && (iter < max_iter)) || (iter < min_iter)) { /* :178 */
+        ++iter;
+        memcpy(t, p, nb); /* Ap = L^-1 A U^-1 p (:181) */
+        pre_right(&P, t);
+        oracle_spmv(n, a_is_csr, Ap, Ai, Ax, t, Apv);
+        pre_left(&P, Apv);
+        const double alpha = gamma_old / dot(n, Apv, p);                   /* :182 */
+        for (int32_t i = 0; i < n; ++i) y[i] += alpha * p[i];               /* :183 */
+        for (int32_t i = 0; i < n; ++i) r[i] += (-alpha) * Apv[i];          /* :184 */
+        const double gamma_new = dot(n, r, r);                              /* :185 */
+        const double beta = gamma_new / gamma_old;                          /* :186 */
+        gamma_old = gamma_new;                                              /* :187 */
+        for (int32_t i = 0; i < n; ++i) p[i] = beta * p[i] + r[i];          /* :188 */
+        res = sqrt(dot(n, r, r));                                           /* :189 */
+    }
+    memcpy(x, y, nb); /* x = U^-1 y (:191) */
+    pre_right(&P, x);
+    *iters = iter;
+    const int ok = (res / initial_res < rel_tol) && (res < abs_tol);
+    *rel_achieved = pow(10.0, log10(res / initial_res));
+    *abs_achieved = pow(10.0, log10(res));
+    free(r); free(y); free(p); free(Apv); free(t);
+    return ok;
+}

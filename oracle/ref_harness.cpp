@@ -138,4 +138,26 @@ int ref_bicgstab(void* p, const double* data, const int32_t* indices, const int3
     return ok ? 1 : 0;
 }
 
+// cg(SPLIT, zero start, min_iter = 1) of the reference (iterative_solvers_implementation.h:133-216) with the IChol0 /
+// ILU0 preconditioner of the handle.  The reference's cg returns true whatever the residual; the flag returned here is
+// the criterion its bicgstab applies (:498).
+int ref_cg(void* p, const double* data, const int32_t* indices, const int32_t* indptr, int32_t n, int is_csr,
+           const double* b, double* x, double rtol, double atol, int32_t max_iter, int32_t* iters,
+           double* rel_achieved, double* abs_achieved) {
+    RefHandle* h = static_cast<RefHandle*>(p);
+    matrix A = view(data, indices, indptr, n, is_csr);
+    vector vb(n, const_cast<double*>(b), true);
+    vector vx(n, x, true);
+    Real rel_tol = -std::log10(rtol), abs_tol = -std::log10(atol);
+    Integer it = max_iter;
+    if (h->kind == 0)
+        cg<Real, matrix, vector>(*h->lu, SPLIT, A, vb, vx, 1, it, rel_tol, abs_tol, true);
+    else
+        cg<Real, matrix, vector>(*h->llt, SPLIT, A, vb, vx, 1, it, rel_tol, abs_tol, true);
+    *iters = it;
+    *rel_achieved = std::pow(10.0, -rel_tol);
+    *abs_achieved = std::pow(10.0, -abs_tol);
+    return (*rel_achieved < rtol && *abs_achieved < atol) ? 1 : 0;
+}
+
 }  // extern "C"

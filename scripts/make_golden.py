@@ -109,6 +109,27 @@ def main():
             rec.update({key + "_apply": y, key + "_apply_trans": yt, key + "_total_nnz": np.array(Pq.total_nnz)})
         np.savez_compressed(os.path.join(out, "factors_%s.npz" % name), **rec)
         print("wrote factors", name, "n", n, [k for k, _, _ in kinds])
+    # SURVEY.md 8(f)1, permuted triangular solves (sparse_implementation.h:4166-4258): factors, pivoting permutations and
+    # apply / apply_trans of the reference's ILUTP / ILUCP on a matrix with a weakened diagonal (so that pivoting happens)
+    for fmt in ("csr", "csc"):
+        A = (random_matrix(120, fmt) - 9.5 * scipy.sparse.eye(120)).asformat(fmt)
+        data, idx, ptr = fields(A)
+        n = A.shape[0]
+        b = np.random.default_rng(13).standard_normal(n)
+        rec = {"A_data": data, "A_indices": idx, "A_indptr": ptr, "is_csr": np.array(fmt == "csr"), "b": b}
+        for key, cls in (("ilutp", ref.ILUTPPreconditioner), ("ilucp", ref.ILUCPPreconditioner)):
+            Pq = cls(data, idx, ptr, fmt == "csr", 10, 1e-3, 1.0, -1, 10.0)
+            for fname, (Fd, Fi, Fp, Fc, _, _) in zip(("L", "U"), Pq.factors_info()):
+                rec.update({"%s_%s_data" % (key, fname): Fd, "%s_%s_indices" % (key, fname): Fi,
+                            "%s_%s_indptr" % (key, fname): Fp, "%s_%s_is_csr" % (key, fname): np.array(Fc)})
+            pl, pr = Pq.permutations()
+            rec[key + "_perm_left"] = np.array([] if pl is None else pl, dtype=np.int32)
+            rec[key + "_perm_right"] = np.array([] if pr is None else pr, dtype=np.int32)
+            y = b.copy(); Pq.apply(y)
+            yt = b.copy(); Pq.apply_trans(yt)
+            rec.update({key + "_apply": y, key + "_apply_trans": yt, key + "_total_nnz": np.array(Pq.total_nnz)})
+        np.savez_compressed(os.path.join(out, "factors_perm_%s.npz" % fmt), **rec)
+        print("wrote permuted factors", fmt)
     # BiCGStab with ILU0 through the reference templates (harness)
     from ilupp_b200 import problems
     A = problems.convdiff3d(12)

@@ -181,3 +181,56 @@ def test_port_apply_on_reference_threshold_factors(name, key):
         U = golden_factor(g, key + "_U").tocsr()
         assert relerr(oracle.port.apply_lu(L, U, g["b"]), g[key + "_apply"]) <= 1e-12
         assert relerr(oracle.port.apply_lu(L, U, g["b"], True), g[key + "_apply_trans"]) <= 1e-12
+
+
+def test_port_cg_matches_reference_cg():
+    """cg (iterative_solvers_implementation.h:133-216): same iteration count and the same residual history (achieved
+    tolerances bit for bit) as the unmodified reference.  The reference's own x is NOT compared: with a zero start it
+    accumulates into an uninitialised vector y (:160 `vector_type y(problem_size)` + sparse_implementation.h:98-102
+    "doesn't initialize by default"), so its solution carries whatever the allocator returned; the port starts y at 0."""
+    if oracle.ref is None:
+        pytest.skip("oracle/_ref not built on this machine")
+    for N in (8, 14):
+        A = P.poisson3d(N)
+        n = A.shape[0]
+        b = A @ np.ones(n)
+        L = oracle.port.ichol0(A)
+        x, it, rel, ab, ok = oracle.port.cg(A, b, (L,), 1e-8, 1e-8, 500)
+        R = oracle.ref.IChol0(A)
+        _, itr, relr, abr, okr = R.cg(A, b, 1e-8, 1e-8, 500)
+        assert ok and okr and it == itr and rel == relr and ab == abr
+        assert np.abs(x - 1.0).max() < 1e-7
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+@pytest.mark.parametrize("key", ["ilutp", "ilucp"])
+def test_permuted_factor_semantics_on_golden(fmt, key):
+    """triangular_solve_perm (sparse_implementation.h:4166-4258) restated as gather / scatter around ordinary triangular
+    solves: L[perm_left, :] and U[:, perm_right] are triangular, apply = scatter_right(U^-1 L^-1 gather_left(b)); pinned
+    on factors, permutations and apply / apply_trans outputs of the reference's ILUTP / ILUCP (pivoting active)"""
+    from helpers import golden_factor, load_golden, relerr
+    g = load_golden("factors_perm_" + fmt)
+    L, U = golden_factor(g, key + "_L").toarray(), golden_factor(g, key + "_U").toarray()
+    pl, pr = g[key + "_perm_left"], g[key + "_perm_right"]
+    n = L.shape[0]
+    assert (pl.size + pr.size) == n and ((pl.size and (pl != np.arange(n)).any()) or (pr.size and (pr != np.arange(n)).any()))
+    Lt = L[pl, :] if pl.size else L
+    Ut = U[:, pr] if pr.size else U
+    assert np.abs(np.triu(Lt, 1)).max() == 0 and np.abs(np.tril(Ut, -1)).max() == 0
+    b = g["b"]
+    t = b[pl] if pl.size else b
+    z = np.linalg.solve(Ut, np.linalg.solve(Lt, t))
+    x = np.empty(n)
+    if pr.size:
+        x[pr] = z
+    else:
+        x = z
+    assert relerr(x, g[key + "_apply"]) <= 1e-10
+    t = b[pr] if pr.size else b                      # transposed operator: gather by perm_right, scatter by perm_left
+    z = np.linalg.solve(Lt.T, np.linalg.solve(Ut.T, t))
+    xt = np.empty(n)
+    if pl.size:
+        xt[pl] = z
+    else:
+        xt = z
+    assert relerr(xt, g[key + "_apply_trans"]) <= 1e-10

@@ -968,3 +968,51 @@ def test_zero_copy_apply_on_pinned_host_vector(ilupp):
                 ilupp.set_option("zero_copy", 0)
                 assert B.stats["launches"] - launches0 == 2
                 assert np.array_equal(hx.numpy(), want)
+
+
+def test_pcg_with_ichol0(ilupp):
+    """preconditioned CG for IChol(0) on the fused Krylov kernels (2 reductions per iteration), against the
+    oracle's restatement of the reference's cg; solve(precond='ichol0') and IChol0Preconditioner.solve() use it"""
+    for N in (12, 40):
+        A = P.poisson3d(N)
+        n = A.shape[0]
+        b = A @ np.ones(n)
+        Lo = oracle.port.ichol0(A)
+        xo, ito, relo, abo, ok = oracle.port.cg(A, b, (Lo,), 1e-8, 1e-8, 2000)
+        assert ok
+        x, (it, rel, ab) = ilupp.solve(A, b, rtol=1e-8, atol=1e-8, max_iter=2000, info=True, precond="ichol0")
+        assert abs(it - ito) <= 2 and rel <= 1e-8 and ab <= 1e-8
+        assert np.abs(x - 1.0).max() < 1e-6 and relerr(x, xo) < 1e-6
+        B = ilupp.IChol0Preconditioner(A)
+        x2, (it2, _, _) = B.solve(b, rtol=1e-8, atol=1e-8, max_iter=2000, info=True)           # default: cg
+        assert it2 == it and np.array_equal(x2, x)
+        x3, (it3, _, _) = B.solve(b, rtol=1e-8, atol=1e-8, max_iter=2000, info=True, method="bicgstab")
+        assert np.abs(x3 - 1.0).max() < 1e-6
+    with pytest.raises(RuntimeError, match="did not converge"):
+        ilupp.solve(A, b, rtol=1e-14, atol=1e-14, max_iter=2, precond="ichol0")
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+@pytest.mark.parametrize("key", ["ilutp", "ilucp"])
+def test_permuted_factors_apply(ilupp, fmt, key):
+    """SURVEY 8(f)1 remainder: factors of the reference's pivoting preconditioners (ILUTP / ILUCP) applied on the GPU with
+    the permutations folded into a gather / scatter around the triangular solves; golden outputs from the reference"""
+    g = load_golden("factors_perm_" + fmt)
+    L, U = golden_factor(g, key + "_L"), golden_factor(g, key + "_U")
+    pl, pr = g[key + "_perm_left"], g[key + "_perm_right"]
+    B = ilupp.FactorsPreconditioner(L, U, perm_left=pl if pl.size else None, perm_right=pr if pr.size else None)
+    y = g["b"].copy()
+    B.apply(y)
+    assert relerr(y, g[key + "_apply"]) <= 1e-11
+    y = g["b"].copy()
+    B.apply_trans(y)
+    assert relerr(y, g[key + "_apply_trans"]) <= 1e-11
+    import torch
+    X = torch.from_numpy(np.asfortranarray(np.stack([g["b"], 2.0 * g["b"]], axis=1))).cuda()   # device path, 2 columns
+    Xd = torch.empty((2, X.shape[0]), dtype=torch.float64, device="cuda").t()
+    Xd.copy_(X)
+    B.apply(Xd)
+    assert relerr(Xd[:, 0].cpu().numpy(), g[key + "_apply"]) <= 1e-11
+    assert relerr(Xd[:, 1].cpu().numpy(), 2.0 * g[key + "_apply"]) <= 1e-11
+    with pytest.raises(ValueError):
+        ilupp.FactorsPreconditioner(L, U, perm_left=np.zeros(L.shape[0], dtype=np.int32))
