@@ -177,6 +177,72 @@ def cpu_reference_apply(steps, warmup):
                       "(the reference has no threading), %d host cores present, CPU: %s" % (steps, os.cpu_count(), cpu_model())}
 
 
+def cpu_reference_batched(seconds=1.5, N=128, rhs=16):
+    """BASELINE config 5 on ONE host core: the reference's ILU0 factor + `rhs` applies of one 2-D Poisson N^2 system,
+    repeated for about `seconds`.  Returns per-system times (the systems are independent and identical in size)."""
+    import oracle
+    P = load_problems()
+    A = P.poisson2d(N)
+    n = A.shape[0]
+    mk = oracle.ref.ILU0 if oracle.ref is not None else None
+    b = P.rhs(n, 0)
+    y = b.copy()
+    t_fac, t_app, reps = [], [], 0
+    t_end = time.perf_counter() + seconds
+    while time.perf_counter() < t_end or reps < 3:
+        t0 = time.perf_counter()
+        if mk is not None:
+            R = mk(A)
+            apply_inplace = R.apply_inplace
+        else:
+            L, U = oracle.port.ilu0(A)
+
+            def apply_inplace(v, L=L, U=U):
+                v[:] = oracle.port.apply_lu(L, U, v)
+        t1 = time.perf_counter()
+        for _ in range(rhs):
+            y[:] = b
+            apply_inplace(y)
+        t2 = time.perf_counter()
+        t_fac.append(t1 - t0)
+        t_app.append((t2 - t1) / rhs)
+        reps += 1
+    return {"factor_ms_per_system": float(np.median(t_fac)) * 1e3, "apply_ms_per_solve": float(np.median(t_app)) * 1e3,
+            "systems": reps, "kind": "reference" if mk is not None else "port"}
+
+
+def run_cpu_batched_worker(args):
+    """one pinned worker of the all-cores figure (spawned by cpu_reference_batched_all_cores)"""
+    try:
+        os.sched_setaffinity(0, {args.core})
+    except Exception:
+        pass
+    print(json.dumps(cpu_reference_batched(seconds=args.seconds)), flush=True)
+
+
+def cpu_reference_batched_all_cores(seconds=1.5):
+    """independent systems are embarrassingly parallel on the host as well -- one pinned
+    single-threaded worker per available core, each factorising + applying its own systems; aggregate throughput."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except Exception:
+        cores = list(range(os.cpu_count() or 1))
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--impl", "cpu-batched-worker", "--core", str(c),
+                               "--seconds", str(seconds)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+             for c in cores]
+    solves_per_s, systems_per_s, ok = 0.0, 0.0, 0
+    for pr in procs:
+        try:
+            out, _ = pr.communicate(timeout=120)
+            r = json.loads(out.strip().splitlines()[-1])
+            solves_per_s += 1e3 / r["apply_ms_per_solve"]
+            systems_per_s += 1e3 / (r["factor_ms_per_system"] + 16 * r["apply_ms_per_solve"])
+            ok += 1
+        except Exception:
+            pr.kill()
+    return {"cores": ok, "solves_per_s": solves_per_s, "systems_per_s_factor_plus_16_applies": systems_per_s}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -194,6 +260,101 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def _time_apply(B, x0, torch, reps=10):
+    x = x0.clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for i in range(reps + 2):
+        x.copy_(x0)
+        torch.cuda.synchronize()
+        e0.record()
+        B.apply(x)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), x.cpu().numpy()
+
+
+def run_extras(args, ilupp, P, torch, dev, local, peak):
+    """Rows beside the headline (rank 0, one GPU): the bit-exact arithmetic mode, the general CSR kernels on the same
+    problem and on a permuted one (no stencil structure), and BASELINE config 4 (deep irregular DAG) -- each with the
+    CPU oracle / reference checked or timed in the same run."""
+    import oracle
+    out = {}
+    reps = 3 if args.quick else 10
+    A = P.poisson3d(GRID)
+    n = A.shape[0]
+    b = P.rhs(n, 0)
+    x0 = torch.from_numpy(b).to(dev)
+    Lo = oracle.port.ichol0(A)
+    yo = oracle.port.apply_llt(Lo, b)
+
+    def row(B, ms, y, yref, ichol=True):
+        by = apply_bytes(B.total_nnz, B.shape[0], ichol)
+        st = B.stats
+        return {"apply_ms": ms, "GBs": by / (ms * 1e-3) / 1e9, "frac_hbm_peak": by / (ms * 1e-3) / 1e9 / peak,
+                "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels"}.get(st["part_mode"], "k_trsv_syncfree"),
+                "levels": list(st["levels"][:2]),
+                "apply_relerr_vs_oracle": float(np.abs(y - yref).max() / np.abs(yref).max()),
+                "factor_ms": dict(zip(("symbolic", "numeric", "pack", "total"), B.timings_ms))}
+
+    # (1) exact arithmetic (the library default): reference operation order, bit for bit
+    ilupp.set_option("exact", 1)
+    B = ilupp.IChol0Preconditioner(A, device=local)
+    ms, y = _time_apply(B, x0, torch, reps)
+    out["exact_mode_128"] = dict(row(B, ms, y, yo), bit_exact=bool(np.array_equal(y, yo)))
+    del B
+    # (2) the general CSR path on the same factor: chunked sync-free kernel, no stencil detection used
+    ilupp.set_option("exact", args.exact)
+    ilupp.set_option("solve_algo", 2)
+    try:
+        B = ilupp.IChol0Preconditioner(A, device=local)
+        ms, y = _time_apply(B, x0, torch, reps)
+        out["general_path_128_lexicographic"] = row(B, ms, y, yo)
+        del B
+        # (3) ... and on a symmetrically permuted copy (random relabelling, seed 1): nothing of the grid is left
+        ilupp.set_option("solve_algo", 0)
+        perm = np.random.default_rng(1).permutation(n)
+        Ap = A[perm][:, perm].tocsr()
+        Ap.sort_indices()
+        B = ilupp.IChol0Preconditioner(Ap, device=local)
+        ms, y = _time_apply(B, x0, torch, reps)
+        Lp = oracle.port.ichol0(Ap)
+        out["general_path_128_random_permutation"] = row(B, ms, y, oracle.port.apply_llt(Lp, b))
+        del B, Ap, Lp
+    finally:
+        ilupp.set_option("solve_algo", 0)
+    # (4) BASELINE config 4: irregular power-law matrix, n = 10^6 (deep DAG), ILU0
+    if not args.quick:
+        Ai = P.irregular_powerlaw()
+        ni = Ai.shape[0]
+        bi = P.rhs(ni, 0)
+        t = time.perf_counter()
+        B = ilupp.ILU0Preconditioner(Ai, device=local)
+        wall = (time.perf_counter() - t) * 1e3
+        ms, y = _time_apply(B, torch.from_numpy(bi).to(dev), torch, 5)
+        cpu = {}
+        if oracle.ref is not None:
+            prev = pin_to_one_core()
+            t = time.perf_counter()
+            R = oracle.ref.ILU0(Ai)
+            cpu["factor_ms"] = (time.perf_counter() - t) * 1e3
+            yr = bi.copy()
+            t = time.perf_counter()
+            R.apply_inplace(yr)
+            cpu["apply_ms"] = (time.perf_counter() - t) * 1e3
+            if prev:
+                os.sched_setaffinity(0, set(prev))
+        else:
+            L, U = oracle.port.ilu0(Ai)
+            yr = oracle.port.apply_lu(L, U, bi)
+        out["irregular_1m"] = dict(row(B, ms, y, yr, ichol=False), create_wall_ms=wall, cpu_reference_one_core=cpu)
+        del B
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import ilupp_b200 as ilupp
@@ -202,6 +363,19 @@ def run_ours(args):
 
     rank, local, world = init_process_group()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    host_cores = None
+    if world > 1:
+        # one process per GPU: give every rank its own slice of the host cores BEFORE it allocates pinned memory, so the
+        # staging buffers of the end-to-end path are first-touched (and later copied) from different cores / memory
+        # controllers instead of all ranks sharing the cores the launcher happened to start them on
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, set(mine))
+            host_cores = [mine[0], mine[-1]]
+        except Exception:
+            pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ilupp.set_option("exact", args.exact)
@@ -308,29 +482,68 @@ def run_ours(args):
         t = time.perf_counter()
         Bb = ilupp.ILU0PreconditionerBatched(pat, vals, device=local)
         create_s = time.perf_counter() - t
-        X = torch.randn((16, (hi - lo) * n1), dtype=torch.float64, device=dev).t()   # column-major (n, 16)
-        Bb.apply(X[:, :1])
+        sym_first = Bb.timings_ms[0]
+        if world > 1 or args.quick:
+            sym_warm = None
+        else:
+            # second creation with a warm allocator: what a solver that re-creates preconditioners pays
+            del Bb
+            torch.cuda.synchronize()
+            Bb = ilupp.ILU0PreconditionerBatched(pat, vals, device=local)
+            sym_warm = Bb.timings_ms[0]
+        X0 = torch.randn((16, (hi - lo) * n1), dtype=torch.float64, device=dev).t()   # column-major (n, 16)
+        X = X0.clone()
+        for _ in range(2):
+            Bb.apply(X)
         torch.cuda.synchronize()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        Bb.apply(X)
-        e1.record(stream)
+        reps = 3 if args.quick else 10
+        bevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for e0, e1 in bevs:
+            X.copy_(X0)
+            e0.record(stream)
+            Bb.apply(X)
+            e1.record(stream)
         torch.cuda.synchronize()
-        apply_ms = max_over_ranks(e0.elapsed_time(e1), dev)
+        bt = np.array([e0.elapsed_time(e1) for e0, e1 in bevs])
+        apply_ms = max_over_ranks(float(np.median(bt)), dev)
+        apply_ms_minmax = [max_over_ranks(float(bt.min()), dev), max_over_ranks(float(bt.max()), dev)]
         fac_ms = max_over_ranks(Bb.timings_ms[1], dev)
-        sym_b = max_over_ranks(Bb.timings_ms[0], dev)
+        sym_b = max_over_ranks(sym_first, dev)
+        # end to end: the 16 right-hand sides of this rank's systems in pinned host memory, copies inside the timed region
+        hX = torch.empty((16, (hi - lo) * n1), dtype=torch.float64).pin_memory()
+        hX.copy_(X0.t())
+        hXn = hX.numpy().T                      # (n, 16) Fortran-ordered view of the pinned buffer
+        Bb.pr.apply_multi(hXn, False)
+        barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        e2e_reps = 2 if args.quick else 3
+        for _ in range(e2e_reps):
+            Bb.pr.apply_multi(hXn, False)
+        b_e2e_ms = max_over_ranks((time.perf_counter() - t) / e2e_reps * 1e3, dev)
         # matrix + pointer terms once, vector term per right-hand side
         by_b = nsys_total * (12.0 * (Bb.total_nnz / (hi - lo)) + 8.0 * (n1 + 1)) + 32.0 * nsys_total * n1 * 16
         batched = {"systems": nsys_total, "rhs_per_system": 16, "n_per_system": n1,
                    "kernel": "k_trsv_plane (one launch per triangular solve, all right-hand sides)" if Bb.stats["launches"] else None,
-                   "factor_numeric_ms": fac_ms, "symbolic_ms": sym_b, "apply16_ms": apply_ms,
+                   "factor_numeric_ms": fac_ms, "symbolic_ms": sym_b, "symbolic_ms_warm_allocator": sym_warm,
+                   "apply16_ms": apply_ms, "apply16_ms_min_max": apply_ms_minmax, "timing": "median of %d CUDA-event pairs, max over ranks" % reps,
                    "apply16_algorithmic_GBs": by_b / (apply_ms * 1e-3) / 1e9,
                    "apply16_pct_hbm_peak": 100.0 * by_b / (apply_ms * 1e-3) / 1e9 / peak / world,
                    "solves_per_s": nsys_total * 16 / (apply_ms * 1e-3),
-                   "systems_per_s": nsys_total / ((fac_ms + apply_ms) * 1e-3), "scaling": "strong"}
+                   "systems_per_s": nsys_total / ((fac_ms + apply_ms) * 1e-3), "scaling": "strong",
+                   "e2e": {"apply16_ms": b_e2e_ms, "solves_per_s": nsys_total * 16 / (b_e2e_ms * 1e-3),
+                           "h2d_bytes": 8 * 16 * nsys_total * n1, "d2h_bytes": 8 * 16 * nsys_total * n1,
+                           "api": "apply_multi on a pinned (n, 16) host array (H2D + both solves + D2H)"}}
+        if rank == 0 and world == 1:
+            c1 = cpu_reference_batched(seconds=0.5 if args.quick else 2.0)
+            batched["cpu_reference_one_core"] = dict(c1, solves_per_s=1e3 / c1["apply_ms_per_solve"], cores=1)
+            batched["cpu_reference_all_cores"] = cpu_reference_batched_all_cores(seconds=0.5 if args.quick else 2.0)
         del Bb, X
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = run_extras(args, ilupp, P, torch, dev, local, peak)
     if rank == 0:
         traffic = None
         try:
@@ -348,7 +561,8 @@ def run_ours(args):
                        "levels_per_solve": list(B.stats["levels"][:2]), "arithmetic": "exact (reference op order)" if args.exact else "fma + reciprocal diagonal",
                        "l2": "inputs larger than L2: each apply streams %.0f MB of factor data (L2 = 126 MB)" % (by / 1e6),
                        "partition": {"ctas": B.stats["nparts"], "mode": B.stats["part_mode"], "grid": list(B.stats["grid"])},
-                       "parallelism": "replicated factors, one RHS per GPU" if world > 1 else "single GPU"},
+                       "parallelism": "replicated factors, one RHS per GPU" if world > 1 else "single GPU",
+                       "host_cores_rank0": host_cores},
             "pct_hbm_peak": 100.0 * value / world / peak,
             "factor_ms": {"symbolic": sym_ms, "numeric": num_ms, "pack": pack_ms, "total": tot_ms,
                           "refactor_numeric_plus_pack": refactor_ms, "create_wall_incl_h2d": create_wall_ms,
@@ -366,6 +580,7 @@ def run_ours(args):
             "clocks": clocks,
             "parity": parity,
             "batched": batched,
+            "extras": extras,
             "wall_s_timed_region": wall,
         }
         print(json.dumps(line), flush=True)
@@ -383,7 +598,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-batched-worker"])
+    ap.add_argument("--core", type=int, default=0, help="(cpu-batched-worker) core to pin to")
+    ap.add_argument("--seconds", type=float, default=1.5, help="(cpu-batched-worker) how long to run")
+    ap.add_argument("--no-extras", action="store_true", help="skip the exact-mode / general-path / irregular rows")
     ap.add_argument("--exact", type=int, default=0, help="1: reference operation order (bit-exact paths), 0: fma")
     ap.add_argument("--no-batched", action="store_true")
     ap.add_argument("--batched-systems", type=int, default=4096)
@@ -392,7 +610,9 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.impl == "cpu-batched-worker":
+        run_cpu_batched_worker(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

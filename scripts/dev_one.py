@@ -3,7 +3,7 @@ names: strip (32 lines x 4096), p2d256, p3d128, cd3d160"""
 import os, sys, time
 import numpy as np
 import scipy.sparse as sp
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.environ.get("ILUB_PKG_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import ilupp_b200 as ilupp
 from ilupp_b200 import problems as P
@@ -32,3 +32,5 @@ for i in range(reps + 2):
     if i >= 2: ts.append(e0.elapsed_time(e1))
 st = B.stats
 print("%s n=%d mode %s ctas %s grid %s: apply med %.1f us" % (name, n, st["part_mode"], st["nparts"], st["grid"], np.median(ts) * 1e3))
+x.copy_(x0); B.apply(x); torch.cuda.synchronize()
+print("checksum: sum %.15e  l2 %.15e  absmax %.15e" % (float(x.sum()), float(x.norm()), float(x.abs().max())))

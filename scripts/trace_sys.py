@@ -1,7 +1,7 @@
 """dev: block-level timeline of the line-systolic solve (option trace).  usage: trace_sys.py <problem> [key=value ...]"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.environ.get("ILUB_PKG_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import ilupp_b200 as ilupp
 from ilupp_b200 import problems as P
