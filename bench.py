@@ -294,7 +294,7 @@ def run_extras(args, ilupp, P, torch, dev, local, peak):
         by = apply_bytes(B.total_nnz, B.shape[0], ichol)
         st = B.stats
         return {"apply_ms": ms, "GBs": by / (ms * 1e-3) / 1e9, "frac_hbm_peak": by / (ms * 1e-3) / 1e9 / peak,
-                "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels"}.get(st["part_mode"], "k_trsv_syncfree"),
+                "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels", 7: "k_trsv_level (one launch per level)"}.get(st["part_mode"], "k_trsv_syncfree"),
                 "levels": list(st["levels"][:2]),
                 "apply_relerr_vs_oracle": float(np.abs(y - yref).max() / np.abs(yref).max()),
                 "factor_ms": dict(zip(("symbolic", "numeric", "pack", "total"), B.timings_ms))}

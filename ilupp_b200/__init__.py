@@ -52,6 +52,14 @@ def get_option(key):
     return _ilupp.get_option(key)
 
 
+def _stage_options(options):
+    """Options for the object about to be created (thread-local in the library, taken over by the next creation on this
+    thread): they are the new object's own settings from its first kernel on, whatever the process-wide defaults are."""
+    if options:
+        for k, v in options.items():
+            _ilupp.stage_option(k, int(v))
+
+
 def _upcast_indices(idx):
     """reference ilupp/__init__.py:38-53: make the index array match the compiled index width."""
     sz, target_sz = idx.dtype.itemsize, _index_size
@@ -253,6 +261,14 @@ class _BaseWrapper(scipy.sparse.linalg.LinearOperator):
         by the watchdog.  (Such a failure is otherwise raised by the next call on the object.)"""
         self.pr.check_status(stream)
 
+    def set_option(self, key, value):
+        """Set a libilub option for THIS object only (process-wide defaults: ilupp_b200.set_option)."""
+        self.pr.set_option(key, int(value))
+
+    def get_option(self, key):
+        """The value of a libilub option in force for this object (its own setting, else the process-wide default)."""
+        return self.pr.get_option(key)
+
     @property
     def timings_ms(self):
         """(symbolic, numeric, packing, total) milliseconds of the last factorisation (CUDA events)."""
@@ -269,8 +285,9 @@ class ILU0Preconditioner(_BaseWrapper):
     Args:
         A: a sparse matrix in CSR or CSC format
     """
-    def __init__(self, A, device=0):
+    def __init__(self, A, device=0, options=None):
         Ad, Ai, Ap, Ao = _matrix_fields(A)
+        _stage_options(options)
         self.pr = _ilupp.ILU0Preconditioner(Ad, Ai, Ap, Ao, device)
         scipy.sparse.linalg.LinearOperator.__init__(self, shape=A.shape, dtype=A.dtype)
 
@@ -282,8 +299,9 @@ class IChol0Preconditioner(_BaseWrapper):
     Args:
         A: a symmetric sparse matrix in CSR or CSC format
     """
-    def __init__(self, A, device=0):
+    def __init__(self, A, device=0, options=None):
         Ad, Ai, Ap, Ao = _matrix_fields(A)
+        _stage_options(options)
         self.pr = _ilupp.IChol0Preconditioner(Ad, Ai, Ap, Ao, device)
         scipy.sparse.linalg.LinearOperator.__init__(self, shape=A.shape, dtype=A.dtype)
 
@@ -356,12 +374,13 @@ class FactorsPreconditioner(_BaseWrapper):
 
 
 class _BatchedWrapper(_BaseWrapper):
-    def _init(self, factory, A, values, device):
+    def _init(self, factory, A, values, device, options=None):
         _, Ai, Ap, Ao = _matrix_fields(A)
         values = np.ascontiguousarray(values, dtype=np.float64)
         if values.ndim != 2 or values.shape[1] != Ai.shape[0]:
             raise RuntimeError("indices and data should have the same size!")
         self.nsys = values.shape[0]
+        _stage_options(options)
         self.pr = factory(values, Ai, Ap, Ao, device)
         N = A.shape[0] * self.nsys
         scipy.sparse.linalg.LinearOperator.__init__(self, shape=(N, N), dtype=np.dtype(np.float64))
@@ -370,13 +389,13 @@ class _BatchedWrapper(_BaseWrapper):
 class ILU0PreconditionerBatched(_BatchedWrapper):
     """ILU(0) of `nsys` independent systems sharing the pattern of `A` (values[nsys, nnz]); behaves like
     ILU0Preconditioner of the block-diagonal matrix (system s owns rows [s*n, (s+1)*n))."""
-    def __init__(self, A, values, device=0):
-        self._init(_ilupp.ILU0PreconditionerBatched, A, values, device)
+    def __init__(self, A, values, device=0, options=None):
+        self._init(_ilupp.ILU0PreconditionerBatched, A, values, device, options)
 
 
 class IChol0PreconditionerBatched(_BatchedWrapper):
-    def __init__(self, A, values, device=0):
-        self._init(_ilupp.IChol0PreconditionerBatched, A, values, device)
+    def __init__(self, A, values, device=0, options=None):
+        self._init(_ilupp.IChol0PreconditionerBatched, A, values, device, options)
 
 
 ########################################

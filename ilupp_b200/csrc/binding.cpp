@@ -275,6 +275,14 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
                  check(ilub_set_permutations(pr.h, g, s, ILUB_HOST, nullptr));
              },
              py::arg("gather_in") = py::none(), py::arg("scatter_out") = py::none())
+        .def("set_option",
+             [](const P& pr, const std::string& k, int64_t v) { check(ilub_set_handle_option(pr.h, k.c_str(), v)); })
+        .def("get_option",
+             [](const P& pr, const std::string& k) {
+                 int64_t v = 0;
+                 check(ilub_get_handle_option(pr.h, k.c_str(), &v));
+                 return v;
+             })
         .def("check_status",
              [](const P& pr, uintptr_t stream) { check(ilub_check_status(pr.h, reinterpret_cast<void*>(stream))); },
              py::arg("stream") = 0)
@@ -426,6 +434,7 @@ PYBIND11_MODULE(_ilupp, m) {
         return c;
     });
     m.def("set_option", [](const std::string& k, int64_t v) { check(ilub_set_option(k.c_str(), v)); });
+    m.def("stage_option", [](const std::string& k, int64_t v) { check(ilub_stage_option(k.c_str(), v)); });
     m.def("get_option", [](const std::string& k) {
         int64_t v = 0;
         check(ilub_get_option(k.c_str(), &v));

@@ -12,14 +12,85 @@
 #include <cub/cub.cuh>
 
 #include <climits>
+#include <cstring>
+#include <mutex>
 
 #include "ilub_common.cuh"
 
 namespace ilub {
 
-Options& options() {
-    static Options o;
-    return o;
+namespace {
+Options g_options;
+std::mutex g_options_mu;
+thread_local Options* tl_active_options = nullptr;
+const OptionField kOptionFields[] = {
+    {"factor_algo", &Options::factor_algo},
+    {"solve_algo", &Options::solve_algo},
+    {"exact", &Options::exact},
+    {"ctas_per_sm", &Options::ctas_per_sm},
+    {"warps_per_cta", &Options::warps_per_cta},
+    {"near_window", &Options::near_window},
+    {"ring_chunks", &Options::ring_chunks},
+    {"wcap", &Options::wcap},
+    {"stages", &Options::stages},
+    {"spin_limit_ms", &Options::spin_limit_ms},
+    {"partition", &Options::partition},
+    {"nparts", &Options::nparts},
+    {"trace", &Options::trace},
+    {"fetch_warps", &Options::fetch_warps},
+    {"halo_entries", &Options::halo_entries},
+    {"fastpath", &Options::fastpath},
+    {"level_align", &Options::level_align},
+    {"align_min_rows", &Options::align_min_rows},
+    {"gate_slack", &Options::gate_slack},
+    {"part_kb", &Options::part_kb},
+    {"factor_group", &Options::factor_group},
+    {"sys_pz", &Options::sys_pz},
+    {"sys_stages", &Options::sys_stages},
+    {"sys_cluster", &Options::sys_cluster},
+    {"sys_plane", &Options::sys_plane},
+    {"zero_copy", &Options::zero_copy},
+    {"sys_tile", &Options::sys_tile},
+    {"tile_fetch", &Options::tile_fetch},
+    {"tile_warps", &Options::tile_warps},
+    {"tile_debug", &Options::tile_debug},
+    {"tile_nst", &Options::tile_nst},
+    {"tile_ring", &Options::tile_ring},
+    {"tile_nap_fwd", &Options::tile_nap_fwd},
+    {"tile_nap_fetch", &Options::tile_nap_fetch},
+    {"tile_nap_tma", &Options::tile_nap_tma},
+    {"plane_r", &Options::plane_r},
+    {"plane_wpc", &Options::plane_wpc},
+    {"plane_npc", &Options::plane_npc},
+    {"levels_cluster", &Options::levels_cluster},
+    {"sys_pdl", &Options::sys_pdl}};
+}  // namespace
+
+Options& options() { return tl_active_options ? *tl_active_options : g_options; }
+const OptionField* option_fields(int* count) {
+    if (count) *count = (int)(sizeof(kOptionFields) / sizeof(kOptionFields[0]));
+    return kOptionFields;
+}
+int option_index(const char* key) {
+    int n = 0;
+    const OptionField* f = option_fields(&n);
+    for (int i = 0; i < n; ++i)
+        if (strcmp(f[i].name, key) == 0) return i;
+    return -1;
+}
+OptionScope::OptionScope(ilub_handle* h) : prev(tl_active_options) {
+    if (!h) return;
+    {
+        std::lock_guard<std::mutex> lock(g_options_mu);
+        h->opt_effective = g_options;
+    }
+    for (const auto& ov : h->opt_overrides) h->opt_effective.*(kOptionFields[ov.first].member) = ov.second;
+    tl_active_options = &h->opt_effective;
+}
+OptionScope::~OptionScope() { tl_active_options = prev; }
+void set_default_option(int field, int64_t value) {
+    std::lock_guard<std::mutex> lock(g_options_mu);
+    g_options.*(kOptionFields[field].member) = value;
 }
 
 namespace {
@@ -193,6 +264,26 @@ __global__ void __launch_bounds__(256) k_levels(SrcDev S, int n, int* level, int
         const int m = __reduce_max_sync(0xffffffffu, valid ? lv + 1 : 0);
         if (lane == 0) atomicMax(nlev, m);
     }
+}
+
+// diagonal positions of the systems 1 .. nsys-1 of a batch: those of system 0 shifted by whole systems
+__global__ void k_dpos_replicate(int n, int n1, int nnz1, int* __restrict__ dpos) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + n1;
+    if (r < n) dpos[r] = dpos[r % n1] + (int)(r / n1) * nnz1;
+}
+// levels of the systems 1 .. nsys-1 of a batch = levels of system 0 (block-diagonal matrix, shared pattern)
+__global__ void k_levels_replicate(int n, int n1, int* __restrict__ level) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + n1;
+    if (r < n) level[r] = level[r % n1];
+}
+// complete 5-/7-point stencil on a lexicographic nx x ny x nz grid: the level of (i, j, k) is i + j + k (mirrored for
+// backward solves)
+__global__ void k_levels_grid(int n, int n1, int nx, int ny, int nz, int backward, int* __restrict__ level) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int q = (int)(r % n1);
+    const int i = q % nx, j = (q / nx) % ny, k = q / (nx * ny);
+    level[r] = backward ? (nx - 1 - i) + (ny - 1 - j) + (nz - 1 - k) : i + j + k;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -600,22 +691,30 @@ int read_status(ilub_handle* h, cudaStream_t s) {
 
 void validate_and_find_diag(ilub_handle* h, cudaStream_t s) {
     const int n = h->n;
+    // a batch is the block-diagonal repetition of ONE pattern (expand_batched): system 0 is checked, its diagonal
+    // positions are shifted into the other systems
+    const int nsys = h->nsys, n1 = n / nsys;
+    const int64_t nnz1 = h->nnz / nsys;
     h->dpos.alloc(n);
     h->status.alloc(8);
     ILUB_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(int) * 8, s));
-    k_validate<<<blocks_for((int64_t)n * 8, 256), 256, 0, s>>>(n, h->ptr.p, h->idx.p, h->dpos.p, h->status.p);
+    k_validate<<<blocks_for((int64_t)n1 * 8, 256), 256, 0, s>>>(n1, h->ptr.p, h->idx.p, h->dpos.p, h->status.p);
     h->launches++;
     read_status(h, s);
+    if (nsys > 1) {
+        k_dpos_replicate<<<blocks_for((int64_t)n - n1, 256), 256, 0, s>>>(n, n1, (int)nnz1, h->dpos.p);
+        h->launches++;
+    }
     DevBuf<unsigned long long> cnt;
     cnt.alloc(2);
     ILUB_CUDA(cudaMemsetAsync(cnt.p, 0, 16, s));
-    k_count_tri<<<blocks_for(n, 256), 256, 0, s>>>(n, h->ptr.p, h->dpos.p, cnt.p);
+    k_count_tri<<<blocks_for(n1, 256), 256, 0, s>>>(n1, h->ptr.p, h->dpos.p, cnt.p);
     h->launches++;
     unsigned long long hc[2];
     ILUB_CUDA(cudaMemcpyAsync(hc, cnt.p, 16, cudaMemcpyDeviceToHost, s));
     ILUB_CUDA(cudaStreamSynchronize(s));
-    h->nnz_lower = (int64_t)hc[0];
-    h->nnz_upper = (int64_t)hc[1];
+    h->nnz_lower = (int64_t)hc[0] * nsys;
+    h->nnz_upper = (int64_t)hc[1] * nsys;
 }
 
 void build_transposed(ilub_handle* h, bool upper, cudaStream_t s) {
@@ -782,26 +881,6 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     T.backward = src.backward;
     T.unit_diag = src.unit_diag;
 
-    // ---- levels
-    T.level.alloc(n);
-    ILUB_CUDA(cudaMemsetAsync(T.level.p, 0xff, sizeof(int) * n, s));
-    DevBuf<int> ctr;
-    ctr.alloc(4);
-    ILUB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int) * 4, s));
-    const long long spin = (long long)opt.spin_limit_ms * h->clock_khz;  // kHz * ms = cycles
-    {
-        DebugTimer t("  levels", s);
-        int occ = 0;
-        ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels, 256, 0));
-        const int grid = std::max(1, occ * h->sm_count);
-        k_levels<<<grid, 256, 0, s>>>(S, n, T.level.p, ctr.p, ctr.p + 1, spin * 4, h->status.p);
-        h->launches++;
-    }
-    read_status(h, s);
-    int hctr[2];
-    ILUB_CUDA(cudaMemcpy(hctr, ctr.p, sizeof(hctr), cudaMemcpyDeviceToHost));
-    T.nlevels = hctr[1];
-
     // ---- structured grids: line-systolic layout (ilub_systolic.cu).  The chunked sync-free layout below is then
     //      only built for slot 0 (the factorisation kernels walk it) or on demand (option solve_algo = 2).
     bool sys_ok;
@@ -809,12 +888,60 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         DebugTimer t("  systolic layout", s);
         sys_ok = opt.solve_algo != 2 && analyse_systolic(h, slot, s);
     }
+
+    // ---- levels.  The systems of a batch share one pattern: the dependency levels of ONE system are computed and
+    //      replicated.  A complete grid stencil (every in-grid neighbour present, checked by the entry count on top of
+    //      the per-entry verification of the systolic analysis) has the closed form i + j + k.
+    const int nsys = h->nsys, n1 = n / nsys;
+    T.level.alloc(n);
+    bool closed_form = false;
+    if (sys_ok) {
+        const SysSolve& Y = T.sys;
+        const int64_t nx = Y.nx, ny = Y.ny, nz = Y.nz1;
+        const int64_t full = (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1);
+        const int64_t have = ((slot == 0 || slot == 3) ? h->nnz_lower : h->nnz_upper) / nsys;
+        closed_form = have == full;
+    }
+    if (closed_form) {
+        DebugTimer t("  levels (closed form)", s);
+        const SysSolve& Y = T.sys;
+        k_levels_grid<<<blocks_for(n, 256), 256, 0, s>>>(n, n1, Y.nx, Y.ny, Y.nz1, src.backward ? 1 : 0, T.level.p);
+        h->launches++;
+        T.nlevels = Y.nx + Y.ny + Y.nz1 - 2;
+    } else {
+        ILUB_CUDA(cudaMemsetAsync(T.level.p, 0xff, sizeof(int) * n1, s));
+        DevBuf<int> ctr;
+        ctr.alloc(4);
+        ILUB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int) * 4, s));
+        const long long spin = (long long)opt.spin_limit_ms * h->clock_khz;  // kHz * ms = cycles
+        {
+            DebugTimer t("  levels", s);
+            int occ = 0;
+            ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels, 256, 0));
+            const int grid = std::max(1, std::min(occ * h->sm_count, (n1 + 31) / 32));
+            k_levels<<<grid, 256, 0, s>>>(S, n1, T.level.p, ctr.p, ctr.p + 1, spin * 4, h->status.p);
+            h->launches++;
+            if (nsys > 1) {
+                k_levels_replicate<<<blocks_for((int64_t)n - n1, 256), 256, 0, s>>>(n, n1, T.level.p);
+                h->launches++;
+            }
+        }
+        read_status(h, s);
+        int hctr[2];
+        ILUB_CUDA(cudaMemcpy(hctr, ctr.p, sizeof(hctr), cudaMemcpyDeviceToHost));
+        T.nlevels = hctr[1];
+    }
     T.built = true;
     if (!sys_ok && deep_wanted(h, slot)) {
         DebugTimer t("  level-loop layout", s);
         analyse_deep(h, slot, s);
         T.part_mode = 5;
         T.nparts = 1;
+    } else if (!sys_ok && few_levels_wanted(h, slot)) {
+        DebugTimer t("  level sets", s);
+        build_level_sets(h, slot, s);  // one launch per level straight from the CSR-read arrays: no packed layout
+        T.part_mode = 7;
+        T.nparts = 0;
     } else if (!sys_ok && levels_wanted(h, slot)) {
         DebugTimer t("  level sets", s);
         build_level_sets(h, slot, s);  // the cooperative level loop walks the CSR-read arrays: no packed layout
@@ -1043,6 +1170,8 @@ void build_level_sets(ilub_handle* h, int slot, cudaStream_t s) {
     ILUB_CUDA(cudaMemcpyAsync(T.lvl_rows.p, dv.Current(), sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
     k_level_ptr<<<blocks_for(T.nlevels + 1, 256), 256, 0, s>>>(n, T.nlevels, dk.Current(), T.lvl_ptr.p);
     h->launches += 3;
+    T.lvl_ptr_host.resize((size_t)T.nlevels + 1);
+    ILUB_CUDA(cudaMemcpyAsync(T.lvl_ptr_host.data(), T.lvl_ptr.p, sizeof(int) * (T.nlevels + 1), cudaMemcpyDeviceToHost, s));
     ILUB_CUDA(cudaStreamSynchronize(s));
     T.lvl_built = true;
 }

@@ -70,6 +70,9 @@ void ensure_solve(ilub_handle* h, int slot, cudaStream_t s) {
 
 typedef std::lock_guard<std::recursive_mutex> HandleLock;
 
+// options staged by this thread for the handle it creates next (ilub_stage_option)
+thread_local std::vector<std::pair<int, int64_t>> tl_staged_options;
+
 // a kernel of an earlier asynchronous (device-path) call gave up: raise it now instead of returning garbage silently
 void raise_deferred(ilub_handle* h, cudaStream_t s) {
     if (!h->host_status || *(volatile int*)h->host_status == 0) return;
@@ -103,6 +106,9 @@ int slot_of(const ilub_handle* h, int which_solve) {
 void create_common(int kind, const double* data, const int32_t* indices, const int32_t* indptr, int32_t n1,
                    int64_t nnz1, int32_t nsys, int is_csr, int where, int device, void* stream, ilub_handle** out,
                    bool prefactored = false) {
+    // options staged by this thread belong to this creation, whether it succeeds or not
+    std::vector<std::pair<int, int64_t>> staged;
+    staged.swap(tl_staged_options);
     ILUB_REQUIRE(out != nullptr, ILUB_ERR_INVALID, "out is null");
     *out = nullptr;
     ILUB_REQUIRE(data && indices && indptr, ILUB_ERR_INVALID, "null matrix array");
@@ -121,6 +127,8 @@ void create_common(int kind, const double* data, const int32_t* indices, const i
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     set_alloc_stream(s);
     std::unique_ptr<ilub_handle> h(new ilub_handle());
+    h->opt_overrides.swap(staged);
+    OptionScope scope(h.get());
     h->kind = kind;
     h->is_csr = is_csr ? 1 : 0;
     h->device = device;
@@ -268,6 +276,7 @@ int ilub_set_permutations(ilub_handle* h, const int32_t* gather_in, const int32_
         ILUB_REQUIRE(h, ILUB_ERR_INVALID, "null handle");
         ILUB_REQUIRE(h->prefactored, ILUB_ERR_INVALID, "permutations belong to factors computed elsewhere (ilub_create_from_factors)");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -294,6 +303,7 @@ int ilub_refactor(ilub_handle* h, const double* data, int where, void* stream) {
     return guarded([&] {
         ILUB_REQUIRE(h && data, ILUB_ERR_INVALID, "null argument");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -341,6 +351,7 @@ int ilub_apply(ilub_handle* h, int transpose, double* x, int64_t ldx, int32_t nr
         ILUB_REQUIRE(nrhs >= 1, ILUB_ERR_INVALID, "nrhs must be >= 1");
         ILUB_REQUIRE(ldx >= h->n, ILUB_ERR_SIZE, "vector has wrong size for preconditioner!");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -405,6 +416,7 @@ int ilub_check_status(ilub_handle* h, void* stream) {
     return guarded([&] {
         ILUB_REQUIRE(h, ILUB_ERR_INVALID, "null handle");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         read_status(h, static_cast<cudaStream_t>(stream));  // synchronises the stream; throws ILUB_ERR_WATCHDOG
         if (h->host_status) *(volatile int*)h->host_status = 0;
@@ -457,6 +469,7 @@ int ilub_get_factor(ilub_handle* h, int which, double* data, int32_t* indices, i
         ILUB_REQUIRE(h && data && indices && indptr, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(which == 0 || (which == 1 && h->kind == KIND_ILU0), ILUB_ERR_INVALID, "no such factor");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -485,6 +498,7 @@ int ilub_get_levels(ilub_handle* h, int which_solve, int32_t* nlevels, int32_t* 
         ILUB_REQUIRE(h, ILUB_ERR_INVALID, "null handle");
         ILUB_REQUIRE(which_solve >= 0 && which_solve < 4, ILUB_ERR_INVALID, "bad which_solve");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -504,6 +518,7 @@ int ilub_get_level_sets(ilub_handle* h, int which_solve, int32_t* level_ptr, int
         ILUB_REQUIRE(h && level_ptr && level_rows, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(which_solve >= 0 && which_solve < 4, ILUB_ERR_INVALID, "bad which_solve");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -522,6 +537,7 @@ int ilub_spmv(ilub_handle* h, const double* x, double* y, int where, void* strea
         ILUB_REQUIRE(h && x && y, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(!h->prefactored, ILUB_ERR_INVALID, "handle was created from factors: it holds no matrix");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -545,6 +561,7 @@ int ilub_bicgstab(ilub_handle* h, const double* b, double* x, double rtol, doubl
         ILUB_REQUIRE(h && b && x && iters && rel_achieved && abs_achieved, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(!h->prefactored, ILUB_ERR_INVALID, "handle was created from factors: it holds no matrix");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -574,6 +591,7 @@ int ilub_pcg(ilub_handle* h, const double* b, double* x, double rtol, double ato
         ILUB_REQUIRE(h && b && x && iters && rel_achieved && abs_achieved, ILUB_ERR_INVALID, "null argument");
         ILUB_REQUIRE(!h->prefactored, ILUB_ERR_INVALID, "handle was created from factors: it holds no matrix");
         HandleLock lock(h->mu);
+        OptionScope scope(h);
         DeviceGuard guard(h->device);
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         set_alloc_stream(s);
@@ -600,97 +618,50 @@ int ilub_pcg(ilub_handle* h, const double* b, double* x, double rtol, double ato
 int ilub_set_option(const char* key, int64_t value) {
     return guarded([&] {
         ILUB_REQUIRE(key, ILUB_ERR_INVALID, "null key");
-        Options& o = options();
-        const std::string k(key);
-        if (k == "factor_algo") o.factor_algo = value;
-        else if (k == "solve_algo") o.solve_algo = value;
-        else if (k == "exact") o.exact = value;
-        else if (k == "ctas_per_sm") o.ctas_per_sm = value;
-        else if (k == "warps_per_cta") o.warps_per_cta = value;
-        else if (k == "near_window") o.near_window = value;
-        else if (k == "ring_chunks") o.ring_chunks = value;
-        else if (k == "wcap") o.wcap = value;
-        else if (k == "stages") o.stages = value;
-        else if (k == "spin_limit_ms") o.spin_limit_ms = value;
-        else if (k == "partition") o.partition = value;
-        else if (k == "nparts") o.nparts = value;
-        else if (k == "trace") o.trace = value;
-        else if (k == "fetch_warps") o.fetch_warps = value;
-        else if (k == "halo_entries") o.halo_entries = value;
-        else if (k == "fastpath") o.fastpath = value;
-        else if (k == "level_align") o.level_align = value;
-        else if (k == "align_min_rows") o.align_min_rows = value;
-        else if (k == "gate_slack") o.gate_slack = value;
-        else if (k == "part_kb") o.part_kb = value;
-        else if (k == "factor_group") o.factor_group = value;
-        else if (k == "sys_pz") o.sys_pz = value;
-        else if (k == "sys_stages") o.sys_stages = value;
-        else if (k == "sys_cluster") o.sys_cluster = value;
-        else if (k == "sys_plane") o.sys_plane = value;
-        else if (k == "zero_copy") o.zero_copy = value;
-        else if (k == "sys_tile") o.sys_tile = value;
-        else if (k == "tile_fetch") o.tile_fetch = value;
-        else if (k == "tile_warps") o.tile_warps = value;
-        else if (k == "tile_debug") o.tile_debug = value;
-        else if (k == "tile_nst") o.tile_nst = value;
-        else if (k == "tile_ring") o.tile_ring = value;
-        else if (k == "tile_nap_fwd") o.tile_nap_fwd = value;
-        else if (k == "tile_nap_fetch") o.tile_nap_fetch = value;
-        else if (k == "tile_nap_tma") o.tile_nap_tma = value;
-        else if (k == "plane_r") o.plane_r = value;
-        else if (k == "plane_wpc") o.plane_wpc = value;
-        else if (k == "plane_npc") o.plane_npc = value;
-        else if (k == "levels_cluster") o.levels_cluster = value;
-        else if (k == "sys_pdl") o.sys_pdl = value;
-        else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
+        const int f = option_index(key);
+        if (f < 0) throw Error{ILUB_ERR_INVALID, std::string("unknown option ") + key};
+        set_default_option(f, value);
     });
 }
 int ilub_get_option(const char* key, int64_t* value) {
     return guarded([&] {
         ILUB_REQUIRE(key && value, ILUB_ERR_INVALID, "null argument");
-        const Options& o = options();
-        const std::string k(key);
-        if (k == "factor_algo") *value = o.factor_algo;
-        else if (k == "solve_algo") *value = o.solve_algo;
-        else if (k == "exact") *value = o.exact;
-        else if (k == "ctas_per_sm") *value = o.ctas_per_sm;
-        else if (k == "warps_per_cta") *value = o.warps_per_cta;
-        else if (k == "near_window") *value = o.near_window;
-        else if (k == "ring_chunks") *value = o.ring_chunks;
-        else if (k == "wcap") *value = o.wcap;
-        else if (k == "stages") *value = o.stages;
-        else if (k == "spin_limit_ms") *value = o.spin_limit_ms;
-        else if (k == "partition") *value = o.partition;
-        else if (k == "nparts") *value = o.nparts;
-        else if (k == "gate_slack") *value = o.gate_slack;
-        else if (k == "part_kb") *value = o.part_kb;
-        else if (k == "factor_group") *value = o.factor_group;
-        else if (k == "sys_pz") *value = o.sys_pz;
-        else if (k == "sys_stages") *value = o.sys_stages;
-        else if (k == "sys_cluster") *value = o.sys_cluster;
-        else if (k == "sys_plane") *value = o.sys_plane;
-        else if (k == "zero_copy") *value = o.zero_copy;
-        else if (k == "sys_tile") *value = o.sys_tile;
-        else if (k == "tile_fetch") *value = o.tile_fetch;
-        else if (k == "tile_warps") *value = o.tile_warps;
-        else if (k == "tile_debug") *value = o.tile_debug;
-        else if (k == "tile_nst") *value = o.tile_nst;
-        else if (k == "tile_ring") *value = o.tile_ring;
-        else if (k == "tile_nap_fwd") *value = o.tile_nap_fwd;
-        else if (k == "tile_nap_fetch") *value = o.tile_nap_fetch;
-        else if (k == "tile_nap_tma") *value = o.tile_nap_tma;
-        else if (k == "plane_r") *value = o.plane_r;
-        else if (k == "plane_wpc") *value = o.plane_wpc;
-        else if (k == "plane_npc") *value = o.plane_npc;
-        else if (k == "levels_cluster") *value = o.levels_cluster;
-        else if (k == "sys_pdl") *value = o.sys_pdl;
-        else if (k == "fetch_warps") *value = o.fetch_warps;
-        else if (k == "halo_entries") *value = o.halo_entries;
-        else if (k == "fastpath") *value = o.fastpath;
-        else if (k == "level_align") *value = o.level_align;
-        else if (k == "align_min_rows") *value = o.align_min_rows;
-        else if (k == "trace") *value = o.trace;
-        else throw Error{ILUB_ERR_INVALID, "unknown option " + k};
+        const int f = option_index(key);
+        if (f < 0) throw Error{ILUB_ERR_INVALID, std::string("unknown option ") + key};
+        OptionScope none(nullptr);
+        *value = options().*(option_fields(nullptr)[f].member);
+    });
+}
+int ilub_stage_option(const char* key, int64_t value) {
+    return guarded([&] {
+        ILUB_REQUIRE(key, ILUB_ERR_INVALID, "null key");
+        const int f = option_index(key);
+        if (f < 0) throw Error{ILUB_ERR_INVALID, std::string("unknown option ") + key};
+        tl_staged_options.emplace_back(f, value);
+    });
+}
+int ilub_set_handle_option(ilub_handle* h, const char* key, int64_t value) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && key, ILUB_ERR_INVALID, "null argument");
+        const int f = option_index(key);
+        if (f < 0) throw Error{ILUB_ERR_INVALID, std::string("unknown option ") + key};
+        HandleLock lock(h->mu);
+        for (auto& ov : h->opt_overrides)
+            if (ov.first == f) {
+                ov.second = value;
+                return;
+            }
+        h->opt_overrides.emplace_back(f, value);
+    });
+}
+int ilub_get_handle_option(ilub_handle* h, const char* key, int64_t* value) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && key && value, ILUB_ERR_INVALID, "null argument");
+        const int f = option_index(key);
+        if (f < 0) throw Error{ILUB_ERR_INVALID, std::string("unknown option ") + key};
+        HandleLock lock(h->mu);
+        OptionScope scope(h);
+        *value = options().*(option_fields(nullptr)[f].member);
     });
 }
 
@@ -754,6 +725,8 @@ int ilub_get_timings(const ilub_handle* h, double out_ms[4]) {
 int ilub_get_stats(const ilub_handle* h, int64_t out[16]) {
     return guarded([&] {
         ILUB_REQUIRE(h && out, ILUB_ERR_INVALID, "null argument");
+        HandleLock lock(const_cast<ilub_handle*>(h)->mu);
+        OptionScope scope(const_cast<ilub_handle*>(h));
         out[0] = h->n;
         out[1] = h->nnz;
         out[2] = h->kind == KIND_ICHOL0 ? h->nnz_lower + h->n : h->nnz_lower + h->nnz_upper + 2 * (int64_t)h->n;

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ilub.h"
@@ -142,7 +143,22 @@ struct Options {
     int64_t plane_npc = 0;      // plane-per-warp: consecutive planes per CTA (0 = auto)
     int64_t plane_wpc = 0;      // plane-per-warp: consumer warps per CTA (0 = as many as shared memory holds, at most 8)
 };
+// The options in force for the calling thread: the process-wide defaults (ilub_set_option), or -- inside an entry point
+// that works on a handle -- the defaults overlaid with that handle's own settings (ilub_set_handle_option, or options
+// staged with ilub_stage_option before the handle was created).  Kernel-selection code only ever calls options().
 Options& options();
+struct OptionField {
+    const char* name;
+    int64_t Options::*member;
+};
+const OptionField* option_fields(int* count);
+int option_index(const char* key);  // -1: unknown
+void set_default_option(int field, int64_t value);
+struct OptionScope {                // installs a handle's effective options for the lifetime of the scope
+    explicit OptionScope(ilub_handle* h);
+    ~OptionScope();
+    Options* prev;
+};
 
 constexpr int kLanes = 32;
 // dependency encoding inside a packed chunk (int32):
@@ -240,7 +256,7 @@ struct TriSolve {
     DevBuf<ulonglong2> mail;      // [n] {x bits, epoch tag}: the global dependency path (one 16-B atomic access)
     unsigned long long epoch = 0;
     int level_aligned = 0;
-    int part_mode = 0;            // 0 contiguous ranges, 2 / 3: strips / pencils from detected strides, 4 line-systolic, 5 level loop (one CTA), 6 cooperative level loop
+    int part_mode = 0;            // 0 contiguous ranges, 2 / 3: strips / pencils from detected strides, 4 line-systolic, 5 level loop (one CTA), 6 cooperative level loop, 7 one launch per level (few wide levels)
     int stride_y = 0, stride_z = 0, grid_y = 1, grid_z = 1;
     // launch configuration of the sync-free kernel, fixed at analysis (near is baked into idx)
     int cfg_warps = 16, cfg_fetch = 2, cfg_ring_chunks = 128, cfg_near = 56, cfg_halo = 2048, cfg_stages = 2,
@@ -249,6 +265,7 @@ struct TriSolve {
     // level-set listing for the level-scheduled variant / ilub_get_level_sets (built on demand)
     DevBuf<long long> trace;      // debug stamps (option trace)
     DevBuf<int> lvl_ptr, lvl_rows;
+    std::vector<int> lvl_ptr_host;  // host copy of lvl_ptr (the one-launch-per-level solve sizes its grids from it)
     bool lvl_built = false;
     bool generic_built = false;   // the chunked sync-free layout above exists (always for slot 0: the factorisation uses it)
     SysSolve sys;                 // line-systolic layout (structured grids), preferred when built
@@ -346,6 +363,13 @@ struct ilub_handle {
     ilub::DevBuf<double> permbuf;
     ilub::DevBuf<double> xalign;        // 16-byte aligned stand-in for an odd-aligned vector (tile-systolic tensor maps)
     ilub::DevBuf<double> scal;          // device scalars for bicgstab
+    // line-systolic CTA tiling of the last plane-coupled solve analysed (the solves of one matrix share the grid, and
+    // the occupancy queries behind the choice cost more than the rest of the analysis): key -> {pz, nst, rz, csize, gzp}
+    long long sys_tiling_key[4] = {-1, -1, -1, -1};
+    int sys_tiling[5] = {0, 0, 0, 0, 0};
+    // per-handle option overrides {field, value} and the effective set while an entry point works on the handle
+    std::vector<std::pair<int, int64_t>> opt_overrides;
+    ilub::Options opt_effective;
     double timings[4] = {0, 0, 0, 0};
     int64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -375,6 +399,7 @@ void pack_solve_values(ilub_handle* h, int which, cudaStream_t s);        // (re
 void build_level_sets(ilub_handle* h, int which, cudaStream_t s);
 bool deep_wanted(const ilub_handle* h, int slot);
 bool levels_wanted(const ilub_handle* h, int slot);   // cooperative level loop (ilub_trsv.cu)
+bool few_levels_wanted(const ilub_handle* h, int slot);  // one launch per level (ilub_trsv.cu)
 void analyse_deep(ilub_handle* h, int slot, cudaStream_t s);
 void pack_deep(ilub_handle* h, int slot, cudaStream_t s);
 void run_deep(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s);

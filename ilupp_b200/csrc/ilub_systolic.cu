@@ -54,9 +54,14 @@ inline int blocks_for(int64_t work, int threads) { return (int)((work + threads 
 __global__ void k_sys_offsets(int n1, SrcDev S, int* list) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n1) return;
+    // what is on the list already (after the first few rows: everything) is recognised without touching it again
+    int known[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) known[k] = *(volatile int*)(list + k);
     for (int q = src_beg(S, r); q < src_end(S, r); ++q) {
         int off = S.dep_idx[q] - r;
         if (off < 0) off = -off;
+        if (off == known[0] || off == known[1] || off == known[2] || off == known[3]) continue;
         bool placed = false;
         for (int k = 0; k < 4 && !placed; ++k) {
             int cur = *(volatile int*)(list + k);
@@ -913,7 +918,13 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
         ILUB_CUDA(cudaFuncSetAttribute(sys_kernel(true, true), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         const int cmax = (int)std::min<int64_t>(16, opt.sys_cluster > 0 ? opt.sys_cluster : 16);
         long best_cost = LONG_MAX;
-        for (int pzc = pz0; pzc <= std::min(pz0 + (opt.sys_pz > 0 ? 0 : 2), std::min(nplanes, std::min(max_warps(2, 8), kMaxYChan))); ++pzc) {
+        const long long key[4] = {G.nyb, nplanes, pz0, cmax};
+        const bool cached = std::equal(key, key + 4, h->sys_tiling_key);
+        if (cached) {
+            pz = h->sys_tiling[0], nst = h->sys_tiling[1], rz = h->sys_tiling[2], csize = h->sys_tiling[3], gzp = h->sys_tiling[4];
+            best_cost = 0;
+        }
+        for (int pzc = pz0; !cached && pzc <= std::min(pz0 + (opt.sys_pz > 0 ? 0 : 2), std::min(nplanes, std::min(max_warps(2, 8), kMaxYChan))); ++pzc) {
             int nstc, rzc;
             fit_rings(pzc, nstc, rzc);
             const int gz = (nplanes + pzc - 1) / pzc;
@@ -943,6 +954,8 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
             }
         }
         if (best_cost == LONG_MAX) return false;
+        std::copy(key, key + 4, h->sys_tiling_key);
+        h->sys_tiling[0] = pz, h->sys_tiling[1] = nst, h->sys_tiling[2] = rz, h->sys_tiling[3] = csize, h->sys_tiling[4] = gzp;
     } else {
         const int mw = max_warps(3, 8);
         const int gyb = (G.nyb + mw - 1) / mw;

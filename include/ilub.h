@@ -201,6 +201,19 @@ ILUB_API int ilub_create_ichol0_batched(const double* values, const int32_t* ind
  *   "ctas_per_sm", "warps_per_cta", "near_window", "spin_limit_ms" : tuning / watchdog */
 ILUB_API int ilub_set_option(const char* key, int64_t value);
 ILUB_API int ilub_get_option(const char* key, int64_t* value);
+/* Options per handle.  ilub_set_option / ilub_get_option above are the process-wide DEFAULTS; every entry point that
+ * works on a handle sees those defaults overlaid with the handle's own settings, so two threads can drive two
+ * preconditioners with different settings (the reference objects are const / re-entrant, preconditioner.h:140-260, and
+ * carry their parameters themselves) without touching shared state:
+ *   ilub_set_handle_option  set `key` for this handle only (takes effect with the next call on the handle; options
+ *                           that select a data layout -- "solve_algo", "sys_*", "nparts" ... -- only matter before
+ *                           the solve they concern has been analysed, i.e. when staged, below);
+ *   ilub_get_handle_option  the value in force for this handle (its own setting, else the default);
+ *   ilub_stage_option       thread-local: `key` = `value` for the NEXT handle this thread creates (ilub_create_*),
+ *                           which takes the staged settings over as its own before anything is analysed or factorised. */
+ILUB_API int ilub_set_handle_option(ilub_handle* h, const char* key, int64_t value);
+ILUB_API int ilub_get_handle_option(ilub_handle* h, const char* key, int64_t* value);
+ILUB_API int ilub_stage_option(const char* key, int64_t value);
 /* milliseconds spent by the last create/refactor on this handle (CUDA events):
  * [0] symbolic analysis, [1] numeric factorisation, [2] solve-layout packing, [3] total */
 ILUB_API int ilub_get_timings(const ilub_handle* h, double out_ms[4]);

@@ -61,6 +61,14 @@ def test_argument_errors_do_not_need_a_gpu():
         assert v.value == probe
         assert lib.ilub_set_option(key, old) == 0
     assert lib.ilub_apply(None, 0, None, C.c_int64(1), C.c_int32(1), 0, None) == 1
+    # per-handle options: unknown keys and null handles are refused; a staged option is consumed by the next creation
+    # of this thread even when that creation fails, and never touches the process-wide default
+    assert lib.ilub_stage_option(b"no_such_option", C.c_int64(1)) == 1
+    assert lib.ilub_set_handle_option(None, b"exact", C.c_int64(0)) == 1
+    assert lib.ilub_get_handle_option(None, b"exact", C.byref(v)) == 1
+    assert lib.ilub_stage_option(b"exact", C.c_int64(0)) == 0
+    assert lib.ilub_create_ilu0(None, None, None, C.c_int32(4), C.c_int64(4), 1, 0, 0, None, C.byref(h)) == 1
+    assert lib.ilub_get_option(b"exact", C.byref(v)) == 0 and v.value == 1
     # factors handed in from elsewhere: same argument checks, no device needed to be refused
     rc = lib.ilub_create_from_factors(0, None, None, None, C.c_int32(4), C.c_int64(4), 1, 0, 0, None, C.byref(h))
     assert rc == 1 and b"null" in lib.ilub_last_error()

@@ -1016,3 +1016,88 @@ def test_permuted_factors_apply(ilupp, fmt, key):
     assert relerr(Xd[:, 1].cpu().numpy(), 2.0 * g[key + "_apply"]) <= 1e-11
     with pytest.raises(ValueError):
         ilupp.FactorsPreconditioner(L, U, perm_left=np.zeros(L.shape[0], dtype=np.int32))
+
+
+# ---- per-handle options, general-path selection, batched analysis ------------------------------------
+def test_per_handle_options_and_threads(ilupp):
+    """Options belong to the object (the reference's preconditioner objects carry their own parameters and are
+    re-entrant, preconditioner.h:140-260): two objects with different arithmetic modes, driven from two threads at the
+    same time, give what each gives alone; the process-wide default is untouched."""
+    import threading
+    A = P.poisson3d(24)
+    b = P.rhs(A.shape[0], 3)
+    Lo = oracle.port.ichol0(A)
+    yo = oracle.port.apply_llt(Lo, b)
+    Be = ilupp.IChol0Preconditioner(A, options={"exact": 1})
+    Bf = ilupp.IChol0Preconditioner(A, options={"exact": 0})
+    assert Be.get_option("exact") == 1 and Bf.get_option("exact") == 0 and ilupp.get_option("exact") == 1
+    ye = b.copy(); Be.apply(ye)
+    yf = b.copy(); Bf.apply(yf)
+    assert np.array_equal(ye, yo)                      # reference operation order: bit for bit
+    assert relerr(yf, yo) <= TOL and not np.array_equal(yf, yo)   # fma + reciprocal: rounding differs
+    out = {}
+
+    def work(name, B, ref):
+        ok = True
+        for _ in range(20):
+            y = b.copy()
+            B.apply(y)
+            ok = ok and np.array_equal(y, ref)
+        out[name] = ok
+
+    ts = [threading.Thread(target=work, args=("exact", Be, ye)), threading.Thread(target=work, args=("fast", Bf, yf))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert out == {"exact": True, "fast": True}
+    Bf.set_option("exact", 1)                          # takes effect with the next call (coefficients are re-packed)
+    y = b.copy(); Bf.apply(y)
+    assert relerr(y, yo) <= TOL
+    assert ilupp.get_option("exact") == 1
+
+
+def test_few_wide_levels_route(ilupp):
+    """A randomly relabelled grid has a handful of very wide levels and no stencil structure: the solve goes through
+    one launch per level (stats part_mode 7), results as the oracle's, levels identical."""
+    A = P.poisson3d(40)
+    n = A.shape[0]
+    perm = np.random.default_rng(1).permutation(n)
+    Ap = A[perm][:, perm].tocsr()
+    Ap.sort_indices()
+    b = P.rhs(n, 1)
+    B = ilupp.ILU0Preconditioner(Ap)
+    assert B.stats["part_mode"] == 7, B.stats
+    L, U = oracle.port.ilu0(Ap)
+    y = b.copy(); B.apply(y)
+    assert np.array_equal(y, oracle.port.apply_lu(L, U, b))
+    y = b.copy(); B.apply_trans(y)
+    assert relerr(y, oracle.port.apply_lu(L, U, b, transpose=True)) <= TOL
+    lev, nlev = B.levels(0)
+    lo, nlo = oracle.port.levels(Ap.indptr, Ap.indices, lower=True)
+    assert nlev == nlo and np.array_equal(lev, lo)
+
+
+def test_batched_levels_replicated_and_closed_form(ilupp):
+    """The systems of a batch share one analysis: levels of every system equal the oracle's levels of one system;
+    a complete stencil takes the closed form, an incomplete one (dropped couplings) the general recurrence."""
+    pat, vals = P.batched_poisson2d(6, 24)
+    B = ilupp.ILU0PreconditionerBatched(pat, vals)
+    n1 = pat.shape[0]
+    for which in (0, 1):
+        lev, nlev = B.levels(which)
+        lo, nlo = oracle.port.levels(pat.indptr, pat.indices, lower=(which == 0))
+        assert nlev == nlo == 2 * 24 - 1
+        assert np.array_equal(lev.reshape(6, n1), np.tile(lo, (6, 1)))
+    # drop the x-couplings of one grid line: still every dependency at a stencil offset, no longer a complete stencil
+    A = P.poisson2d(24).tolil()
+    for i in range(24 * 5 + 1, 24 * 6):
+        A[i, i - 1] = 0
+        A[i - 1, i] = 0
+    A = A.tocsr(); A.eliminate_zeros(); A.sort_indices()
+    B = ilupp.ILU0Preconditioner(A)
+    L, U = oracle.port.ilu0(A)
+    lev, nlev = B.levels(0)
+    lo, nlo = oracle.port.levels(A.indptr, A.indices, lower=True)
+    assert nlev == nlo and np.array_equal(lev, lo)
+    b = P.rhs(A.shape[0], 2)
+    y = b.copy(); B.apply(y)
+    assert np.array_equal(y, oracle.port.apply_lu(L, U, b))
