@@ -261,6 +261,13 @@ class _BaseWrapper(scipy.sparse.linalg.LinearOperator):
         by the watchdog.  (Such a failure is otherwise raised by the next call on the object.)"""
         self.pr.check_status(stream)
 
+    def write_binary(self, filename):
+        """Save the factors in the reference's binary matrix format as `<filename>-L.isp` (and `<filename>-R.isp` for
+        two-factor preconditioners): the file pair of the reference's ILUC / ILUT `write_binary`
+        (preconditioner_implementation.h:960-980, sparse_implementation.h:3839-3860).  Restore with
+        `FactorsPreconditioner.read_binary(filename)`."""
+        self.pr.write_binary(str(filename))
+
     def set_option(self, key, value):
         """Set a libilub option for THIS object only (process-wide defaults: ilupp_b200.set_option)."""
         self.pr.set_option(key, int(value))
@@ -371,6 +378,29 @@ class FactorsPreconditioner(_BaseWrapper):
             self.pr.set_permutations(None if perm_left is None else np.asarray(perm_left, dtype=_index_dtype),
                                      None if perm_right is None else np.asarray(perm_right, dtype=_index_dtype))
         scipy.sparse.linalg.LinearOperator.__init__(self, shape=L.shape, dtype=np.dtype(np.float64))
+
+
+    @classmethod
+    def read_binary(cls, filename, device=0):
+        """Restore a preconditioner from `<filename>-L.isp` [+ `<filename>-R.isp`] (written by `write_binary` here or by
+        the reference's ILUC / ILUT `write_binary`): L U when both files exist, L L^T when only the first does."""
+        import os
+        L = read_isp(str(filename) + "-L.isp")
+        U = read_isp(str(filename) + "-R.isp") if os.path.exists(str(filename) + "-R.isp") else None
+        return cls(L, U, device=device)
+
+
+def read_isp(path):
+    """A sparse matrix from the reference's `.isp` binary file (matrix_sparse::read_binary,
+    sparse_implementation.h:3814-3837) as a scipy CSR / CSC matrix."""
+    return _matrix_from_info(*_ilupp.isp_read(str(path)))
+
+
+def write_isp(path, A):
+    """Write the CSR / CSC matrix `A` as the reference's `.isp` binary file (matrix_sparse::write_binary,
+    sparse_implementation.h:3839-3860), byte for byte what the reference writes for the same matrix."""
+    Ad, Ai, Ap, Ao = _matrix_fields(A)
+    _ilupp.isp_write(str(path), Ad, Ai, Ap, Ao, A.shape[0], A.shape[1])
 
 
 class _BatchedWrapper(_BaseWrapper):

@@ -275,6 +275,8 @@ py::class_<P> wrapPreconditioner(py::module& m, const char* classname) {  // bin
                  check(ilub_set_permutations(pr.h, g, s, ILUB_HOST, nullptr));
              },
              py::arg("gather_in") = py::none(), py::arg("scatter_out") = py::none())
+        .def("write_binary",
+             [](const P& pr, const std::string& filename) { check(ilub_write_binary(pr.h, filename.c_str(), nullptr)); })
         .def("set_option",
              [](const P& pr, const std::string& k, int64_t v) { check(ilub_set_handle_option(pr.h, k.c_str(), v)); })
         .def("get_option",
@@ -434,6 +436,25 @@ PYBIND11_MODULE(_ilupp, m) {
         return c;
     });
     m.def("set_option", [](const std::string& k, int64_t v) { check(ilub_set_option(k.c_str(), v)); });
+    // the reference's .isp matrix files (matrix_sparse::read_binary / write_binary, sparse_implementation.h:3814-3860)
+    m.def("isp_read", [](const std::string& path) {
+        int32_t rows = 0, cols = 0;
+        int64_t nnz = 0;
+        int is_csr = 1;
+        check(ilub_isp_dims(path.c_str(), &rows, &cols, &nnz, &is_csr));
+        py::array_t<double> data(nnz);
+        py::array_t<int32_t> indices(nnz), indptr((is_csr ? rows : cols) + 1);
+        check(ilub_isp_read(path.c_str(), data.mutable_data(), indices.mutable_data(), indptr.mutable_data()));
+        return py::make_tuple(data, indices, indptr, is_csr != 0, rows, cols);
+    });
+    m.def("isp_write", [](const std::string& path, py::array_t<double, py::array::c_style | py::array::forcecast> data,
+                          py::array_t<int32_t, py::array::c_style | py::array::forcecast> indices,
+                          py::array_t<int32_t, py::array::c_style | py::array::forcecast> indptr, bool is_csr, int32_t rows,
+                          int32_t cols) {
+        if (indices.size() != data.size()) throw std::runtime_error("indices and data should have the same size!");
+        if (indptr.size() != (is_csr ? rows : cols) + 1) throw std::runtime_error("indptr has the wrong size!");
+        check(ilub_isp_write(path.c_str(), rows, cols, is_csr ? 1 : 0, data.data(), indices.data(), indptr.data(), data.size()));
+    });
     m.def("stage_option", [](const std::string& k, int64_t v) { check(ilub_stage_option(k.c_str(), v)); });
     m.def("get_option", [](const std::string& k) {
         int64_t v = 0;

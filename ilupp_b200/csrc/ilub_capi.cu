@@ -5,6 +5,8 @@
 #include <memory>
 #include <vector>
 
+#include <cstdio>
+
 #include "ilub_common.cuh"
 
 using namespace ilub;
@@ -488,6 +490,101 @@ int ilub_get_factor(ilub_handle* h, int which, double* data, int32_t* indices, i
             ILUB_CUDA(cudaMemcpyAsync(indices, i.p, sizeof(int) * nnz, cudaMemcpyDeviceToHost, s));
             ILUB_CUDA(cudaMemcpyAsync(indptr, p.p, sizeof(int) * (h->n + 1), cudaMemcpyDeviceToHost, s));
             ILUB_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+// ---- persistence: the reference's raw `.isp` dump of a matrix_sparse<double> (sparse_implementation.h:3814-3860):
+// int32 rows, cols, pointer_size, nnz; int32 orientation (ROW = 0, COLUMN = 1, declarations.h:83); then
+// pointer[pointer_size], indices[nnz] (int32) and data[nnz] (double), nothing else
+namespace {
+struct IspHeader {
+    int32_t rows, cols, pointer_size, nnz, orientation;
+};
+void isp_write_file(const std::string& path, int32_t rows, int32_t cols, int orientation, const double* data,
+                    const int32_t* indices, const int32_t* indptr, int32_t nnz) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw Error{ILUB_ERR_INVALID, "cannot write " + path};
+    const IspHeader hd = {rows, cols, (orientation == 0 ? rows : cols) + 1, nnz, orientation};
+    bool ok = fwrite(&hd, sizeof(int32_t), 5, f) == 5;
+    ok = ok && fwrite(indptr, sizeof(int32_t), (size_t)hd.pointer_size, f) == (size_t)hd.pointer_size;
+    ok = ok && fwrite(indices, sizeof(int32_t), (size_t)nnz, f) == (size_t)nnz;
+    ok = ok && fwrite(data, sizeof(double), (size_t)nnz, f) == (size_t)nnz;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw Error{ILUB_ERR_INVALID, "error writing " + path};
+}
+IspHeader isp_read_header(FILE* f, const std::string& path) {
+    IspHeader hd;
+    if (fread(&hd, sizeof(int32_t), 5, f) != 5) throw Error{ILUB_ERR_INVALID, "error reading " + path + " (header)"};
+    const bool sane = hd.rows >= 0 && hd.cols >= 0 && hd.nnz >= 0 && (hd.orientation == 0 || hd.orientation == 1) &&
+                      hd.pointer_size == (hd.orientation == 0 ? hd.rows : hd.cols) + 1;
+    if (!sane) throw Error{ILUB_ERR_INVALID, path + " is not an .isp matrix file (int32 indices, double values)"};
+    return hd;
+}
+}  // namespace
+
+int ilub_isp_write(const char* path, int32_t rows, int32_t cols, int is_csr, const double* data, const int32_t* indices,
+                   const int32_t* indptr, int64_t nnz) {
+    return guarded([&] {
+        ILUB_REQUIRE(path && data && indices && indptr, ILUB_ERR_INVALID, "null argument");
+        ILUB_REQUIRE(rows >= 0 && cols >= 0 && nnz >= 0 && nnz < ((int64_t)1 << 31), ILUB_ERR_SIZE, "bad matrix dimensions");
+        isp_write_file(path, rows, cols, is_csr ? 0 : 1, data, indices, indptr, (int32_t)nnz);
+    });
+}
+int ilub_isp_dims(const char* path, int32_t* rows, int32_t* cols, int64_t* nnz, int* is_csr) {
+    return guarded([&] {
+        ILUB_REQUIRE(path && rows && cols && nnz && is_csr, ILUB_ERR_INVALID, "null argument");
+        FILE* f = fopen(path, "rb");
+        if (!f) throw Error{ILUB_ERR_INVALID, std::string("cannot read ") + path};
+        IspHeader hd;
+        try {
+            hd = isp_read_header(f, path);
+        } catch (...) {
+            fclose(f);
+            throw;
+        }
+        fclose(f);
+        *rows = hd.rows;
+        *cols = hd.cols;
+        *nnz = hd.nnz;
+        *is_csr = hd.orientation == 0;
+    });
+}
+int ilub_isp_read(const char* path, double* data, int32_t* indices, int32_t* indptr) {
+    return guarded([&] {
+        ILUB_REQUIRE(path && data && indices && indptr, ILUB_ERR_INVALID, "null argument");
+        FILE* f = fopen(path, "rb");
+        if (!f) throw Error{ILUB_ERR_INVALID, std::string("cannot read ") + path};
+        bool ok = false;
+        try {
+            const IspHeader hd = isp_read_header(f, path);
+            ok = fread(indptr, sizeof(int32_t), (size_t)hd.pointer_size, f) == (size_t)hd.pointer_size;
+            ok = ok && fread(indices, sizeof(int32_t), (size_t)hd.nnz, f) == (size_t)hd.nnz;
+            ok = ok && fread(data, sizeof(double), (size_t)hd.nnz, f) == (size_t)hd.nnz;
+        } catch (...) {
+            fclose(f);
+            throw;
+        }
+        fclose(f);
+        if (!ok) throw Error{ILUB_ERR_INVALID, std::string("error reading ") + path + " (truncated)"};
+    });
+}
+int ilub_write_binary(ilub_handle* h, const char* filename, void* stream) {
+    return guarded([&] {
+        ILUB_REQUIRE(h && filename, ILUB_ERR_INVALID, "null argument");
+        HandleLock lock(h->mu);
+        const int nf = h->kind == KIND_ILU0 ? 2 : 1;
+        for (int which = 0; which < nf; ++which) {
+            int64_t nnz = 0;
+            int is_csr = 1;
+            if (ilub_factor_dims(h, which, &nnz, &is_csr) != ILUB_OK) throw Error{ILUB_ERR_INVALID, g_last_error};
+            std::vector<double> d((size_t)nnz);
+            std::vector<int32_t> i((size_t)nnz), p((size_t)h->n + 1);
+            if (ilub_get_factor(h, which, d.data(), i.data(), p.data(), ILUB_HOST, stream) != ILUB_OK)
+                throw Error{ILUB_ERR_CUDA, g_last_error};
+            // file names of ILUCPreconditioner::write_binary (preconditioner_implementation.h:960-970)
+            isp_write_file(std::string(filename) + (which == 0 ? "-L.isp" : "-R.isp"), h->n, h->n, is_csr ? 0 : 1, d.data(),
+                           i.data(), p.data(), (int32_t)nnz);
         }
     });
 }

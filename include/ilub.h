@@ -147,6 +147,23 @@ ILUB_API int ilub_factor_dims(const ilub_handle* h, int which, int64_t* nnz, int
  * factor `which` into caller-allocated buffers (data[nnz], indices[nnz], indptr[n+1]) */
 ILUB_API int ilub_get_factor(ilub_handle* h, int which, double* data, int32_t* indices, int32_t* indptr,
                              int where, void* stream);
+/* ---- persistence ------------------------------------------------------------
+ * The reference's raw binary dump of a sparse matrix, `.isp` (matrix_sparse::write_binary / read_binary,
+ * sparse_implementation.h:3814-3860: int32 rows, cols, pointer_size, nnz, orientation (ROW = 0, COLUMN = 1), then
+ * pointer[], indices[] as int32 and data[] as double), byte for byte.
+ *   ilub_write_binary   the factors of the handle in reference layout (what ilub_get_factor returns) as
+ *                       "<filename>-L.isp" and, for two-factor handles, "<filename>-R.isp" -- the file pair of the
+ *                       reference's ILUCPreconditioner / ILUTPreconditioner::write_binary
+ *                       (preconditioner_implementation.h:960-980); the reference's generic LU / LL^T classes, which
+ *                       ILU0 / IChol0 use, only inherit the stub that throws (preconditioner.h:118-119).
+ *   ilub_isp_dims / ilub_isp_read / ilub_isp_write   plain file access for FFI callers (no device needed): read a
+ *                       file into caller-allocated arrays (indptr[rows + 1] for a row-oriented matrix, [cols + 1]
+ *                       otherwise) and hand them to ilub_create_from_factors to restore a handle. */
+ILUB_API int ilub_write_binary(ilub_handle* h, const char* filename, void* stream);
+ILUB_API int ilub_isp_dims(const char* path, int32_t* rows, int32_t* cols, int64_t* nnz, int* is_csr);
+ILUB_API int ilub_isp_read(const char* path, double* data, int32_t* indices, int32_t* indptr);
+ILUB_API int ilub_isp_write(const char* path, int32_t rows, int32_t cols, int is_csr, const double* data,
+                            const int32_t* indices, const int32_t* indptr, int64_t nnz);
 /* parity hook (no reference equivalent -- its solves are sequential): level of every row in the
  * dependency DAG of one of the triangular solves.  level_of_row[n]; nlevels may be NULL. */
 ILUB_API int ilub_get_levels(ilub_handle* h, int which_solve, int32_t* nlevels, int32_t* level_of_row, int where,

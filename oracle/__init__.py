@@ -182,6 +182,13 @@ class _RefPrecond:
             self._ref.lib.ref_destroy(self._h)
             self._h = None
 
+    def write_factor_binary(self, which, path):
+        """factor `which` dumped by the reference's matrix_sparse::write_binary"""
+        f = self._ref.lib.ref_write_factor_binary
+        f.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        if f(self._h, which, str(path).encode()) != 0:
+            raise RuntimeError("reference write_binary failed")
+
     def apply(self, x, transpose=False):
         y = np.array(x, dtype=np.float64, copy=True).ravel()
         self._ref.lib.ref_apply(self._h, int(bool(transpose)), y)
@@ -239,6 +246,26 @@ class _Ref:
         if hasattr(L, "ref_cg"):
             L.ref_cg.argtypes = L.ref_bicgstab.argtypes
             L.ref_cg.restype = C.c_int
+
+    def write_matrix_binary(self, A, path):
+        """`A` dumped by the reference's own matrix_sparse::write_binary (.isp)"""
+        ptr, idx, val, is_csr = _csr_arrays(A)
+        f = self.lib.ref_write_matrix_binary
+        f.argtypes = [_f64p, _i32p, _i32p, C.c_int32, C.c_int, C.c_char_p]
+        if f(val, idx, ptr, A.shape[0], int(is_csr), str(path).encode()) != 0:
+            raise RuntimeError("reference write_binary failed")
+
+    def read_matrix_binary(self, path, cap_nnz, cap_ptr):
+        """an .isp file read back by the reference's own matrix_sparse::read_binary"""
+        f = self.lib.ref_read_matrix_binary
+        f.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int), _f64p,
+                      _i32p, _i32p, C.c_int64, C.c_int64]
+        rows, cols, nnz, is_csr = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int()
+        data, idx, ptr = np.empty(cap_nnz), np.empty(cap_nnz, np.int32), np.empty(cap_ptr, np.int32)
+        if f(str(path).encode(), C.byref(rows), C.byref(cols), C.byref(nnz), C.byref(is_csr), data, idx, ptr, cap_nnz, cap_ptr) != 0:
+            raise RuntimeError("reference read_binary failed")
+        np_ = (rows.value if is_csr.value else cols.value) + 1
+        return _mk(ptr[:np_].copy(), idx[:nnz.value].copy(), data[:nnz.value].copy(), bool(is_csr.value), rows.value)
 
     def _create(self, fn, A):
         ptr, idx, val, is_csr = _csr_arrays(A)

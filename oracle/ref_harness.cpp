@@ -104,6 +104,47 @@ void ref_get_factor(void* p, int which, double* data, int32_t* indices, int32_t*
     std::memcpy(indptr, M.pointer, sizeof(Integer) * (h->n + 1));
 }
 
+// factor `which` of the handle dumped by the reference's own matrix_sparse::write_binary
+// (sparse_implementation.h:3839-3860): the .isp layout ILUC/ILUT::write_binary use for "<name>-L.isp" / "-R.isp"
+// (preconditioner_implementation.h:960-970)
+int ref_write_factor_binary(void* p, int which, const char* filename) {
+    try {
+        factor(static_cast<RefHandle*>(p), which).write_binary(filename);
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+// a matrix given as arrays, dumped / re-read by the reference's write_binary / read_binary (round trip oracle)
+int ref_write_matrix_binary(const double* data, const int32_t* indices, const int32_t* indptr, int32_t n, int is_csr,
+                            const char* filename) {
+    try {
+        view(data, indices, indptr, n, is_csr).write_binary(filename);
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+int ref_read_matrix_binary(const char* filename, int32_t* rows, int32_t* cols, int32_t* nnz, int* is_csr, double* data,
+                           int32_t* indices, int32_t* indptr, int64_t cap_nnz, int64_t cap_ptr) {
+    try {
+        matrix M;
+        M.read_binary(filename);
+        *rows = M.rows();
+        *cols = M.columns();
+        *nnz = M.actual_non_zeroes();
+        *is_csr = (M.orientation == ROW);
+        const Integer np = (M.orientation == ROW ? M.rows() : M.columns()) + 1;
+        if (*nnz > cap_nnz || np > cap_ptr) return 2;
+        std::memcpy(data, M.data, sizeof(double) * *nnz);
+        std::memcpy(indices, M.indices, sizeof(Integer) * *nnz);
+        std::memcpy(indptr, M.pointer, sizeof(Integer) * np);
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
 // y = A x, through the same member bicgstab uses (sparse_implementation.h:3151-3158)
 void ref_spmv(const double* data, const int32_t* indices, const int32_t* indptr, int32_t n, int is_csr,
               const double* x, double* y) {

@@ -130,6 +130,15 @@ def main():
             rec.update({key + "_apply": y, key + "_apply_trans": yt, key + "_total_nnz": np.array(Pq.total_nnz)})
         np.savez_compressed(os.path.join(out, "factors_perm_%s.npz" % fmt), **rec)
         print("wrote permuted factors", fmt)
+    # .isp files written by the reference's own matrix_sparse::write_binary (sparse_implementation.h:3839-3860)
+    # -- the ILU0 factors of the nonsymmetric tridiagonal problem (CSR and CSC input: ROW- and COLUMN-oriented files)
+    g = np.load(os.path.join(out, "nonsym_tridiag_csr.npz"))
+    for fmt in ("csr", "csc"):
+        A = scipy.sparse.csr_matrix((g["A_data"], g["A_indices"], g["A_indptr"])).asformat(fmt)
+        R = oracle.ref.ILU0(A)
+        R.write_factor_binary(0, os.path.join(out, "isp_ilu0_tridiag_%s-L.isp" % fmt))
+        R.write_factor_binary(1, os.path.join(out, "isp_ilu0_tridiag_%s-R.isp" % fmt))
+    print("wrote .isp fixtures")
     # BiCGStab with ILU0 through the reference templates (harness)
     from ilupp_b200 import problems
     A = problems.convdiff3d(12)

@@ -155,3 +155,71 @@ def test_factors_preconditioner_argument_checks():
     if ilupp._ilupp.device_count() == 0:
         with pytest.raises(RuntimeError, match="no CUDA device"):
             ilupp.FactorsPreconditioner(L, U)
+
+
+# ---- persistence: the reference's .isp matrix files -------------------------------------
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_isp_files_written_by_the_reference(fmt, tmp_path):
+    """tests/golden/isp_*.isp were written by the unmodified reference's matrix_sparse::write_binary
+    (scripts/make_golden.py): reading them gives the reference's factors, writing those back gives the same bytes."""
+    import ilupp_b200 as ilupp
+    g = np.load(os.path.join(GOLD, "nonsym_tridiag_%s.npz" % fmt))
+    for side, key in (("L", "ilu0_L"), ("R", "ilu0_U")):
+        path = os.path.join(GOLD, "isp_ilu0_tridiag_%s-%s.isp" % (fmt, side))
+        M = ilupp.read_isp(path)
+        assert scipy.sparse.isspmatrix_csr(M) == bool(g[key + "_is_csr"])
+        assert np.array_equal(M.data, g[key + "_data"]) and np.array_equal(M.indices, g[key + "_indices"])
+        assert np.array_equal(M.indptr, g[key + "_indptr"])
+        out = tmp_path / "again.isp"
+        ilupp.write_isp(out, M)
+        assert open(out, "rb").read() == open(path, "rb").read()
+
+
+def test_isp_c_abi_and_errors(tmp_path):
+    lib = C.CDLL(LIB)
+    lib.ilub_last_error.restype = C.c_char_p
+    path = os.path.join(GOLD, "isp_ilu0_tridiag_csr-L.isp").encode()
+    rows, cols, nnz, is_csr = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int()
+    assert lib.ilub_isp_dims(path, C.byref(rows), C.byref(cols), C.byref(nnz), C.byref(is_csr)) == 0
+    assert (rows.value, cols.value, nnz.value, is_csr.value) == (50, 50, 99, 1)
+    data, idx, ptr = np.empty(99), np.empty(99, np.int32), np.empty(51, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.ilub_isp_read(path, vp(data), vp(idx), vp(ptr)) == 0
+    assert ptr[0] == 0 and ptr[-1] == 99 and idx.max() == 49
+    out = str(tmp_path / "copy.isp").encode()
+    assert lib.ilub_isp_write(out, rows, cols, 1, vp(data), vp(idx), vp(ptr), C.c_int64(99)) == 0
+    assert open(out, "rb").read() == open(path, "rb").read()
+    # not there / truncated / not an .isp file: refused with a message, nothing read
+    assert lib.ilub_isp_dims(b"/nonexistent/x.isp", C.byref(rows), C.byref(cols), C.byref(nnz), C.byref(is_csr)) == 1
+    bad = tmp_path / "bad.isp"
+    bad.write_bytes(open(path, "rb").read()[:100])
+    assert lib.ilub_isp_read(str(bad).encode(), vp(data), vp(idx), vp(ptr)) == 1 and b"truncated" in lib.ilub_last_error()
+    bad.write_bytes(b"\x01" * 64)
+    assert lib.ilub_isp_dims(str(bad).encode(), C.byref(rows), C.byref(cols), C.byref(nnz), C.byref(is_csr)) == 1
+    assert lib.ilub_write_binary(None, b"x", None) == 1
+
+
+def test_isp_round_trip_through_the_compiled_reference(tmp_path):
+    """ours -> reference read_binary and reference write_binary -> ours, on a random rectangular-free CSR / CSC matrix
+    (needs oracle/_ref: the unmodified reference compiled by oracle/Makefile)."""
+    import oracle
+    if oracle.ref is None:
+        pytest.skip("oracle/_ref not built")
+    import ilupp_b200 as ilupp
+    rng = np.random.default_rng(7)
+    for fmt in ("csr", "csc"):
+        A = (scipy.sparse.random(40, 40, density=0.15, random_state=3, format=fmt) + scipy.sparse.eye(40)).asformat(fmt)
+        A.sort_indices()
+        A.data = rng.standard_normal(A.nnz)
+        A.indices = A.indices.astype(np.int32); A.indptr = A.indptr.astype(np.int32)
+        ours, theirs = tmp_path / ("ours_%s.isp" % fmt), tmp_path / ("ref_%s.isp" % fmt)
+        ilupp.write_isp(ours, A)
+        oracle.ref.write_matrix_binary(A, theirs)
+        assert open(ours, "rb").read() == open(theirs, "rb").read()
+        B = oracle.ref.read_matrix_binary(ours, A.nnz, 41)
+        assert type(B) is type(A) and np.array_equal(B.data, A.data) and np.array_equal(B.indices, A.indices)
+        Cm = ilupp.read_isp(theirs)
+        assert type(Cm) is type(A) and np.array_equal(Cm.data, A.data) and np.array_equal(Cm.indptr, A.indptr)

@@ -1101,3 +1101,33 @@ def test_batched_levels_replicated_and_closed_form(ilupp):
     b = P.rhs(A.shape[0], 2)
     y = b.copy(); B.apply(y)
     assert np.array_equal(y, oracle.port.apply_lu(L, U, b))
+
+
+def test_write_binary_matches_reference_files_and_restores(ilupp, tmp_path):
+    """Persistence: the factors a handle writes are byte for byte the files the unmodified reference
+    writes for its ILU0 factors of the same matrix (tests/golden/isp_*.isp), and a handle restored from them applies
+    like the original."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for fmt in ("csr", "csc"):
+        g = load_golden("nonsym_tridiag_%s" % fmt)
+        A = golden_matrix(g)
+        B = ilupp.ILU0Preconditioner(A)
+        B.write_binary(tmp_path / ("f_" + fmt))
+        for side in ("L", "R"):
+            mine = open(tmp_path / ("f_%s-%s.isp" % (fmt, side)), "rb").read()
+            assert mine == open(os.path.join(gold, "isp_ilu0_tridiag_%s-%s.isp" % (fmt, side)), "rb").read()
+        R = ilupp.FactorsPreconditioner.read_binary(tmp_path / ("f_" + fmt))
+        for tr in (False, True):
+            y = g["b"].copy(); (B.apply_trans if tr else B.apply)(y)
+            z = g["b"].copy(); (R.apply_trans if tr else R.apply)(z)
+            assert np.array_equal(y, z)
+    S = golden_matrix(load_golden("laplace2d_csr"), "S")
+    B = ilupp.IChol0Preconditioner(S)
+    B.write_binary(tmp_path / "chol")
+    assert not os.path.exists(tmp_path / "chol-R.isp")
+    R = ilupp.FactorsPreconditioner.read_binary(tmp_path / "chol")
+    b = P.rhs(S.shape[0], 5)
+    y = b.copy(); B.apply(y)
+    z = b.copy(); R.apply(z)
+    assert np.array_equal(y, z) and R.total_nnz == B.total_nnz
