@@ -266,6 +266,27 @@ __global__ void __launch_bounds__(256) k_levels(SrcDev S, int n, int* level, int
     }
 }
 
+// level-packed layout: entry count of every position of the (level, row) listing, then the entries themselves
+__global__ void k_lev_count(int n, SrcDev S, const int* __restrict__ rows, int* __restrict__ cnt) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int row = rows[s];
+    cnt[s] = src_end(S, row) - src_beg(S, row);
+}
+__global__ void k_lev_fill(int n, SrcDev S, int unit_diag, const int* __restrict__ rows, const int* __restrict__ ptr,
+                           int* __restrict__ idx, int* __restrict__ srcpos, int* __restrict__ dpos) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int row = rows[s];
+    const int b = src_beg(S, row), e = src_end(S, row);
+    const int p = ptr[s];
+    for (int j = 0; j < e - b; ++j) {
+        const int q = S.reverse ? e - 1 - j : b + j;  // the order the reference accumulates in
+        idx[p + j] = S.dep_idx[q];
+        srcpos[p + j] = S.val_pos ? S.val_pos[q] : q;
+    }
+    dpos[s] = unit_diag ? -1 : S.diag_pos[row];
+}
 // diagonal positions of the systems 1 .. nsys-1 of a batch: those of system 0 shifted by whole systems
 __global__ void k_dpos_replicate(int n, int n1, int nnz1, int* __restrict__ dpos) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + n1;
@@ -939,7 +960,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         T.nparts = 1;
     } else if (!sys_ok && few_levels_wanted(h, slot)) {
         DebugTimer t("  level sets", s);
-        build_level_sets(h, slot, s);  // one launch per level straight from the CSR-read arrays: no packed layout
+        build_level_packed(h, slot, s);  // rows and entries in (level, row) order: every level is one contiguous stream
         T.part_mode = 7;
         T.nparts = 0;
     } else if (!sys_ok && levels_wanted(h, slot)) {
@@ -1139,6 +1160,12 @@ void pack_solve_values(ilub_handle* h, int slot, cudaStream_t s) {
     if (!T.built) return;
     if (T.sys.built) pack_systolic(h, slot, s);
     if (T.deep.built) pack_deep(h, slot, s);
+    if (T.lev.built) {
+        if (T.lev.nent > 0)
+            k_pack_values<<<blocks_for(T.lev.nent, 256), 256, 0, s>>>(T.lev.nent, T.lev.srcpos.p, h->lu.p, T.lev.val.p);
+        k_pack_diag<<<blocks_for(h->n, 256), 256, 0, s>>>(h->n, T.lev.dpos.p, h->lu.p, T.lev.diag.p);
+        h->launches += 2;
+    }
     if (!T.generic_built) return;
     const int64_t nent = T.nslabs * 32;
     const int64_t nlane = (int64_t)T.nchunks * 32;
@@ -1174,6 +1201,39 @@ void build_level_sets(ilub_handle* h, int slot, cudaStream_t s) {
     ILUB_CUDA(cudaMemcpyAsync(T.lvl_ptr_host.data(), T.lvl_ptr.p, sizeof(int) * (T.nlevels + 1), cudaMemcpyDeviceToHost, s));
     ILUB_CUDA(cudaStreamSynchronize(s));
     T.lvl_built = true;
+}
+
+void build_level_packed(ilub_handle* h, int slot, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    if (T.lev.built) return;
+    build_level_sets(h, slot, s);
+    const int n = h->n;
+    const SolveSource src = solve_source(h, slot);
+    const SrcDev S = to_dev(src);
+    DevBuf<int> cnt;
+    cnt.alloc((size_t)n + 1);
+    ILUB_CUDA(cudaMemsetAsync(cnt.p + n, 0, sizeof(int), s));
+    k_lev_count<<<blocks_for(n, 256), 256, 0, s>>>(n, S, T.lvl_rows.p, cnt.p);
+    T.lev.ptr.alloc((size_t)n + 1);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, T.lev.ptr.p, n + 1, s);
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(tb);
+    ILUB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, T.lev.ptr.p, n + 1, s));
+    int nent = 0;
+    ILUB_CUDA(cudaMemcpyAsync(&nent, T.lev.ptr.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    T.lev.nent = nent;
+    T.lev.idx.alloc((size_t)std::max(nent, 1));
+    T.lev.srcpos.alloc((size_t)std::max(nent, 1));
+    T.lev.val.alloc((size_t)std::max(nent, 1));
+    T.lev.dpos.alloc((size_t)n);
+    T.lev.diag.alloc((size_t)n);
+    k_lev_fill<<<blocks_for(n, 256), 256, 0, s>>>(n, S, src.unit_diag ? 1 : 0, T.lvl_rows.p, T.lev.ptr.p, T.lev.idx.p,
+                                                  T.lev.srcpos.p, T.lev.dpos.p);
+    h->launches += 3;
+    ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here
+    T.lev.built = true;
 }
 
 void expand_batched(ilub_handle* h, const int* ptr1, const int* idx1, int32_t n1, int64_t nnz1, int32_t nsys,

@@ -268,6 +268,18 @@ struct TriSolve {
     std::vector<int> lvl_ptr_host;  // host copy of lvl_ptr (the one-launch-per-level solve sizes its grids from it)
     bool lvl_built = false;
     bool generic_built = false;   // the chunked sync-free layout above exists (always for slot 0: the factorisation uses it)
+    // level-packed layout (few very wide levels, part_mode 7): rows in (level, row) order = lvl_rows; their entries,
+    // in the order the reference consumes them, packed contiguously in the same order
+    struct LevPacked {
+        bool built = false;
+        int64_t nent = 0;
+        DevBuf<int> ptr;     // [n + 1] first entry of every position
+        DevBuf<int> idx;     // [nent] dependency (original row index)
+        DevBuf<int> srcpos;  // [nent] position of the coefficient in the factor value array
+        DevBuf<int> dpos;    // [n] position of the diagonal (-1: unit diagonal)
+        DevBuf<double> val;  // [nent]
+        DevBuf<double> diag; // [n]
+    } lev;
     SysSolve sys;                 // line-systolic layout (structured grids), preferred when built
     DeepSolve deep;               // level-loop layout (deep narrow DAGs)
 };
@@ -397,6 +409,7 @@ void analyse_solve(ilub_handle* h, int which, cudaStream_t s);            // lev
 void analyse_generic(ilub_handle* h, int which, cudaStream_t s);          // partition + chunked sync-free layout
 void pack_solve_values(ilub_handle* h, int which, cudaStream_t s);        // (re)fill val/diag from lu
 void build_level_sets(ilub_handle* h, int which, cudaStream_t s);
+void build_level_packed(ilub_handle* h, int slot, cudaStream_t s);  // level-packed layout of a few-wide-levels solve
 bool deep_wanted(const ilub_handle* h, int slot);
 bool levels_wanted(const ilub_handle* h, int slot);   // cooperative level loop (ilub_trsv.cu)
 bool few_levels_wanted(const ilub_handle* h, int slot);  // one launch per level (ilub_trsv.cu)

@@ -701,6 +701,61 @@ inline int blocks_for(int64_t work, int threads) { return (int)((work + threads 
 
 }  // namespace
 
+// one level of the level-packed layout (few very wide levels): thread s resolves position s of the (level, row)
+// listing; index / coefficient / diagonal streams are contiguous across the threads of a warp, only the solution vector
+// is gathered (it fits the L2)
+template <bool EXACT>
+__global__ void k_trsv_level_packed(const int* __restrict__ rows, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                    const double* __restrict__ val, const double* __restrict__ diag, int begin, int end,
+                                    double* x) {
+    // Programmatic dependent launch: the kernel of the NEXT level may be scheduled right away; like this one it first
+    // fetches everything that does not depend on the solve (its rows, extents, diagonal and the first four index /
+    // coefficient pairs) and only then waits for the previous level's grid to complete -- launch latency and two of the
+    // three dependent memory round trips of a level overlap with the level before.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int s = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = s < end;
+    int row = 0, b = 0, e = 0;
+    double d = 1.0;
+    int dep[4] = {-1, -1, -1, -1};
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    if (live) {
+        row = rows[s];
+        b = ptr[s];
+        e = ptr[s + 1];
+        d = diag[s];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (b + u < e) {
+                dep[u] = idx[b + u];
+                c[u] = val[b + u];
+            }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!live) return;
+    double acc = x[row];
+    for (int j0 = b; j0 < e; j0 += 4) {
+        double xv[4];
+        if (j0 > b) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dep[u] = -1;
+                c[u] = 0.0;
+                if (j0 + u < e) {
+                    dep[u] = idx[j0 + u];
+                    c[u] = val[j0 + u];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = dep[u] >= 0 ? __ldcg(x + dep[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (dep[u] >= 0) acc = sub_mul<EXACT>(acc, c[u], xv[u]);
+    }
+    x[row] = EXACT ? __ddiv_rn(acc, d) : acc / d;
+}
+
 // many levels of moderate width: the cooperative level loop (the chunked kernel's contiguous row ranges serialise on
 // such DAGs: measured 92 ms against 5 ms on ILUT factors of a 64^3 Poisson matrix)
 bool levels_wanted(const ilub_handle* h, int slot) {
@@ -727,7 +782,37 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     ILUB_REQUIRE(T.built, ILUB_ERR_INVALID, "solve not analysed");
     const Options& opt = options();
     const bool exact = opt.exact != 0;
-    if (opt.solve_algo == 1 || few_levels_wanted(h, slot)) {
+    if (opt.solve_algo == 0 && few_levels_wanted(h, slot)) {
+        if (!T.lev.built) {
+            build_level_packed(h, slot, s);
+            pack_solve_values(h, slot, s);
+        }
+        const std::vector<int>& lptr = T.lvl_ptr_host;
+        for (int c = 0; c < nrhs; ++c) {
+            double* xc = x + (int64_t)c * ldx;
+            for (int l = 0; l < T.nlevels; ++l) {
+                const int cnt = lptr[l + 1] - lptr[l];
+                if (cnt <= 0) continue;
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(blocks_for(cnt, 128), 1, 1);
+                cfg.blockDim = dim3(128, 1, 1);
+                cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                ILUB_CUDA(cudaLaunchKernelEx(&cfg, exact ? k_trsv_level_packed<true> : k_trsv_level_packed<false>,
+                                             (const int*)T.lvl_rows.p, (const int*)T.lev.ptr.p, (const int*)T.lev.idx.p,
+                                             (const double*)T.lev.val.p, (const double*)T.lev.diag.p, lptr[l], lptr[l + 1], xc));
+                h->launches++;
+            }
+        }
+        ILUB_CUDA(cudaGetLastError());
+        return;
+    }
+    if (opt.solve_algo == 1) {
         build_level_sets(h, slot, s);
         const std::vector<int>& lptr = T.lvl_ptr_host;
         const SolveSource src = solve_source(h, slot);
