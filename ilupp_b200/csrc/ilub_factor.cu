@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int
 
 template <int G, bool ICHOL>
 void launch_levels_g(bool exact, cudaStream_t s, FactorParams P, const int* lvl_ptr, int nlevels, unsigned* barrier,
-                     int sm_count) {
+                     int sm_count, int64_t nrows) {
     void* kern = exact ? (void*)k_factor_levels<G, ICHOL, true> : (void*)k_factor_levels<G, ICHOL, false>;
     // few, fat CTAs: the barrier costs one atomic and one polling thread per CTA
     const int block = 512;
@@ -460,19 +460,25 @@ void launch_levels_g(bool exact, cudaStream_t s, FactorParams P, const int* lvl_
     int occ = 0;
     ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
     ILUB_REQUIRE(occ > 0, ILUB_ERR_CUDA, "level-loop factorisation kernel does not fit on an SM");
-    const int grid = std::min(occ, 2) * sm_count;  // (measured: two CTAs per SM beat one; the level time is row latency, not the barrier)
+    int grid = std::min(occ, 2) * sm_count;  // (measured: two CTAs per SM beat one; the level time is row latency, not the barrier)
+    // deep narrow DAGs (a handful of rows per level): every CTA that joins the barrier makes the level longer and only
+    // a few row groups have work -- the grid is sized to twice an average level (irregular power-law matrix, n = 10^6,
+    // 9 rows per level: ONE CTA, whose barrier is a __syncthreads and an uncontended atomic)
+    const int64_t avg = (nrows + nlevels - 1) / std::max(1, nlevels);
+    const int ng = block / G;
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (2 * avg + ng - 1) / ng));
     void* args[] = {(void*)&P, (void*)&lvl_ptr, (void*)&nlevels, (void*)&barrier};
     ILUB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));
 }
 
 template <bool ICHOL>
 void launch_levels(int G, bool exact, cudaStream_t s, const FactorParams& P, const int* lvl_ptr, int nlevels,
-                   unsigned* barrier, int sm_count) {
+                   unsigned* barrier, int sm_count, int64_t nrows) {
     switch (G) {
-        case 4: launch_levels_g<4, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count); break;
-        case 8: launch_levels_g<8, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count); break;
-        case 16: launch_levels_g<16, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count); break;
-        default: launch_levels_g<32, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count); break;
+        case 4: launch_levels_g<4, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count, nrows); break;
+        case 8: launch_levels_g<8, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count, nrows); break;
+        case 16: launch_levels_g<16, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count, nrows); break;
+        default: launch_levels_g<32, ICHOL>(exact, s, P, lvl_ptr, nlevels, barrier, sm_count, nrows); break;
     }
 }
 
@@ -590,9 +596,9 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
         P.lvl_rows = T.lvl_rows.p;
         P.lvl_begin = P.lvl_end = 0;
         if (ichol)
-            launch_levels<true>(G, exact, s, P, T.lvl_ptr.p, T.nlevels, h->fbarrier.p, h->sm_count);
+            launch_levels<true>(G, exact, s, P, T.lvl_ptr.p, T.nlevels, h->fbarrier.p, h->sm_count, h->n);
         else
-            launch_levels<false>(G, exact, s, P, T.lvl_ptr.p, T.nlevels, h->fbarrier.p, h->sm_count);
+            launch_levels<false>(G, exact, s, P, T.lvl_ptr.p, T.nlevels, h->fbarrier.p, h->sm_count, h->n);
         h->launches++;
     } else if (algo == 2) {
         if (h->fflag.n < (size_t)h->n) {
