@@ -294,7 +294,7 @@ def run_extras(args, ilupp, P, torch, dev, local, peak):
         by = apply_bytes(B.total_nnz, B.shape[0], ichol)
         st = B.stats
         return {"apply_ms": ms, "GBs": by / (ms * 1e-3) / 1e9, "frac_hbm_peak": by / (ms * 1e-3) / 1e9 / peak,
-                "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels", 7: "k_trsv_level_packed (one launch per level, programmatic dependent launch)"}.get(st["part_mode"], "k_trsv_syncfree"),
+                "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels", 7: "k_trsv_level_packed (one launch per level, programmatic dependent launch)", 8: "k_trsv_block"}.get(st["part_mode"], "k_trsv_syncfree"),
                 "levels": list(st["levels"][:2]),
                 "apply_relerr_vs_oracle": float(np.abs(y - yref).max() / np.abs(yref).max()),
                 "factor_ms": dict(zip(("symbolic", "numeric", "pack", "total"), B.timings_ms))}
@@ -569,7 +569,7 @@ def run_ours(args):
                           "first_creation": {"symbolic": first_sym_ms, "create_wall_incl_h2d": first_create_wall_ms},
                           "numeric_schedule": ("stencil path: pivot recurrence on the line-systolic kernel" if not args.exact else
                                                "level loop (one cooperative launch, grid barrier per level), rows staged in shared memory")},
-            "roofline": {"bound": "hbm", "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels", 7: "k_trsv_level_packed"}.get(B.stats["part_mode"], "k_trsv_syncfree"), "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels", 7: "k_trsv_level_packed", 8: "k_trsv_block"}.get(B.stats["part_mode"], "k_trsv_syncfree"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": by / 2.0, "avg_launch_ms": kernel_ms,
                          "second_bound": "dependency critical path: %d levels per solve" % B.stats["levels"][0]},

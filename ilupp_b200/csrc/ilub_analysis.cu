@@ -63,7 +63,8 @@ const OptionField kOptionFields[] = {
     {"plane_wpc", &Options::plane_wpc},
     {"plane_npc", &Options::plane_npc},
     {"levels_cluster", &Options::levels_cluster},
-    {"sys_pdl", &Options::sys_pdl}};
+    {"sys_pdl", &Options::sys_pdl},
+    {"deep_block", &Options::deep_block}};
 }  // namespace
 
 Options& options() { return tl_active_options ? *tl_active_options : g_options; }
@@ -953,7 +954,12 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         T.nlevels = hctr[1];
     }
     T.built = true;
-    if (!sys_ok && deep_wanted(h, slot)) {
+    if (!sys_ok && block_wanted(h, slot)) {
+        DebugTimer t("  block-sequential layout", s);
+        analyse_block(h, slot, s);
+        T.part_mode = 8;
+        T.nparts = 1;
+    } else if (!sys_ok && deep_wanted(h, slot)) {
         DebugTimer t("  level-loop layout", s);
         analyse_deep(h, slot, s);
         T.part_mode = 5;
@@ -1160,6 +1166,7 @@ void pack_solve_values(ilub_handle* h, int slot, cudaStream_t s) {
     if (!T.built) return;
     if (T.sys.built) pack_systolic(h, slot, s);
     if (T.deep.built) pack_deep(h, slot, s);
+    if (T.blk.built) pack_block(h, slot, s);
     if (T.lev.built) {
         if (T.lev.nent > 0)
             k_pack_values<<<blocks_for(T.lev.nent, 256), 256, 0, s>>>(T.lev.nent, T.lev.srcpos.p, h->lu.p, T.lev.val.p);

@@ -1,0 +1,505 @@
+// Block-sequential sparse triangular solve for DEEP, NARROW, BAND-LOCAL dependency DAGs (BASELINE config 4: an irregular
+// matrix whose solves have ~10^5 levels of ~9 rows, half of every row's dependencies within 64 rows of the diagonal) --
+// replaces matrix_sparse::triangular_solve (sparse_implementation.h:4040-4087) for such matrices in the fast arithmetic
+// mode; `exact` keeps the level loop of ilub_deep.cu, which reproduces the reference's accumulation order bit for bit.
+//
+// The level loop (ilub_deep.cu) pays one CTA barrier plus shared-memory round trips per LEVEL: 0.79 us x 113,837 levels.
+// Here the rows are taken in their natural solve order in blocks of 32 consecutive rows, one row per lane of ONE compute
+// warp, and nothing inside a block synchronises across warps:
+//   * dependencies older than W = 512 rows ("far": the random long-range entries, 9.4 of the 19 per row) are final long
+//     before the block is reached: stager warps, 11 blocks ahead of the compute warp, gather them from the solution vector
+//     through L2 and reduce them into r_i = b_i / d_i - sum c_ij x_j, so they never touch the critical path;
+//   * dependencies in the last W rows but in an earlier block ("recent") are a gather from a shared-memory ring of the
+//     most recent 1024 solved values;
+//   * dependencies inside the block ("local") form a tiny triangular system: x is held one value per lane and refined by
+//     Jacobi sweeps x_i <- r_i - sum_local c_ij x_j with the x_j exchanged by warp shuffles; after s sweeps every row whose
+//     local dependency chain has at most s links is exact, so depth(block) sweeps -- 3 to 6 for this matrix, precomputed
+//     per block -- solve it exactly (same operations as forward substitution, no iteration error).
+// The critical path is therefore ~n / 32 blocks of (ring gather + depth x (shuffle + FMA) rounds) instead of ~n / 9 levels
+// of (barrier + shared-memory round trips).  Long rows (more near entries than a lane handles in registers) are rare and
+// are reduced cooperatively by the whole warp.  Coefficients are pre-divided by the diagonal; the result differs from the
+// reference's operation order by rounding only (tests hold it to 1e-12).
+#include <algorithm>
+#include <cstdio>
+
+#include <cub/cub.cuh>
+
+#include "ilub_common.cuh"
+#include "ilub_ptx.cuh"
+
+namespace ilub {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kBlk = 32;           // rows per block = lanes of the compute warp
+constexpr int kWin = 512;          // rows of history a "recent" dependency may reach back (older ones are "far")
+constexpr int kRing = 1024;        // shared-memory ring of solved values (>= kWin + 2 * kBlk, power of two)
+constexpr int kSlots = 12;         // staged blocks in flight: the stagers run up to kSlots - 1 blocks ahead
+constexpr int kStagers = 11;       // stager warps
+constexpr int kSlotCap = 640;      // near entries of one block staged in shared memory (more: read from global)
+constexpr int kRegLoc = 8;         // local entries a lane keeps in registers (more: the row is "long")
+constexpr int kRegRec = 32;        // recent entries a lane gathers itself (more: the row is "long")
+
+inline int blocks_for(int64_t work, int threads) { return (int)((work + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------ analysis
+// solve position of a row / row of a solve position: q = backward ? n - 1 - row : row
+__device__ __forceinline__ int mirror(int backward, int n, int v) { return backward ? n - 1 - v : v; }
+
+// per solve position: how many far / recent / local entries
+__global__ void k_blk_count(int n, SrcDev S, int* __restrict__ cf, int* __restrict__ cr, int* __restrict__ cl) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int row = mirror(S.backward, n, q);
+    const int b0 = (q / kBlk) * kBlk;
+    int f = 0, r = 0, l = 0;
+    for (int e = src_beg(S, row); e < src_end(S, row); ++e) {
+        const int pd = mirror(S.backward, n, S.dep_idx[e]);
+        if (pd >= b0) ++l;
+        else if (pd >= b0 - kWin) ++r;
+        else ++f;
+    }
+    cf[q] = f;
+    cr[q] = r;
+    cl[q] = l;
+}
+__global__ void k_blk_sum(int n, const int* __restrict__ a, const int* __restrict__ b, int* __restrict__ c) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) c[q] = a[q] + b[q];
+}
+// entries in place: far list; near list = recent entries, then local entries
+__global__ void k_blk_fill(int n, SrcDev S, const int* __restrict__ fptr, const int* __restrict__ nptr,
+                           const int* __restrict__ cr, int* __restrict__ fpos, int* __restrict__ fsrc,
+                           int* __restrict__ npos, int* __restrict__ nsrc, int* __restrict__ dsrc) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int row = mirror(S.backward, n, q);
+    const int b0 = (q / kBlk) * kBlk;
+    int pf = fptr[q], pr = nptr[q], pl = nptr[q] + cr[q];
+    for (int e = src_beg(S, row); e < src_end(S, row); ++e) {
+        const int pd = mirror(S.backward, n, S.dep_idx[e]);
+        const int vp = S.val_pos ? S.val_pos[e] : e;
+        if (pd >= b0) {
+            npos[pl] = pd;
+            nsrc[pl++] = vp;
+        } else if (pd >= b0 - kWin) {
+            npos[pr] = pd;
+            nsrc[pr++] = vp;
+        } else {
+            fpos[pf] = pd;
+            fsrc[pf++] = vp;
+        }
+    }
+    dsrc[q] = S.diag_pos ? S.diag_pos[row] : -1;
+}
+// per block: depth of the local dependency DAG (sweeps needed), widest recent / local list among its regular rows, and the
+// mask of "long" rows (handled cooperatively).  One warp per block.
+__global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, const int* __restrict__ cr,
+                           const int* __restrict__ npos, int4* __restrict__ bmeta) {
+    const int K = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (K >= nblocks) return;
+    const int q = K * kBlk + lane;
+    const bool live = q < n;
+    const int nb = live ? nptr[q] : 0, ne = live ? nptr[q + 1] : 0;
+    const int nrec = live ? cr[q] : 0, nloc = ne - nb - nrec;
+    const bool islong = nloc > kRegLoc || nrec > kRegRec;
+    int ll = 0;
+    for (int it = 0; it < kBlk; ++it) {  // local levels by relaxation: at most 31 rounds
+        int nl = 0;
+        for (int t = 0; t < kBlk - 1; ++t) {  // (uniform trip count: the shuffles below need every lane)
+            const bool has = t < nloc;
+            const int src = has ? npos[nb + nrec + t] - K * kBlk : 0;
+            const int v = __shfl_sync(FULL, ll, src);
+            if (has) nl = max(nl, v + 1);
+        }
+        const bool changed = nl != ll;
+        ll = nl;
+        if (!__any_sync(FULL, changed)) break;
+    }
+    const int depth = __reduce_max_sync(FULL, ll);
+    const int maxrec = __reduce_max_sync(FULL, islong ? 0 : nrec);
+    const int maxloc = __reduce_max_sync(FULL, islong ? 0 : nloc);
+    const unsigned lmask = __ballot_sync(FULL, islong);
+    if (lane == 0) bmeta[K] = make_int4(depth, maxrec, maxloc, (int)lmask);
+}
+// coefficient values in the layout's order, pre-divided by the row's diagonal
+__global__ void k_blk_pack(int n, const int* __restrict__ fptr, const int* __restrict__ nptr, const int* __restrict__ fsrc,
+                           const int* __restrict__ nsrc, const int* __restrict__ dsrc, const double* __restrict__ lu,
+                           double* __restrict__ fval, double* __restrict__ nval, double* __restrict__ rdiag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = (int)(t >> 3), gl = (int)(t & 7);
+    if (q >= n) return;
+    const double dinv = dsrc[q] >= 0 ? 1.0 / lu[dsrc[q]] : 1.0;
+    if (gl == 0) rdiag[q] = dinv;
+    for (int e = fptr[q] + gl; e < fptr[q + 1]; e += 8) fval[e] = lu[fsrc[e]] * dinv;
+    for (int e = nptr[q] + gl; e < nptr[q + 1]; e += 8) nval[e] = lu[nsrc[e]] * dinv;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct BlockParams {
+    int n, nblocks, backward;
+    const int* fptr;
+    const int* fpos;
+    const double* fval;
+    const int* nptr;
+    const int* cr;  // recent entries per position (the rest of its near list is local)
+    const int* npos;
+    const double* nval;
+    const double* rdiag;
+    const int4* bmeta;
+    double* x;  // right-hand side in, solution out (natural row order)
+    int* status;
+    unsigned spin_iters;
+    int trace;  // debug (option trace): the compute warp prints where its cycles went
+};
+
+struct BlockSlot {
+    double r[kBlk];            // b_i / d_i minus the far dependencies
+    double nval[kSlotCap];     // near entries of the block (all rows, concatenated)
+    int npos[kSlotCap];
+    int off[kBlk];             // first near entry of every row inside the slot (or inside the global arrays: big blocks)
+    int nrec[kBlk], nloc[kBlk];
+    int4 meta;                 // {depth, widest recent list, widest local list, mask of long rows} (k_blk_meta)
+    int big;                   // the block's near entries did not fit: read them from global memory
+};
+struct BlockSmem {
+    double ring[kRing];
+    double xs[kBlk];           // the block's current values (cooperative long rows read them here)
+    BlockSlot slot[kSlots];
+    int staged[kSlots];        // block number + 1 whose data the slot holds
+    int progress;              // blocks completed by the compute warp
+};
+
+#define BLK_SPIN(spins, code)                                            \
+    if ((++(spins) & 0x3ffu) == 0) {                                     \
+        if ((spins) >= P.spin_iters || *(volatile int*)P.status != 0) {   \
+            atomicCAS(P.status, 0, code);                                \
+            return;                                                      \
+        }                                                                \
+    }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- stager: far dependencies + near lists of block K
+__device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, int w, int lane) {
+    unsigned spins = 0;
+    for (int K = w; K < P.nblocks; K += kStagers) {
+        BlockSlot& L = M.slot[K % kSlots];
+        // the slot is free once block K - kSlots is done; then every far dependency (older than kWin rows) is final too
+        while (*(volatile int*)&M.progress < K - kSlots + 1) {
+            __nanosleep(100);
+            BLK_SPIN(spins, 401)
+        }
+        fence_acq_rel_cta();
+        const int q = K * kBlk + lane;
+        const bool live = q < P.n;
+        const int row = live ? (P.backward ? P.n - 1 - q : q) : 0;
+        const int fb = live ? __ldg(P.fptr + q) : 0, fe = live ? __ldg(P.fptr + q + 1) : 0;
+        double r = live ? P.x[row] * __ldg(P.rdiag + q) : 0.0;
+        const bool flong = fe - fb > 64;
+        if (!flong) {
+            for (int e0 = fb; e0 < fe; e0 += 8) {
+                double c[8], v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    c[u] = 0.0;
+                    v[u] = 0.0;
+                    if (e0 + u < fe) {
+                        const int pd = __ldg(P.fpos + e0 + u);
+                        c[u] = __ldg(P.fval + e0 + u);
+                        v[u] = __ldcg(P.x + (P.backward ? P.n - 1 - pd : pd));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r = fma(-c[u], v[u], r);
+            }
+        }
+        // hub rows: the whole warp strides over the row's far list
+        unsigned fm = __ballot_sync(FULL, flong);
+        while (fm) {
+            const int src = __ffs(fm) - 1;
+            fm &= fm - 1;
+            const int b = __shfl_sync(FULL, fb, src), e = __shfl_sync(FULL, fe, src);
+            double part = 0.0;
+            for (int t = b + lane; t < e; t += 32) {
+                const int pd = __ldg(P.fpos + t);
+                part = fma(__ldg(P.fval + t), __ldcg(P.x + (P.backward ? P.n - 1 - pd : pd)), part);
+            }
+            part = warp_sum(part);
+            if (lane == src) r -= part;
+        }
+        // near lists
+        const int nb = live ? __ldg(P.nptr + q) : 0, ne = live ? __ldg(P.nptr + q + 1) : 0;
+        const int nb0 = __shfl_sync(FULL, nb, 0);
+        const int q_last = min(P.n, K * kBlk + kBlk);
+        const int ne_all = __ldg(P.nptr + q_last);
+        const int total = ne_all - nb0;
+        const bool big = total > kSlotCap;
+        if (!big)
+            for (int t = lane; t < total; t += 32) {
+                L.npos[t] = __ldg(P.npos + nb0 + t);
+                L.nval[t] = __ldg(P.nval + nb0 + t);
+            }
+        const int nrec = live ? __ldg(P.cr + q) : 0;
+        L.r[lane] = r;
+        L.off[lane] = big ? nb : nb - nb0;
+        L.nrec[lane] = nrec;
+        L.nloc[lane] = ne - nb - nrec;
+        if (lane == 0) {
+            L.big = big ? 1 : 0;
+            L.meta = __ldg(P.bmeta + K);
+        }
+        __syncwarp();
+        fence_acq_rel_cta();
+        if (lane == 0) *(volatile int*)&M.staged[K % kSlots] = K + 1;
+    }
+}
+
+// ---------------------------------------------------------------- compute warp: the blocks, one after the other
+// One block.  BIG = the block's near entries live in global memory (they did not fit the slot); NL = local entries per
+// lane held in registers (4 or 8: every lane runs NL shuffles per sweep, absent entries carry coefficient 0).
+// A lone warp is bound by the latency of whatever it issues in sequence, so every phase requests all its operands first
+// and the loops have compile-time trip counts (no branch, no divergence check in front of the shuffles).
+template <bool BIG, int NL>
+__device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, BlockSlot& L, int K, int lane, int depth,
+                                           int maxrec, unsigned lmask, long long* tt) {
+    long long c0 = tt ? clock64() : 0;
+    const int* np = BIG ? P.npos : L.npos;
+    const double* nv = BIG ? P.nval : L.nval;
+    const int off = L.off[lane];
+    const int nrec = L.nrec[lane], nloc = L.nloc[lane];
+    const bool islong = (lmask >> lane) & 1u;
+    double r = L.r[lane];
+    const int b0 = K * kBlk;
+    // local entries first: their loads overlap with the recent gather below
+    int lsrc[NL];
+    double lco[NL];
+#pragma unroll
+    for (int t = 0; t < NL; ++t) {
+        const bool has = !islong && t < nloc;
+        lsrc[t] = has ? np[off + nrec + t] - b0 : lane;
+        lco[t] = has ? nv[off + nrec + t] : 0.0;
+    }
+    // ---- recent dependencies: the ring, eight entries per round (all indices, then all values, then the arithmetic)
+    for (int t0 = 0; t0 < maxrec; t0 += 8) {
+        int pp[8];
+        double cc[8], vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool has = !islong && t0 + u < nrec;
+            pp[u] = has ? np[off + t0 + u] : 0;
+            cc[u] = has ? nv[off + t0 + u] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) vv[u] = M.ring[pp[u] & (kRing - 1)];
+        double r1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+            r = fma(-cc[u], vv[u], r);
+            r1 = fma(-cc[u + 1], vv[u + 1], r1);
+        }
+        r += r1;
+    }
+    if (tt) { const long long c = clock64(); tt[0] += c - c0; c0 = c; }
+    unsigned lm = lmask;
+    while (lm) {  // long rows: the warp strides over the row's recent list
+        const int src = __ffs(lm) - 1;
+        lm &= lm - 1;
+        const int o = __shfl_sync(FULL, off, src), c = __shfl_sync(FULL, nrec, src);
+        double part = 0.0;
+        for (int t = lane; t < c; t += 32) part = fma(nv[o + t], M.ring[np[o + t] & (kRing - 1)], part);
+        part = warp_sum(part);
+        if (lane == src) r -= part;
+    }
+    if (tt) { const long long c = clock64(); tt[1] += c - c0; c0 = c; }
+    // ---- local dependencies: Jacobi sweeps over the block, values exchanged by shuffles
+    double x = r;
+    for (int s = 0; s < depth; ++s) {
+        double acc = r, acc1 = 0.0;
+        if (lmask) {  // (rare) long rows take their local sum from the values in shared memory
+            M.xs[lane] = x;
+            __syncwarp();
+            unsigned l2 = lmask;
+            while (l2) {
+                const int src = __ffs(l2) - 1;
+                l2 &= l2 - 1;
+                const int o = __shfl_sync(FULL, off + nrec, src), c = __shfl_sync(FULL, nloc, src);
+                double part = 0.0;
+                for (int t = lane; t < c; t += 32) part = fma(nv[o + t], M.xs[np[o + t] - b0], part);
+                part = warp_sum(part);
+                if (lane == src) acc -= part;
+            }
+            __syncwarp();
+        }
+        double v[NL];
+#pragma unroll
+        for (int t = 0; t < NL; ++t) v[t] = __shfl_sync(FULL, x, lsrc[t]);
+#pragma unroll
+        for (int t = 0; t < NL; t += 2) {
+            acc = fma(-lco[t], v[t], acc);
+            acc1 = fma(-lco[t + 1], v[t + 1], acc1);
+        }
+        x = acc + acc1;
+    }
+    if (tt) { const long long c = clock64(); tt[2] += c - c0; }
+    return x;
+}
+
+__device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, int lane) {
+    unsigned spins = 0;
+    long long tt[3] = {0, 0, 0};
+    long long* ttp = P.trace ? tt : nullptr;
+    long long t_wait = 0, t_body = 0, t_pub = 0, sum_depth = 0, n_long = 0, sum_maxrec = 0, sum_maxloc = 0, n_big = 0;
+    for (int K = 0; K < P.nblocks; ++K) {
+        BlockSlot& L = M.slot[K % kSlots];
+        long long c0 = P.trace ? clock64() : 0;
+        while (*(volatile int*)&M.staged[K % kSlots] != K + 1) BLK_SPIN(spins, 402)
+        fence_acq_rel_cta();
+        if (P.trace) { const long long c = clock64(); t_wait += c - c0; c0 = c; }
+        const int4 bm = L.meta;
+        const int depth = bm.x, maxrec = bm.y, maxloc = bm.z;
+        const unsigned lmask = (unsigned)bm.w;
+        double x;
+        if (L.big) x = blk_body<true, 8>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
+        else if (maxloc <= 4) x = blk_body<false, 4>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
+        else x = blk_body<false, 8>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
+        if (P.trace) { const long long c = clock64(); t_body += c - c0; c0 = c; sum_depth += depth; n_long += lmask != 0; sum_maxrec += maxrec; sum_maxloc += maxloc; n_big += L.big; }
+        // ---- publish
+        const int q = K * kBlk + lane;
+        M.ring[q & (kRing - 1)] = x;
+        if (q < P.n) __stcg(P.x + (P.backward ? P.n - 1 - q : q), x);
+        __syncwarp();
+        fence_acq_rel_cta();
+        if (lane == 0) *(volatile int*)&M.progress = K + 1;
+        if (P.trace) { const long long c = clock64(); t_pub += c - c0; }
+    }
+    if (P.trace && lane == 0) {
+        const double nb = (double)P.nblocks;
+        printf("  body: loads + recent %.0f, long recent %.0f, sweeps %.0f\n", tt[0] / nb, tt[1] / nb, tt[2] / nb);
+        printf("block solve: %d blocks | cycles per block: wait %.0f body %.0f publish %.0f | depth %.2f maxrec %.2f maxloc %.2f, blocks with long rows %.1f %%, big blocks %.2f %%\n",
+               P.nblocks, t_wait / nb, t_body / nb, t_pub / nb, sum_depth / nb, sum_maxrec / nb, sum_maxloc / nb, 100.0 * n_long / nb, 100.0 * n_big / nb);
+    }
+}
+
+__global__ void __launch_bounds__((1 + kStagers) * 32, 1) k_trsv_block(const BlockParams P) {
+    extern __shared__ __align__(16) unsigned char blk_smem_raw[];
+    BlockSmem& M = *reinterpret_cast<BlockSmem*>(blk_smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = threadIdx.x; t < kRing; t += blockDim.x) M.ring[t] = 0.0;
+    if (threadIdx.x < kSlots) M.staged[threadIdx.x] = 0;
+    if (threadIdx.x == 0) M.progress = 0;
+    __syncthreads();
+    if (warp == 0) blk_compute(P, M, lane);
+    else blk_stager(P, M, warp - 1, lane);
+}
+
+}  // namespace
+
+// ================================================================================================== host
+bool block_wanted(const ilub_handle* h, int slot) {
+    const Options& opt = options();
+    if (opt.exact != 0 || opt.deep_block == 0) return false;
+    return deep_wanted(h, slot) && h->nsys == 1;
+}
+
+void analyse_block(ilub_handle* h, int slot, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    BlockSolve& B = T.blk;
+    if (B.built) return;
+    const int n = h->n;
+    const SolveSource src = solve_source(h, slot);
+    const SrcDev S = to_dev(src);
+    DevBuf<int> cf, cl;
+    cf.alloc((size_t)n + 1);
+    cl.alloc((size_t)n + 1);
+    B.cr.alloc((size_t)n + 1);
+    DevBuf<int> cn;
+    cn.alloc((size_t)n + 1);
+    k_blk_count<<<blocks_for(n, 256), 256, 0, s>>>(n, S, cf.p, B.cr.p, cl.p);
+    B.fptr.alloc((size_t)n + 1);
+    B.nptr.alloc((size_t)n + 1);
+    ILUB_CUDA(cudaMemsetAsync(cf.p + n, 0, sizeof(int), s));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, cf.p, B.fptr.p, n + 1, s);
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(tb);
+    ILUB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cf.p, B.fptr.p, n + 1, s));
+    k_blk_sum<<<blocks_for(n, 256), 256, 0, s>>>(n, B.cr.p, cl.p, cn.p);
+    ILUB_CUDA(cudaMemsetAsync(cn.p + n, 0, sizeof(int), s));
+    size_t tb2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, cn.p, B.nptr.p, n + 1, s);
+    if (tb2 > tmp.n) tmp.alloc(tb2);
+    size_t tbb = tmp.n;
+    ILUB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tbb, cn.p, B.nptr.p, n + 1, s));
+    int ends[2] = {0, 0};
+    ILUB_CUDA(cudaMemcpyAsync(&ends[0], B.fptr.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaMemcpyAsync(&ends[1], B.nptr.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    B.nfar = ends[0];
+    B.nnear = ends[1];
+    B.fpos.alloc((size_t)std::max(1, B.nfar));
+    B.fsrc.alloc((size_t)std::max(1, B.nfar));
+    B.fval.alloc((size_t)std::max(1, B.nfar));
+    B.npos.alloc((size_t)std::max(1, B.nnear));
+    B.nsrc.alloc((size_t)std::max(1, B.nnear));
+    B.nval.alloc((size_t)std::max(1, B.nnear));
+    B.dsrc.alloc((size_t)n);
+    B.rdiag.alloc((size_t)n);
+    k_blk_fill<<<blocks_for(n, 256), 256, 0, s>>>(n, S, B.fptr.p, B.nptr.p, B.cr.p, B.fpos.p, B.fsrc.p, B.npos.p, B.nsrc.p,
+                                                 B.dsrc.p);
+    B.nblocks = (n + kBlk - 1) / kBlk;
+    B.bmeta.alloc((size_t)B.nblocks);
+    k_blk_meta<<<blocks_for((int64_t)B.nblocks * 32, 256), 256, 0, s>>>(n, B.nblocks, B.nptr.p, B.cr.p, B.npos.p, B.bmeta.p);
+    h->launches += 6;
+    ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here
+    B.packed = false;
+    B.built = true;
+}
+
+void pack_block(ilub_handle* h, int slot, cudaStream_t s) {
+    BlockSolve& B = h->solve[slot].blk;
+    if (!B.built) return;
+    k_blk_pack<<<blocks_for((int64_t)h->n * 8, 256), 256, 0, s>>>(h->n, B.fptr.p, B.nptr.p, B.fsrc.p, B.nsrc.p, B.dsrc.p, h->lu.p,
+                                                                 B.fval.p, B.nval.p, B.rdiag.p);
+    h->launches++;
+    B.packed = true;
+}
+
+void run_block(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    BlockSolve& B = T.blk;
+    if (!B.packed) pack_block(h, slot, s);
+    const size_t smem = sizeof(BlockSmem);
+    static thread_local unsigned attr_set[1] = {0};
+    if (first_use_on_this_device(attr_set, 0))
+        ILUB_CUDA(cudaFuncSetAttribute(k_trsv_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BlockParams P;
+    P.n = h->n;
+    P.nblocks = B.nblocks;
+    P.backward = T.backward ? 1 : 0;
+    P.fptr = B.fptr.p;
+    P.fpos = B.fpos.p;
+    P.fval = B.fval.p;
+    P.nptr = B.nptr.p;
+    P.cr = B.cr.p;
+    P.npos = B.npos.p;
+    P.nval = B.nval.p;
+    P.rdiag = B.rdiag.p;
+    P.bmeta = B.bmeta.p;
+    P.status = h->status.p;
+    P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 20, (long long)options().spin_limit_ms * h->clock_khz / 32));
+    P.trace = options().trace != 0 ? 1 : 0;
+    for (int c = 0; c < nrhs; ++c) {
+        P.x = x + (int64_t)c * ldx;
+        k_trsv_block<<<1, (1 + kStagers) * 32, smem, s>>>(P);
+        h->launches++;
+    }
+    ILUB_CUDA(cudaGetLastError());
+}
+
+}  // namespace ilub

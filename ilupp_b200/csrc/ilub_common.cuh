@@ -137,6 +137,7 @@ struct Options {
     int64_t tile_debug = 0;     // tile-systolic: debug switches (timing experiments only)
     int64_t tile_warps = 0;     // tile-systolic: compute warps per CTA (0 = auto: 4, or 6 when the grid needs them)
     int64_t zero_copy = 0;      // apply() on a pinned host vector: the solve kernels read / write it directly over PCIe (1: both ways, 2: out only, 3: in only). Measured SLOWER than staged copies (64-byte PCIe requests): 0.91-1.06 ms against 0.79 ms at 128^3, so off
+    int64_t deep_block = 1;     // deep narrow DAGs, fast arithmetic: block-sequential kernel (ilub_block.cu) instead of the level loop (0 = level loop)
     int64_t sys_plane = 1;      // plane-per-warp kernel for grids without a plane-to-plane dependency: 0 off, 1 auto, 2 whenever applicable
     int64_t plane_r = 1;        // plane-per-warp: right-hand sides per warp (1 or 2)
     int64_t levels_cluster = 1; // cooperative level loop: one thread-block cluster with the hardware barrier when the levels fit (0: always the grid barrier)
@@ -222,6 +223,20 @@ struct DeepSolve {
     DevBuf<double> bs, xs;  // [n] right-hand side / solution in solve order
 };
 
+// Block-sequential layout (ilub_block.cu: deep, narrow, band-local DAGs in the fast arithmetic mode): rows in their
+// natural solve order in blocks of 32; per row a "far" list (dependencies older than 512 rows, reduced ahead of time by
+// stager warps) and a "near" list (recent entries, then the entries inside the row's own block)
+struct BlockSolve {
+    bool built = false, packed = false;
+    int nblocks = 0, nfar = 0, nnear = 0;
+    DevBuf<int> fptr, fpos, fsrc;   // far lists: [n + 1], dependency position, coefficient source in lu
+    DevBuf<int> nptr, npos, nsrc;   // near lists
+    DevBuf<int> cr;                 // [n] recent entries per row (the rest of its near list is local)
+    DevBuf<int> dsrc;               // [n] diagonal source in lu (-1: unit)
+    DevBuf<double> fval, nval, rdiag;
+    DevBuf<int4> bmeta;             // [nblocks] {depth of the local DAG, widest recent list, widest local list, long-row mask}
+};
+
 // One triangular solve packed in solve order (see DESIGN.md "data layout in HBM").
 struct TriSolve {
     bool built = false;
@@ -282,6 +297,7 @@ struct TriSolve {
     } lev;
     SysSolve sys;                 // line-systolic layout (structured grids), preferred when built
     DeepSolve deep;               // level-loop layout (deep narrow DAGs)
+    BlockSolve blk;               // block-sequential layout (deep narrow band-local DAGs, fast arithmetic)
 };
 
 // Transposed pattern of the strict lower or strict upper triangle (for scatter-form solves).
@@ -411,6 +427,10 @@ void pack_solve_values(ilub_handle* h, int which, cudaStream_t s);        // (re
 void build_level_sets(ilub_handle* h, int which, cudaStream_t s);
 void build_level_packed(ilub_handle* h, int slot, cudaStream_t s);  // level-packed layout of a few-wide-levels solve
 bool deep_wanted(const ilub_handle* h, int slot);
+bool block_wanted(const ilub_handle* h, int slot);   // block-sequential solve (ilub_block.cu)
+void analyse_block(ilub_handle* h, int slot, cudaStream_t s);
+void pack_block(ilub_handle* h, int slot, cudaStream_t s);
+void run_block(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s);
 bool levels_wanted(const ilub_handle* h, int slot);   // cooperative level loop (ilub_trsv.cu)
 bool few_levels_wanted(const ilub_handle* h, int slot);  // one launch per level (ilub_trsv.cu)
 void analyse_deep(ilub_handle* h, int slot, cudaStream_t s);

@@ -51,9 +51,16 @@ inline int blocks_for(int64_t work, int threads) { return (int)((work + threads 
 
 // ------------------------------------------------------------------------------------------------ analysis
 // distinct |row - dependency| offsets of the rows [0, n1): list[0..3] (0 = empty), list[4] = overflow flag
-__global__ void k_sys_offsets(int n1, SrcDev S, int* list) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n1) return;
+// (a SAMPLE of the rows -- `nruns` runs of 256 consecutive rows spread over the system, so that every grid direction
+// varies inside the sample: k_sys_map below verifies every entry of every row against the offsets found here, so an offset
+// that only unsampled rows have makes the map fail -- the same outcome as finding it here)
+__global__ void k_sys_offsets(int n1, int nruns, SrcDev S, int* list) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int run = t >> 8;
+    if (run >= nruns) return;
+    const int64_t r64 = (int64_t)run * (n1 / nruns) + (t & 255);
+    if (r64 >= n1) return;
+    const int r = (int)r64;
     // what is on the list already (after the first few rows: everything) is recognised without touching it again
     int known[4];
 #pragma unroll
@@ -830,7 +837,8 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
     DevBuf<int> dl;
     dl.alloc(8);
     ILUB_CUDA(cudaMemsetAsync(dl.p, 0, sizeof(int) * 8, s));
-    k_sys_offsets<<<blocks_for(n1, 256), 256, 0, s>>>(n1, S, dl.p);
+    const int nruns = std::max(1, std::min(32, n1 / 256));
+    k_sys_offsets<<<nruns, 256, 0, s>>>(n1, nruns, S, dl.p);
     h->launches++;
     int hl[8];
     ILUB_CUDA(cudaMemcpyAsync(hl, dl.p, sizeof(hl), cudaMemcpyDeviceToHost, s));

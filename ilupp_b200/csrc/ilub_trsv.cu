@@ -839,8 +839,16 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
         run_systolic(h, slot, x, ldx, nrhs, s);
         return;
     }
+    if (block_wanted(h, slot)) {
+        if (!T.blk.built) analyse_block(h, slot, s);
+        run_block(h, slot, x, ldx, nrhs, s);
+        return;
+    }
     if (deep_wanted(h, slot)) {
-        if (!T.deep.built) analyse_deep(h, slot, s);
+        if (!T.deep.built) {
+            analyse_deep(h, slot, s);
+            pack_deep(h, slot, s);
+        }
         run_deep(h, slot, x, ldx, nrhs, s);
         return;
     }
