@@ -13,8 +13,8 @@
 //     most recent 1024 solved values;
 //   * dependencies inside the block ("local") form a tiny triangular system: x is held one value per lane and refined by
 //     Jacobi sweeps x_i <- r_i - sum_local c_ij x_j with the x_j exchanged by warp shuffles; after s sweeps every row whose
-//     local dependency chain has at most s links is exact, so depth(block) sweeps -- 3 to 6 for this matrix, precomputed
-//     per block -- solve it exactly (same operations as forward substitution, no iteration error).
+//     local dependency chain has at most s links is exact, so depth(block) sweeps -- 4 on average for this matrix,
+//     precomputed per block -- solve it exactly (same operations as forward substitution, no iteration error).
 // The critical path is therefore ~n / 32 blocks of (ring gather + depth x (shuffle + FMA) rounds) instead of ~n / 9 levels
 // of (barrier + shared-memory round trips).  Long rows (more near entries than a lane handles in registers) are rare and
 // are reduced cooperatively by the whole warp.  Coefficients are pre-divided by the diagonal; the result differs from the
@@ -117,11 +117,20 @@ __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, con
         ll = nl;
         if (!__any_sync(FULL, changed)) break;
     }
-    const int depth = __reduce_max_sync(FULL, ll);
+    const int depth_all = __reduce_max_sync(FULL, ll);
+    const int depth_reg = __reduce_max_sync(FULL, islong ? 0 : ll);
+    // are the long rows leaves of the block's local DAG (no local entry of any row points at them)?  Then their local sum
+    // is only needed once, after the last sweep
+    unsigned pointed = 0;
+    for (int t = 0; t < kBlk - 1; ++t)
+        if (t < nloc) pointed |= 1u << (npos[nb + nrec + t] - K * kBlk);
+    pointed = __reduce_or_sync(FULL, pointed);
     const int maxrec = __reduce_max_sync(FULL, islong ? 0 : nrec);
     const int maxloc = __reduce_max_sync(FULL, islong ? 0 : nloc);
     const unsigned lmask = __ballot_sync(FULL, islong);
-    if (lane == 0) bmeta[K] = make_int4(depth, maxrec, maxloc, (int)lmask);
+    const int leaf = (lmask & pointed) == 0 ? 1 : 0;
+    const int depth = leaf ? depth_reg : depth_all;  // (leaves are evaluated behind the sweeps: they need none themselves)
+    if (lane == 0) bmeta[K] = make_int4(depth | (leaf << 16), maxrec, maxloc, (int)lmask);
 }
 // coefficient values in the layout's order, pre-divided by the row's diagonal
 __global__ void k_blk_pack(int n, const int* __restrict__ fptr, const int* __restrict__ nptr, const int* __restrict__ fsrc,
@@ -266,8 +275,10 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
 // A lone warp is bound by the latency of whatever it issues in sequence, so every phase requests all its operands first
 // and the loops have compile-time trip counts (no branch, no divergence check in front of the shuffles).
 template <bool BIG, int NL>
-__device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, BlockSlot& L, int K, int lane, int depth,
+__device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, BlockSlot& L, int K, int lane, int depthw,
                                            int maxrec, unsigned lmask, long long* tt) {
+    const int depth = depthw & 0xffff;
+    const bool leaf = (depthw >> 16) != 0;  // long rows are leaves of the local DAG: their local sum is taken once, at the end
     long long c0 = tt ? clock64() : 0;
     const int* np = BIG ? P.npos : L.npos;
     const double* nv = BIG ? P.nval : L.nval;
@@ -285,7 +296,8 @@ __device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, B
         lsrc[t] = has ? np[off + nrec + t] - b0 : lane;
         lco[t] = has ? nv[off + nrec + t] : 0.0;
     }
-    // ---- recent dependencies: the ring, eight entries per round (all indices, then all values, then the arithmetic)
+    // ---- recent dependencies: the ring, eight entries per round (all indices, then all values, then the arithmetic;
+    //      sixteen per round measured slower: 699 against 539 cycles per block)
     for (int t0 = 0; t0 < maxrec; t0 += 8) {
         int pp[8];
         double cc[8], vv[8];
@@ -321,7 +333,7 @@ __device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, B
     double x = r;
     for (int s = 0; s < depth; ++s) {
         double acc = r, acc1 = 0.0;
-        if (lmask) {  // (rare) long rows take their local sum from the values in shared memory
+        if (lmask && !leaf) {  // (rare) long rows take their local sum from the values in shared memory
             M.xs[lane] = x;
             __syncwarp();
             unsigned l2 = lmask;
@@ -346,6 +358,21 @@ __device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, B
         }
         x = acc + acc1;
     }
+    if (lmask && leaf) {
+        M.xs[lane] = x;
+        __syncwarp();
+        unsigned l2 = lmask;
+        while (l2) {
+            const int src = __ffs(l2) - 1;
+            l2 &= l2 - 1;
+            const int o = __shfl_sync(FULL, off + nrec, src), c = __shfl_sync(FULL, nloc, src);
+            double part = 0.0;
+            for (int t = lane; t < c; t += 32) part = fma(nv[o + t], M.xs[np[o + t] - b0], part);
+            part = warp_sum(part);
+            if (lane == src) x = r - part;
+        }
+        __syncwarp();
+    }
     if (tt) { const long long c = clock64(); tt[2] += c - c0; }
     return x;
 }
@@ -359,16 +386,18 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
         BlockSlot& L = M.slot[K % kSlots];
         long long c0 = P.trace ? clock64() : 0;
         while (*(volatile int*)&M.staged[K % kSlots] != K + 1) BLK_SPIN(spins, 402)
-        fence_acq_rel_cta();
+        fence_acq_rel_cta();  // (a volatile poll + one fence measured faster than ld.acquire polls: 125 against 185 cycles)
         if (P.trace) { const long long c = clock64(); t_wait += c - c0; c0 = c; }
         const int4 bm = L.meta;
         const int depth = bm.x, maxrec = bm.y, maxloc = bm.z;
         const unsigned lmask = (unsigned)bm.w;
         double x;
         if (L.big) x = blk_body<true, 8>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
+        else if (maxloc <= 2) x = blk_body<false, 2>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
         else if (maxloc <= 4) x = blk_body<false, 4>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
+        else if (maxloc <= 6) x = blk_body<false, 6>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
         else x = blk_body<false, 8>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
-        if (P.trace) { const long long c = clock64(); t_body += c - c0; c0 = c; sum_depth += depth; n_long += lmask != 0; sum_maxrec += maxrec; sum_maxloc += maxloc; n_big += L.big; }
+        if (P.trace) { const long long c = clock64(); t_body += c - c0; c0 = c; sum_depth += depth & 0xffff; n_long += lmask != 0; sum_maxrec += maxrec; sum_maxloc += maxloc; n_big += L.big; }
         // ---- publish
         const int q = K * kBlk + lane;
         M.ring[q & (kRing - 1)] = x;

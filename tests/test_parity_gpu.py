@@ -1131,3 +1131,38 @@ def test_write_binary_matches_reference_files_and_restores(ilupp, tmp_path):
     y = b.copy(); B.apply(y)
     z = b.copy(); R.apply(z)
     assert np.array_equal(y, z) and R.total_nnz == B.total_nnz
+
+
+def test_block_sequential_solve(ilupp):
+    """Deep, narrow, band-local DAGs in the fast arithmetic mode go through the block-sequential kernel (ilub_block.cu,
+    stats part_mode 8): all four solves against the oracle, hub rows (cooperative long-row path) and a matrix whose blocks
+    have deep local chains included; the level loop (option deep_block = 0) and the exact mode give the same answer."""
+    import scipy.sparse as sp
+    cases = [P.irregular_powerlaw(n=60000, max_len=2048, seed=7)]
+    # a banded matrix with every sub-diagonal inside a 32-row block present: local chains as deep as the block
+    n = 20000
+    rng = np.random.default_rng(3)
+    Bd = sp.diags([rng.uniform(-0.4, -0.1, n - k) for k in (1, 2, 5, 40, 700)], [-1, -2, -5, -40, -700], shape=(n, n))
+    cases.append((Bd + Bd.T * 0.5 + sp.eye(n) * 4.0).tocsr())
+    for A in cases:
+        A.sort_indices()
+        A.indices = A.indices.astype(np.int32); A.indptr = A.indptr.astype(np.int32)
+        n = A.shape[0]
+        b = P.rhs(n, 4)
+        Lo, Uo = oracle.port.ilu0(A)
+        Bf = ilupp.ILU0Preconditioner(A, options={"exact": 0})
+        assert Bf.stats["part_mode"] == 8, Bf.stats
+        Bl = ilupp.ILU0Preconditioner(A, options={"exact": 0, "deep_block": 0})
+        assert Bl.stats["part_mode"] == 5
+        for tr in (False, True):
+            yo = oracle.port.apply_lu(Lo, Uo, b, tr)
+            y = b.copy(); (Bf.apply_trans if tr else Bf.apply)(y)
+            z = b.copy(); (Bl.apply_trans if tr else Bl.apply)(z)
+            assert relerr(y, yo) <= TOL and relerr(z, yo) <= TOL
+        Bf.set_option("exact", 1)     # the exact mode keeps the level loop (the factors stay the fast-mode ones)
+        y = b.copy(); Bf.apply(y)
+        assert relerr(y, oracle.port.apply_lu(Lo, Uo, b)) <= TOL
+        Be = ilupp.ILU0Preconditioner(A, options={"exact": 1})
+        assert Be.stats["part_mode"] == 5
+        y = b.copy(); Be.apply(y)
+        assert np.array_equal(y, oracle.port.apply_lu(Lo, Uo, b))
