@@ -35,7 +35,7 @@ constexpr int kBlk = 32;           // rows per block = lanes of the compute warp
 constexpr int kWin = 512;          // rows of history a "recent" dependency may reach back (older ones are "far")
 constexpr int kRing = 1024;        // shared-memory ring of solved values (>= kWin + 2 * kBlk, power of two)
 constexpr int kSlots = 12;         // staged blocks in flight: the stagers run up to kSlots - 1 blocks ahead
-constexpr int kStagers = 11;       // stager warps
+constexpr int kStagers = 9;        // stager warps
 constexpr int kSlotCap = 640;      // near entries of one block staged in shared memory (more: read from global)
 constexpr int kRegLoc = 8;         // local entries a lane keeps in registers (more: the row is "long")
 constexpr int kRegRec = 32;        // recent entries a lane gathers itself (more: the row is "long")
@@ -415,7 +415,8 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
     }
 }
 
-__global__ void __launch_bounds__((1 + kStagers) * 32, 1) k_trsv_block(const BlockParams P) {
+constexpr int kWarps = 12;  // warp 0 computes; warps 4 and 8 (its scheduler) stay idle; the other nine stage
+__global__ void __launch_bounds__(kWarps * 32, 1) k_trsv_block(const BlockParams P) {
     extern __shared__ __align__(16) unsigned char blk_smem_raw[];
     BlockSmem& M = *reinterpret_cast<BlockSmem*>(blk_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -423,8 +424,10 @@ __global__ void __launch_bounds__((1 + kStagers) * 32, 1) k_trsv_block(const Blo
     if (threadIdx.x < kSlots) M.staged[threadIdx.x] = 0;
     if (threadIdx.x == 0) M.progress = 0;
     __syncthreads();
+    // the compute warp has its scheduler (warps 0, 4, 8) to itself: every issue slot a stager takes there is latency on
+    // the critical path
     if (warp == 0) blk_compute(P, M, lane);
-    else blk_stager(P, M, warp - 1, lane);
+    else if ((warp & 3) != 0) blk_stager(P, M, warp - 1 - (warp >> 2), lane);
 }
 
 }  // namespace
@@ -525,7 +528,7 @@ void run_block(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.trace = options().trace != 0 ? 1 : 0;
     for (int c = 0; c < nrhs; ++c) {
         P.x = x + (int64_t)c * ldx;
-        k_trsv_block<<<1, (1 + kStagers) * 32, smem, s>>>(P);
+        k_trsv_block<<<1, kWarps * 32, smem, s>>>(P);
         h->launches++;
     }
     ILUB_CUDA(cudaGetLastError());
