@@ -40,6 +40,9 @@ struct FactorParams {
     // word) for the rare rows longer than 4 * G entries -- hub rows of irregular matrices, which the slow row routines
     // would otherwise turn into milliseconds on the critical path
     int big_cap;
+    // level loop on deep narrow DAGs: the last `nprefetch` CTAs of the grid do not factorise; they run a few levels ahead
+    // of the working CTAs and pull what those levels will read into L2 (see k_factor_levels)
+    int nprefetch;
 };
 
 // first position in [b, e) with idx >= c
@@ -417,9 +420,61 @@ __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int
     const int gshift = (lane / G) * G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gshift);
     const int ng = blockDim.x / G;
-    const int64_t g = (int64_t)blockIdx.x * ng + threadIdx.x / G;
-    const int64_t gstride = (int64_t)gridDim.x * ng;
     long long t0 = 0;
+    const int nwork = (int)gridDim.x - P.nprefetch;
+    if ((int)blockIdx.x >= nwork) {
+        // ---- prefetch CTA.  On a deep narrow DAG a level is ~9 dependent memory round trips of a handful of rows, and
+        // the matrix (hundreds of MB) does not live in L2: every one of them is an HBM miss.  Nothing about WHERE a row
+        // will read is dynamic, so these warps walk the rows of the levels 2 .. 2 + kAhead ahead of the workers and
+        // touch row i itself, {diagonal position, row end} of its strictly-lower columns and the upper parts (indices,
+        // values) of those rows with prefetch.global.L2 -- a pure hint (the values are re-read coherently from L2 when
+        // they are needed), which turns the workers' misses into L2 hits.
+        constexpr int kAhead = 24, kMaxRowsPerLevel = 512;
+        const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const int pw = ((int)blockIdx.x - nwork) * nw + warp, pstride = P.nprefetch * nw;
+        int done = 0;
+        unsigned spins = 0;
+        while (true) {
+            const int cur = (int)(ld_relaxed_gpu_u32(barrier) / (unsigned)nwork);
+            if (cur >= nlevels - 1 || *(volatile int*)P.status != 0) break;
+            const int lo = max(done, cur + 2), hi = min(nlevels, cur + 2 + kAhead);
+            if (lo >= hi) {
+                __nanosleep(200);
+                if ((++spins & 0xffffu) == 0) {
+                    if (t0 == 0) t0 = clock64();
+                    if (clock64() - t0 > P.spin_limit) break;
+                }
+                continue;
+            }
+            for (int l = lo; l < hi; ++l) {
+                const int b = __ldg(lvl_ptr + l), e = min(__ldg(lvl_ptr + l + 1), b + kMaxRowsPerLevel);
+                for (int s = b + pw; s < e; s += pstride) {
+                    const int i = P.lvl_rows[s];
+                    const int p0 = P.ptr[i], dp = P.dpos[i], pe = P.ptr[i + 1];
+                    for (int t = p0 + lane * 16; t < pe; t += 32 * 16) {  // row i: 128 bytes of values per line
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.a + t));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.idx + t));
+                    }
+                    for (int t = p0 + lane; t < dp; t += 32) {  // rows k of the strictly-lower columns
+                        const int k = P.idx[t];
+                        const int dk = P.dpos[k], ek = P.ptr[k + 1];
+                        for (int q = dk; q < ek; q += 16) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lu + q));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.idx + q));
+                        }
+                        if (ek > dk) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.lu + ek - 1));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.idx + ek - 1));
+                        }
+                    }
+                }
+            }
+            done = hi;
+        }
+        return;
+    }
+    const int64_t g = (int64_t)blockIdx.x * ng + threadIdx.x / G;
+    const int64_t gstride = (int64_t)nwork * ng;
     for (int l = 0; l < nlevels; ++l) {
         const int b = __ldg(lvl_ptr + l), e = __ldg(lvl_ptr + l + 1);
         for (int64_t s = b + g; s < e; s += gstride) {
@@ -432,7 +487,7 @@ __global__ void __launch_bounds__(512) k_factor_levels(FactorParams P, const int
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(barrier, 1u);
-            const unsigned target = (unsigned)(l + 1) * gridDim.x;
+            const unsigned target = (unsigned)(l + 1) * (unsigned)nwork;
             unsigned spins = 0;
             while (ld_relaxed_gpu_u32(barrier) < target) {
                 if ((++spins & 1023u) == 0) {
@@ -467,6 +522,9 @@ void launch_levels_g(bool exact, cudaStream_t s, FactorParams P, const int* lvl_
     const int64_t avg = (nrows + nlevels - 1) / std::max(1, nlevels);
     const int ng = block / G;
     grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (2 * avg + ng - 1) / ng));
+    // ... and when that leaves most of the chip idle and the levels are many, two more CTAs prefetch ahead of the workers
+    P.nprefetch = (grid <= 4 && nlevels > 1024) ? 2 : 0;
+    grid += P.nprefetch;
     void* args[] = {(void*)&P, (void*)&lvl_ptr, (void*)&nlevels, (void*)&barrier};
     ILUB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), args, smem, s));
 }
@@ -573,6 +631,7 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
     // solve limit (one minute by default)
     P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz * 40;
     P.big_cap = 0;  // (set below, once the lanes per row are known)
+    P.nprefetch = 0;
     int G = (int)opt.factor_group;
     if (G != 4 && G != 8 && G != 16 && G != 32) {
         const double avg = (double)h->nnz / (double)h->n;
