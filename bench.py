@@ -297,7 +297,7 @@ def run_extras(args, ilupp, P, torch, dev, local, peak):
                 "kernel": {4: "k_trsv_systolic", 5: "k_trsv_deep", 6: "k_trsv_levels", 7: "k_trsv_level_packed (one launch per level, programmatic dependent launch)", 8: "k_trsv_block"}.get(st["part_mode"], "k_trsv_syncfree"),
                 "levels": list(st["levels"][:2]),
                 "apply_relerr_vs_oracle": float(np.abs(y - yref).max() / np.abs(yref).max()),
-                "factor_ms": dict(zip(("symbolic", "numeric", "pack", "total"), B.timings_ms))}
+                "factor_ms_first_creation_of_this_shape": dict(zip(("symbolic", "numeric", "pack", "total"), B.timings_ms))}
 
     # (1) exact arithmetic (the library default): reference operation order, bit for bit
     ilupp.set_option("exact", 1)
