@@ -551,6 +551,18 @@ void launch_g(bool exact, int grid, int block, cudaStream_t s, const FactorParam
         else
             ILUB_CUDA(cudaFuncSetAttribute(k_factor<G, ICHOL, SYNCFREE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
+    if (SYNCFREE) {
+        // the sync-free schedule only makes progress when every CTA is resident (rows wait for rows of other CTAs)
+        int occ = 0, dev = 0, sms = 0;
+        if (exact)
+            ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor<G, ICHOL, SYNCFREE, true>, block, smem));
+        else
+            ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor<G, ICHOL, SYNCFREE, false>, block, smem));
+        ILUB_CUDA(cudaGetDevice(&dev));
+        ILUB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        ILUB_REQUIRE((int64_t)occ * sms >= grid, ILUB_ERR_CUDA,
+                     "sync-free factorisation: the grid cannot be co-resident on this device (lower nparts / ctas_per_sm, or use factor_algo 1 or 3)");
+    }
     if (exact)
         k_factor<G, ICHOL, SYNCFREE, true><<<grid, block, smem, s>>>(P);
     else

@@ -942,6 +942,11 @@ bool analyse_systolic(ilub_handle* h, int slot, cudaStream_t s) {
                 const int gzpc = (gz + c - 1) / c * c;
                 if ((int64_t)G.nyb * gzpc > h->sm_count) continue;
                 if (c > 1 && G.nyb * gzpc / c > max_active_clusters(k, c, block, sm)) continue;
+                if (c == 1) {  // no cluster: plain occupancy says whether the whole grid is resident at once
+                    int occ = 0;
+                    ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, block, sm));
+                    if ((int64_t)occ * h->sm_count < (int64_t)G.nyb * gzpc) continue;
+                }
                 // cost model (ns on the z chain): global hop 1500, DSMEM hop 300, local hop 120; two compute warps
                 // on one scheduler slow every step of the task
                 const long glob = gzpc / c - 1, dsm = gz - 1 - glob, loc = nplanes - gz;

@@ -956,6 +956,34 @@ void run_solve(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
             ILUB_CUDA(cudaFuncSetAttribute(k_trsv_syncfree<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            227 * 1024));
     }
+    {   // the sync-free kernel only makes progress when every CTA is resident (chunks wait for chunks of other CTAs):
+        // checked against the occupancy of this very configuration; one launch per level needs no co-residency
+        int occ = 0;
+        if (exact)
+            ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trsv_syncfree<true>, T.cfg_warps * 32, T.cfg_smem));
+        else
+            ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trsv_syncfree<false>, T.cfg_warps * 32, T.cfg_smem));
+        if ((int64_t)occ * h->sm_count < T.nparts) {
+            build_level_sets(h, slot, s);
+            const std::vector<int>& lptr = T.lvl_ptr_host;
+            const SolveSource src = solve_source(h, slot);
+            const SrcDev S = to_dev(src);
+            for (int c = 0; c < nrhs; ++c) {
+                double* xc = x + (int64_t)c * ldx;
+                for (int l = 0; l < T.nlevels; ++l) {
+                    const int cnt = lptr[l + 1] - lptr[l];
+                    if (cnt <= 0) continue;
+                    if (exact)
+                        k_trsv_level<true><<<blocks_for(cnt, 128), 128, 0, s>>>(S, h->lu.p, src.unit_diag ? 1 : 0, T.lvl_rows.p, lptr[l], lptr[l + 1], xc);
+                    else
+                        k_trsv_level<false><<<blocks_for(cnt, 128), 128, 0, s>>>(S, h->lu.p, src.unit_diag ? 1 : 0, T.lvl_rows.p, lptr[l], lptr[l + 1], xc);
+                    h->launches++;
+                }
+            }
+            ILUB_CUDA(cudaGetLastError());
+            return;
+        }
+    }
     for (int c = 0; c < nrhs; ++c) {
         P.epoch = ++T.epoch;  // 64-bit tag: never wraps, the mailbox is never reset
         P.x = x + (int64_t)c * ldx;
