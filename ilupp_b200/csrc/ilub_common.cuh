@@ -205,6 +205,7 @@ struct SysSolve {
     // stencil factorisation on the same kernel (slot 0 only): value / partner positions and the product stream
     bool ftried = false, fbuilt = false;
     DevBuf<int> fsrc, fpart;
+    DevBuf<int> frow;        // [nnz of one system] row of every entry of the CSR-read arrays (k_stencil_finish works per entry)
     DevBuf<double> fcoef;
     unsigned long long epoch = 0;
 };

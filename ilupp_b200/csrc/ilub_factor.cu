@@ -609,7 +609,8 @@ void factor_prepare(ilub_handle* h, cudaStream_t s) {
         DevBuf<int> m;
         m.alloc(1);
         ILUB_CUDA(cudaMemsetAsync(m.p, 0, sizeof(int), s));
-        k_max_row_len<<<(h->n + 255) / 256, 256, 0, s>>>(h->n, h->ptr.p, m.p);
+        const int n1 = h->n / h->nsys;  // (the systems of a batch share one pattern)
+        k_max_row_len<<<(n1 + 255) / 256, 256, 0, s>>>(n1, h->ptr.p, m.p);
         int v = 0;
         ILUB_CUDA(cudaMemcpyAsync(&v, m.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         ILUB_CUDA(cudaStreamSynchronize(s));

@@ -233,19 +233,35 @@ __global__ void k_sys_pack_factor(int64_t total, int per_task, int nyb, int nz1,
 }
 // from the pivots to the factor on A's pattern: ILU(0): L_ik = a_ik / d_k, U = a with the pivot on the diagonal;
 // IChol(0): L_ik = a_ik / sqrt(d_k), L_ii = sqrt(d_i)
-__global__ void k_stencil_finish(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
-                                 const int* __restrict__ dpos, const double* __restrict__ a,
-                                 const double* __restrict__ d, double* __restrict__ lu, int ichol) {
+// per row: the factor the strictly-lower entries of the COLUMN of that row are scaled with (1 / d, IChol: 1 / sqrt(d)) --
+// one square root and one division per row instead of one of each per entry below
+__global__ void k_stencil_scale(int n, const double* __restrict__ d, int ichol, double* __restrict__ rs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rs[i] = ichol ? 1.0 / sqrt(d[i]) : 1.0 / d[i];
+}
+// row of every entry of ONE system (8 lanes per row)
+__global__ void k_stencil_rowof(int n1, const int* __restrict__ ptr, int* __restrict__ rowof) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int i = (int)(t >> 3), gl = (int)(t & 7);
-    if (i >= n) return;
-    const int p0 = ptr[i], p1 = ichol ? dpos[i] + 1 : ptr[i + 1], dp = dpos[i];
-    for (int p = p0 + gl; p < p1; p += 8) {
-        double v = a[p];
-        if (p < dp) v = ichol ? v / sqrt(d[idx[p]]) : v / d[idx[p]];
-        else if (p == dp) v = ichol ? sqrt(d[i]) : d[i];
-        lu[p] = v;
-    }
+    if (i >= n1) return;
+    for (int p = ptr[i] + gl; p < ptr[i + 1]; p += 8) rowof[p] = i;
+}
+// the factor on A's pattern from the pivots: one thread per ENTRY (fully coalesced value streams); everything structural
+// comes from the arrays of one system (rowof, idx, dpos of system 0: the systems of a batch repeat them)
+__global__ void k_stencil_finish(int64_t nnz, int nnz1, int n1, const int* __restrict__ rowof, const int* __restrict__ idx,
+                                 const int* __restrict__ dpos, const double* __restrict__ a, const double* __restrict__ d,
+                                 const double* __restrict__ rs, double* __restrict__ lu, int ichol) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    const int sys = (int)(p / nnz1);
+    const int p1 = (int)(p - (int64_t)sys * nnz1);
+    const int r1 = __ldg(rowof + p1), dp1 = __ldg(dpos + r1);
+    if (ichol && p1 > dp1) return;  // (IChol(0): the strict upper part of the array is not used)
+    const int64_t base = (int64_t)sys * n1;
+    double v = a[p];
+    if (p1 < dp1) v *= rs[base + __ldg(idx + p1)];
+    else if (p1 == dp1) v = ichol ? sqrt(d[base + r1]) : d[base + r1];
+    lu[p] = v;
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -1194,9 +1210,18 @@ void factor_stencil(ilub_handle* h, cudaStream_t s) {
                                                              Y.fpart.p, h->a.p, Y.fcoef.p);
     if (Y.tile) launch_tile(h, 0, h->fpivot.p, h->n, 1, s, Y.fcoef.p);
     else launch_systolic(h, 0, h->fpivot.p, h->n, 1, s, Y.fcoef.p);
-    k_stencil_finish<<<blocks_for((int64_t)h->n * 8, 256), 256, 0, s>>>(h->n, h->ptr.p, h->idx.p, h->dpos.p, h->a.p, h->fpivot.p,
-                                                                       h->lu.p, ichol);
-    h->launches += 2;
+    h->work.ensure((size_t)h->n);  // (vector workspace: free between applies)
+    k_stencil_scale<<<blocks_for(h->n, 256), 256, 0, s>>>(h->n, h->fpivot.p, ichol, h->work.p);
+    const int n1 = h->n / h->nsys;
+    const int nnz1 = (int)(h->nnz / h->nsys);
+    if (Y.frow.n < (size_t)nnz1) {
+        Y.frow.alloc((size_t)nnz1);
+        k_stencil_rowof<<<blocks_for((int64_t)n1 * 8, 256), 256, 0, s>>>(n1, h->ptr.p, Y.frow.p);
+        h->launches++;
+    }
+    k_stencil_finish<<<blocks_for(h->nnz, 256), 256, 0, s>>>(h->nnz, nnz1, n1, Y.frow.p, h->idx.p, h->dpos.p, h->a.p, h->fpivot.p,
+                                                            h->work.p, h->lu.p, ichol);
+    h->launches += 3;
     ILUB_CUDA(cudaGetLastError());
 }
 
