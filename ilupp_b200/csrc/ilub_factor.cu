@@ -585,7 +585,8 @@ __global__ void k_max_row_len(int n, const int* __restrict__ ptr, int* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int v = i < n ? ptr[i + 1] - ptr[i] : 0;
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+    // (one look at the running maximum first: after the first few warps hardly anybody has to touch the contended word)
+    if ((threadIdx.x & 31) == 0 && v > *(volatile int*)out) atomicMax(out, v);
 }
 
 int factor_schedule(const ilub_handle* h) {
