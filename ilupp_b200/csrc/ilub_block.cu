@@ -95,7 +95,8 @@ __global__ void k_blk_fill(int n, SrcDev S, const int* __restrict__ fptr, const 
 // per block: depth of the local dependency DAG (sweeps needed), widest recent / local list among its regular rows, and the
 // mask of "long" rows (handled cooperatively).  One warp per block.
 __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, const int* __restrict__ cr,
-                           const int* __restrict__ npos, int4* __restrict__ bmeta) {
+                           const int* __restrict__ npos, int4* __restrict__ bmeta, int* __restrict__ llev,
+                           int* __restrict__ bdepth) {
     const int K = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (K >= nblocks) return;
@@ -131,6 +132,8 @@ __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, con
     const int leaf = (lmask & pointed) == 0 ? 1 : 0;
     const int depth = leaf ? depth_reg : depth_all;  // (leaves are evaluated behind the sweeps: they need none themselves)
     if (lane == 0) bmeta[K] = make_int4(depth | (leaf << 16), maxrec, maxloc, (int)lmask);
+    if (live) llev[q] = ll;
+    if (lane == 0) bdepth[K] = depth_all;
 }
 // coefficient values in the layout's order, pre-divided by the row's diagonal
 __global__ void k_blk_pack(int n, const int* __restrict__ fptr, const int* __restrict__ nptr, const int* __restrict__ fsrc,
@@ -486,7 +489,10 @@ void analyse_block(ilub_handle* h, int slot, cudaStream_t s) {
                                                  B.dsrc.p);
     B.nblocks = (n + kBlk - 1) / kBlk;
     B.bmeta.alloc((size_t)B.nblocks);
-    k_blk_meta<<<blocks_for((int64_t)B.nblocks * 32, 256), 256, 0, s>>>(n, B.nblocks, B.nptr.p, B.cr.p, B.npos.p, B.bmeta.p);
+    B.llev.alloc((size_t)n);
+    B.bdepth.alloc((size_t)B.nblocks);
+    k_blk_meta<<<blocks_for((int64_t)B.nblocks * 32, 256), 256, 0, s>>>(n, B.nblocks, B.nptr.p, B.cr.p, B.npos.p, B.bmeta.p,
+                                                                       B.llev.p, B.bdepth.p);
     h->launches += 6;
     ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here
     B.packed = false;

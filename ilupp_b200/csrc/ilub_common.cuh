@@ -236,6 +236,8 @@ struct BlockSolve {
     DevBuf<int> dsrc;               // [n] diagonal source in lu (-1: unit)
     DevBuf<double> fval, nval, rdiag;
     DevBuf<int4> bmeta;             // [nblocks] {depth of the local DAG, widest recent list, widest local list, long-row mask}
+    DevBuf<int> llev;               // [n] level of every row inside its block's local DAG (the block factorisation walks them)
+    DevBuf<int> bdepth;             // [nblocks] deepest local level of the block (all rows)
 };
 
 // One triangular solve packed in solve order (see DESIGN.md "data layout in HBM").
@@ -382,6 +384,9 @@ struct ilub_handle {
     ilub::TriSolve solve[4];
     ilub::DevBuf<unsigned char> fflag;  // factorisation row flags
     ilub::DevBuf<unsigned> fbarrier;    // grid barrier of the level-loop factorisation
+    ilub::DevBuf<unsigned> fblock;      // hand-shake words of the block-sequential factorisation (k_factor_block)
+    unsigned fblock_epoch = 0;
+    ilub::DevBuf<int> fnfar;            // [n] far eliminations per row (k_factor_block)
     ilub::DevBuf<double> fpivot;        // pivots of the stencil factorisation
     int max_row_len = -1;               // longest row of the CSR-read arrays (computed once, factor_prepare)
     unsigned fepoch = 0;
@@ -432,6 +437,7 @@ bool block_wanted(const ilub_handle* h, int slot);   // block-sequential solve (
 void analyse_block(ilub_handle* h, int slot, cudaStream_t s);
 void pack_block(ilub_handle* h, int slot, cudaStream_t s);
 void run_block(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s);
+bool factor_block(ilub_handle* h, cudaStream_t s);  // block-sequential ILU(0) for deep narrow DAGs (ilub_factor.cu); false: not applicable
 bool levels_wanted(const ilub_handle* h, int slot);   // cooperative level loop (ilub_trsv.cu)
 bool few_levels_wanted(const ilub_handle* h, int slot);  // one launch per level (ilub_trsv.cu)
 void analyse_deep(ilub_handle* h, int slot, cudaStream_t s);

@@ -12,6 +12,7 @@
 // in ascending column order via an ordered shuffle reduction), so with `exact` arithmetic the
 // factors are bit-for-bit those of the reference compiled without FMA contraction.
 #include <algorithm>
+#include <cstring>
 
 #include "ilub_common.cuh"
 #include "ilub_ptx.cuh"
@@ -198,18 +199,22 @@ __device__ __forceinline__ int lower_bound_s(const int* s, int b, int e, int c) 
     return b;
 }
 
+// kb / ke: the strictly-lower entries [kb, ke) of the row are eliminated (ke < 0: all of them); from_lu: the row's current
+// values are taken from the factor array (an earlier call has eliminated [0, kb)) instead of from A.  The elimination
+// runs in ascending column order whatever the split, so splitting a row does not change a single operation.
 template <int G, bool SYNCFREE, bool EXACT>
-__device__ __forceinline__ bool ilu0_row_fast(const FactorParams& P, int i, int gl, unsigned gmask, const RowSmem<G>& R) {
+__device__ __forceinline__ bool ilu0_row_fast(const FactorParams& P, int i, int gl, unsigned gmask, const RowSmem<G>& R,
+                                              int kb = 0, int ke = -1, bool from_lu = false) {
     const int p0 = P.ptr[i], p1 = P.ptr[i + 1], dp = P.dpos[i];
-    const int len = p1 - p0, nl = dp - p0;
+    const int len = p1 - p0, nl = ke < 0 ? dp - p0 : ke;
     for (int t = gl; t < len; t += G) {  // ILU0.hpp:37
         R.idx[t] = __ldg(P.idx + p0 + t);
-        R.val[t] = P.a[p0 + t];
+        R.val[t] = from_lu ? __ldcg(P.lu + p0 + t) : P.a[p0 + t];
     }
     __syncwarp(gmask);
     long long t0 = 0;
     bool ok = true;
-    for (int t = gl; t < nl; t += G) {
+    for (int t = kb + gl; t < nl; t += G) {
         const int k = R.idx[t];
         if (!wait_row<SYNCFREE>(P, k, t0)) ok = false;
         const int dk = P.dpos[k];
@@ -235,8 +240,8 @@ __device__ __forceinline__ bool ilu0_row_fast(const FactorParams& P, int i, int 
         }
     };
 #pragma unroll
-    for (int u = 0; u < PF; ++u) fetch(u, pc[u], pu[u]);
-    for (int kk0 = 0; kk0 < nl; kk0 += PF) {  // ILU0.hpp:47-62, ascending k
+    for (int u = 0; u < PF; ++u) fetch(kb + u, pc[u], pu[u]);
+    for (int kk0 = kb; kk0 < nl; kk0 += PF) {  // ILU0.hpp:47-62, ascending k
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
             const int kk = kk0 + u;
@@ -589,6 +594,150 @@ __global__ void k_max_row_len(int n, const int* __restrict__ ptr, int* out) {
     if ((threadIdx.x & 31) == 0 && v > *(volatile int*)out) atomicMax(out, v);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Block-sequential ILU(0) for deep, narrow, band-local DAGs (BASELINE config 4) -- the factorisation counterpart of
+// ilub_block.cu.  The level loop pays ~23 us per level there (a handful of rows, each a chain of dependent fetches of the
+// rows it eliminates with).  Rows are taken in natural order in blocks of 32 (the blocks of the solve's layout):
+//   * the eliminations of a row with FAR rows k (more than kFarWin rows back: the random long-range half of its lower
+//     part) only need rows that are final long before the row's block is reached: the groups of the STAGER CTAs take one
+//     block each, up to kFarWin / 32 blocks ahead of the front, and eliminate [0, nfar) of every row of their block --
+//     all the HBM latency of those fetches is off the critical path;
+//   * ONE CTA walks the blocks in order and finishes the rows: the remaining (near) eliminations [nfar, nl), level by
+//     level of the block's local DAG (rows of one local level in parallel, one group each, __syncthreads between levels).
+// Every row still sees its eliminations in ascending column order, so the result is the level loop's bit for bit.
+constexpr int kFarWin = 8192;
+
+template <int G, bool EXACT>
+__device__ __forceinline__ void factor_row_range(const FactorParams& P, int i, int gl, unsigned gmask, const RowSmem<G>& R,
+                                                 unsigned char* big, int kb, int ke, bool from_lu) {
+    const int len = P.ptr[i + 1] - P.ptr[i];
+    if (len <= RowSmem<G>::L) {
+        ilu0_row_fast<G, false, EXACT>(P, i, gl, gmask, R, kb, ke, from_lu);
+        return;
+    }
+    int* lock = reinterpret_cast<int*>(big + (size_t)28 * P.big_cap);  // (the caller guarantees len <= big_cap)
+    if (gl == 0)
+        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(64);
+    __syncwarp(gmask);
+    const RowSmem<G> RB(big, P.big_cap);
+    ilu0_row_fast<G, false, EXACT>(P, i, gl, gmask, RB, kb, ke, from_lu);
+    __syncwarp(gmask);
+    if (gl == 0) {
+        __threadfence_block();
+        atomicExch(lock, 0);
+    }
+}
+
+// number of strictly-lower entries of row i whose column is below `limit` (they come first: columns ascend)
+__device__ __forceinline__ int count_far(const FactorParams& P, int i, int limit) {
+    int b = P.ptr[i], e = P.dpos[i];
+    const int b0 = b;
+    while (b < e) {
+        const int m = (b + e) >> 1;
+        if (__ldg(P.idx + m) < limit) b = m + 1;
+        else e = m;
+    }
+    return b - b0;
+}
+
+// far eliminations per row (static: pattern only), computed once per handle
+__global__ void k_factor_count_far(FactorParams P, int* __restrict__ nfar) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const int limit = (i / 32) * 32 - kFarWin;
+    nfar[i] = limit > 0 ? count_far(P, i, limit) : 0;
+}
+
+template <int G, bool EXACT>
+__global__ void __launch_bounds__(512) k_factor_block(FactorParams P, int nblocks, const int* __restrict__ llev,
+                                                      const int* __restrict__ bdepth, const int* __restrict__ nfar_of,
+                                                      unsigned* far_done /*[nblocks]*/,
+                                                      unsigned* progress, unsigned* next_block, unsigned epoch) {
+    extern __shared__ __align__(16) unsigned char factor_smem[];
+    __shared__ int abort_flag;
+    const RowSmem<G> R(factor_smem + (size_t)(threadIdx.x / G) * RowSmem<G>::kBytes);
+    unsigned char* big = factor_smem + (size_t)(blockDim.x / G) * RowSmem<G>::kBytes;
+    if (P.big_cap > 0) {
+        if (threadIdx.x == 0) *reinterpret_cast<int*>(big + (size_t)28 * P.big_cap) = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int gshift = (lane / G) * G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gshift);
+    const int grp = threadIdx.x / G, ng = blockDim.x / G;
+    long long t0 = 0;
+    if (blockIdx.x > 0) {
+        // ---- stager groups: one block of rows at a time, the far eliminations of each of its rows
+        while (true) {
+            unsigned K = 0;
+            if (gl == 0) K = atomicAdd(next_block, 1u);
+            K = __shfl_sync(gmask, K, gshift);
+            if ((int)K >= nblocks) break;
+            const int r0 = (int)K * 32;
+            const int limit = r0 - kFarWin;  // rows below `limit` are final once the front has passed block K - kFarWin / 32
+            if (limit > 0) {
+                const unsigned need = (unsigned)(limit + 31) / 32u;
+                unsigned spins = 0;
+                while (ld_relaxed_gpu_u32(progress) < need) {
+                    __nanosleep(500);
+                    if ((++spins & 0x3ffu) == 0) {
+                        if (t0 == 0) t0 = clock64();
+                        if (clock64() - t0 > P.spin_limit || *(volatile int*)P.status != 0) {
+                            atomicCAS(P.status, 0, 103);
+                            return;
+                        }
+                    }
+                }
+                __threadfence();
+                for (int i = r0; i < min(P.n, r0 + 32); ++i) {
+                    const int nfar = __ldg(nfar_of + i);
+                    if (nfar > 0) factor_row_range<G, EXACT>(P, i, gl, gmask, R, big, 0, nfar, false);
+                }
+            }
+            __syncwarp(gmask);
+            __threadfence();
+            if (gl == 0) st_relaxed_gpu_u32(far_done + K, epoch);
+        }
+        return;
+    }
+    // ---- the front: blocks in order, the near eliminations level by level of the block's local DAG
+    for (int K = 0; K < nblocks; ++K) {
+        if (threadIdx.x == 0) {
+            unsigned spins = 0;
+            while (ld_relaxed_gpu_u32(far_done + K) != epoch) {
+                if ((++spins & 0x3ffu) == 0) {
+                    if (t0 == 0) t0 = clock64();
+                    if (clock64() - t0 > P.spin_limit || *(volatile int*)P.status != 0) {
+                        atomicCAS(P.status, 0, 104);
+                        break;
+                    }
+                }
+            }
+            __threadfence();
+        }
+        if (threadIdx.x == 0) abort_flag = *(volatile int*)P.status != 0 ? 1 : 0;
+        __syncthreads();
+        if (abort_flag) return;
+        const int r0 = K * 32;
+        const int depth = __ldg(bdepth + K);
+        for (int lv = 0; lv <= depth; ++lv) {
+            for (int g = grp; g < 32; g += ng) {
+                const int i = r0 + g;
+                if (i < P.n && __ldg(llev + i) == lv) {
+                    const int nfar = __ldg(nfar_of + i);
+                    factor_row_range<G, EXACT>(P, i, gl, gmask, R, big, nfar, -1, nfar > 0);
+                }
+            }
+            __syncthreads();  // the rows of this local level are final (and visible) before the next level reads them
+        }
+        if (threadIdx.x == 0) {
+            __threadfence();
+            st_relaxed_gpu_u32(progress, (unsigned)(K + 1));
+        }
+    }
+}
+
 int factor_schedule(const ilub_handle* h) {
     const TriSolve& T = h->solve[0];
     const int algo = (int)options().factor_algo;
@@ -601,6 +750,67 @@ int factor_schedule(const ilub_handle* h) {
                                                              // launch per level measure alike (config 4: 2.9 / 3.2 s),
                                                              // sync-free is 3x slower there
     return 2;
+}
+
+template <int G>
+static void launch_factor_block(bool exact, cudaStream_t s, const FactorParams& P, int nblocks, const int* llev, const int* bdepth,
+                                const int* nfar, unsigned* far_done, unsigned* progress, unsigned* next_block, unsigned epoch) {
+    const int block = 512, stagers = 8;
+    const size_t smem = (size_t)(block / G) * RowSmem<G>::kBytes + (P.big_cap > 0 ? (size_t)28 * P.big_cap + 16 : 0);
+    if (exact) {
+        ILUB_CUDA(cudaFuncSetAttribute(k_factor_block<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_factor_block<G, true><<<1 + stagers, block, smem, s>>>(P, nblocks, llev, bdepth, nfar, far_done, progress, next_block, epoch);
+    } else {
+        ILUB_CUDA(cudaFuncSetAttribute(k_factor_block<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_factor_block<G, false><<<1 + stagers, block, smem, s>>>(P, nblocks, llev, bdepth, nfar, far_done, progress, next_block, epoch);
+    }
+}
+
+// block-sequential ILU(0): deep narrow DAGs whose L solve has the block layout of ilub_block.cu (its local levels)
+bool factor_block(ilub_handle* h, cudaStream_t s) {
+    const Options& opt = options();
+    TriSolve& T = h->solve[0];
+    if (opt.deep_block == 0 || h->kind != KIND_ILU0 || h->nsys != 1 || !T.blk.built || !T.blk.llev.p) return false;
+    if (h->max_row_len > 4096) return false;  // (rows beyond the big row buffer keep the level loop's slow path)
+    FactorParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = h->n;
+    P.ptr = h->ptr.p;
+    P.idx = h->idx.p;
+    P.dpos = h->dpos.p;
+    P.a = h->a.p;
+    P.lu = h->lu.p;
+    P.status = h->status.p;
+    P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz * 40;
+    int G = (int)opt.factor_group;
+    if (G != 8 && G != 16 && G != 32) {
+        const double avg = (double)h->nnz / (double)h->n;
+        G = avg <= 10 ? 8 : (avg <= 24 ? 16 : 32);
+    }
+    P.big_cap = h->max_row_len > 4 * G ? std::min(4096, (h->max_row_len + 63) / 64 * 64) : 0;
+    const int nblocks = T.blk.nblocks;
+    // hand-shake words: [0] progress, [1] next block of the stagers, [2 ..] far_done per block (epoch-tagged: never reset)
+    if (h->fblock.n < (size_t)nblocks + 2) {
+        h->fblock.alloc((size_t)nblocks + 2);
+        ILUB_CUDA(cudaMemsetAsync(h->fblock.p, 0, sizeof(unsigned) * ((size_t)nblocks + 2), s));
+        h->fblock_epoch = 0;
+    }
+    ILUB_CUDA(cudaMemsetAsync(h->fblock.p, 0, sizeof(unsigned) * 2, s));
+    if (h->fnfar.n < (size_t)h->n) {
+        h->fnfar.alloc((size_t)h->n);
+        k_factor_count_far<<<(h->n + 255) / 256, 256, 0, s>>>(P, h->fnfar.p);
+        h->launches++;
+    }
+    const unsigned epoch = ++h->fblock_epoch;
+    const bool exact = opt.exact != 0;
+    switch (G) {
+        case 8: launch_factor_block<8>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
+        case 16: launch_factor_block<16>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
+        default: launch_factor_block<32>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
+    }
+    ILUB_CUDA(cudaGetLastError());
+    h->launches++;
+    return true;
 }
 
 // symbolic work the chosen schedule needs on top of the level numbers: the (level, row) listing, or the chunked
@@ -661,7 +871,9 @@ void factor_numeric(ilub_handle* h, cudaStream_t s) {
         factor_stencil(h, s);
         return;
     }
-    if (algo == 3) {
+    if (algo == 3 && (int64_t)T.nlevels * 64 > (int64_t)h->n && factor_block(h, s)) {
+        // (deep narrow DAG with the block layout at hand: block-sequential schedule)
+    } else if (algo == 3) {
         if (h->fbarrier.n < 1) h->fbarrier.alloc(1);
         ILUB_CUDA(cudaMemsetAsync(h->fbarrier.p, 0, sizeof(unsigned), s));
         P.fflag = nullptr;

@@ -20,6 +20,9 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_relaxed_gpu_u32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_relaxed_gpu_u8(const unsigned char* p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
