@@ -193,7 +193,7 @@ __global__ void k_tri_unpack(int64_t nt, const unsigned long long* __restrict__ 
 // pass of 31 shuffles in lane order -- lane k is final when the pass reaches it, because its own in-warp
 // dependencies are lanes below k.
 __global__ void __launch_bounds__(256) k_levels(SrcDev S, int n, int* level, int* ticket, int* nlev,
-                                                long long spin_limit, int* status) {
+                                                long long spin_limit, int* status, int nproc) {
     const int lane = threadIdx.x & 31;
     volatile int* vlevel = level;
     while (true) {
@@ -201,9 +201,9 @@ __global__ void __launch_bounds__(256) k_levels(SrcDev S, int n, int* level, int
         if (lane == 0) t = atomicAdd(ticket, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         const int64_t base = (int64_t)t * 32;
-        if (base >= n) break;
+        if (base >= nproc) break;  // (nproc < n: only the first rows of the solve order -- a probe of the DAG's shape)
         const int64_t r = base + lane;
-        const bool valid = r < n;
+        const bool valid = r < nproc;
         const int row = valid ? (S.backward ? n - 1 - (int)r : (int)r) : 0;
         int p = valid ? src_beg(S, row) : 0;
         const int e = valid ? src_end(S, row) : 0;
@@ -936,22 +936,49 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         ctr.alloc(4);
         ILUB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int) * 4, s));
         const long long spin = (long long)opt.spin_limit_ms * h->clock_khz;  // kHz * ms = cycles
-        {
-            DebugTimer t("  levels", s);
-            int occ = 0;
-            ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels, 256, 0));
-            const int grid = std::max(1, std::min(occ * h->sm_count, (n1 + 31) / 32));
-            k_levels<<<grid, 256, 0, s>>>(S, n1, T.level.p, ctr.p, ctr.p + 1, spin * 4, h->status.p);
+        int occ = 0;
+        ILUB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_levels, 256, 0));
+        // Large matrices are probed first: the levels of the first 65,536 rows of the solve order tell a deep narrow DAG
+        // (fewer than 64 rows per level) from a wide one.  On a deep one the sync-free propagation below costs ~2.7 us per
+        // level (0.3 s per solve at n = 10^6); the block layout (pattern only) is built instead and the levels come
+        // out of the block-sequential kernel in the (max, +1) semiring (ilub_block.cu), exactly the same numbers.
+        constexpr int kProbe = 65536;
+        bool via_block = false;
+        if (!sys_ok && nsys == 1 && opt.deep_block != 0 && opt.solve_algo == 0 && n1 >= 4 * kProbe) {
+            DebugTimer t("  levels (probe)", s);
+            const int grid = std::max(1, std::min(occ * h->sm_count, kProbe / 32));
+            k_levels<<<grid, 256, 0, s>>>(S, n1, T.level.p, ctr.p, ctr.p + 1, spin * 4, h->status.p, kProbe);
             h->launches++;
-            if (nsys > 1) {
-                k_levels_replicate<<<blocks_for((int64_t)n - n1, 256), 256, 0, s>>>(n, n1, T.level.p);
-                h->launches++;
+            read_status(h, s);
+            int hp[2];
+            ILUB_CUDA(cudaMemcpy(hp, ctr.p, sizeof(hp), cudaMemcpyDeviceToHost));
+            if ((int64_t)hp[1] * 64 > kProbe) {
+                DebugTimer t2("  levels (block-sequential)", s);
+                analyse_block(h, slot, s);
+                T.nlevels = levels_block(h, slot, s);
+                read_status(h, s);
+                via_block = true;
+            } else {
+                ILUB_CUDA(cudaMemsetAsync(T.level.p, 0xff, sizeof(int) * n1, s));
+                ILUB_CUDA(cudaMemsetAsync(ctr.p, 0, sizeof(int) * 4, s));
             }
         }
-        read_status(h, s);
-        int hctr[2];
-        ILUB_CUDA(cudaMemcpy(hctr, ctr.p, sizeof(hctr), cudaMemcpyDeviceToHost));
-        T.nlevels = hctr[1];
+        if (!via_block) {
+            {
+                DebugTimer t("  levels", s);
+                const int grid = std::max(1, std::min(occ * h->sm_count, (n1 + 31) / 32));
+                k_levels<<<grid, 256, 0, s>>>(S, n1, T.level.p, ctr.p, ctr.p + 1, spin * 4, h->status.p, n1);
+                h->launches++;
+                if (nsys > 1) {
+                    k_levels_replicate<<<blocks_for((int64_t)n - n1, 256), 256, 0, s>>>(n, n1, T.level.p);
+                    h->launches++;
+                }
+            }
+            read_status(h, s);
+            int hctr[2];
+            ILUB_CUDA(cudaMemcpy(hctr, ctr.p, sizeof(hctr), cudaMemcpyDeviceToHost));
+            T.nlevels = hctr[1];
+        }
     }
     T.built = true;
     if (!sys_ok && block_wanted(h, slot)) {

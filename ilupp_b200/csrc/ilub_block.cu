@@ -433,9 +433,244 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_trsv_block(const BlockParams
     else if ((warp & 3) != 0) blk_stager(P, M, warp - 1 - (warp >> 2), lane);
 }
 
+// ------------------------------------------------------------------------------------------------ dependency levels
+// The same schedule in the (max, +1) semiring: level(i) = max over the dependencies of level(dep) + 1.  The sync-free level
+// propagation of ilub_analysis.cu costs 2.7 us per level on such a DAG (0.3 s per solve at n = 10^6); here the far maxima
+// are reduced ahead of time by the stagers, recent ones come from a ring, and the block's local levels settle in
+// depth(block) sweeps of 32-bit shuffles.
+struct LevelParams {
+    int n, nblocks, backward;
+    const int* fptr;
+    const int* fpos;
+    const int* nptr;
+    const int* cr;
+    const int* npos;
+    const int4* bmeta;
+    int* level;  // [n] by original row
+    int* nlev;   // max level + 1
+    int* status;
+    unsigned spin_iters;
+};
+struct LevelSlot {
+    int m[kBlk];             // max over the far dependencies of (level + 1)
+    int npos[kSlotCap];
+    int off[kBlk], nrec[kBlk], nloc[kBlk];
+    int4 meta;
+    int big;
+};
+struct LevelSmem {
+    int ring[kRing];
+    int xs[kBlk];
+    LevelSlot slot[kSlots];
+    int staged[kSlots];
+    int progress;
+};
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+#define LEV_SPIN(spins, code)                                            \
+    if ((++(spins) & 0x3ffu) == 0) {                                     \
+        if ((spins) >= P.spin_iters || *(volatile int*)P.status != 0) {   \
+            atomicCAS(P.status, 0, code);                                \
+            return;                                                      \
+        }                                                                \
+    }
+
+__device__ __forceinline__ void lev_stager(const LevelParams& P, LevelSmem& M, int w, int lane) {
+    unsigned spins = 0;
+    for (int K = w; K < P.nblocks; K += kStagers) {
+        LevelSlot& L = M.slot[K % kSlots];
+        while (*(volatile int*)&M.progress < K - kSlots + 1) {
+            __nanosleep(100);
+            LEV_SPIN(spins, 411)
+        }
+        fence_acq_rel_cta();
+        const int q = K * kBlk + lane;
+        const bool live = q < P.n;
+        const int fb = live ? __ldg(P.fptr + q) : 0, fe = live ? __ldg(P.fptr + q + 1) : 0;
+        int m = 0;
+        const bool flong = fe - fb > 64;
+        if (!flong) {
+            for (int e0 = fb; e0 < fe; e0 += 8) {
+                int v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = -1;
+                    if (e0 + u < fe) {
+                        const int pd = __ldg(P.fpos + e0 + u);
+                        v[u] = __ldcg(P.level + (P.backward ? P.n - 1 - pd : pd));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) m = max(m, v[u] + 1);
+            }
+        }
+        unsigned fm = __ballot_sync(FULL, flong);
+        while (fm) {
+            const int src = __ffs(fm) - 1;
+            fm &= fm - 1;
+            const int b = __shfl_sync(FULL, fb, src), e = __shfl_sync(FULL, fe, src);
+            int part = 0;
+            for (int t = b + lane; t < e; t += 32) {
+                const int pd = __ldg(P.fpos + t);
+                part = max(part, __ldcg(P.level + (P.backward ? P.n - 1 - pd : pd)) + 1);
+            }
+            part = warp_max(part);
+            if (lane == src) m = max(m, part);
+        }
+        const int nb = live ? __ldg(P.nptr + q) : 0, ne = live ? __ldg(P.nptr + q + 1) : 0;
+        const int nb0 = __shfl_sync(FULL, nb, 0);
+        const int total = __ldg(P.nptr + min(P.n, K * kBlk + kBlk)) - nb0;
+        const bool big = total > kSlotCap;
+        if (!big)
+            for (int t = lane; t < total; t += 32) L.npos[t] = __ldg(P.npos + nb0 + t);
+        const int nrec = live ? __ldg(P.cr + q) : 0;
+        L.m[lane] = m;
+        L.off[lane] = big ? nb : nb - nb0;
+        L.nrec[lane] = nrec;
+        L.nloc[lane] = ne - nb - nrec;
+        if (lane == 0) {
+            L.big = big ? 1 : 0;
+            L.meta = __ldg(P.bmeta + K);
+        }
+        __syncwarp();
+        fence_acq_rel_cta();
+        if (lane == 0) *(volatile int*)&M.staged[K % kSlots] = K + 1;
+    }
+}
+
+__device__ __forceinline__ void lev_compute(const LevelParams& P, LevelSmem& M, int lane) {
+    unsigned spins = 0;
+    int top = 0;
+    for (int K = 0; K < P.nblocks; ++K) {
+        LevelSlot& L = M.slot[K % kSlots];
+        while (*(volatile int*)&M.staged[K % kSlots] != K + 1) LEV_SPIN(spins, 412)
+        fence_acq_rel_cta();
+        const int4 bm = L.meta;
+        // (the sweeps of the solve may skip leaves; a level needs every row: depth of ALL rows = regular depth, or one
+        //  more when the long rows are leaves)
+        const int depth = (bm.x & 0xffff) + ((bm.x >> 16) ? 1 : 0);
+        const int maxrec = bm.y;
+        const unsigned lmask = (unsigned)bm.w;
+        const int* np = L.big ? P.npos : L.npos;
+        const int off = L.off[lane], nrec = L.nrec[lane], nloc = L.nloc[lane];
+        const bool islong = (lmask >> lane) & 1u;
+        const int b0 = K * kBlk;
+        int m = L.m[lane];
+        for (int t0 = 0; t0 < maxrec; t0 += 8) {
+            int pp[8], vv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pp[u] = (!islong && t0 + u < nrec) ? np[off + t0 + u] : -1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) vv[u] = pp[u] >= 0 ? M.ring[pp[u] & (kRing - 1)] : -1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) m = max(m, vv[u] + 1);
+        }
+        unsigned lm = lmask;
+        while (lm) {
+            const int src = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const int o = __shfl_sync(FULL, off, src), c = __shfl_sync(FULL, nrec, src);
+            int part = 0;
+            for (int t = lane; t < c; t += 32) part = max(part, M.ring[np[o + t] & (kRing - 1)] + 1);
+            part = warp_max(part);
+            if (lane == src) m = max(m, part);
+        }
+        int lsrc[kRegLoc];
+        bool lhas[kRegLoc];
+#pragma unroll
+        for (int t = 0; t < kRegLoc; ++t) {
+            lhas[t] = !islong && t < nloc;
+            lsrc[t] = lhas[t] ? np[off + nrec + t] - b0 : lane;
+        }
+        int x = m;
+        for (int s = 0; s < depth; ++s) {
+            int acc = m;
+            if (lmask) {
+                M.xs[lane] = x;
+                __syncwarp();
+                unsigned l2 = lmask;
+                while (l2) {
+                    const int src = __ffs(l2) - 1;
+                    l2 &= l2 - 1;
+                    const int o = __shfl_sync(FULL, off + nrec, src), c = __shfl_sync(FULL, nloc, src);
+                    int part = 0;
+                    for (int t = lane; t < c; t += 32) part = max(part, M.xs[np[o + t] - b0] + 1);
+                    part = warp_max(part);
+                    if (lane == src) acc = max(acc, part);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int t = 0; t < kRegLoc; ++t) {
+                const int v = __shfl_sync(FULL, x, lsrc[t]);
+                if (lhas[t]) acc = max(acc, v + 1);
+            }
+            x = acc;
+        }
+        const int q = b0 + lane;
+        M.ring[q & (kRing - 1)] = x;
+        if (q < P.n) {
+            __stcg(P.level + (P.backward ? P.n - 1 - q : q), x);
+            top = max(top, x + 1);
+        }
+        __syncwarp();
+        fence_acq_rel_cta();
+        if (lane == 0) *(volatile int*)&M.progress = K + 1;
+    }
+    top = warp_max(top);
+    if (lane == 0) *P.nlev = top;
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 1) k_levels_block(const LevelParams P) {
+    extern __shared__ __align__(16) unsigned char blk_smem_raw[];
+    LevelSmem& M = *reinterpret_cast<LevelSmem*>(blk_smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = threadIdx.x; t < kRing; t += blockDim.x) M.ring[t] = 0;
+    if (threadIdx.x < kSlots) M.staged[threadIdx.x] = 0;
+    if (threadIdx.x == 0) M.progress = 0;
+    __syncthreads();
+    if (warp == 0) lev_compute(P, M, lane);
+    else if ((warp & 3) != 0) lev_stager(P, M, warp - 1 - (warp >> 2), lane);
+}
+
 }  // namespace
 
 // ================================================================================================== host
+// dependency levels of solve `slot` through the block layout (which must exist); returns the number of levels
+int levels_block(ilub_handle* h, int slot, cudaStream_t s) {
+    TriSolve& T = h->solve[slot];
+    BlockSolve& B = T.blk;
+    const size_t smem = sizeof(LevelSmem);
+    static thread_local unsigned attr_set[1] = {0};
+    if (first_use_on_this_device(attr_set, 0))
+        ILUB_CUDA(cudaFuncSetAttribute(k_levels_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DevBuf<int> nlev;
+    nlev.alloc(1);
+    LevelParams P;
+    P.n = h->n;
+    P.nblocks = B.nblocks;
+    P.backward = T.backward ? 1 : 0;
+    P.fptr = B.fptr.p;
+    P.fpos = B.fpos.p;
+    P.nptr = B.nptr.p;
+    P.cr = B.cr.p;
+    P.npos = B.npos.p;
+    P.bmeta = B.bmeta.p;
+    P.level = T.level.p;
+    P.nlev = nlev.p;
+    P.status = h->status.p;
+    P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 20, (long long)options().spin_limit_ms * h->clock_khz / 32));
+    k_levels_block<<<1, kWarps * 32, smem, s>>>(P);
+    h->launches++;
+    int v = 0;
+    ILUB_CUDA(cudaMemcpyAsync(&v, nlev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    return v;
+}
+
 bool block_wanted(const ilub_handle* h, int slot) {
     const Options& opt = options();
     if (opt.exact != 0 || opt.deep_block == 0) return false;

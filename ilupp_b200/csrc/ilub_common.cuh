@@ -437,6 +437,7 @@ bool block_wanted(const ilub_handle* h, int slot);   // block-sequential solve (
 void analyse_block(ilub_handle* h, int slot, cudaStream_t s);
 void pack_block(ilub_handle* h, int slot, cudaStream_t s);
 void run_block(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaStream_t s);
+int levels_block(ilub_handle* h, int slot, cudaStream_t s);  // dependency levels through the block layout (ilub_block.cu)
 bool factor_block(ilub_handle* h, cudaStream_t s);  // block-sequential ILU(0) for deep narrow DAGs (ilub_factor.cu); false: not applicable
 bool levels_wanted(const ilub_handle* h, int slot);   // cooperative level loop (ilub_trsv.cu)
 bool few_levels_wanted(const ilub_handle* h, int slot);  // one launch per level (ilub_trsv.cu)
