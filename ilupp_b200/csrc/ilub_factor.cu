@@ -12,6 +12,7 @@
 // in ascending column order via an ordered shuffle reduction), so with `exact` arithmetic the
 // factors are bit-for-bit those of the reference compiled without FMA contraction.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 
 #include "ilub_common.cuh"
@@ -202,25 +203,32 @@ __device__ __forceinline__ int lower_bound_s(const int* s, int b, int e, int c) 
 // kb / ke: the strictly-lower entries [kb, ke) of the row are eliminated (ke < 0: all of them); from_lu: the row's current
 // values are taken from the factor array (an earlier call has eliminated [0, kb)) instead of from A.  The elimination
 // runs in ascending column order whatever the split, so splitting a row does not change a single operation.
+// do_stage / do_write / meta_to: a row may be eliminated in two calls that keep it in the group's buffer in between -- the
+// first call stages it, fetches the static {first upper entry, row end} of ALL rows up to meta_to and does not write the row
+// back; the second neither stages nor looks the extents up again, only the pivots of its own range.
 template <int G, bool SYNCFREE, bool EXACT>
 __device__ __forceinline__ bool ilu0_row_fast(const FactorParams& P, int i, int gl, unsigned gmask, const RowSmem<G>& R,
-                                              int kb = 0, int ke = -1, bool from_lu = false) {
+                                              int kb = 0, int ke = -1, bool from_lu = false, bool do_stage = true,
+                                              bool do_write = true, int meta_to = -1) {
     const int p0 = P.ptr[i], p1 = P.ptr[i + 1], dp = P.dpos[i];
     const int len = p1 - p0, nl = ke < 0 ? dp - p0 : ke;
-    for (int t = gl; t < len; t += G) {  // ILU0.hpp:37
-        R.idx[t] = __ldg(P.idx + p0 + t);
-        R.val[t] = from_lu ? __ldcg(P.lu + p0 + t) : P.a[p0 + t];
+    if (do_stage) {
+        for (int t = gl; t < len; t += G) {  // ILU0.hpp:37
+            R.idx[t] = __ldg(P.idx + p0 + t);
+            R.val[t] = from_lu ? __ldcg(P.lu + p0 + t) : P.a[p0 + t];
+        }
+        __syncwarp(gmask);
     }
-    __syncwarp(gmask);
     long long t0 = 0;
     bool ok = true;
-    for (int t = kb + gl; t < nl; t += G) {
+    for (int t = kb + gl; t < max(nl, meta_to); t += G) {
         const int k = R.idx[t];
         if (!wait_row<SYNCFREE>(P, k, t0)) ok = false;
-        const int dk = P.dpos[k];
-        R.ra[t] = dk + 1;
-        R.rb[t] = P.ptr[k + 1];
-        R.piv[t] = __ldcg(P.lu + dk);
+        if (do_stage) {
+            R.ra[t] = P.dpos[k] + 1;
+            R.rb[t] = P.ptr[k + 1];
+        }
+        if (t < nl) R.piv[t] = __ldcg(P.lu + R.ra[t] - 1);
     }
     if (SYNCFREE && !__all_sync(gmask, ok)) return false;
     __syncwarp(gmask);
@@ -267,7 +275,8 @@ __device__ __forceinline__ bool ilu0_row_fast(const FactorParams& P, int i, int 
         }
     }
     __syncwarp(gmask);
-    for (int t = gl; t < len; t += G) P.lu[p0 + t] = R.val[t];
+    if (do_write)
+        for (int t = gl; t < len; t += G) P.lu[p0 + t] = R.val[t];
     return true;
 }
 
@@ -609,10 +618,11 @@ constexpr int kFarWin = 8192;
 
 template <int G, bool EXACT>
 __device__ __forceinline__ void factor_row_range(const FactorParams& P, int i, int gl, unsigned gmask, const RowSmem<G>& R,
-                                                 unsigned char* big, int kb, int ke, bool from_lu) {
+                                                 unsigned char* big, int kb, int ke, bool from_lu, bool do_stage = true,
+                                                 bool do_write = true, int meta_to = -1) {
     const int len = P.ptr[i + 1] - P.ptr[i];
     if (len <= RowSmem<G>::L) {
-        ilu0_row_fast<G, false, EXACT>(P, i, gl, gmask, R, kb, ke, from_lu);
+        ilu0_row_fast<G, false, EXACT>(P, i, gl, gmask, R, kb, ke, from_lu, do_stage, do_write, meta_to);
         return;
     }
     int* lock = reinterpret_cast<int*>(big + (size_t)28 * P.big_cap);  // (the caller guarantees len <= big_cap)
@@ -651,6 +661,7 @@ __global__ void k_factor_count_far(FactorParams P, int* __restrict__ nfar) {
 template <int G, bool EXACT>
 __global__ void __launch_bounds__(512) k_factor_block(FactorParams P, int nblocks, const int* __restrict__ llev,
                                                       const int* __restrict__ bdepth, const int* __restrict__ nfar_of,
+                                                      const int* __restrict__ nptr, const int* __restrict__ crec,
                                                       unsigned* far_done /*[nblocks]*/,
                                                       unsigned* progress, unsigned* next_block, unsigned epoch) {
     extern __shared__ __align__(16) unsigned char factor_smem[];
@@ -702,7 +713,9 @@ __global__ void __launch_bounds__(512) k_factor_block(FactorParams P, int nblock
         return;
     }
     // ---- the front: blocks in order, the near eliminations level by level of the block's local DAG
+    long long tw = 0, tl = 0, tbig = 0, nbig = 0, nlev_sum = 0;  // (debug, P.epoch != 0: where the front's time goes)
     for (int K = 0; K < nblocks; ++K) {
+        long long c0 = P.epoch ? clock64() : 0;
         if (threadIdx.x == 0) {
             unsigned spins = 0;
             while (ld_relaxed_gpu_u32(far_done + K) != epoch) {
@@ -721,21 +734,54 @@ __global__ void __launch_bounds__(512) k_factor_block(FactorParams P, int nblock
         if (abort_flag) return;
         const int r0 = K * 32;
         const int depth = __ldg(bdepth + K);
-        for (int lv = 0; lv <= depth; ++lv) {
+        if (P.epoch) { const long long c = clock64(); tw += c - c0; c0 = c; nlev_sum += depth + 1; }
+        // step 1, all rows of the block at once (they do not depend on each other here): the near eliminations with rows
+        // of EARLIER blocks -- those are final.  A row with local dependencies then stays in its group's buffer ...
+        constexpr bool kPersist = (512 / G) >= 32;  // (one group per row of the block: the buffer survives until step 2)
+        for (int g = grp; g < 32; g += ng) {
+            const int i = r0 + g;
+            if (i < P.n) {
+                const int nfar = __ldg(nfar_of + i);
+                const int nloc = (__ldg(nptr + i + 1) - __ldg(nptr + i)) - __ldg(crec + i);
+                const int nl = P.dpos[i] - P.ptr[i];
+                const bool small = P.ptr[i + 1] - P.ptr[i] <= RowSmem<G>::L;
+                const bool keep = kPersist && small && nloc > 0;
+                if (nl - nloc > nfar || nloc == 0 || keep)
+                    factor_row_range<G, EXACT>(P, i, gl, gmask, R, big, nfar, nl - nloc, nfar > 0, true, !keep, keep ? nl : -1);
+            }
+        }
+        __syncthreads();
+        if (P.epoch) { const long long c = clock64(); tl += c - c0; c0 = c; }
+        // ... step 2, level by level of the block's local DAG: the eliminations with rows of the block itself
+        for (int lv = 1; lv <= depth; ++lv) {
+            bool hasbig = false;
             for (int g = grp; g < 32; g += ng) {
                 const int i = r0 + g;
                 if (i < P.n && __ldg(llev + i) == lv) {
                     const int nfar = __ldg(nfar_of + i);
-                    factor_row_range<G, EXACT>(P, i, gl, gmask, R, big, nfar, -1, nfar > 0);
+                    const int nloc = (__ldg(nptr + i + 1) - __ldg(nptr + i)) - __ldg(crec + i);
+                    const int nl = P.dpos[i] - P.ptr[i];
+                    const bool small = P.ptr[i + 1] - P.ptr[i] <= RowSmem<G>::L;
+                    const bool keep = kPersist && small;
+                    hasbig = !small;
+                    // (a row whose step 1 had nothing to do and was skipped still holds A's values)
+                    const bool touched = nl - nloc > nfar || nfar > 0;
+                    if (keep) factor_row_range<G, EXACT>(P, i, gl, gmask, R, big, nl - nloc, nl, true, false, true, -1);
+                    else factor_row_range<G, EXACT>(P, i, gl, gmask, R, big, nl - nloc, nl, touched, true, true, -1);
                 }
             }
-            __syncthreads();  // the rows of this local level are final (and visible) before the next level reads them
+            const int anybig = __syncthreads_or(hasbig ? 1 : 0);  // the rows of this local level are final (and visible) before the next level reads them
+            if (P.epoch) { const long long c = clock64(); if (anybig) { tbig += c - c0; ++nbig; } else tl += c - c0; c0 = c; }
         }
         if (threadIdx.x == 0) {
             __threadfence();
             st_relaxed_gpu_u32(progress, (unsigned)(K + 1));
         }
     }
+    if (P.epoch && threadIdx.x == 0)
+        printf("factor front: %d blocks, %lld local levels | cycles per block: wait %.0f, levels without long rows %.0f, with %.0f | %lld levels with a long row, %.0f cycles each; %.0f cycles per other level\n",
+               nblocks, nlev_sum, (double)tw / nblocks, (double)tl / nblocks, (double)tbig / nblocks, nbig, nbig ? (double)tbig / nbig : 0.0,
+               (double)tl / (double)(nlev_sum - nbig));
 }
 
 int factor_schedule(const ilub_handle* h) {
@@ -754,15 +800,15 @@ int factor_schedule(const ilub_handle* h) {
 
 template <int G>
 static void launch_factor_block(bool exact, cudaStream_t s, const FactorParams& P, int nblocks, const int* llev, const int* bdepth,
-                                const int* nfar, unsigned* far_done, unsigned* progress, unsigned* next_block, unsigned epoch) {
+                                const int* nfar, const int* nptr, const int* crec, unsigned* far_done, unsigned* progress, unsigned* next_block, unsigned epoch) {
     const int block = 512, stagers = 8;
     const size_t smem = (size_t)(block / G) * RowSmem<G>::kBytes + (P.big_cap > 0 ? (size_t)28 * P.big_cap + 16 : 0);
     if (exact) {
         ILUB_CUDA(cudaFuncSetAttribute(k_factor_block<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_factor_block<G, true><<<1 + stagers, block, smem, s>>>(P, nblocks, llev, bdepth, nfar, far_done, progress, next_block, epoch);
+        k_factor_block<G, true><<<1 + stagers, block, smem, s>>>(P, nblocks, llev, bdepth, nfar, nptr, crec, far_done, progress, next_block, epoch);
     } else {
         ILUB_CUDA(cudaFuncSetAttribute(k_factor_block<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_factor_block<G, false><<<1 + stagers, block, smem, s>>>(P, nblocks, llev, bdepth, nfar, far_done, progress, next_block, epoch);
+        k_factor_block<G, false><<<1 + stagers, block, smem, s>>>(P, nblocks, llev, bdepth, nfar, nptr, crec, far_done, progress, next_block, epoch);
     }
 }
 
@@ -782,6 +828,7 @@ bool factor_block(ilub_handle* h, cudaStream_t s) {
     P.lu = h->lu.p;
     P.status = h->status.p;
     P.spin_limit = (long long)opt.spin_limit_ms * h->clock_khz * 40;
+    P.epoch = opt.trace != 0 ? 1u : 0u;  // (debug print of the front's time split)
     int G = (int)opt.factor_group;
     if (G != 8 && G != 16 && G != 32) {
         const double avg = (double)h->nnz / (double)h->n;
@@ -804,9 +851,9 @@ bool factor_block(ilub_handle* h, cudaStream_t s) {
     const unsigned epoch = ++h->fblock_epoch;
     const bool exact = opt.exact != 0;
     switch (G) {
-        case 8: launch_factor_block<8>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
-        case 16: launch_factor_block<16>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
-        default: launch_factor_block<32>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
+        case 8: launch_factor_block<8>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, T.blk.nptr.p, T.blk.cr.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
+        case 16: launch_factor_block<16>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, T.blk.nptr.p, T.blk.cr.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
+        default: launch_factor_block<32>(exact, s, P, nblocks, T.blk.llev.p, T.blk.bdepth.p, h->fnfar.p, T.blk.nptr.p, T.blk.cr.p, h->fblock.p + 2, h->fblock.p, h->fblock.p + 1, epoch); break;
     }
     ILUB_CUDA(cudaGetLastError());
     h->launches++;
