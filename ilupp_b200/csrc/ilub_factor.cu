@@ -659,7 +659,7 @@ __global__ void k_factor_count_far(FactorParams P, int* __restrict__ nfar) {
 }
 
 template <int G, bool EXACT>
-__global__ void __launch_bounds__(512) k_factor_block(FactorParams P, int nblocks, const int* __restrict__ llev,
+__global__ void __launch_bounds__(512, 1) k_factor_block(FactorParams P, int nblocks, const int* __restrict__ llev,
                                                       const int* __restrict__ bdepth, const int* __restrict__ nfar_of,
                                                       const int* __restrict__ nptr, const int* __restrict__ crec,
                                                       unsigned* far_done /*[nblocks]*/,
