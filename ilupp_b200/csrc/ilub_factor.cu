@@ -638,6 +638,35 @@ __device__ __forceinline__ void factor_row_range(const FactorParams& P, int i, i
     }
 }
 
+// Second step of a row of the block factorisation that stayed in its group's buffer (see k_factor_block): the
+// eliminations [kb, ke) are all with rows of the SAME block, and every such row of at most RowSmem<G>::L entries still sits,
+// final, in the buffer of the group that owns it (group = row - r0): pivot and upper part are read from shared memory --
+// no global round trip on the critical path of a local level.  (Longer rows of the block are read from the factor array.)
+template <int G, bool EXACT>
+__device__ __forceinline__ void ilu0_row_local(const FactorParams& P, int i, int r0, int gl, unsigned gmask, const RowSmem<G>& R,
+                                               unsigned char* smem_base, int kb, int ke) {
+    const int p0 = P.ptr[i], len = P.ptr[i + 1] - p0;
+    for (int kk = kb; kk < ke; ++kk) {  // ILU0.hpp:47-62, ascending k
+        const int k = R.idx[kk];
+        const int pk = __ldg(P.ptr + k), qb = R.ra[kk], qe = R.rb[kk];  // row k: [pk, qe), upper part [qb, qe)
+        const bool in_smem = qe - pk <= RowSmem<G>::L;
+        const RowSmem<G> RK(smem_base + (size_t)(k - r0) * RowSmem<G>::kBytes);
+        const double wkk = R.val[kk];
+        const double ukk = in_smem ? RK.val[qb - 1 - pk] : __ldcg(P.lu + qb - 1);
+        const double lik = EXACT ? __ddiv_rn(wkk, ukk) : wkk / ukk;  // ILU0.hpp:52
+        for (int q = qb + gl; q < qe; q += G) {  // U[i, k+1:] -= L_ik * U[k, k+1:]   (ILU0.hpp:55-59)
+            const int c = in_smem ? RK.idx[q - pk] : __ldg(P.idx + q);
+            const double uu = in_smem ? RK.val[q - pk] : __ldcg(P.lu + q);
+            const int pos = lower_bound_s(R.idx, kk + 1, len, c);
+            if (pos < len && R.idx[pos] == c) R.val[pos] = sub_mul<EXACT>(R.val[pos], lik, uu);
+        }
+        __syncwarp(gmask);
+        if (gl == 0) R.val[kk] = lik;  // ILU0.hpp:61
+    }
+    __syncwarp(gmask);
+    for (int t = gl; t < len; t += G) P.lu[p0 + t] = R.val[t];
+}
+
 // number of strictly-lower entries of row i whose column is below `limit` (they come first: columns ascend)
 __device__ __forceinline__ int count_far(const FactorParams& P, int i, int limit) {
     int b = P.ptr[i], e = P.dpos[i];
@@ -713,7 +742,7 @@ __global__ void __launch_bounds__(512, 1) k_factor_block(FactorParams P, int nbl
         return;
     }
     // ---- the front: blocks in order, the near eliminations level by level of the block's local DAG
-    long long tw = 0, tl = 0, tbig = 0, nbig = 0, nlev_sum = 0;  // (debug, P.epoch != 0: where the front's time goes)
+    long long tw = 0, tl = 0, tbig = 0, nbig = 0, nlev_sum = 0, tstep1 = 0;  // (debug, P.epoch != 0: where the front's time goes)
     for (int K = 0; K < nblocks; ++K) {
         long long c0 = P.epoch ? clock64() : 0;
         if (threadIdx.x == 0) {
@@ -751,7 +780,7 @@ __global__ void __launch_bounds__(512, 1) k_factor_block(FactorParams P, int nbl
             }
         }
         __syncthreads();
-        if (P.epoch) { const long long c = clock64(); tl += c - c0; c0 = c; }
+        if (P.epoch) { const long long c = clock64(); tstep1 += c - c0; c0 = c; }
         // ... step 2, level by level of the block's local DAG: the eliminations with rows of the block itself
         for (int lv = 1; lv <= depth; ++lv) {
             bool hasbig = false;
@@ -766,7 +795,7 @@ __global__ void __launch_bounds__(512, 1) k_factor_block(FactorParams P, int nbl
                     hasbig = !small;
                     // (a row whose step 1 had nothing to do and was skipped still holds A's values)
                     const bool touched = nl - nloc > nfar || nfar > 0;
-                    if (keep) factor_row_range<G, EXACT>(P, i, gl, gmask, R, big, nl - nloc, nl, true, false, true, -1);
+                    if (keep) ilu0_row_local<G, EXACT>(P, i, r0, gl, gmask, R, factor_smem, nl - nloc, nl);
                     else factor_row_range<G, EXACT>(P, i, gl, gmask, R, big, nl - nloc, nl, touched, true, true, -1);
                 }
             }
@@ -779,6 +808,7 @@ __global__ void __launch_bounds__(512, 1) k_factor_block(FactorParams P, int nbl
         }
     }
     if (P.epoch && threadIdx.x == 0)
+        printf("factor front: step 1 %.0f cycles per block\n", (double)tstep1 / nblocks);
         printf("factor front: %d blocks, %lld local levels | cycles per block: wait %.0f, levels without long rows %.0f, with %.0f | %lld levels with a long row, %.0f cycles each; %.0f cycles per other level\n",
                nblocks, nlev_sum, (double)tw / nblocks, (double)tl / nblocks, (double)tbig / nblocks, nbig, nbig ? (double)tbig / nbig : 0.0,
                (double)tl / (double)(nlev_sum - nbig));
