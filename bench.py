@@ -333,6 +333,10 @@ def run_extras(args, ilupp, P, torch, dev, local, peak):
         t = time.perf_counter()
         B = ilupp.ILU0Preconditioner(Ai, device=local)
         wall = (time.perf_counter() - t) * 1e3
+        first = dict(zip(("symbolic", "numeric", "pack", "total"), B.timings_ms))
+        del B                       # second creation: the library's allocator holds the blocks of this shape now
+        torch.cuda.synchronize()
+        B = ilupp.ILU0Preconditioner(Ai, device=local)
         ms, y = _time_apply(B, torch.from_numpy(bi).to(dev), torch, 5)
         cpu = {}
         if oracle.ref is not None:
@@ -349,7 +353,10 @@ def run_extras(args, ilupp, P, torch, dev, local, peak):
         else:
             L, U = oracle.port.ilu0(Ai)
             yr = oracle.port.apply_lu(L, U, bi)
-        out["irregular_1m"] = dict(row(B, ms, y, yr, ichol=False), create_wall_ms=wall, cpu_reference_one_core=cpu)
+        r4 = row(B, ms, y, yr, ichol=False)
+        r4["factor_ms_warm_allocator"] = r4.pop("factor_ms_first_creation_of_this_shape")
+        r4["factor_ms_first_creation_of_this_shape"] = first
+        out["irregular_1m"] = dict(r4, create_wall_ms_first=wall, cpu_reference_one_core=cpu)
         del B
     return out
 
