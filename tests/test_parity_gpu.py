@@ -1166,3 +1166,36 @@ def test_block_sequential_solve(ilupp):
         assert Be.stats["part_mode"] == 5
         y = b.copy(); Be.apply(y)
         assert np.array_equal(y, oracle.port.apply_lu(Lo, Uo, b))
+
+
+@pytest.mark.parametrize("exact", [1, 0])
+def test_block_paths_ragged_size(ilupp, exact):
+    """Deep DAG whose size is not a multiple of the 32-row blocks and large enough for the probe: levels through
+    k_levels_block, factorisation through k_factor_block (bit for bit in exact mode), solve through k_trsv_block (fast
+    mode) -- all against the oracle."""
+    n = 300007
+    A = P.irregular_powerlaw(n=n, seed=11)
+    b = P.rhs(n, 6)
+    B = ilupp.ILU0Preconditioner(A, options={"exact": exact})
+    assert B.stats["part_mode"] == (5 if exact else 8), B.stats
+    Lo, Uo = oracle.port.ilu0(A)
+    L, U = B.factors()
+    assert same_pattern(L, Lo) and same_pattern(U, Uo)
+    assert relerr(L.data, Lo.data) <= TOL and relerr(U.data, Uo.data) <= TOL
+    if exact:
+        assert np.array_equal(L.data, Lo.data) and np.array_equal(U.data, Uo.data)
+    for which, lower in ((0, True), (1, False)):
+        lev, nlev = B.levels(which)
+        lo, nlo = oracle.port.levels(A.indptr, A.indices, lower=lower)
+        assert nlev == nlo and np.array_equal(lev, lo)
+    for tr in (False, True):
+        y = b.copy(); (B.apply_trans if tr else B.apply)(y)
+        yo = oracle.port.apply_lu(Lo, Uo, b, tr)
+        assert relerr(y, yo) <= TOL
+        if exact:
+            assert np.array_equal(y, yo)
+    A2 = A.copy(); A2.data = A.data * 1.25      # numeric re-factorisation on the unchanged pattern
+    B.refactor(A2)
+    L2o, U2o = oracle.port.ilu0(A2)
+    L2, U2 = B.factors()
+    assert relerr(L2.data, L2o.data) <= TOL and relerr(U2.data, U2o.data) <= TOL
