@@ -984,7 +984,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
     if (T.blk.built && !deep_wanted(h, slot)) {  // (the probe was wrong about the DAG: the layout is of no use)
         BlockSolve& B = T.blk;
         B.fptr.release(); B.fpos.release(); B.fsrc.release(); B.nptr.release(); B.npos.release(); B.nsrc.release();
-        B.cr.release(); B.dsrc.release(); B.fval.release(); B.nval.release(); B.rdiag.release(); B.bmeta.release();
+        B.cr.release(); B.co.release(); B.dsrc.release(); B.fval.release(); B.nval.release(); B.rdiag.release(); B.bmeta.release();
         B.llev.release(); B.bdepth.release();
         B.built = B.packed = false;
     }

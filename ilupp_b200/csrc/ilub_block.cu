@@ -4,10 +4,11 @@
 // mode; `exact` keeps the level loop of ilub_deep.cu, which reproduces the reference's accumulation order bit for bit.
 //
 // The level loop (ilub_deep.cu) pays one CTA barrier plus shared-memory round trips per LEVEL: 0.79 us x 113,837 levels.
-// Here the rows are taken in their natural solve order in blocks of 32 consecutive rows, one row per lane of ONE compute
-// warp, and nothing inside a block synchronises across warps:
+// Here the rows are taken in their natural solve order in blocks of 32 consecutive rows, one row per lane of a compute
+// warp (two warps take the blocks alternately: what a block needs from blocks older than the previous one is done while
+// the previous one is still being finished), and nothing inside a block synchronises across warps:
 //   * dependencies older than W = 512 rows ("far": the random long-range entries, 9.4 of the 19 per row) are final long
-//     before the block is reached: stager warps, 11 blocks ahead of the compute warp, gather them from the solution vector
+//     before the block is reached: stager warps, up to 11 blocks ahead of the compute warps, gather them from the solution vector
 //     through L2 and reduce them into r_i = b_i / d_i - sum c_ij x_j, so they never touch the critical path;
 //   * dependencies in the last W rows but in an earlier block ("recent") are a gather from a shared-memory ring of the
 //     most recent 1024 solved values;
@@ -35,7 +36,7 @@ constexpr int kBlk = 32;           // rows per block = lanes of the compute warp
 constexpr int kWin = 512;          // rows of history a "recent" dependency may reach back (older ones are "far")
 constexpr int kRing = 1024;        // shared-memory ring of solved values (>= kWin + 2 * kBlk, power of two)
 constexpr int kSlots = 12;         // staged blocks in flight: the stagers run up to kSlots - 1 blocks ahead
-constexpr int kStagers = 9;        // stager warps
+constexpr int kStagers = 6;        // stager warps
 constexpr int kSlotCap = 640;      // near entries of one block staged in shared memory (more: read from global)
 constexpr int kRegLoc = 8;         // local entries a lane keeps in registers (more: the row is "long")
 constexpr int kRegRec = 32;        // recent entries a lane gathers itself (more: the row is "long")
@@ -47,21 +48,27 @@ inline int blocks_for(int64_t work, int threads) { return (int)((work + threads 
 __device__ __forceinline__ int mirror(int backward, int n, int v) { return backward ? n - 1 - v : v; }
 
 // per solve position: how many far / recent / local entries
-__global__ void k_blk_count(int n, SrcDev S, int* __restrict__ cf, int* __restrict__ cr, int* __restrict__ cl) {
+// ("recent" = older than the previous block, then the previous block itself: the two compute warps take the first part
+//  one block ahead of time, see blk_compute)
+__global__ void k_blk_count(int n, SrcDev S, int* __restrict__ cf, int* __restrict__ cr, int* __restrict__ cl,
+                            int* __restrict__ co) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const int row = mirror(S.backward, n, q);
     const int b0 = (q / kBlk) * kBlk;
-    int f = 0, r = 0, l = 0;
+    int f = 0, r = 0, l = 0, o = 0;
     for (int e = src_beg(S, row); e < src_end(S, row); ++e) {
         const int pd = mirror(S.backward, n, S.dep_idx[e]);
         if (pd >= b0) ++l;
-        else if (pd >= b0 - kWin) ++r;
-        else ++f;
+        else if (pd >= b0 - kWin) {
+            ++r;
+            if (pd < b0 - kBlk) ++o;
+        } else ++f;
     }
     cf[q] = f;
     cr[q] = r;
     cl[q] = l;
+    co[q] = o;
 }
 __global__ void k_blk_sum(int n, const int* __restrict__ a, const int* __restrict__ b, int* __restrict__ c) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,22 +76,25 @@ __global__ void k_blk_sum(int n, const int* __restrict__ a, const int* __restric
 }
 // entries in place: far list; near list = recent entries, then local entries
 __global__ void k_blk_fill(int n, SrcDev S, const int* __restrict__ fptr, const int* __restrict__ nptr,
-                           const int* __restrict__ cr, int* __restrict__ fpos, int* __restrict__ fsrc,
-                           int* __restrict__ npos, int* __restrict__ nsrc, int* __restrict__ dsrc) {
+                           const int* __restrict__ cr, const int* __restrict__ co, int* __restrict__ fpos,
+                           int* __restrict__ fsrc, int* __restrict__ npos, int* __restrict__ nsrc, int* __restrict__ dsrc) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const int row = mirror(S.backward, n, q);
     const int b0 = (q / kBlk) * kBlk;
-    int pf = fptr[q], pr = nptr[q], pl = nptr[q] + cr[q];
+    int pf = fptr[q], po = nptr[q], pp = nptr[q] + co[q], pl = nptr[q] + cr[q];
     for (int e = src_beg(S, row); e < src_end(S, row); ++e) {
         const int pd = mirror(S.backward, n, S.dep_idx[e]);
         const int vp = S.val_pos ? S.val_pos[e] : e;
         if (pd >= b0) {
             npos[pl] = pd;
             nsrc[pl++] = vp;
+        } else if (pd >= b0 - kBlk) {
+            npos[pp] = pd;
+            nsrc[pp++] = vp;
         } else if (pd >= b0 - kWin) {
-            npos[pr] = pd;
-            nsrc[pr++] = vp;
+            npos[po] = pd;
+            nsrc[po++] = vp;
         } else {
             fpos[pf] = pd;
             fsrc[pf++] = vp;
@@ -95,7 +105,7 @@ __global__ void k_blk_fill(int n, SrcDev S, const int* __restrict__ fptr, const 
 // per block: depth of the local dependency DAG (sweeps needed), widest recent / local list among its regular rows, and the
 // mask of "long" rows (handled cooperatively).  One warp per block.
 __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, const int* __restrict__ cr,
-                           const int* __restrict__ npos, int4* __restrict__ bmeta, int* __restrict__ llev,
+                           const int* __restrict__ co, const int* __restrict__ npos, int4* __restrict__ bmeta, int* __restrict__ llev,
                            int* __restrict__ bdepth) {
     const int K = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,7 +136,10 @@ __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, con
     for (int t = 0; t < kBlk - 1; ++t)
         if (t < nloc) pointed |= 1u << (npos[nb + nrec + t] - K * kBlk);
     pointed = __reduce_or_sync(FULL, pointed);
-    const int maxrec = __reduce_max_sync(FULL, islong ? 0 : nrec);
+    const int nold = live ? co[q] : 0;
+    const int maxold = __reduce_max_sync(FULL, islong ? 0 : nold);
+    const int maxprev = __reduce_max_sync(FULL, islong ? 0 : nrec - nold);
+    const int maxrec = maxold | (maxprev << 16);  // (widest older / previous-block list among the regular rows)
     const int maxloc = __reduce_max_sync(FULL, islong ? 0 : nloc);
     const unsigned lmask = __ballot_sync(FULL, islong);
     const int leaf = (lmask & pointed) == 0 ? 1 : 0;
@@ -156,6 +169,7 @@ struct BlockParams {
     const double* fval;
     const int* nptr;
     const int* cr;  // recent entries per position (the rest of its near list is local)
+    const int* co;  // ... of which older than the previous block (they come first)
     const int* npos;
     const double* nval;
     const double* rdiag;
@@ -171,13 +185,13 @@ struct BlockSlot {
     double nval[kSlotCap];     // near entries of the block (all rows, concatenated)
     int npos[kSlotCap];
     int off[kBlk];             // first near entry of every row inside the slot (or inside the global arrays: big blocks)
-    int nrec[kBlk], nloc[kBlk];
-    int4 meta;                 // {depth, widest recent list, widest local list, mask of long rows} (k_blk_meta)
+    int nrec[kBlk], nloc[kBlk], nold[kBlk];
+    int4 meta;                 // {depth, widest older | previous-block list, widest local list, mask of long rows} (k_blk_meta)
     int big;                   // the block's near entries did not fit: read them from global memory
 };
 struct BlockSmem {
     double ring[kRing];
-    double xs[kBlk];           // the block's current values (cooperative long rows read them here)
+    double xs[2][kBlk];        // the block's current values, per compute warp (cooperative long rows read them here)
     BlockSlot slot[kSlots];
     int staged[kSlots];        // block number + 1 whose data the slot holds
     int progress;              // blocks completed by the compute warp
@@ -262,6 +276,7 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
         L.off[lane] = big ? nb : nb - nb0;
         L.nrec[lane] = nrec;
         L.nloc[lane] = ne - nb - nrec;
+        L.nold[lane] = live ? __ldg(P.co + q) : 0;
         if (lane == 0) {
             L.big = big ? 1 : 0;
             L.meta = __ldg(P.bmeta + K);
@@ -272,41 +287,24 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
     }
 }
 
-// ---------------------------------------------------------------- compute warp: the blocks, one after the other
-// One block.  BIG = the block's near entries live in global memory (they did not fit the slot); NL = local entries per
-// lane held in registers (4 or 8: every lane runs NL shuffles per sweep, absent entries carry coefficient 0).
-// A lone warp is bound by the latency of whatever it issues in sequence, so every phase requests all its operands first
-// and the loops have compile-time trip counts (no branch, no divergence check in front of the shuffles).
-template <bool BIG, int NL>
-__device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, BlockSlot& L, int K, int lane, int depthw,
-                                           int maxrec, unsigned lmask, long long* tt) {
-    const int depth = depthw & 0xffff;
-    const bool leaf = (depthw >> 16) != 0;  // long rows are leaves of the local DAG: their local sum is taken once, at the end
-    long long c0 = tt ? clock64() : 0;
-    const int* np = BIG ? P.npos : L.npos;
-    const double* nv = BIG ? P.nval : L.nval;
-    const int off = L.off[lane];
-    const int nrec = L.nrec[lane], nloc = L.nloc[lane];
-    const bool islong = (lmask >> lane) & 1u;
-    double r = L.r[lane];
-    const int b0 = K * kBlk;
-    // local entries first: their loads overlap with the recent gather below
-    int lsrc[NL];
-    double lco[NL];
-#pragma unroll
-    for (int t = 0; t < NL; ++t) {
-        const bool has = !islong && t < nloc;
-        lsrc[t] = has ? np[off + nrec + t] - b0 : lane;
-        lco[t] = has ? nv[off + nrec + t] : 0.0;
-    }
-    // ---- recent dependencies: the ring, eight entries per round (all indices, then all values, then the arithmetic;
-    //      sixteen per round measured slower: 699 against 539 cycles per block)
-    for (int t0 = 0; t0 < maxrec; t0 += 8) {
+// ---------------------------------------------------------------- compute warps: the blocks, one after the other
+// TWO warps take the blocks alternately.  A block is two phases: (A) everything that only needs blocks up to K - 2 --
+// slot data into registers, the recent entries OLDER than the previous block -- and (B) what needs block K - 1: the
+// entries that point into the previous block, the local sweeps, the publication.  Phase A of block K + 1 (other warp) runs
+// beside phase B of block K, so only B is on the critical path.
+// BIG = the block's near entries live in global memory (they did not fit the slot); NL = local entries per lane held in
+// registers (2 / 4 / 6 / 8: every lane runs NL shuffles per sweep, absent entries carry coefficient 0).  A lone warp is
+// bound by the latency of whatever it issues in sequence, so every phase requests all its operands first and the loops
+// have compile-time trip counts (no branch, no divergence check in front of the shuffles).
+template <bool BIG>
+__device__ __forceinline__ double blk_gather(const BlockSmem& M, const int* np, const double* nv, int off, int cnt, int maxcnt,
+                                             bool islong, double r) {
+    for (int t0 = 0; t0 < maxcnt; t0 += 8) {  // eight entries per round: all indices, then all ring values, then the arithmetic
         int pp[8];
         double cc[8], vv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const bool has = !islong && t0 + u < nrec;
+            const bool has = !islong && t0 + u < cnt;
             pp[u] = has ? np[off + t0 + u] : 0;
             cc[u] = has ? nv[off + t0 + u] : 0.0;
         }
@@ -320,24 +318,64 @@ __device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, B
         }
         r += r1;
     }
-    if (tt) { const long long c = clock64(); tt[0] += c - c0; c0 = c; }
-    unsigned lm = lmask;
-    while (lm) {  // long rows: the warp strides over the row's recent list
-        const int src = __ffs(lm) - 1;
-        lm &= lm - 1;
-        const int o = __shfl_sync(FULL, off, src), c = __shfl_sync(FULL, nrec, src);
+    return r;
+}
+// long rows: the warp strides over entries [first, first + cnt) of every long row's list
+__device__ __forceinline__ double blk_gather_long(const BlockSmem& M, const int* np, const double* nv, unsigned lmask, int first,
+                                                  int cnt, int lane, double r) {
+    while (lmask) {
+        const int src = __ffs(lmask) - 1;
+        lmask &= lmask - 1;
+        const int o = __shfl_sync(FULL, first, src), c = __shfl_sync(FULL, cnt, src);
         double part = 0.0;
         for (int t = lane; t < c; t += 32) part = fma(nv[o + t], M.ring[np[o + t] & (kRing - 1)], part);
         part = warp_sum(part);
         if (lane == src) r -= part;
     }
-    if (tt) { const long long c = clock64(); tt[1] += c - c0; c0 = c; }
-    // ---- local dependencies: Jacobi sweeps over the block, values exchanged by shuffles
+    return r;
+}
+
+template <bool BIG, int NL>
+__device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, BlockSlot& L, int K, int cw, int lane, int depthw,
+                                          int maxrec, unsigned lmask, unsigned& spins) {
+    const int depth = depthw & 0xffff;
+    const bool leaf = (depthw >> 16) != 0;  // long rows are leaves of the local DAG: their local sum is taken once, at the end
+    const int maxold = maxrec & 0xffff, maxprev = maxrec >> 16;
+    const int* np = BIG ? P.npos : L.npos;
+    const double* nv = BIG ? P.nval : L.nval;
+    const int off = L.off[lane];
+    const int nrec = L.nrec[lane], nloc = L.nloc[lane], nold = L.nold[lane];
+    const bool islong = (lmask >> lane) & 1u;
+    double r = L.r[lane];
+    const int b0 = K * kBlk;
+    // ---- phase A: local entries into registers, the recent entries older than the previous block
+    int lsrc[NL];
+    double lco[NL];
+#pragma unroll
+    for (int t = 0; t < NL; ++t) {
+        const bool has = !islong && t < nloc;
+        lsrc[t] = has ? np[off + nrec + t] - b0 : lane;
+        lco[t] = has ? nv[off + nrec + t] : 0.0;
+    }
+    r = blk_gather<BIG>(M, np, nv, off, nold, maxold, islong, r);
+    r = blk_gather_long(M, np, nv, lmask, off, nold, lane, r);
+    // ---- phase B: block K - 1 is complete
+    while (*(volatile int*)&M.progress < K) {
+        if ((++spins & 0x3ffu) == 0 && (spins >= P.spin_iters || *(volatile int*)P.status != 0)) {
+            atomicCAS(P.status, 0, 403);
+            return false;
+        }
+    }
+    fence_acq_rel_cta();
+    r = blk_gather<BIG>(M, np, nv, off + nold, nrec - nold, maxprev, islong, r);
+    r = blk_gather_long(M, np, nv, lmask, off + nold, nrec - nold, lane, r);
+    // local dependencies: Jacobi sweeps over the block, values exchanged by shuffles
+    double* xs = M.xs[cw];
     double x = r;
     for (int s = 0; s < depth; ++s) {
         double acc = r, acc1 = 0.0;
         if (lmask && !leaf) {  // (rare) long rows take their local sum from the values in shared memory
-            M.xs[lane] = x;
+            xs[lane] = x;
             __syncwarp();
             unsigned l2 = lmask;
             while (l2) {
@@ -345,7 +383,7 @@ __device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, B
                 l2 &= l2 - 1;
                 const int o = __shfl_sync(FULL, off + nrec, src), c = __shfl_sync(FULL, nloc, src);
                 double part = 0.0;
-                for (int t = lane; t < c; t += 32) part = fma(nv[o + t], M.xs[np[o + t] - b0], part);
+                for (int t = lane; t < c; t += 32) part = fma(nv[o + t], xs[np[o + t] - b0], part);
                 part = warp_sum(part);
                 if (lane == src) acc -= part;
             }
@@ -362,7 +400,7 @@ __device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, B
         x = acc + acc1;
     }
     if (lmask && leaf) {
-        M.xs[lane] = x;
+        xs[lane] = x;
         __syncwarp();
         unsigned l2 = lmask;
         while (l2) {
@@ -370,55 +408,53 @@ __device__ __forceinline__ double blk_body(const BlockParams& P, BlockSmem& M, B
             l2 &= l2 - 1;
             const int o = __shfl_sync(FULL, off + nrec, src), c = __shfl_sync(FULL, nloc, src);
             double part = 0.0;
-            for (int t = lane; t < c; t += 32) part = fma(nv[o + t], M.xs[np[o + t] - b0], part);
+            for (int t = lane; t < c; t += 32) part = fma(nv[o + t], xs[np[o + t] - b0], part);
             part = warp_sum(part);
             if (lane == src) x = r - part;
         }
         __syncwarp();
     }
-    if (tt) { const long long c = clock64(); tt[2] += c - c0; }
-    return x;
+    // ---- publish
+    const int q = b0 + lane;
+    M.ring[q & (kRing - 1)] = x;
+    if (q < P.n) __stcg(P.x + (P.backward ? P.n - 1 - q : q), x);
+    __syncwarp();
+    fence_acq_rel_cta();
+    if (lane == 0) *(volatile int*)&M.progress = K + 1;
+    return true;
 }
 
-__device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, int lane) {
+__device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, int cw, int lane) {
     unsigned spins = 0;
-    long long tt[3] = {0, 0, 0};
-    long long* ttp = P.trace ? tt : nullptr;
-    long long t_wait = 0, t_body = 0, t_pub = 0, sum_depth = 0, n_long = 0, sum_maxrec = 0, sum_maxloc = 0, n_big = 0;
-    for (int K = 0; K < P.nblocks; ++K) {
+    long long t_wait = 0, t_block = 0;
+    for (int K = cw; K < P.nblocks; K += 2) {
         BlockSlot& L = M.slot[K % kSlots];
         long long c0 = P.trace ? clock64() : 0;
         while (*(volatile int*)&M.staged[K % kSlots] != K + 1) BLK_SPIN(spins, 402)
+        // phase A reads ring values of blocks up to K - 2
+        while (*(volatile int*)&M.progress < K - 1) BLK_SPIN(spins, 404)
         fence_acq_rel_cta();  // (a volatile poll + one fence measured faster than ld.acquire polls: 125 against 185 cycles)
         if (P.trace) { const long long c = clock64(); t_wait += c - c0; c0 = c; }
         const int4 bm = L.meta;
         const int depth = bm.x, maxrec = bm.y, maxloc = bm.z;
         const unsigned lmask = (unsigned)bm.w;
-        double x;
-        if (L.big) x = blk_body<true, 8>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
-        else if (maxloc <= 2) x = blk_body<false, 2>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
-        else if (maxloc <= 4) x = blk_body<false, 4>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
-        else if (maxloc <= 6) x = blk_body<false, 6>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
-        else x = blk_body<false, 8>(P, M, L, K, lane, depth, maxrec, lmask, ttp);
-        if (P.trace) { const long long c = clock64(); t_body += c - c0; c0 = c; sum_depth += depth & 0xffff; n_long += lmask != 0; sum_maxrec += maxrec; sum_maxloc += maxloc; n_big += L.big; }
-        // ---- publish
-        const int q = K * kBlk + lane;
-        M.ring[q & (kRing - 1)] = x;
-        if (q < P.n) __stcg(P.x + (P.backward ? P.n - 1 - q : q), x);
-        __syncwarp();
-        fence_acq_rel_cta();
-        if (lane == 0) *(volatile int*)&M.progress = K + 1;
-        if (P.trace) { const long long c = clock64(); t_pub += c - c0; }
+        bool ok;
+        if (L.big) ok = blk_block<true, 8>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
+        else if (maxloc <= 2) ok = blk_block<false, 2>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
+        else if (maxloc <= 4) ok = blk_block<false, 4>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
+        else if (maxloc <= 6) ok = blk_block<false, 6>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
+        else ok = blk_block<false, 8>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
+        if (!ok) return;
+        if (P.trace) t_block += clock64() - c0;
     }
     if (P.trace && lane == 0) {
-        const double nb = (double)P.nblocks;
-        printf("  body: loads + recent %.0f, long recent %.0f, sweeps %.0f\n", tt[0] / nb, tt[1] / nb, tt[2] / nb);
-        printf("block solve: %d blocks | cycles per block: wait %.0f body %.0f publish %.0f | depth %.2f maxrec %.2f maxloc %.2f, blocks with long rows %.1f %%, big blocks %.2f %%\n",
-               P.nblocks, t_wait / nb, t_body / nb, t_pub / nb, sum_depth / nb, sum_maxrec / nb, sum_maxloc / nb, 100.0 * n_long / nb, 100.0 * n_big / nb);
+        const double nb = (double)((P.nblocks + 1 - cw) / 2);
+        printf("block solve, compute warp %d: %d blocks | cycles per own block: wait for slot / older blocks %.0f, phases A + B (incl. the wait for the previous block) %.0f\n",
+               cw, (int)nb, t_wait / nb, t_block / nb);
     }
 }
 
-constexpr int kWarps = 12;  // warp 0 computes; warps 4 and 8 (its scheduler) stay idle; the other nine stage
+constexpr int kWarps = 12;  // warps 0 and 1 compute; warps 4, 5, 8, 9 (their schedulers) stay idle; the other six stage
 __global__ void __launch_bounds__(kWarps * 32, 1) k_trsv_block(const BlockParams P) {
     extern __shared__ __align__(16) unsigned char blk_smem_raw[];
     BlockSmem& M = *reinterpret_cast<BlockSmem*>(blk_smem_raw);
@@ -427,11 +463,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_trsv_block(const BlockParams
     if (threadIdx.x < kSlots) M.staged[threadIdx.x] = 0;
     if (threadIdx.x == 0) M.progress = 0;
     __syncthreads();
-    // the compute warp has its scheduler (warps 0, 4, 8) to itself: every issue slot a stager takes there is latency on
-    // the critical path
-    if (warp == 0) blk_compute(P, M, lane);
-    else if ((warp & 3) != 0) blk_stager(P, M, warp - 1 - (warp >> 2), lane);
+    // the compute warps have their schedulers (warps 0, 4, 8 and 1, 5, 9) to themselves: every issue slot a stager takes
+    // there is latency on the critical path
+    if (warp < 2) blk_compute(P, M, warp, lane);
+    else if ((warp & 3) >= 2) blk_stager(P, M, (warp >> 2) * 2 + ((warp & 3) - 2), lane);
 }
+
+}  // namespace
+namespace {
 
 // ------------------------------------------------------------------------------------------------ dependency levels
 // The same schedule in the (max, +1) semiring: level(i) = max over the dependencies of level(dep) + 1.  The sync-free level
@@ -478,9 +517,10 @@ __device__ __forceinline__ int warp_max(int v) {
         }                                                                \
     }
 
+constexpr int kLevStagers = 9;  // (k_levels_block: one compute warp, nine stagers)
 __device__ __forceinline__ void lev_stager(const LevelParams& P, LevelSmem& M, int w, int lane) {
     unsigned spins = 0;
-    for (int K = w; K < P.nblocks; K += kStagers) {
+    for (int K = w; K < P.nblocks; K += kLevStagers) {
         LevelSlot& L = M.slot[K % kSlots];
         while (*(volatile int*)&M.progress < K - kSlots + 1) {
             __nanosleep(100);
@@ -552,7 +592,7 @@ __device__ __forceinline__ void lev_compute(const LevelParams& P, LevelSmem& M, 
         // (the sweeps of the solve may skip leaves; a level needs every row: depth of ALL rows = regular depth, or one
         //  more when the long rows are leaves)
         const int depth = (bm.x & 0xffff) + ((bm.x >> 16) ? 1 : 0);
-        const int maxrec = bm.y;
+        const int maxrec = (bm.y & 0xffff) + (bm.y >> 16);  // (bound of the recent loop: older + previous-block lists)
         const unsigned lmask = (unsigned)bm.w;
         const int* np = L.big ? P.npos : L.npos;
         const int off = L.off[lane], nrec = L.nrec[lane], nloc = L.nloc[lane];
@@ -688,9 +728,10 @@ void analyse_block(ilub_handle* h, int slot, cudaStream_t s) {
     cf.alloc((size_t)n + 1);
     cl.alloc((size_t)n + 1);
     B.cr.alloc((size_t)n + 1);
+    B.co.alloc((size_t)n + 1);
     DevBuf<int> cn;
     cn.alloc((size_t)n + 1);
-    k_blk_count<<<blocks_for(n, 256), 256, 0, s>>>(n, S, cf.p, B.cr.p, cl.p);
+    k_blk_count<<<blocks_for(n, 256), 256, 0, s>>>(n, S, cf.p, B.cr.p, cl.p, B.co.p);
     B.fptr.alloc((size_t)n + 1);
     B.nptr.alloc((size_t)n + 1);
     ILUB_CUDA(cudaMemsetAsync(cf.p + n, 0, sizeof(int), s));
@@ -720,13 +761,13 @@ void analyse_block(ilub_handle* h, int slot, cudaStream_t s) {
     B.nval.alloc((size_t)std::max(1, B.nnear));
     B.dsrc.alloc((size_t)n);
     B.rdiag.alloc((size_t)n);
-    k_blk_fill<<<blocks_for(n, 256), 256, 0, s>>>(n, S, B.fptr.p, B.nptr.p, B.cr.p, B.fpos.p, B.fsrc.p, B.npos.p, B.nsrc.p,
+    k_blk_fill<<<blocks_for(n, 256), 256, 0, s>>>(n, S, B.fptr.p, B.nptr.p, B.cr.p, B.co.p, B.fpos.p, B.fsrc.p, B.npos.p, B.nsrc.p,
                                                  B.dsrc.p);
     B.nblocks = (n + kBlk - 1) / kBlk;
     B.bmeta.alloc((size_t)B.nblocks);
     B.llev.alloc((size_t)n);
     B.bdepth.alloc((size_t)B.nblocks);
-    k_blk_meta<<<blocks_for((int64_t)B.nblocks * 32, 256), 256, 0, s>>>(n, B.nblocks, B.nptr.p, B.cr.p, B.npos.p, B.bmeta.p,
+    k_blk_meta<<<blocks_for((int64_t)B.nblocks * 32, 256), 256, 0, s>>>(n, B.nblocks, B.nptr.p, B.cr.p, B.co.p, B.npos.p, B.bmeta.p,
                                                                        B.llev.p, B.bdepth.p);
     h->launches += 6;
     ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here
@@ -760,6 +801,7 @@ void run_block(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.fval = B.fval.p;
     P.nptr = B.nptr.p;
     P.cr = B.cr.p;
+    P.co = B.co.p;
     P.npos = B.npos.p;
     P.nval = B.nval.p;
     P.rdiag = B.rdiag.p;

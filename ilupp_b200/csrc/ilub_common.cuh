@@ -233,6 +233,7 @@ struct BlockSolve {
     DevBuf<int> fptr, fpos, fsrc;   // far lists: [n + 1], dependency position, coefficient source in lu
     DevBuf<int> nptr, npos, nsrc;   // near lists
     DevBuf<int> cr;                 // [n] recent entries per row (the rest of its near list is local)
+    DevBuf<int> co;                 // [n] ... of which older than the previous block (first in the list)
     DevBuf<int> dsrc;               // [n] diagonal source in lu (-1: unit)
     DevBuf<double> fval, nval, rdiag;
     DevBuf<int4> bmeta;             // [nblocks] {depth of the local DAG, widest recent list, widest local list, long-row mask}
