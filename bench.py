@@ -325,6 +325,51 @@ def run_extras(args, ilupp, P, torch, dev, local, peak):
         del B, Ap, Lp
     finally:
         ilupp.set_option("solve_algo", 0)
+    # (3b) BASELINE config 3: ILU0 on convection-diffusion 160^3, apply + the device-resident BiCGStab to 1e-8
+    if not args.quick:
+        import scipy.sparse as sp
+        A3 = P.convdiff3d(160)
+        n3 = A3.shape[0]
+        b3 = A3 @ np.ones(n3)
+        B = ilupp.ILU0Preconditioner(A3, device=local)
+        ms, y = _time_apply(B, torch.from_numpy(P.rhs(n3, 0)).to(dev), torch, reps)
+        L3, U3 = oracle.port.ilu0(A3)
+        r3 = row(B, ms, y, oracle.port.apply_lu(L3, U3, P.rhs(n3, 0)), ichol=False)
+        B.solve(b3, 1e-8, 1e-8, 2000, info=True, method="bicgstab")      # warm-up (analysis of the solver's buffers)
+        t = time.perf_counter()
+        x3, (it3, rel3, abs3) = B.solve(b3, 1e-8, 1e-8, 2000, info=True, method="bicgstab")
+        solve_ms = (time.perf_counter() - t) * 1e3
+        r3["bicgstab"] = {"iterations": int(it3), "ms": solve_ms, "ms_per_iteration": solve_ms / max(1, int(it3)),
+                          "max_abs_error_vs_ones": float(np.abs(x3 - 1.0).max()),
+                          "reference_iterations_recorded": 139, "reference_ms_per_iteration_recorded": 308.0}
+        out["convdiff_160_ilu0"] = r3
+        del B, A3, L3, U3
+    # (3c) SURVEY 8(f)1: factors of the reference's threshold factorisations (computed on the CPU by the compiled
+    #      reference, oracle/_ref) applied on the GPU through FactorsPreconditioner -- 3-D Poisson 96^3
+    m = None if args.quick else oracle.ref_module()
+    if m is not None:
+        import scipy.sparse as sp
+        Af = P.poisson3d(96)
+        Af.indices = Af.indices.astype(np.int32)
+        Af.indptr = Af.indptr.astype(np.int32)
+        nf = Af.shape[0]
+        bf = P.rhs(nf, 0)
+        for key, make in (("ilut_fill10_1e-3", lambda: m.ILUTPreconditioner(Af.data, Af.indices, Af.indptr, True, 10, 1e-3)),
+                          ("icholt_fill5_1e-3", lambda: m.ICholTPreconditioner(Af.data, Af.indices, Af.indptr, True, 5, 1e-3))):
+            t = time.perf_counter()
+            R = make()
+            rf = (time.perf_counter() - t) * 1e3
+            fs = [(sp.csr_matrix if f[3] else sp.csc_matrix)((f[0], f[1], f[2]), shape=(nf, nf)) for f in R.factors_info()]
+            B = ilupp.FactorsPreconditioner(fs[0], fs[1] if len(fs) > 1 else None, device=local)
+            ms, y = _time_apply(B, torch.from_numpy(bf).to(dev), torch, 5)
+            yr = bf.copy()
+            t = time.perf_counter()
+            R.apply(yr)
+            ra = (time.perf_counter() - t) * 1e3
+            rr = row(B, ms, y, yr, ichol=len(fs) == 1)
+            rr["reference_cpu_one_core"] = {"factor_ms": rf, "apply_ms": ra}
+            out["reference_factors_96_" + key] = rr
+            del B, R
     # (4) BASELINE config 4: irregular power-law matrix, n = 10^6 (deep DAG), ILU0
     if not args.quick:
         Ai = P.irregular_powerlaw()
