@@ -2,7 +2,9 @@
 usage: dev_block.py [n]"""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.environ.get("ILUB_PKG_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("ILUB_PKG_ROOT"):
+    sys.path.insert(0, os.environ["ILUB_PKG_ROOT"])
 import torch
 import ilupp_b200 as ilupp
 from ilupp_b200 import problems as P
