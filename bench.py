@@ -498,6 +498,15 @@ def run_ours(args):
     barrier()
     torch.cuda.synchronize()
     with ClockSampler(local) as clk:
+        # the timed region below lasts a few milliseconds -- shorter than one nvidia-smi sampling period -- so the same
+        # workload first runs back to back for about 0.6 s (untimed) and the sampler sees the clocks the timed steps run
+        # at: same kernels, same stream, no gap before the timed loop
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < (0.2 if args.quick else 0.6):
+            for _ in range(50):
+                B.apply(x)
+            torch.cuda.synchronize()
+        launches0 = B.stats["launches"]
         t_wall0 = time.perf_counter()
         for k in range(args.steps):
             x.copy_(x0)               # restore the right-hand side (not timed: outside the event pair)
@@ -660,7 +669,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                     "ms_per_step": e2e_s * 1e3, "api": "IChol0Preconditioner.apply(numpy array in pinned host memory)"},
             "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": dict(clocks, sampled="nvidia-smi every 100 ms over 0.6 s of the same apply loop run back to back + the timed steps"),
             "parity": parity,
             "batched": batched,
             "extras": extras,
