@@ -1199,3 +1199,20 @@ def test_block_paths_ragged_size(ilupp, exact):
     L2o, U2o = oracle.port.ilu0(A2)
     L2, U2 = B.factors()
     assert relerr(L2.data, L2o.data) <= TOL and relerr(U2.data, U2o.data) <= TOL
+
+
+def test_syncfree_configuration_that_cannot_be_resident_is_refused(ilupp):
+    """The chunked sync-free kernel needs every CTA resident.  A configuration that cannot be (eight CTAs per SM do not fit
+    the shared memory its chunks need) is refused when the solve is analysed -- no dead-lock, no watchdog; the default
+    configuration of the same matrix gives the oracle's results."""
+    A = random_matrix(20000, "csr").tocsr()
+    A.sort_indices()
+    A.indices = A.indices.astype(np.int32); A.indptr = A.indptr.astype(np.int32)
+    b = P.rhs(A.shape[0], 8)
+    with pytest.raises(RuntimeError):
+        ilupp.ILU0Preconditioner(A, options={"solve_algo": 2, "ctas_per_sm": 8, "nparts": 600, "exact": 1})
+    B = ilupp.ILU0Preconditioner(A, options={"solve_algo": 2, "exact": 1})
+    Lo, Uo = oracle.port.ilu0(A)
+    for tr in (False, True):
+        y = b.copy(); (B.apply_trans if tr else B.apply)(y)
+        assert np.array_equal(y, oracle.port.apply_lu(Lo, Uo, b, tr))
