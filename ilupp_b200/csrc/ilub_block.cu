@@ -102,8 +102,9 @@ __global__ void k_blk_fill(int n, SrcDev S, const int* __restrict__ fptr, const 
     }
     dsrc[q] = S.diag_pos ? S.diag_pos[row] : -1;
 }
-// per block: depth of the local dependency DAG (sweeps needed), widest recent / local list among its regular rows, and the
-// mask of "long" rows (handled cooperatively).  One warp per block.
+// per block: depth of the local dependency DAG (sweeps needed), widest recent / local list among the rows that keep that
+// list in registers, and two masks of "long" rows: more than kRegRec recent entries (the warp gathers them cooperatively)
+// and more than kRegLoc local entries (the lane walks its own list in shared memory).  One warp per block.
 __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, const int* __restrict__ cr,
                            const int* __restrict__ co, const int* __restrict__ npos, int4* __restrict__ bmeta, int* __restrict__ llev,
                            int* __restrict__ bdepth) {
@@ -114,7 +115,7 @@ __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, con
     const bool live = q < n;
     const int nb = live ? nptr[q] : 0, ne = live ? nptr[q + 1] : 0;
     const int nrec = live ? cr[q] : 0, nloc = ne - nb - nrec;
-    const bool islong = nloc > kRegLoc || nrec > kRegRec;
+    const bool lrec = nrec > kRegRec, lloc = nloc > kRegLoc;
     int ll = 0;
     for (int it = 0; it < kBlk; ++it) {  // local levels by relaxation: at most 31 rounds
         int nl = 0;
@@ -129,22 +130,22 @@ __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, con
         if (!__any_sync(FULL, changed)) break;
     }
     const int depth_all = __reduce_max_sync(FULL, ll);
-    const int depth_reg = __reduce_max_sync(FULL, islong ? 0 : ll);
-    // are the long rows leaves of the block's local DAG (no local entry of any row points at them)?  Then their local sum
-    // is only needed once, after the last sweep
+    const int depth_reg = __reduce_max_sync(FULL, lloc ? 0 : ll);
+    // are the rows with long local lists leaves of the block's local DAG (no local entry of any row points at them)?  Then
+    // their local sum is only needed once, after the last sweep
     unsigned pointed = 0;
     for (int t = 0; t < kBlk - 1; ++t)
         if (t < nloc) pointed |= 1u << (npos[nb + nrec + t] - K * kBlk);
     pointed = __reduce_or_sync(FULL, pointed);
     const int nold = live ? co[q] : 0;
-    const int maxold = __reduce_max_sync(FULL, islong ? 0 : nold);
-    const int maxprev = __reduce_max_sync(FULL, islong ? 0 : nrec - nold);
-    const int maxrec = maxold | (maxprev << 16);  // (widest older / previous-block list among the regular rows)
-    const int maxloc = __reduce_max_sync(FULL, islong ? 0 : nloc);
-    const unsigned lmask = __ballot_sync(FULL, islong);
-    const int leaf = (lmask & pointed) == 0 ? 1 : 0;
+    const int maxold = __reduce_max_sync(FULL, lrec ? 0 : nold);
+    const int maxprev = __reduce_max_sync(FULL, lrec ? 0 : nrec - nold);
+    const int maxrec = maxold | (maxprev << 16);  // (widest older / previous-block list among the rows that gather their own)
+    const int maxloc = __reduce_max_sync(FULL, lloc ? 0 : nloc);
+    const unsigned mrec = __ballot_sync(FULL, lrec), mloc = __ballot_sync(FULL, lloc);
+    const int leaf = (mloc & pointed) == 0 ? 1 : 0;
     const int depth = leaf ? depth_reg : depth_all;  // (leaves are evaluated behind the sweeps: they need none themselves)
-    if (lane == 0) bmeta[K] = make_int4(depth | (leaf << 16), maxrec, maxloc, (int)lmask);
+    if (lane == 0) bmeta[K] = make_int4(depth | (leaf << 16) | (maxloc << 20), maxrec, (int)mloc, (int)mrec);
     if (live) llev[q] = ll;
     if (lane == 0) bdepth[K] = depth_all;
 }
@@ -186,12 +187,12 @@ struct BlockSlot {
     int npos[kSlotCap];
     int off[kBlk];             // first near entry of every row inside the slot (or inside the global arrays: big blocks)
     int nrec[kBlk], nloc[kBlk], nold[kBlk];
-    int4 meta;                 // {depth, widest older | previous-block list, widest local list, mask of long rows} (k_blk_meta)
+    int4 meta;                 // {depth | leaf << 16 | widest local list << 20, widest older | previous-block list, long-local mask, long-recent mask}
     int big;                   // the block's near entries did not fit: read them from global memory
 };
 struct BlockSmem {
     double ring[kRing];
-    double xs[2][kBlk];        // the block's current values, per compute warp (cooperative long rows read them here)
+    double xs[2][kBlk];        // the block's current values, per compute warp (rows with long local lists read them here)
     BlockSlot slot[kSlots];
     int staged[kSlots];        // block number + 1 whose data the slot holds
     int progress;              // blocks completed by the compute warp
@@ -335,17 +336,37 @@ __device__ __forceinline__ double blk_gather_long(const BlockSmem& M, const int*
     return r;
 }
 
+// a row with a long local list: the lane walks it itself, values from the block's copy in shared memory (two chains)
+__device__ __forceinline__ double blk_local_long(const int* np, const double* nv, const double* xs, int first, int cnt, int b0) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int t = 0; t < cnt; t += 4) {
+        int pp[4];
+        double cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool has = t + u < cnt;
+            pp[u] = has ? np[first + t + u] - b0 : 0;
+            cc[u] = has ? nv[first + t + u] : 0.0;
+        }
+        a0 = fma(cc[0], xs[pp[0]], a0);
+        a1 = fma(cc[1], xs[pp[1]], a1);
+        a0 = fma(cc[2], xs[pp[2]], a0);
+        a1 = fma(cc[3], xs[pp[3]], a1);
+    }
+    return a0 + a1;
+}
+
 template <bool BIG, int NL>
 __device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, BlockSlot& L, int K, int cw, int lane, int depthw,
-                                          int maxrec, unsigned lmask, unsigned& spins) {
+                                          int maxrec, unsigned mloc, unsigned mrec, unsigned& spins) {
     const int depth = depthw & 0xffff;
-    const bool leaf = (depthw >> 16) != 0;  // long rows are leaves of the local DAG: their local sum is taken once, at the end
+    const bool leaf = ((depthw >> 16) & 1) != 0;  // long local lists belong to leaves of the local DAG: summed once, at the end
     const int maxold = maxrec & 0xffff, maxprev = maxrec >> 16;
     const int* np = BIG ? P.npos : L.npos;
     const double* nv = BIG ? P.nval : L.nval;
     const int off = L.off[lane];
     const int nrec = L.nrec[lane], nloc = L.nloc[lane], nold = L.nold[lane];
-    const bool islong = (lmask >> lane) & 1u;
+    const bool lrec = (mrec >> lane) & 1u, lloc = (mloc >> lane) & 1u;
     double r = L.r[lane];
     const int b0 = K * kBlk;
     // ---- phase A: local entries into registers, the recent entries older than the previous block
@@ -353,12 +374,12 @@ __device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, Bl
     double lco[NL];
 #pragma unroll
     for (int t = 0; t < NL; ++t) {
-        const bool has = !islong && t < nloc;
+        const bool has = !lloc && t < nloc;
         lsrc[t] = has ? np[off + nrec + t] - b0 : lane;
         lco[t] = has ? nv[off + nrec + t] : 0.0;
     }
-    r = blk_gather<BIG>(M, np, nv, off, nold, maxold, islong, r);
-    r = blk_gather_long(M, np, nv, lmask, off, nold, lane, r);
+    r = blk_gather<BIG>(M, np, nv, off, nold, maxold, lrec, r);
+    r = blk_gather_long(M, np, nv, mrec, off, nold, lane, r);
     // ---- phase B: block K - 1 is complete
     while (*(volatile int*)&M.progress < K) {
         if ((++spins & 0x3ffu) == 0 && (spins >= P.spin_iters || *(volatile int*)P.status != 0)) {
@@ -367,26 +388,17 @@ __device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, Bl
         }
     }
     fence_acq_rel_cta();
-    r = blk_gather<BIG>(M, np, nv, off + nold, nrec - nold, maxprev, islong, r);
-    r = blk_gather_long(M, np, nv, lmask, off + nold, nrec - nold, lane, r);
+    r = blk_gather<BIG>(M, np, nv, off + nold, nrec - nold, maxprev, lrec, r);
+    r = blk_gather_long(M, np, nv, mrec, off + nold, nrec - nold, lane, r);
     // local dependencies: Jacobi sweeps over the block, values exchanged by shuffles
     double* xs = M.xs[cw];
     double x = r;
     for (int s = 0; s < depth; ++s) {
         double acc = r, acc1 = 0.0;
-        if (lmask && !leaf) {  // (rare) long rows take their local sum from the values in shared memory
+        if (mloc && !leaf) {  // (rare) a long local list that others depend on: its lane reads the block from shared memory
             xs[lane] = x;
             __syncwarp();
-            unsigned l2 = lmask;
-            while (l2) {
-                const int src = __ffs(l2) - 1;
-                l2 &= l2 - 1;
-                const int o = __shfl_sync(FULL, off + nrec, src), c = __shfl_sync(FULL, nloc, src);
-                double part = 0.0;
-                for (int t = lane; t < c; t += 32) part = fma(nv[o + t], xs[np[o + t] - b0], part);
-                part = warp_sum(part);
-                if (lane == src) acc -= part;
-            }
+            if (lloc) acc -= blk_local_long(np, nv, xs, off + nrec, nloc, b0);
             __syncwarp();
         }
         double v[NL];
@@ -399,19 +411,10 @@ __device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, Bl
         }
         x = acc + acc1;
     }
-    if (lmask && leaf) {
+    if (mloc && leaf) {
         xs[lane] = x;
         __syncwarp();
-        unsigned l2 = lmask;
-        while (l2) {
-            const int src = __ffs(l2) - 1;
-            l2 &= l2 - 1;
-            const int o = __shfl_sync(FULL, off + nrec, src), c = __shfl_sync(FULL, nloc, src);
-            double part = 0.0;
-            for (int t = lane; t < c; t += 32) part = fma(nv[o + t], xs[np[o + t] - b0], part);
-            part = warp_sum(part);
-            if (lane == src) x = r - part;
-        }
+        if (lloc) x = r - blk_local_long(np, nv, xs, off + nrec, nloc, b0);
         __syncwarp();
     }
     // ---- publish
@@ -436,14 +439,14 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
         fence_acq_rel_cta();  // (a volatile poll + one fence measured faster than ld.acquire polls: 125 against 185 cycles)
         if (P.trace) { const long long c = clock64(); t_wait += c - c0; c0 = c; }
         const int4 bm = L.meta;
-        const int depth = bm.x, maxrec = bm.y, maxloc = bm.z;
-        const unsigned lmask = (unsigned)bm.w;
+        const int depth = bm.x, maxrec = bm.y, maxloc = (bm.x >> 20) & 0xf;
+        const unsigned mloc = (unsigned)bm.z, mrec = (unsigned)bm.w;
         bool ok;
-        if (L.big) ok = blk_block<true, 8>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
-        else if (maxloc <= 2) ok = blk_block<false, 2>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
-        else if (maxloc <= 4) ok = blk_block<false, 4>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
-        else if (maxloc <= 6) ok = blk_block<false, 6>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
-        else ok = blk_block<false, 8>(P, M, L, K, cw, lane, depth, maxrec, lmask, spins);
+        if (L.big) ok = blk_block<true, 8>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
+        else if (maxloc <= 2) ok = blk_block<false, 2>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
+        else if (maxloc <= 4) ok = blk_block<false, 4>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
+        else if (maxloc <= 6) ok = blk_block<false, 6>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
+        else ok = blk_block<false, 8>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
         if (!ok) return;
         if (P.trace) t_block += clock64() - c0;
     }
@@ -591,9 +594,9 @@ __device__ __forceinline__ void lev_compute(const LevelParams& P, LevelSmem& M, 
         const int4 bm = L.meta;
         // (the sweeps of the solve may skip leaves; a level needs every row: depth of ALL rows = regular depth, or one
         //  more when the long rows are leaves)
-        const int depth = (bm.x & 0xffff) + ((bm.x >> 16) ? 1 : 0);
+        const int depth = (bm.x & 0xffff) + ((bm.x >> 16) & 1);
         const int maxrec = (bm.y & 0xffff) + (bm.y >> 16);  // (bound of the recent loop: older + previous-block lists)
-        const unsigned lmask = (unsigned)bm.w;
+        const unsigned lmask = (unsigned)(bm.z | bm.w);  // (here a row long in either list is handled by the whole warp)
         const int* np = L.big ? P.npos : L.npos;
         const int off = L.off[lane], nrec = L.nrec[lane], nloc = L.nloc[lane];
         const bool islong = (lmask >> lane) & 1u;

@@ -236,7 +236,7 @@ struct BlockSolve {
     DevBuf<int> co;                 // [n] ... of which older than the previous block (first in the list)
     DevBuf<int> dsrc;               // [n] diagonal source in lu (-1: unit)
     DevBuf<double> fval, nval, rdiag;
-    DevBuf<int4> bmeta;             // [nblocks] {depth of the local DAG, widest recent list, widest local list, long-row mask}
+    DevBuf<int4> bmeta;             // [nblocks] {depth | leaf << 16 | widest local list << 20, widest recent lists, long-local mask, long-recent mask}
     DevBuf<int> llev;               // [n] level of every row inside its block's local DAG (the block factorisation walks them)
     DevBuf<int> bdepth;             // [nblocks] deepest local level of the block (all rows)
 };
