@@ -985,7 +985,7 @@ void analyse_solve(ilub_handle* h, int slot, cudaStream_t s) {
         BlockSolve& B = T.blk;
         B.fptr.release(); B.fpos.release(); B.fsrc.release(); B.nptr.release(); B.npos.release(); B.nsrc.release();
         B.cr.release(); B.co.release(); B.dsrc.release(); B.fval.release(); B.nval.release(); B.rdiag.release(); B.bmeta.release();
-        B.llev.release(); B.bdepth.release();
+        B.llev.release(); B.bdepth.release(); B.cptr.release(); B.cpos.release(); B.cval.release();
         B.built = B.packed = false;
     }
     if (!sys_ok && block_wanted(h, slot)) {

@@ -35,10 +35,19 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int kBlk = 32;           // rows per block = lanes of the compute warp
 constexpr int kWin = 512;          // rows of history a "recent" dependency may reach back (older ones are "far")
 constexpr int kRing = 1024;        // shared-memory ring of solved values (>= kWin + 2 * kBlk, power of two)
-constexpr int kSlots = 12;         // staged blocks in flight: the stagers run up to kSlots - 1 blocks ahead
-constexpr int kStagers = 6;        // stager warps
+#ifndef BLK_SLOTS
+#define BLK_SLOTS 12
+#endif
+#ifndef BLK_STAGERS
+#define BLK_STAGERS 8
+#endif
+constexpr int kSlots = BLK_SLOTS;         // staged blocks in flight: the stagers run up to kSlots - 1 blocks ahead
+constexpr int kStagers = BLK_STAGERS;        // stager warps
+static_assert(kSlots <= kWin / kBlk + 1, "a stager starts block K once block K - kSlots is done: its far dependencies (older than kWin rows) must be final by then");
 constexpr int kSlotCap = 640;      // near entries of one block staged in shared memory (more: read from global)
 constexpr int kRegLoc = 8;         // local entries a lane keeps in registers (more: the row is "long")
+constexpr int kRegClo = 16;        // entries of a row's solved local system (closure) a lane keeps in registers
+constexpr int kCloCap = 256;       // closure entries of one block staged in shared memory (more: the block runs the sweeps)
 constexpr int kRegRec = 32;        // recent entries a lane gathers itself (more: the row is "long")
 
 inline int blocks_for(int64_t work, int threads) { return (int)((work + threads - 1) / threads); }
@@ -107,7 +116,7 @@ __global__ void k_blk_fill(int n, SrcDev S, const int* __restrict__ fptr, const 
 // and more than kRegLoc local entries (the lane walks its own list in shared memory).  One warp per block.
 __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, const int* __restrict__ cr,
                            const int* __restrict__ co, const int* __restrict__ npos, int4* __restrict__ bmeta, int* __restrict__ llev,
-                           int* __restrict__ bdepth) {
+                           int* __restrict__ bdepth, unsigned* __restrict__ cmask, int* __restrict__ ccnt) {
     const int K = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (K >= nblocks) return;
@@ -116,27 +125,40 @@ __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, con
     const int nb = live ? nptr[q] : 0, ne = live ? nptr[q + 1] : 0;
     const int nrec = live ? cr[q] : 0, nloc = ne - nb - nrec;
     const bool lrec = nrec > kRegRec, lloc = nloc > kRegLoc;
+    const int widest = __reduce_max_sync(FULL, nloc);
+    unsigned direct = 0;
+    for (int t = 0; t < nloc; ++t) direct |= 1u << (npos[nb + nrec + t] - K * kBlk);
+    // local levels, and the transitive closure of the local dependencies (the pattern of the block's solved local system),
+    // by relaxation: at most 31 rounds
     int ll = 0;
-    for (int it = 0; it < kBlk; ++it) {  // local levels by relaxation: at most 31 rounds
+    unsigned reach = direct;
+    for (int it = 0; it < kBlk; ++it) {
         int nl = 0;
-        for (int t = 0; t < kBlk - 1; ++t) {  // (uniform trip count: the shuffles below need every lane)
+        unsigned nr = direct;
+        for (int t = 0; t < widest; ++t) {  // (uniform trip count: the shuffles below need every lane)
             const bool has = t < nloc;
             const int src = has ? npos[nb + nrec + t] - K * kBlk : 0;
             const int v = __shfl_sync(FULL, ll, src);
-            if (has) nl = max(nl, v + 1);
+            const unsigned m = __shfl_sync(FULL, reach, src);
+            if (has) {
+                nl = max(nl, v + 1);
+                nr |= m;
+            }
         }
-        const bool changed = nl != ll;
+        const bool changed = nl != ll || nr != reach;
         ll = nl;
+        reach = nr;
         if (!__any_sync(FULL, changed)) break;
+    }
+    if (live) {
+        cmask[q] = reach;
+        ccnt[q] = __popc(reach);
     }
     const int depth_all = __reduce_max_sync(FULL, ll);
     const int depth_reg = __reduce_max_sync(FULL, lloc ? 0 : ll);
     // are the rows with long local lists leaves of the block's local DAG (no local entry of any row points at them)?  Then
     // their local sum is only needed once, after the last sweep
-    unsigned pointed = 0;
-    for (int t = 0; t < kBlk - 1; ++t)
-        if (t < nloc) pointed |= 1u << (npos[nb + nrec + t] - K * kBlk);
-    pointed = __reduce_or_sync(FULL, pointed);
+    const unsigned pointed = __reduce_or_sync(FULL, direct);
     const int nold = live ? co[q] : 0;
     const int maxold = __reduce_max_sync(FULL, lrec ? 0 : nold);
     const int maxprev = __reduce_max_sync(FULL, lrec ? 0 : nrec - nold);
@@ -162,6 +184,49 @@ __global__ void k_blk_pack(int n, const int* __restrict__ fptr, const int* __res
     for (int e = nptr[q] + gl; e < nptr[q + 1]; e += 8) nval[e] = lu[nsrc[e]] * dinv;
 }
 
+// closure positions of a row = the set bits of its mask, ascending
+__global__ void k_blk_clo_fill(int n, const int* __restrict__ cptr, const unsigned* __restrict__ cmask, int* __restrict__ cpos) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    unsigned m = cmask[q];
+    int p = cptr[q];
+    while (m) {
+        cpos[p++] = __ffs(m) - 1;
+        m &= m - 1;
+    }
+}
+// values of the solved local systems: N = (I + L_local)^-1 - I, row by row in solve order (every local dependency of a row is
+// an earlier row of the block): N_i = - sum_j l_ij (e_j + N_j).  One warp per block, lane = COLUMN of N (columns are
+// independent, so the row loop needs no synchronisation); the dense 32 x 32 block lives in shared memory.
+constexpr int kCloWarps = 4;
+__global__ void __launch_bounds__(kCloWarps * 32) k_blk_clo_pack(int n, int nblocks, const int* __restrict__ nptr,
+                                                                const int* __restrict__ cr, const int* __restrict__ npos,
+                                                                const double* __restrict__ nval, const int* __restrict__ cptr,
+                                                                const int* __restrict__ cpos, double* __restrict__ cval) {
+    __shared__ double Ms[kCloWarps][kBlk * 33];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = blockIdx.x * kCloWarps + w;
+    if (K >= nblocks) return;
+    double* M = Ms[w];
+    const int b0 = K * kBlk;
+    const int q = b0 + lane;
+    const bool live = q < n;
+    const int my_lb = live ? nptr[q] + cr[q] : 0, my_le = live ? nptr[q + 1] : 0;
+    if (__reduce_max_sync(FULL, my_le - my_lb) == 0) return;  // (no local dependency in the block: nothing to store)
+    for (int i = 0; i < kBlk; ++i) {
+        const int lb = __shfl_sync(FULL, my_lb, i), le = __shfl_sync(FULL, my_le, i);
+        double acc = 0.0;
+        for (int e = lb; e < le; ++e) {
+            const int j = __ldg(npos + e) - b0;
+            acc = fma(-__ldg(nval + e), (lane == j ? 1.0 : 0.0) + M[j * 33 + lane], acc);
+        }
+        M[i * 33 + lane] = acc;
+    }
+    __syncwarp();
+    if (live)
+        for (int e = cptr[q]; e < cptr[q + 1]; ++e) cval[e] = M[lane * 33 + cpos[e]];
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 struct BlockParams {
     int n, nblocks, backward;
@@ -175,6 +240,9 @@ struct BlockParams {
     const double* nval;
     const double* rdiag;
     const int4* bmeta;
+    const int* cptr;  // solved local systems (closure lists)
+    const int* cpos;
+    const double* cval;
     double* x;  // right-hand side in, solution out (natural row order)
     int* status;
     unsigned spin_iters;
@@ -189,6 +257,10 @@ struct BlockSlot {
     int nrec[kBlk], nloc[kBlk], nold[kBlk];
     int4 meta;                 // {depth | leaf << 16 | widest local list << 20, widest older | previous-block list, long-local mask, long-recent mask}
     int big;                   // the block's near entries did not fit: read them from global memory
+    double cval[kCloCap];      // the block's solved local system (closure lists, all rows concatenated)
+    int cpos[kCloCap];
+    int coff[kBlk], ccnt[kBlk];
+    int clo;                   // ... is staged (else: the block runs Jacobi sweeps over its local entries)
 };
 struct BlockSmem {
     double ring[kRing];
@@ -213,24 +285,77 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------- stager: far dependencies + near lists of block K
+// A stager is a chain of dependent HBM reads (pointers -> entries -> solved values), about 0.8 us each.  Everything that does
+// not depend on the solve's progress -- pointers, counts, the first far entries, the near and closure lists -- is requested
+// BEFORE the stager waits for its slot, in two rounds of independent loads; only the solved values and the slot writes
+// come behind the wait.
+constexpr int kStageNear = 4;  // near / closure entries per lane held in registers across the wait (x 32 lanes)
+constexpr int kStageClo = 2;
 __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, int w, int lane) {
     unsigned spins = 0;
     for (int K = w; K < P.nblocks; K += kStagers) {
         BlockSlot& L = M.slot[K % kSlots];
+        const int q = K * kBlk + lane;
+        const bool live = q < P.n;
+        const int row = live ? (P.backward ? P.n - 1 - q : q) : 0;
+        const int q_last = min(P.n, K * kBlk + kBlk);
+        // round 1: pointers and per-row scalars
+        const int fb = live ? __ldg(P.fptr + q) : 0, fe = live ? __ldg(P.fptr + q + 1) : 0;
+        const int nb = live ? __ldg(P.nptr + q) : 0, ne = live ? __ldg(P.nptr + q + 1) : 0;
+        const int cb = live ? __ldg(P.cptr + q) : 0, ce = live ? __ldg(P.cptr + q + 1) : 0;
+        const int ne_all = __ldg(P.nptr + q_last), ce_all = __ldg(P.cptr + q_last);
+        const int nrec = live ? __ldg(P.cr + q) : 0, nold = live ? __ldg(P.co + q) : 0;
+        const double rd = live ? __ldg(P.rdiag + q) : 0.0;
+        const double bq = live ? P.x[row] : 0.0;  // (the right-hand side: the row's own value is not solved yet)
+        int4 meta = make_int4(0, 0, 0, 0);
+        if (lane == 0) meta = __ldg(P.bmeta + K);
+        const int nb0 = __shfl_sync(FULL, nb, 0), cb0 = __shfl_sync(FULL, cb, 0);
+        const int total = ne_all - nb0, ctotal = ce_all - cb0;
+        const bool big = total > kSlotCap;
+        const bool clo = !big && ctotal <= kCloCap;
+        const bool flong = fe - fb > 64;
+        // round 2: entries
+        int fp[8];
+        double fc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool has = !flong && fb + u < fe;
+            fp[u] = has ? __ldg(P.fpos + fb + u) : -1;
+            fc[u] = has ? __ldg(P.fval + fb + u) : 0.0;
+        }
+        int npr[kStageNear], cpr[kStageClo];
+        double nvr[kStageNear], cvr[kStageClo];
+#pragma unroll
+        for (int u = 0; u < kStageNear; ++u) {
+            const int t = lane + 32 * u;
+            const bool has = !big && t < total;
+            npr[u] = has ? __ldg(P.npos + nb0 + t) : 0;
+            nvr[u] = has ? __ldg(P.nval + nb0 + t) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kStageClo; ++u) {
+            const int t = lane + 32 * u;
+            const bool has = clo && t < ctotal;
+            cpr[u] = has ? __ldg(P.cpos + cb0 + t) : 0;
+            cvr[u] = has ? __ldg(P.cval + cb0 + t) : 0.0;
+        }
         // the slot is free once block K - kSlots is done; then every far dependency (older than kWin rows) is final too
         while (*(volatile int*)&M.progress < K - kSlots + 1) {
             __nanosleep(100);
             BLK_SPIN(spins, 401)
         }
         fence_acq_rel_cta();
-        const int q = K * kBlk + lane;
-        const bool live = q < P.n;
-        const int row = live ? (P.backward ? P.n - 1 - q : q) : 0;
-        const int fb = live ? __ldg(P.fptr + q) : 0, fe = live ? __ldg(P.fptr + q + 1) : 0;
-        double r = live ? P.x[row] * __ldg(P.rdiag + q) : 0.0;
-        const bool flong = fe - fb > 64;
+        // round 3: solved values of the far dependencies
+        double r = bq * rd;
+        {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = fp[u] >= 0 ? __ldcg(P.x + (P.backward ? P.n - 1 - fp[u] : fp[u])) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r = fma(-fc[u], v[u], r);
+        }
         if (!flong) {
-            for (int e0 = fb; e0 < fe; e0 += 8) {
+            for (int e0 = fb + 8; e0 < fe; e0 += 8) {
                 double c[8], v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -260,27 +385,44 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
             part = warp_sum(part);
             if (lane == src) r -= part;
         }
-        // near lists
-        const int nb = live ? __ldg(P.nptr + q) : 0, ne = live ? __ldg(P.nptr + q + 1) : 0;
-        const int nb0 = __shfl_sync(FULL, nb, 0);
-        const int q_last = min(P.n, K * kBlk + kBlk);
-        const int ne_all = __ldg(P.nptr + q_last);
-        const int total = ne_all - nb0;
-        const bool big = total > kSlotCap;
+        // the slot
+#pragma unroll
+        for (int u = 0; u < kStageNear; ++u) {
+            const int t = lane + 32 * u;
+            if (!big && t < total) {
+                L.npos[t] = npr[u];
+                L.nval[t] = nvr[u];
+            }
+        }
         if (!big)
-            for (int t = lane; t < total; t += 32) {
+            for (int t = lane + 32 * kStageNear; t < total; t += 32) {
                 L.npos[t] = __ldg(P.npos + nb0 + t);
                 L.nval[t] = __ldg(P.nval + nb0 + t);
             }
-        const int nrec = live ? __ldg(P.cr + q) : 0;
+#pragma unroll
+        for (int u = 0; u < kStageClo; ++u) {
+            const int t = lane + 32 * u;
+            if (clo && t < ctotal) {
+                L.cpos[t] = cpr[u];
+                L.cval[t] = cvr[u];
+            }
+        }
+        if (clo)
+            for (int t = lane + 32 * kStageClo; t < ctotal; t += 32) {
+                L.cpos[t] = __ldg(P.cpos + cb0 + t);
+                L.cval[t] = __ldg(P.cval + cb0 + t);
+            }
+        L.coff[lane] = cb - cb0;
+        L.ccnt[lane] = ce - cb;
         L.r[lane] = r;
         L.off[lane] = big ? nb : nb - nb0;
         L.nrec[lane] = nrec;
         L.nloc[lane] = ne - nb - nrec;
-        L.nold[lane] = live ? __ldg(P.co + q) : 0;
+        L.nold[lane] = nold;
         if (lane == 0) {
             L.big = big ? 1 : 0;
-            L.meta = __ldg(P.bmeta + K);
+            L.clo = clo ? 1 : 0;
+            L.meta = meta;
         }
         __syncwarp();
         fence_acq_rel_cta();
@@ -427,6 +569,86 @@ __device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, Bl
     return true;
 }
 
+// a row whose solved local system has more than kRegClo entries: the lane walks its list itself
+__device__ __forceinline__ double blk_clo_long(const int* cp, const double* cv, const double* xs, int first, int cnt) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int t = 0; t < cnt; t += 4) {
+        int pp[4];
+        double cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool has = t + u < cnt;
+            pp[u] = has ? cp[first + t + u] : 0;
+            cc[u] = has ? cv[first + t + u] : 0.0;
+        }
+        a0 = fma(cc[0], xs[pp[0]], a0);
+        a1 = fma(cc[1], xs[pp[1]], a1);
+        a0 = fma(cc[2], xs[pp[2]], a0);
+        a1 = fma(cc[3], xs[pp[3]], a1);
+    }
+    return a0 + a1;
+}
+// The block with its local system solved ahead of time (k_blk_clo_pack): x = r + N r, ONE exchange of the 32 right-hand
+// sides instead of depth(block) dependent sweeps.  NC = closure entries per lane held in registers (4 / 8 / 12 / 16).
+template <int NC>
+__device__ __forceinline__ bool blk_block_clo(const BlockParams& P, BlockSmem& M, BlockSlot& L, int K, int cw, int lane, int maxrec,
+                                              unsigned mrec, unsigned mclo, unsigned& spins) {
+    const int maxold = maxrec & 0xffff, maxprev = maxrec >> 16;
+    const int* np = L.npos;
+    const double* nv = L.nval;
+    const int off = L.off[lane];
+    const int nrec = L.nrec[lane], nold = L.nold[lane];
+    const int coff = L.coff[lane], ccnt = L.ccnt[lane];
+    const bool lrec = (mrec >> lane) & 1u, lclo = (mclo >> lane) & 1u;
+    double r = L.r[lane];
+    const int b0 = K * kBlk;
+    // ---- phase A: the closure list into registers, the recent entries older than the previous block
+    int csrc[NC];
+    double cco[NC];
+#pragma unroll
+    for (int t = 0; t < NC; ++t) {
+        const bool has = !lclo && t < ccnt;
+        csrc[t] = has ? L.cpos[coff + t] : lane;
+        cco[t] = has ? L.cval[coff + t] : 0.0;
+    }
+    r = blk_gather<false>(M, np, nv, off, nold, maxold, lrec, r);
+    r = blk_gather_long(M, np, nv, mrec, off, nold, lane, r);
+    // ---- phase B: block K - 1 is complete
+    while (*(volatile int*)&M.progress < K) {
+        if ((++spins & 0x3ffu) == 0 && (spins >= P.spin_iters || *(volatile int*)P.status != 0)) {
+            atomicCAS(P.status, 0, 403);
+            return false;
+        }
+    }
+    fence_acq_rel_cta();
+    r = blk_gather<false>(M, np, nv, off + nold, nrec - nold, maxprev, lrec, r);
+    r = blk_gather_long(M, np, nv, mrec, off + nold, nrec - nold, lane, r);
+    double* xs = M.xs[cw];
+    if (mclo) {
+        xs[lane] = r;
+        __syncwarp();
+    }
+    double v[NC];
+#pragma unroll
+    for (int t = 0; t < NC; ++t) v[t] = __shfl_sync(FULL, r, csrc[t]);
+    double a[4] = {r, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int t = 0; t < NC; ++t) a[t & 3] = fma(cco[t], v[t], a[t & 3]);
+    double x = (a[0] + a[1]) + (a[2] + a[3]);
+    if (mclo) {
+        if (lclo) x = r + blk_clo_long(L.cpos, L.cval, xs, coff, ccnt);
+        __syncwarp();
+    }
+    // ---- publish
+    const int q = b0 + lane;
+    M.ring[q & (kRing - 1)] = x;
+    if (q < P.n) __stcg(P.x + (P.backward ? P.n - 1 - q : q), x);
+    __syncwarp();
+    fence_acq_rel_cta();
+    if (lane == 0) *(volatile int*)&M.progress = K + 1;
+    return true;
+}
+
 __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, int cw, int lane) {
     unsigned spins = 0;
     long long t_wait = 0, t_block = 0;
@@ -442,7 +664,15 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
         const int depth = bm.x, maxrec = bm.y, maxloc = (bm.x >> 20) & 0xf;
         const unsigned mloc = (unsigned)bm.z, mrec = (unsigned)bm.w;
         bool ok;
-        if (L.big) ok = blk_block<true, 8>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
+        if (L.clo) {
+            const int ccnt = L.ccnt[lane];
+            const unsigned mclo = __ballot_sync(FULL, ccnt > kRegClo);
+            const int maxclo = __reduce_max_sync(FULL, ccnt > kRegClo ? 0 : ccnt);
+            if (maxclo <= 4) ok = blk_block_clo<4>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
+            else if (maxclo <= 8) ok = blk_block_clo<8>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
+            else if (maxclo <= 12) ok = blk_block_clo<12>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
+            else ok = blk_block_clo<16>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
+        } else if (L.big) ok = blk_block<true, 8>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
         else if (maxloc <= 2) ok = blk_block<false, 2>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
         else if (maxloc <= 4) ok = blk_block<false, 4>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
         else if (maxloc <= 6) ok = blk_block<false, 6>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
@@ -457,7 +687,7 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
     }
 }
 
-constexpr int kWarps = 12;  // warps 0 and 1 compute; warps 4, 5, 8, 9 (their schedulers) stay idle; the other six stage
+constexpr int kWarps = 2 * kStagers;  // warps 0 and 1 compute; warps 4, 5, 8, 9 (their schedulers) stay idle; the other six stage
 __global__ void __launch_bounds__(kWarps * 32, 1) k_trsv_block(const BlockParams P) {
     extern __shared__ __align__(16) unsigned char blk_smem_raw[];
     BlockSmem& M = *reinterpret_cast<BlockSmem*>(blk_smem_raw);
@@ -667,7 +897,8 @@ __device__ __forceinline__ void lev_compute(const LevelParams& P, LevelSmem& M, 
     if (lane == 0) *P.nlev = top;
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 1) k_levels_block(const LevelParams P) {
+constexpr int kLevWarps = 12;
+__global__ void __launch_bounds__(kLevWarps * 32, 1) k_levels_block(const LevelParams P) {
     extern __shared__ __align__(16) unsigned char blk_smem_raw[];
     LevelSmem& M = *reinterpret_cast<LevelSmem*>(blk_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -706,7 +937,7 @@ int levels_block(ilub_handle* h, int slot, cudaStream_t s) {
     P.nlev = nlev.p;
     P.status = h->status.p;
     P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 20, (long long)options().spin_limit_ms * h->clock_khz / 32));
-    k_levels_block<<<1, kWarps * 32, smem, s>>>(P);
+    k_levels_block<<<1, kLevWarps * 32, smem, s>>>(P);
     h->launches++;
     int v = 0;
     ILUB_CUDA(cudaMemcpyAsync(&v, nlev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -770,9 +1001,22 @@ void analyse_block(ilub_handle* h, int slot, cudaStream_t s) {
     B.bmeta.alloc((size_t)B.nblocks);
     B.llev.alloc((size_t)n);
     B.bdepth.alloc((size_t)B.nblocks);
+    DevBuf<unsigned> cmask;
+    cmask.alloc((size_t)n);
     k_blk_meta<<<blocks_for((int64_t)B.nblocks * 32, 256), 256, 0, s>>>(n, B.nblocks, B.nptr.p, B.cr.p, B.co.p, B.npos.p, B.bmeta.p,
-                                                                       B.llev.p, B.bdepth.p);
-    h->launches += 6;
+                                                                       B.llev.p, B.bdepth.p, cmask.p, cn.p);
+    // closure lists of the solved local systems
+    B.cptr.alloc((size_t)n + 1);
+    ILUB_CUDA(cudaMemsetAsync(cn.p + n, 0, sizeof(int), s));
+    tbb = tmp.n;
+    ILUB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tbb, cn.p, B.cptr.p, n + 1, s));
+    ILUB_CUDA(cudaMemcpyAsync(&ends[0], B.cptr.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ILUB_CUDA(cudaStreamSynchronize(s));
+    B.nclo = ends[0];
+    B.cpos.alloc((size_t)std::max(1, B.nclo));
+    B.cval.alloc((size_t)std::max(1, B.nclo));
+    k_blk_clo_fill<<<blocks_for(n, 256), 256, 0, s>>>(n, B.cptr.p, cmask.p, B.cpos.p);
+    h->launches += 8;
     ILUB_CUDA(cudaStreamSynchronize(s));  // temporaries die here
     B.packed = false;
     B.built = true;
@@ -783,7 +1027,9 @@ void pack_block(ilub_handle* h, int slot, cudaStream_t s) {
     if (!B.built) return;
     k_blk_pack<<<blocks_for((int64_t)h->n * 8, 256), 256, 0, s>>>(h->n, B.fptr.p, B.nptr.p, B.fsrc.p, B.nsrc.p, B.dsrc.p, h->lu.p,
                                                                  B.fval.p, B.nval.p, B.rdiag.p);
-    h->launches++;
+    k_blk_clo_pack<<<blocks_for(B.nblocks, kCloWarps), kCloWarps * 32, 0, s>>>(h->n, B.nblocks, B.nptr.p, B.cr.p, B.npos.p, B.nval.p,
+                                                                              B.cptr.p, B.cpos.p, B.cval.p);
+    h->launches += 2;
     B.packed = true;
 }
 
@@ -809,6 +1055,9 @@ void run_block(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.nval = B.nval.p;
     P.rdiag = B.rdiag.p;
     P.bmeta = B.bmeta.p;
+    P.cptr = B.cptr.p;
+    P.cpos = B.cpos.p;
+    P.cval = B.cval.p;
     P.status = h->status.p;
     P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 20, (long long)options().spin_limit_ms * h->clock_khz / 32));
     P.trace = options().trace != 0 ? 1 : 0;

@@ -239,6 +239,11 @@ struct BlockSolve {
     DevBuf<int4> bmeta;             // [nblocks] {depth | leaf << 16 | widest local list << 20, widest recent lists, long-local mask, long-recent mask}
     DevBuf<int> llev;               // [n] level of every row inside its block's local DAG (the block factorisation walks them)
     DevBuf<int> bdepth;             // [nblocks] deepest local level of the block (all rows)
+    // the block's local system solved ahead of time: row i of (I + L_local)^-1 - I on the transitive closure of the row's
+    // local dependencies, so that the solve needs ONE exchange of values inside the block instead of depth(block) sweeps
+    int nclo = 0;
+    DevBuf<int> cptr, cpos;         // [n + 1], position inside the block (0 .. 31)
+    DevBuf<double> cval;
 };
 
 // One triangular solve packed in solve order (see DESIGN.md "data layout in HBM").
