@@ -36,7 +36,7 @@ constexpr int kBlk = 32;           // rows per block = lanes of the compute warp
 constexpr int kWin = 512;          // rows of history a "recent" dependency may reach back (older ones are "far")
 constexpr int kRing = 1024;        // shared-memory ring of solved values (>= kWin + 2 * kBlk, power of two)
 #ifndef BLK_SLOTS
-#define BLK_SLOTS 12
+#define BLK_SLOTS 16
 #endif
 #ifndef BLK_STAGERS
 #define BLK_STAGERS 8
@@ -268,6 +268,7 @@ struct BlockSmem {
     BlockSlot slot[kSlots];
     int staged[kSlots];        // block number + 1 whose data the slot holds
     int progress;              // blocks completed by the compute warp
+    long long tick[2];
 };
 
 #define BLK_SPIN(spins, code)                                            \
@@ -291,6 +292,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // come behind the wait.
 constexpr int kStageNear = 4;  // near / closure entries per lane held in registers across the wait (x 32 lanes)
 constexpr int kStageClo = 2;
+#ifndef BLK_FARREG
+#define BLK_FARREG 16
+#endif
+#ifndef BLK_HUB
+#define BLK_HUB 4
+#endif
+constexpr int kHubUnroll = BLK_HUB;
+constexpr int kFarReg = BLK_FARREG;  // far entries per lane requested before the wait
 __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, int w, int lane) {
     unsigned spins = 0;
     for (int K = w; K < P.nblocks; K += kStagers) {
@@ -315,10 +324,10 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
         const bool clo = !big && ctotal <= kCloCap;
         const bool flong = fe - fb > 64;
         // round 2: entries
-        int fp[8];
-        double fc[8];
+        int fp[kFarReg];
+        double fc[kFarReg];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kFarReg; ++u) {
             const bool has = !flong && fb + u < fe;
             fp[u] = has ? __ldg(P.fpos + fb + u) : -1;
             fc[u] = has ? __ldg(P.fval + fb + u) : 0.0;
@@ -348,14 +357,19 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
         // round 3: solved values of the far dependencies
         double r = bq * rd;
         {
-            double v[8];
+            double v[kFarReg];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = fp[u] >= 0 ? __ldcg(P.x + (P.backward ? P.n - 1 - fp[u] : fp[u])) : 0.0;
+            for (int u = 0; u < kFarReg; ++u) v[u] = fp[u] >= 0 ? __ldcg(P.x + (P.backward ? P.n - 1 - fp[u] : fp[u])) : 0.0;
+            double r1 = 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) r = fma(-fc[u], v[u], r);
+            for (int u = 0; u < kFarReg; u += 2) {
+                r = fma(-fc[u], v[u], r);
+                r1 = fma(-fc[u + 1], v[u + 1], r1);
+            }
+            r += r1;
         }
         if (!flong) {
-            for (int e0 = fb + 8; e0 < fe; e0 += 8) {
+            for (int e0 = fb + kFarReg; e0 < fe; e0 += 8) {
                 double c[8], v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -378,9 +392,19 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
             fm &= fm - 1;
             const int b = __shfl_sync(FULL, fb, src), e = __shfl_sync(FULL, fe, src);
             double part = 0.0;
-            for (int t = b + lane; t < e; t += 32) {
-                const int pd = __ldg(P.fpos + t);
-                part = fma(__ldg(P.fval + t), __ldcg(P.x + (P.backward ? P.n - 1 - pd : pd)), part);
+            for (int t = b + lane; t < e; t += 32 * kHubUnroll) {  // (kHubUnroll strides requested together)
+                int pd[kHubUnroll];
+                double c[kHubUnroll], v[kHubUnroll];
+#pragma unroll
+                for (int u = 0; u < kHubUnroll; ++u) {
+                    const bool has = t + 32 * u < e;
+                    pd[u] = has ? __ldg(P.fpos + t + 32 * u) : -1;
+                    c[u] = has ? __ldg(P.fval + t + 32 * u) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kHubUnroll; ++u) v[u] = pd[u] >= 0 ? __ldcg(P.x + (P.backward ? P.n - 1 - pd[u] : pd[u])) : 0.0;
+#pragma unroll
+                for (int u = 0; u < kHubUnroll; ++u) part = fma(c[u], v[u], part);
             }
             part = warp_sum(part);
             if (lane == src) r -= part;
@@ -590,6 +614,19 @@ __device__ __forceinline__ double blk_clo_long(const int* cp, const double* cv, 
 }
 // The block with its local system solved ahead of time (k_blk_clo_pack): x = r + N r, ONE exchange of the 32 right-hand
 // sides instead of depth(block) dependent sweeps.  NC = closure entries per lane held in registers (4 / 8 / 12 / 16).
+#ifdef BLK_TIMERS  // dev builds: where the cycles of a block go (printed with option trace)
+__device__ long long g_blk_tick[2][6];
+#define BLK_TICK(i)                                                   \
+    {                                                                 \
+        const long long c_ = clock64();                               \
+        if (lane == 0) g_blk_tick[cw][i] += c_ - M.tick[cw];          \
+        M.tick[cw] = c_;                                              \
+    }
+#define BLK_TICK_START M.tick[cw] = clock64();
+#else
+#define BLK_TICK(i)
+#define BLK_TICK_START
+#endif
 template <int NC>
 __device__ __forceinline__ bool blk_block_clo(const BlockParams& P, BlockSmem& M, BlockSlot& L, int K, int cw, int lane, int maxrec,
                                               unsigned mrec, unsigned mclo, unsigned& spins) {
@@ -602,17 +639,20 @@ __device__ __forceinline__ bool blk_block_clo(const BlockParams& P, BlockSmem& M
     const bool lrec = (mrec >> lane) & 1u, lclo = (mclo >> lane) & 1u;
     double r = L.r[lane];
     const int b0 = K * kBlk;
-    // ---- phase A: the closure list into registers, the recent entries older than the previous block
+    BLK_TICK_START
+    // ---- phase A: the closure list into registers (a long list: its first NC entries), the recent entries older than the
+    // previous block
     int csrc[NC];
     double cco[NC];
 #pragma unroll
     for (int t = 0; t < NC; ++t) {
-        const bool has = !lclo && t < ccnt;
+        const bool has = t < ccnt;
         csrc[t] = has ? L.cpos[coff + t] : lane;
         cco[t] = has ? L.cval[coff + t] : 0.0;
     }
     r = blk_gather<false>(M, np, nv, off, nold, maxold, lrec, r);
     r = blk_gather_long(M, np, nv, mrec, off, nold, lane, r);
+    BLK_TICK(0)
     // ---- phase B: block K - 1 is complete
     while (*(volatile int*)&M.progress < K) {
         if ((++spins & 0x3ffu) == 0 && (spins >= P.spin_iters || *(volatile int*)P.status != 0)) {
@@ -621,8 +661,10 @@ __device__ __forceinline__ bool blk_block_clo(const BlockParams& P, BlockSmem& M
         }
     }
     fence_acq_rel_cta();
+    BLK_TICK(1)
     r = blk_gather<false>(M, np, nv, off + nold, nrec - nold, maxprev, lrec, r);
     r = blk_gather_long(M, np, nv, mrec, off + nold, nrec - nold, lane, r);
+    BLK_TICK(2)
     double* xs = M.xs[cw];
     if (mclo) {
         xs[lane] = r;
@@ -635,10 +677,11 @@ __device__ __forceinline__ bool blk_block_clo(const BlockParams& P, BlockSmem& M
 #pragma unroll
     for (int t = 0; t < NC; ++t) a[t & 3] = fma(cco[t], v[t], a[t & 3]);
     double x = (a[0] + a[1]) + (a[2] + a[3]);
-    if (mclo) {
-        if (lclo) x = r + blk_clo_long(L.cpos, L.cval, xs, coff, ccnt);
+    if (mclo) {  // (only NC = kRegClo gets here with a long list: the lane adds the entries beyond its registers)
+        if (lclo) x += blk_clo_long(L.cpos, L.cval, xs, coff + kRegClo, ccnt - kRegClo);
         __syncwarp();
     }
+    BLK_TICK(3)
     // ---- publish
     const int q = b0 + lane;
     M.ring[q & (kRing - 1)] = x;
@@ -646,6 +689,7 @@ __device__ __forceinline__ bool blk_block_clo(const BlockParams& P, BlockSmem& M
     __syncwarp();
     fence_acq_rel_cta();
     if (lane == 0) *(volatile int*)&M.progress = K + 1;
+    BLK_TICK(4)
     return true;
 }
 
@@ -667,7 +711,7 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
         if (L.clo) {
             const int ccnt = L.ccnt[lane];
             const unsigned mclo = __ballot_sync(FULL, ccnt > kRegClo);
-            const int maxclo = __reduce_max_sync(FULL, ccnt > kRegClo ? 0 : ccnt);
+            const int maxclo = __reduce_max_sync(FULL, min(ccnt, kRegClo));
             if (maxclo <= 4) ok = blk_block_clo<4>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
             else if (maxclo <= 8) ok = blk_block_clo<8>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
             else if (maxclo <= 12) ok = blk_block_clo<12>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
@@ -684,6 +728,11 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
         const double nb = (double)((P.nblocks + 1 - cw) / 2);
         printf("block solve, compute warp %d: %d blocks | cycles per own block: wait for slot / older blocks %.0f, phases A + B (incl. the wait for the previous block) %.0f\n",
                cw, (int)nb, t_wait / nb, t_block / nb);
+#ifdef BLK_TIMERS
+        printf("  closure blocks, warp %d: phase A %.0f | wait for the previous block %.0f | entries into it %.0f | exchange %.0f | publish %.0f\n", cw,
+               g_blk_tick[cw][0] / nb, g_blk_tick[cw][1] / nb, g_blk_tick[cw][2] / nb, g_blk_tick[cw][3] / nb, g_blk_tick[cw][4] / nb);
+        for (int i = 0; i < 6; ++i) g_blk_tick[cw][i] = 0;
+#endif
     }
 }
 

@@ -41,11 +41,11 @@ else:
         L, U = oracle.port.ilu0(A); ref = oracle.port.apply_lu(L, U, b)
     else:
         ref = oracle.port.apply_llt(oracle.port.ichol0(A), b)
-    print(case, "ok, relerr vs oracle %.2e" % (np.abs(y - ref).max() / np.abs(ref).max()))
+    print(case, "ok, relerr vs oracle %.2e" % (np.abs(y - ref).max() / np.abs(ref).max()), "part_mode", B.stats.get("part_mode"))
 PY
-for tool in memcheck racecheck; do
-  for c in systolic systolic_exact plane syncfree levels deep; do
+for tool in ${TOOLS:-memcheck racecheck}; do
+  for c in ${CASES:-systolic systolic_exact plane syncfree levels deep}; do
     echo "=== $tool $c"
     timeout 600 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_case.py $c 2>&1 | grep -v "^$" | tail -6
   done
-done 2>&1 | tee gpurun_out/sanitizer_r2.log
+done 2>&1 | tee gpurun_out/sanitizer_${TAG:-r2}.log
