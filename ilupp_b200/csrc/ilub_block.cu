@@ -243,7 +243,8 @@ struct BlockParams {
     const int* cptr;  // solved local systems (closure lists)
     const int* cpos;
     const double* cval;
-    double* x;  // right-hand side in, solution out (natural row order)
+    double* x;  // right-hand side in, solution out (natural row order); CTA c takes column c: x + c * ldx
+    long long ldx;
     int* status;
     unsigned spin_iters;
     int trace;  // debug (option trace): the compute warp prints where its cycles went
@@ -737,7 +738,10 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
 }
 
 constexpr int kWarps = 2 * kStagers;  // warps 0 and 1 compute; warps 4, 5, 8, 9 (their schedulers) stay idle; the other six stage
-__global__ void __launch_bounds__(kWarps * 32, 1) k_trsv_block(const BlockParams P) {
+__global__ void __launch_bounds__(kWarps * 32, 1) k_trsv_block(const BlockParams P0) {
+    // one CTA per right-hand side: the columns of a multi-vector apply are independent solves on different SMs
+    BlockParams P = P0;
+    P.x += (long long)blockIdx.x * P0.ldx;
     extern __shared__ __align__(16) unsigned char blk_smem_raw[];
     BlockSmem& M = *reinterpret_cast<BlockSmem*>(blk_smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1110,11 +1114,10 @@ void run_block(ilub_handle* h, int slot, double* x, int64_t ldx, int nrhs, cudaS
     P.status = h->status.p;
     P.spin_iters = (unsigned)std::min<long long>(0x7fffffffll, std::max<long long>(1 << 20, (long long)options().spin_limit_ms * h->clock_khz / 32));
     P.trace = options().trace != 0 ? 1 : 0;
-    for (int c = 0; c < nrhs; ++c) {
-        P.x = x + (int64_t)c * ldx;
-        k_trsv_block<<<1, kWarps * 32, smem, s>>>(P);
-        h->launches++;
-    }
+    P.x = x;
+    P.ldx = ldx;
+    k_trsv_block<<<nrhs, kWarps * 32, smem, s>>>(P);
+    h->launches++;
     ILUB_CUDA(cudaGetLastError());
 }
 

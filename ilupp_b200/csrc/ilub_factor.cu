@@ -807,11 +807,12 @@ __global__ void __launch_bounds__(512, 1) k_factor_block(FactorParams P, int nbl
             st_relaxed_gpu_u32(progress, (unsigned)(K + 1));
         }
     }
-    if (P.epoch && threadIdx.x == 0)
+    if (P.epoch && threadIdx.x == 0) {
         printf("factor front: step 1 %.0f cycles per block\n", (double)tstep1 / nblocks);
         printf("factor front: %d blocks, %lld local levels | cycles per block: wait %.0f, levels without long rows %.0f, with %.0f | %lld levels with a long row, %.0f cycles each; %.0f cycles per other level\n",
                nblocks, nlev_sum, (double)tw / nblocks, (double)tl / nblocks, (double)tbig / nblocks, nbig, nbig ? (double)tbig / nbig : 0.0,
                (double)tl / (double)(nlev_sum - nbig));
+    }
 }
 
 int factor_schedule(const ilub_handle* h) {

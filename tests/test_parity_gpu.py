@@ -1159,6 +1159,11 @@ def test_block_sequential_solve(ilupp):
             y = b.copy(); (Bf.apply_trans if tr else Bf.apply)(y)
             z = b.copy(); (Bl.apply_trans if tr else Bl.apply)(z)
             assert relerr(y, yo) <= TOL and relerr(z, yo) <= TOL
+        X = P.rhs(n, 9, k=3)          # several right-hand sides: one CTA per column, the same numbers as one at a time
+        Y = Bf @ X
+        for c in range(3):
+            yc = X[:, c].copy(); Bf.apply(yc)
+            assert np.array_equal(Y[:, c], yc)
         Bf.set_option("exact", 1)     # the exact mode keeps the level loop (the factors stay the fast-mode ones)
         y = b.copy(); Bf.apply(y)
         assert relerr(y, oracle.port.apply_lu(Lo, Uo, b)) <= TOL
@@ -1169,7 +1174,7 @@ def test_block_sequential_solve(ilupp):
 
 
 @pytest.mark.parametrize("exact", [1, 0])
-def test_block_paths_ragged_size(ilupp, exact):
+def test_block_paths_ragged_size(ilupp, exact, capfd):
     """Deep DAG whose size is not a multiple of the 32-row blocks and large enough for the probe: levels through
     k_levels_block, factorisation through k_factor_block (bit for bit in exact mode), solve through k_trsv_block (fast
     mode) -- all against the oracle."""
@@ -1194,6 +1199,9 @@ def test_block_paths_ragged_size(ilupp, exact):
         assert relerr(y, yo) <= TOL
         if exact:
             assert np.array_equal(y, yo)
+    import torch
+    torch.cuda.synchronize()
+    assert capfd.readouterr().out == ""   # (the kernels' debug timers print only under option trace)
     A2 = A.copy(); A2.data = A.data * 1.25      # numeric re-factorisation on the unchanged pattern
     B.refactor(A2)
     L2o, U2o = oracle.port.ilu0(A2)
