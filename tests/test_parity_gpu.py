@@ -1202,11 +1202,16 @@ def test_block_paths_ragged_size(ilupp, exact, capfd):
     import torch
     torch.cuda.synchronize()
     assert capfd.readouterr().out == ""   # (the kernels' debug timers print only under option trace)
-    A2 = A.copy(); A2.data = A.data * 1.25      # numeric re-factorisation on the unchanged pattern
+    # numeric re-factorisation on the unchanged pattern (values perturbed entry by entry: the solve's packed coefficients
+    # and the blocks' solved local systems must follow)
+    A2 = A.copy(); A2.data = A.data * np.random.default_rng(2).uniform(0.95, 1.05, A.nnz)
     B.refactor(A2)
     L2o, U2o = oracle.port.ilu0(A2)
     L2, U2 = B.factors()
     assert relerr(L2.data, L2o.data) <= TOL and relerr(U2.data, U2o.data) <= TOL
+    for tr in (False, True):
+        y = b.copy(); (B.apply_trans if tr else B.apply)(y)
+        assert relerr(y, oracle.port.apply_lu(L2o, U2o, b, tr)) <= TOL
 
 
 def test_syncfree_configuration_that_cannot_be_resident_is_refused(ilupp):
