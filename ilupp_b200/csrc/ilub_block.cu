@@ -291,10 +291,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 // not depend on the solve's progress -- pointers, counts, the first far entries, the near and closure lists -- is requested
 // BEFORE the stager waits for its slot, in two rounds of independent loads; only the solved values and the slot writes
 // come behind the wait.
-constexpr int kStageNear = 4;  // near / closure entries per lane held in registers across the wait (x 32 lanes)
+#ifndef BLK_STAGENEAR
+#define BLK_STAGENEAR 2
+#endif
+constexpr int kStageNear = BLK_STAGENEAR;  // near / closure entries per lane held in registers across the wait (x 32 lanes)
 constexpr int kStageClo = 2;
 #ifndef BLK_FARREG
-#define BLK_FARREG 16
+#define BLK_FARREG 8
 #endif
 #ifndef BLK_HUB
 #define BLK_HUB 4
@@ -355,8 +358,19 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
             BLK_SPIN(spins, 401)
         }
         fence_acq_rel_cta();
-        // round 3: solved values of the far dependencies
+        // round 3: solved values of the far dependencies; the entries of a following round (rows with more than kFarReg far
+        // entries) are requested together with the solved values of the round before, so that a round costs one trip to
+        // memory instead of two
         double r = bq * rd;
+        int gp[8];
+        double gc[8];
+        int e0 = fb + kFarReg;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool has = !flong && e0 + u < fe;
+            gp[u] = has ? __ldg(P.fpos + e0 + u) : -1;
+            gc[u] = has ? __ldg(P.fval + e0 + u) : 0.0;
+        }
         {
             double v[kFarReg];
 #pragma unroll
@@ -369,21 +383,25 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
             }
             r += r1;
         }
-        if (!flong) {
-            for (int e0 = fb + kFarReg; e0 < fe; e0 += 8) {
-                double c[8], v[8];
+        while (__any_sync(FULL, !flong && e0 < fe)) {
+            double gv[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    c[u] = 0.0;
-                    v[u] = 0.0;
-                    if (e0 + u < fe) {
-                        const int pd = __ldg(P.fpos + e0 + u);
-                        c[u] = __ldg(P.fval + e0 + u);
-                        v[u] = __ldcg(P.x + (P.backward ? P.n - 1 - pd : pd));
-                    }
-                }
+            for (int u = 0; u < 8; ++u) gv[u] = gp[u] >= 0 ? __ldcg(P.x + (P.backward ? P.n - 1 - gp[u] : gp[u])) : 0.0;
+            int hp[8];
+            double hc[8];
+            e0 += 8;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) r = fma(-c[u], v[u], r);
+            for (int u = 0; u < 8; ++u) {
+                const bool has = !flong && e0 + u < fe;
+                hp[u] = has ? __ldg(P.fpos + e0 + u) : -1;
+                hc[u] = has ? __ldg(P.fval + e0 + u) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r = fma(-gc[u], gv[u], r);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                gp[u] = hp[u];
+                gc[u] = hc[u];
             }
         }
         // hub rows: the whole warp strides over the row's far list
