@@ -280,6 +280,18 @@ struct BlockSmem {
         }                                                                \
     }
 
+// (the rare paths -- long rows -- are kept out of line: inlined into every variant of the block routine they are most of its
+//  code, and a lone warp that runs every instruction once per block pays for instruction fetch)
+#ifdef BLK_INLINE_RARE
+#define BLK_RARE __device__ __forceinline__
+#else
+#define BLK_RARE __device__ __noinline__
+#endif
+#ifdef BLK_NOINLINE_HOT
+#define BLK_HOT __device__ __noinline__
+#else
+#define BLK_HOT __device__ __forceinline__
+#endif
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -292,12 +304,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // BEFORE the stager waits for its slot, in two rounds of independent loads; only the solved values and the slot writes
 // come behind the wait.
 #ifndef BLK_STAGENEAR
-#define BLK_STAGENEAR 2
+#define BLK_STAGENEAR 4
 #endif
 constexpr int kStageNear = BLK_STAGENEAR;  // near / closure entries per lane held in registers across the wait (x 32 lanes)
 constexpr int kStageClo = 2;
 #ifndef BLK_FARREG
-#define BLK_FARREG 8
+#define BLK_FARREG 16
 #endif
 #ifndef BLK_HUB
 #define BLK_HUB 4
@@ -483,7 +495,7 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
 // bound by the latency of whatever it issues in sequence, so every phase requests all its operands first and the loops
 // have compile-time trip counts (no branch, no divergence check in front of the shuffles).
 template <bool BIG>
-__device__ __forceinline__ double blk_gather(const BlockSmem& M, const int* np, const double* nv, int off, int cnt, int maxcnt,
+BLK_HOT double blk_gather(const BlockSmem& M, const int* np, const double* nv, int off, int cnt, int maxcnt,
                                              bool islong, double r) {
     for (int t0 = 0; t0 < maxcnt; t0 += 8) {  // eight entries per round: all indices, then all ring values, then the arithmetic
         int pp[8];
@@ -507,7 +519,7 @@ __device__ __forceinline__ double blk_gather(const BlockSmem& M, const int* np, 
     return r;
 }
 // long rows: the warp strides over entries [first, first + cnt) of every long row's list
-__device__ __forceinline__ double blk_gather_long(const BlockSmem& M, const int* np, const double* nv, unsigned lmask, int first,
+BLK_RARE double blk_gather_long(const BlockSmem& M, const int* np, const double* nv, unsigned lmask, int first,
                                                   int cnt, int lane, double r) {
     while (lmask) {
         const int src = __ffs(lmask) - 1;
@@ -522,7 +534,7 @@ __device__ __forceinline__ double blk_gather_long(const BlockSmem& M, const int*
 }
 
 // a row with a long local list: the lane walks it itself, values from the block's copy in shared memory (two chains)
-__device__ __forceinline__ double blk_local_long(const int* np, const double* nv, const double* xs, int first, int cnt, int b0) {
+BLK_RARE double blk_local_long(const int* np, const double* nv, const double* xs, int first, int cnt, int b0) {
     double a0 = 0.0, a1 = 0.0;
     for (int t = 0; t < cnt; t += 4) {
         int pp[4];
@@ -564,7 +576,7 @@ __device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, Bl
         lco[t] = has ? nv[off + nrec + t] : 0.0;
     }
     r = blk_gather<BIG>(M, np, nv, off, nold, maxold, lrec, r);
-    r = blk_gather_long(M, np, nv, mrec, off, nold, lane, r);
+    if (mrec) r = blk_gather_long(M, np, nv, mrec, off, nold, lane, r);
     // ---- phase B: block K - 1 is complete
     while (*(volatile int*)&M.progress < K) {
         if ((++spins & 0x3ffu) == 0 && (spins >= P.spin_iters || *(volatile int*)P.status != 0)) {
@@ -574,7 +586,7 @@ __device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, Bl
     }
     fence_acq_rel_cta();
     r = blk_gather<BIG>(M, np, nv, off + nold, nrec - nold, maxprev, lrec, r);
-    r = blk_gather_long(M, np, nv, mrec, off + nold, nrec - nold, lane, r);
+    if (mrec) r = blk_gather_long(M, np, nv, mrec, off + nold, nrec - nold, lane, r);
     // local dependencies: Jacobi sweeps over the block, values exchanged by shuffles
     double* xs = M.xs[cw];
     double x = r;
@@ -613,7 +625,7 @@ __device__ __forceinline__ bool blk_block(const BlockParams& P, BlockSmem& M, Bl
 }
 
 // a row whose solved local system has more than kRegClo entries: the lane walks its list itself
-__device__ __forceinline__ double blk_clo_long(const int* cp, const double* cv, const double* xs, int first, int cnt) {
+BLK_RARE double blk_clo_long(const int* cp, const double* cv, const double* xs, int first, int cnt) {
     double a0 = 0.0, a1 = 0.0;
     for (int t = 0; t < cnt; t += 4) {
         int pp[4];
@@ -632,7 +644,7 @@ __device__ __forceinline__ double blk_clo_long(const int* cp, const double* cv, 
     return a0 + a1;
 }
 // The block with its local system solved ahead of time (k_blk_clo_pack): x = r + N r, ONE exchange of the 32 right-hand
-// sides instead of depth(block) dependent sweeps.  NC = closure entries per lane held in registers (4 / 8 / 12 / 16).
+// sides instead of depth(block) dependent sweeps.  NC = closure entries per lane held in registers (8 / 16).
 #ifdef BLK_TIMERS  // dev builds: where the cycles of a block go (printed with option trace)
 __device__ long long g_blk_tick[2][6];
 #define BLK_TICK(i)                                                   \
@@ -670,7 +682,7 @@ __device__ __forceinline__ bool blk_block_clo(const BlockParams& P, BlockSmem& M
         cco[t] = has ? L.cval[coff + t] : 0.0;
     }
     r = blk_gather<false>(M, np, nv, off, nold, maxold, lrec, r);
-    r = blk_gather_long(M, np, nv, mrec, off, nold, lane, r);
+    if (mrec) r = blk_gather_long(M, np, nv, mrec, off, nold, lane, r);
     BLK_TICK(0)
     // ---- phase B: block K - 1 is complete
     while (*(volatile int*)&M.progress < K) {
@@ -682,7 +694,7 @@ __device__ __forceinline__ bool blk_block_clo(const BlockParams& P, BlockSmem& M
     fence_acq_rel_cta();
     BLK_TICK(1)
     r = blk_gather<false>(M, np, nv, off + nold, nrec - nold, maxprev, lrec, r);
-    r = blk_gather_long(M, np, nv, mrec, off + nold, nrec - nold, lane, r);
+    if (mrec) r = blk_gather_long(M, np, nv, mrec, off + nold, nrec - nold, lane, r);
     BLK_TICK(2)
     double* xs = M.xs[cw];
     if (mclo) {
@@ -731,10 +743,10 @@ __device__ __forceinline__ void blk_compute(const BlockParams& P, BlockSmem& M, 
             const int ccnt = L.ccnt[lane];
             const unsigned mclo = __ballot_sync(FULL, ccnt > kRegClo);
             const int maxclo = __reduce_max_sync(FULL, min(ccnt, kRegClo));
-            if (maxclo <= 4) ok = blk_block_clo<4>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
-            else if (maxclo <= 8) ok = blk_block_clo<8>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
-            else if (maxclo <= 12) ok = blk_block_clo<12>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
-            else ok = blk_block_clo<16>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
+            // (two variants only: with more, the instruction footprint of the compute warps costs more than the spared shuffles)
+            if (maxclo <= 8) ok = blk_block_clo<8>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
+            else
+            ok = blk_block_clo<16>(P, M, L, K, cw, lane, maxrec, mrec, mclo, spins);
         } else if (L.big) ok = blk_block<true, 8>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
         else if (maxloc <= 2) ok = blk_block<false, 2>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
         else if (maxloc <= 4) ok = blk_block<false, 4>(P, M, L, K, cw, lane, depth, maxrec, mloc, mrec, spins);
