@@ -150,9 +150,12 @@ __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, con
         reach = nr;
         if (!__any_sync(FULL, changed)) break;
     }
+    // a block whose closure would not fit its slot keeps the sweeps: nothing is stored for it (bit 30 of the first meta word;
+    // this also bounds the closure arrays by kCloCap / kBlk entries per row)
+    const bool noclo = __reduce_add_sync(FULL, live ? __popc(reach) : 0) > kCloCap;
     if (live) {
-        cmask[q] = reach;
-        ccnt[q] = __popc(reach);
+        cmask[q] = noclo ? 0u : reach;
+        ccnt[q] = noclo ? 0 : __popc(reach);
     }
     const int depth_all = __reduce_max_sync(FULL, ll);
     const int depth_reg = __reduce_max_sync(FULL, lloc ? 0 : ll);
@@ -167,7 +170,7 @@ __global__ void k_blk_meta(int n, int nblocks, const int* __restrict__ nptr, con
     const unsigned mrec = __ballot_sync(FULL, lrec), mloc = __ballot_sync(FULL, lloc);
     const int leaf = (mloc & pointed) == 0 ? 1 : 0;
     const int depth = leaf ? depth_reg : depth_all;  // (leaves are evaluated behind the sweeps: they need none themselves)
-    if (lane == 0) bmeta[K] = make_int4(depth | (leaf << 16) | (maxloc << 20), maxrec, (int)mloc, (int)mrec);
+    if (lane == 0) bmeta[K] = make_int4(depth | (leaf << 16) | (maxloc << 20) | ((noclo ? 1 : 0) << 30), maxrec, (int)mloc, (int)mrec);
     if (live) llev[q] = ll;
     if (lane == 0) bdepth[K] = depth_all;
 }
@@ -212,7 +215,8 @@ __global__ void __launch_bounds__(kCloWarps * 32) k_blk_clo_pack(int n, int nblo
     const int q = b0 + lane;
     const bool live = q < n;
     const int my_lb = live ? nptr[q] + cr[q] : 0, my_le = live ? nptr[q + 1] : 0;
-    if (__reduce_max_sync(FULL, my_le - my_lb) == 0) return;  // (no local dependency in the block: nothing to store)
+    const int my_cn = live ? cptr[q + 1] - cptr[q] : 0;
+    if (__reduce_max_sync(FULL, my_cn) == 0) return;  // (no local dependency in the block, or a block that keeps the sweeps)
     for (int i = 0; i < kBlk; ++i) {
         const int lb = __shfl_sync(FULL, my_lb, i), le = __shfl_sync(FULL, my_le, i);
         double acc = 0.0;
@@ -256,7 +260,7 @@ struct BlockSlot {
     int npos[kSlotCap];
     int off[kBlk];             // first near entry of every row inside the slot (or inside the global arrays: big blocks)
     int nrec[kBlk], nloc[kBlk], nold[kBlk];
-    int4 meta;                 // {depth | leaf << 16 | widest local list << 20, widest older | previous-block list, long-local mask, long-recent mask}
+    int4 meta;                 // {depth | leaf << 16 | widest local list << 20 | no closure << 30, widest older | previous-block list, long-local mask, long-recent mask}
     int big;                   // the block's near entries did not fit: read them from global memory
     double cval[kCloCap];      // the block's solved local system (closure lists, all rows concatenated)
     int cpos[kCloCap];
@@ -337,7 +341,7 @@ __device__ __forceinline__ void blk_stager(const BlockParams& P, BlockSmem& M, i
         const int nb0 = __shfl_sync(FULL, nb, 0), cb0 = __shfl_sync(FULL, cb, 0);
         const int total = ne_all - nb0, ctotal = ce_all - cb0;
         const bool big = total > kSlotCap;
-        const bool clo = !big && ctotal <= kCloCap;
+        const bool clo = !big && ((__shfl_sync(FULL, meta.x, 0) >> 30) & 1) == 0 && ctotal <= kCloCap;
         const bool flong = fe - fb > 64;
         // round 2: entries
         int fp[kFarReg];
